@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE — runs the UNMODIFIED reference decoder in-process.
+
+Only usable where ``/root/reference`` is mounted (the build container, not the
+GPU box).  It is used by ``tests/golden/make_golden.py`` to produce the golden
+vectors that pin ``oracle/wefax_oracle.py``, and by the container-only tests.
+Nothing on the product path may import this.
+
+Recipe: stub matplotlib (``wefax.py:6,9,10`` import it for debug
+plots only), chdir to the reference root (``config.py:11`` opens
+``config/config.json`` CWD-relative), patch ``wefax.time.sleep`` (the reference
+sleeps 7.0 s per ``process()``: ``wefax.py:59,73,75,77,193,202``).
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("WEFAX_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "wefax.py"))
+
+
+def _stub_matplotlib() -> None:
+    if "matplotlib" in sys.modules and not getattr(sys.modules["matplotlib"], "_wefax_stub", False):
+        return  # a real matplotlib is importable; leave it alone
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.ticker",
+                 "matplotlib.animation", "matplotlib.cm"):
+        mod = types.ModuleType(name)
+        mod._wefax_stub = True
+        sys.modules.setdefault(name, mod)
+    sys.modules["matplotlib.ticker"].FormatStrFormatter = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].ticker = sys.modules["matplotlib.ticker"]
+    sys.modules["matplotlib"].animation = sys.modules["matplotlib.animation"]
+    sys.modules["matplotlib"].cm = sys.modules["matplotlib.cm"]
+
+
+@contextlib.contextmanager
+def _in_reference_root():
+    cwd = os.getcwd()
+    os.chdir(REFERENCE_ROOT)
+    try:
+        yield
+    finally:
+        os.chdir(cwd)
+
+
+def import_reference():
+    """Import the reference's ``wefax`` module (cached) with sleeps patched out."""
+    if not reference_available():
+        raise RuntimeError(f"reference not mounted at {REFERENCE_ROOT}")
+    if "wefax" in sys.modules and getattr(sys.modules["wefax"], "_is_reference", False):
+        return sys.modules["wefax"]
+    try:
+        import matplotlib  # noqa: F401
+    except Exception:
+        _stub_matplotlib()
+    with _in_reference_root():
+        sys.path.insert(0, REFERENCE_ROOT)
+        try:
+            import wefax  # the reference module, not ours
+        finally:
+            sys.path.remove(REFERENCE_ROOT)
+    wefax.time.sleep = lambda s: None
+    wefax._is_reference = True
+    return wefax
+
+
+def run_reference(wav_path: str, lpm: int = 120) -> dict:
+    """``Demodulator(wav, lpm).process()`` of the reference; returns every attribute.
+
+    If ``process()`` raises (e.g. the ``ValueError`` from ``max([])`` at
+    ``wefax.py:294``), the exception is returned under ``"error"`` with whatever
+    attributes were set before it.
+    """
+    wefax = import_reference()
+    wav_path = os.path.abspath(wav_path)
+    out: dict = {"error": None}
+    with _in_reference_root():
+        d = wefax.Demodulator(wav_path, lines_per_minute=lpm, tcp_stream=True, quiet=True)
+        try:
+            d.process()
+        except Exception as exc:  # the caller compares error type + message
+            out["error"] = (type(exc).__name__, str(exc))
+        finally:
+            if sys.stdout is not sys.__stdout__:
+                try:
+                    sys.stdout.close()
+                except Exception:
+                    pass
+            sys.stdout = sys.__stdout__
+    for name in ("sample_rate", "length", "start_frame"):
+        if hasattr(d, name):
+            out[name] = getattr(d, name)
+    if hasattr(d, "audio_data"):
+        out["audio_data"] = np.asarray(d.audio_data, dtype=np.float64)
+    if hasattr(d, "demodulated_data"):
+        out["demodulated_data"] = np.asarray(d.demodulated_data, dtype=np.float64)
+    if hasattr(d, "digitalized_data"):
+        out["digitalized_data"] = np.asarray(d.digitalized_data, dtype=np.int64)
+    if hasattr(d, "phasing_signals"):
+        out["phasing_signals"] = [int(v) for v in d.phasing_signals]
+    if hasattr(d, "output_image"):
+        out["output_image"] = np.asarray(d.output_image)
+    out["progress_titles"] = [m.get("progress_title", m.get("message_content"))
+                              for m in d.websocket_stack]
+    return out
