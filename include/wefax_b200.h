@@ -1,0 +1,167 @@
+/*
+ * wefax_b200 — C-ABI of the B200-native WEFAX file-decoding hot path.
+ *
+ * The reference (wojlin/WEFAX) has no plugin / FFI interface: its decode path is
+ * the Python class wefax.Demodulator (wefax.py:18-408) whose process()
+ * (wefax.py:46-93) calls scipy / numpy / Pillow.  This library sits BELOW a
+ * Demodulator-compatible Python class (wefax_b200/wefax.py) and replaces, call
+ * for call, the third-party routines process() runs:
+ *
+ *   wefax.py:349,360-373  wavfile.read + __merge_channels   -> int16 ingest (+ wrapping stereo merge)
+ *   wefax.py:384          scipy.signal.resample             -> FFT-domain resample to 11025 Hz
+ *   wefax.py:68-72        iirnotch + filtfilt               -> zero-phase notch (exact edge handling)
+ *   wefax.py:174-175      hilbert + medfilt(abs, 5)         -> length-N analytic signal, envelope, median-5
+ *   wefax.py:196-200,216  percentile / round / clip         -> global 0.5 / 99.5 percentile grey map
+ *   wefax.py:221-294      pattern_search + peak grouping    -> phasing search, start_frame
+ *   wefax.py:296-327      putpixel loop + Image.resize      -> line raster, x4 vertical bicubic (Pillow-exact)
+ *
+ * Plain pointers and sizes only; no torch / numpy types.  One context is used
+ * from one host thread at a time; several contexts (one per GPU / stream) may be
+ * used concurrently.  Every entry point returns a wefax_status; the message of
+ * the last failure of a context is available from wefax_last_error().
+ * There is NO CPU fallback: without a CUDA device wefax_ctx_create() fails.
+ */
+#ifndef WEFAX_B200_H
+#define WEFAX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WEFAX_ABI_VERSION 1
+#define WEFAX_TARGET_RATE 11025   /* wefax.py:60 */
+#define WEFAX_MAX_PEAKS 100       /* wefax.py:251 */
+
+typedef struct wefax_ctx wefax_ctx;
+
+typedef enum {
+    WEFAX_OK = 0,
+    WEFAX_ERR_INVALID = 1,      /* bad argument */
+    WEFAX_ERR_CUDA = 2,         /* CUDA runtime failure (message in wefax_last_error) */
+    WEFAX_ERR_NOMEM = 3,        /* device allocation failed */
+    WEFAX_ERR_UNSUPPORTED = 4   /* e.g. notch impulse response too long for the FIR path */
+} wefax_status;
+
+/* Per-recording outcome (wefax_batch_out.status), mirrors the exceptions the
+ * reference's process() propagates. */
+#define WEFAX_REC_OK 0
+#define WEFAX_REC_NO_GROUPS 1   /* wefax.py:294  max([]) -> ValueError            */
+#define WEFAX_REC_NO_LINES 2    /* wefax.py:304  putpixel on a 0-line image -> IndexError */
+#define WEFAX_REC_NAN 4         /* wefax.py:216  int(nan): high == low percentile  */
+
+/* wefax_batch_desc.flags */
+#define WEFAX_F_PCM_ON_DEVICE 1u   /* pcm points to device memory                 */
+#define WEFAX_F_OUT_ON_DEVICE 2u   /* every non-NULL output points to device mem  */
+
+/* ---- context -------------------------------------------------------------- */
+
+/* stream: a cudaStream_t owned by the caller, or NULL to let the context create
+ * its own.  All work of this context is issued on that stream. */
+int wefax_ctx_create(int device, void *stream, wefax_ctx **out);
+void wefax_ctx_destroy(wefax_ctx *ctx);
+const char *wefax_last_error(const wefax_ctx *ctx);
+int wefax_ctx_sync(wefax_ctx *ctx);
+void *wefax_ctx_stream(wefax_ctx *ctx);
+/* number of kernels this context has launched so far (bench accounting) */
+long long wefax_ctx_launch_count(const wefax_ctx *ctx);
+/* cap on the scratch memory one decode wave may use (default 24 GiB); recordings
+ * of a batch are processed in waves that fit. */
+int wefax_ctx_set_workspace_limit(wefax_ctx *ctx, long long bytes);
+int wefax_abi_version(void);
+int wefax_device_count(void);
+
+/* ---- host-side helpers (no GPU needed) ------------------------------------ */
+
+/* Constants the reference derives from LPM with Python float semantics
+ * (wefax.py:33,223,225,229,264-266,298). */
+typedef struct {
+    double frame_len;     /* 1 / (lpm / 60)                         */
+    int n1, n0;           /* samples(0.005), samples(0.001)         */
+    int template_len;     /* 2*n1 + n0                              */
+    int mindistance;      /* int(frame_len * sr * 0.8)              */
+    int width;            /* int(frame_len * sr)                    */
+    double dev_min, dev_max;   /* frame_len*sr -/+ 500 (exclusive)  */
+} wefax_line_constants;
+int wefax_line_constants_for(double lpm, int sample_rate, wefax_line_constants *out);
+
+/* int(11025 * (n_frames / sample_rate))  (wefax.py:357,384) */
+long long wefax_resampled_length(long long n_frames, int sample_rate);
+
+/* scipy.signal.iirnotch(f0, Q, fs) (wefax.py:68-70) */
+int wefax_notch_coefficients(double f0, double q, double fs, double b[3], double a[3]);
+
+/* How an n-point transform is decomposed: number of passes, the radix-R of each
+ * pass, and (bluestein != 0) the padded length used for non-smooth n. */
+int wefax_fft_plan_describe(long long n, int *n_passes, int pass_len[8], long long *bluestein_len);
+
+/* ---- the decode path ------------------------------------------------------ */
+
+typedef struct {
+    int n_recordings;
+    long long n_frames;      /* input frames per recording (all recordings of a batch are equal) */
+    int channels;            /* 1, or 2 = interleaved L,R merged as in wefax.py:372 */
+    int sample_rate;         /* of the input; != 11025 triggers the FFT resample   */
+    double notch_freq;       /* config.json notch_filter_frequency (wefax.py:63: int()) */
+    double notch_q;          /* config.json notch_filter_quality_factor            */
+    unsigned flags;
+} wefax_batch_desc;
+
+/* Outputs.  Any pointer may be NULL (that output is then not produced / copied).
+ * audio / demodulated / digitalized / raster live where WEFAX_F_OUT_ON_DEVICE says;
+ * the small per-recording results (peaks .. low_high) are ALWAYS host pointers.
+ * n_out = n_frames if sample_rate == 11025 else wefax_resampled_length().
+ * Per-recording strides: audio/demodulated/digitalized n_out elements; peaks and
+ * phasing WEFAX_MAX_PEAKS ints; raster raster_stride bytes (>= 4*(n_out/width)*width). */
+typedef struct {
+    float *audio;            /* wefax.py:72   audio_data after filtfilt (int16 scale)  */
+    float *demodulated;      /* wefax.py:74   demodulated_data                          */
+    uint8_t *digitalized;    /* wefax.py:76   digitalized_data (0..255)                 */
+    int32_t *peaks;          /* wefax.py:261  pattern_search() positions                */
+    int32_t *n_peaks;
+    int32_t *phasing;        /* wefax.py:78   phasing_signals                           */
+    int32_t *n_phasing;
+    int64_t *start_frame;    /* wefax.py:80                                             */
+    int32_t *height;         /* raster rows = 4 * ((n_out - start_frame) / width)       */
+    int32_t *status;         /* WEFAX_REC_* bits                                        */
+    double *low_high;        /* 2 per recording: the 0.5 / 99.5 percentiles             */
+    uint8_t *raster;         /* wefax.py:82-84 output_image, row-major (height, width)  */
+    long long raster_stride;
+} wefax_batch_out;
+
+/* lpm: one value per recording (wefax.py:20,42). */
+int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm,
+                       const double *lpm, const wefax_batch_out *out);
+
+/* ---- stage-level entry points (parity tests of single stages) -------------- */
+
+/* Complex DFT of `batch` sequences of length n, natural order in and out, host
+ * pointers, interleaved (re, im) float32.  inverse != 0 applies the 1/n scale. */
+int wefax_fft_c2c(wefax_ctx *ctx, long long n, int batch, const float *in, float *out, int inverse);
+
+/* |scipy.signal.hilbert(x)| without the median filter; host pointers. */
+int wefax_hilbert_envelope(wefax_ctx *ctx, long long n, int batch, const float *x, float *env);
+
+/* scipy.signal.resample(x, num) for real float32 input; host pointers. */
+int wefax_resample(wefax_ctx *ctx, long long n, long long num, int batch, const float *x, float *y);
+
+/* scipy.signal.filtfilt(*iirnotch(f0, q, 11025), x) on float32 input; host pointers. */
+int wefax_filtfilt(wefax_ctx *ctx, long long n, int batch, double notch_freq, double notch_q, const float *x,
+                   float *y);
+
+/* medfilt(env, 5) -> demodulated (optional), percentiles -> low_high (2 per recording),
+ * grey map -> digitalized; status gets WEFAX_REC_NAN per recording.  Host pointers.
+ * (wefax.py:175,196-200,216 on a given |hilbert| envelope) */
+int wefax_digitalize(wefax_ctx *ctx, long long n, int batch, const float *envelope, float *demodulated,
+                     uint8_t *digitalized, double *low_high, int32_t *status);
+
+/* Phasing search + raster on given digitalized data (wefax.py:218-327).  Host pointers;
+ * uses out->peaks .. out->status and out->raster / raster_stride; other fields ignored. */
+int wefax_sync_raster(wefax_ctx *ctx, long long n, int batch, const uint8_t *digitalized, const double *lpm,
+                      const wefax_batch_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEFAX_B200_H */

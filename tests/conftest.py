@@ -15,6 +15,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "reference: needs /root/reference mounted (build container only)")
+    config.addinivalue_line("markers", "slow: larger transforms (still seconds on a B200)")
 
 
 def golden_full_names():

@@ -1,0 +1,371 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the oracle
+(oracle/wefax_oracle.py) on the same inputs and against the golden vectors made
+by the unmodified reference (tests/golden).
+
+Tolerances (BASELINE.json north_star):
+  * float stages (audio_data, demodulated_data): max|d| / max|ref| <= 1e-4
+    (the CUDA path computes in fp32, the reference in float64);
+  * detected line starts (peaks / phasing_signals / start_frame): bit-exact
+    - always on identical digitalized input (stage test),
+    - end to end wherever the fp32 envelope does not flip a grey level that the
+      greedy picker is sensitive to (all committed golden cases);
+  * output pixels: >= 99.9 % within +-1 grey level end to end, bit-exact on
+    identical digitalized input.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_full_names, load_digests, load_golden_full
+from oracle import wefax_oracle as O
+from wefax_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_TOL = 1e-4
+PIXEL_FRACTION = 0.999
+
+
+@pytest.fixture(scope="module")
+def dec():
+    from wefax_b200.decoder import Decoder
+    d = Decoder(0)
+    yield d
+    d.close()
+
+
+def rel_err(a, ref):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - ref).max() / np.abs(ref).max())
+
+
+def frac_within_one(a, ref):
+    d = np.abs(np.asarray(a, dtype=np.int64) - np.asarray(ref, dtype=np.int64))
+    return float((d <= 1).mean()), int(d.max(initial=0))
+
+
+# --------------------------------------------------------------------------- FFT engine
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 11, 13, 16, 60, 105, 256, 1001, 4096, 8192,
+                               11025, 2 * 3 * 5 * 7 * 11 * 13, 49 * 225, 65536, 330750, 275625,
+                               1000 * 6615 // 5, 2 ** 20, 3 ** 12, 13 ** 5])
+def test_fft_matches_numpy(dec, n):
+    rng = np.random.default_rng(n)
+    batch = 3 if n < 100000 else 1
+    x = (rng.normal(size=(batch, n)) + 1j * rng.normal(size=(batch, n))).astype(np.complex64)
+    ref = np.fft.fft(x.astype(np.complex128), axis=-1)
+    y = dec.fft(x)
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 2e-6
+    xb = dec.fft(y, inverse=True)
+    assert np.abs(xb - x).max() / np.abs(x).max() < 4e-6
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("n", [6_615_000, 13_230_000])
+def test_fft_large(dec, n):
+    rng = np.random.default_rng(1)
+    x = (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
+    ref = np.fft.fft(x.astype(np.complex128))
+    y = dec.fft(x)
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 4e-6
+
+
+# --------------------------------------------------------------------------- single stages
+@pytest.mark.parametrize("n", [10, 11, 64, 2047, 2048, 2049, 4095, 11025, 100003, 330750])
+def test_filtfilt_stage(dec, n):
+    rng = np.random.default_rng(n)
+    x = np.round(rng.normal(size=(2, n)) * 6000).astype(np.float32)
+    b, a = O.notch_coefficients(2600, 1, 11025)
+    ref = np.stack([O.filtfilt(b, a, r.astype(np.float64)) for r in x])
+    y = dec.filtfilt(x)
+    assert rel_err(y, ref) < 2e-6
+
+
+def test_filtfilt_other_notch_settings(dec):
+    rng = np.random.default_rng(5)
+    x = np.round(rng.normal(size=5000) * 6000).astype(np.float32)
+    for f0, q in ((2600, 2), (1900, 0.7), (3000, 3)):
+        b, a = O.notch_coefficients(f0, q, 11025)
+        assert rel_err(dec.filtfilt(x, f0, q), O.filtfilt(b, a, x.astype(np.float64))) < 5e-6
+
+
+def test_filtfilt_rejects_short_input(dec):
+    with pytest.raises(ValueError, match="greater than padlen"):
+        dec.filtfilt(np.zeros(9, dtype=np.float32))
+
+
+@pytest.mark.parametrize("n", [2, 3, 16, 1000, 11025, 100003, 99991, 330750, 2 ** 17 + 1])
+def test_hilbert_envelope_stage(dec, n):
+    """abs(hilbert(x)); 100003, 99991 and 2**17+1 have large prime factors (Bluestein)."""
+    rng = np.random.default_rng(n)
+    t = np.arange(n)
+    x = (4000 * np.sin(2 * np.pi * 0.17 * t + 3 * np.sin(2 * np.pi * 0.001 * t)) +
+         rng.normal(size=n) * 300).astype(np.float32)
+    ref = np.abs(O.hilbert(x.astype(np.float64)))
+    y = dec.hilbert_envelope(np.stack([x, x[::-1].copy()]))
+    assert rel_err(y[0], ref) < 1e-5
+    assert rel_err(y[1], np.abs(O.hilbert(x[::-1].astype(np.float64)))) < 1e-5
+
+
+@pytest.mark.parametrize("n,num", [(48000, 11025), (48001, 11025), (44100, 11025), (8000, 11025), (8001, 11026),
+                                   (12000, 12000), (100003, 22973), (480000, 110250), (22050, 11025), (22051, 11025)])
+def test_resample_stage(dec, n, num):
+    rng = np.random.default_rng(n + num)
+    x = np.round(rng.normal(size=(2, n)) * 5000).astype(np.float32)
+    ref = np.stack([O.resample(r.astype(np.float64), num) for r in x])
+    y = dec.resample(x, num)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("n", [5, 6, 100, 1023, 4096, 11025, 330750, 1_000_003])
+def test_digitalize_stage_bit_exact(dec, n):
+    """median-5, percentiles and rounding on an identical float32 envelope: integers bit-exact."""
+    rng = np.random.default_rng(n)
+    env = (np.abs(rng.normal(size=(2, n))) * 3000 + 50 * rng.random(size=(2, n))).astype(np.float32)
+    env[1, : n // 3] = env[1, 0]          # long runs of duplicates
+    dem, dig, lh, st = dec.digitalize(env)
+    for r in range(2):
+        m = O.medfilt5(env[r].astype(np.float64))
+        assert np.array_equal(dem[r].astype(np.float64), m)
+        d, low, high = O.digitalize(m)
+        assert lh[r, 0] == low and lh[r, 1] == high
+        assert st[r] == 0
+        assert np.array_equal(dig[r].astype(np.int64), d)
+
+
+def test_digitalize_constant_envelope_flags_nan(dec):
+    env = np.full((1, 5000), 7.0, dtype=np.float32)
+    _, _, lh, st = dec.digitalize(env)
+    assert st[0] == 4 and lh[0, 0] == lh[0, 1]
+
+
+def _oracle_sync_image(dig, lpm):
+    consts = O.line_constants(lpm)
+    peaks = O.pattern_search(dig, consts)
+    try:
+        ph = O.find_phasing(peaks, consts)
+    except ValueError as e:
+        return peaks, None, None, ("ValueError", str(e))
+    sf = ph[-1] if ph else 0
+    try:
+        img = O.convert_to_image(dig[sf:], consts["width"])
+    except IndexError as e:
+        return peaks, ph, None, ("IndexError", str(e))
+    return peaks, ph, img, None
+
+
+@pytest.mark.parametrize("name", sorted(load_digests()["cases"]))
+def test_sync_and_raster_bit_exact_on_oracle_digitalized(dec, name):
+    """Line starts and pixels on the oracle's own digitalized data: bit-exact."""
+    c = load_digests()["cases"][name]
+    pcm = synth.synth_recording(**c["synth"])
+    o = O.decode(pcm, c["synth"].get("sample_rate", 11025), c["lpm"])
+    dig = o["digitalized_data"]
+    res = dec.sync_raster(dig.astype(np.uint8), c["lpm"])
+    assert res.peaks[0] == o["peaks"]
+    if o["error"] is None:
+        assert res.status[0] == 0
+        assert res.phasing_signals[0] == list(o["phasing_signals"])
+        assert int(res.start_frame[0]) == o["start_frame"]
+        assert np.array_equal(res.image(0), o["output_image"])
+    else:
+        assert type(res.error(0)).__name__ == o["error"][0] and str(res.error(0)) == o["error"][1]
+
+
+@pytest.mark.parametrize("lpm", [60, 90, 100, 120, 180, 240, 75, 360])
+def test_sync_and_raster_random_digitalized(dec, lpm):
+    """Random grey levels with dips every ~line: exercises replacement / opening / grouping."""
+    rng = np.random.default_rng(lpm)
+    consts = O.line_constants(lpm)
+    n = consts["width"] * 130 + 77
+    dig = rng.integers(60, 256, size=(3, n)).astype(np.uint8)
+    for r in range(3):
+        period = consts["width"] + (0.5 if r == 0 else (3 if r == 1 else -7))
+        for k in range(int(n / period)):
+            s = int(k * period + 100 * r)
+            dig[r, s: s + consts["template_len"]] = rng.integers(0, 8 + 40 * r)
+    dig[2, : 20 * consts["width"]] = 200      # a long flat start: ties and late first peak
+    res = dec.sync_raster(dig, lpm)
+    for r in range(3):
+        peaks, ph, img, err = _oracle_sync_image(dig[r].astype(np.int64), lpm)
+        assert res.peaks[r] == peaks
+        if err is None:
+            assert res.status[r] == 0 and res.phasing_signals[r] == list(ph)
+            assert np.array_equal(res.image(r), img)
+        else:
+            assert type(res.error(r)).__name__ == err[0]
+
+
+def test_sync_short_and_degenerate_inputs(dec):
+    for n, lpm in ((30, 120), (59, 120), (60, 120), (5000, 120), (5512, 120), (5513, 120), (11100, 120)):
+        rng = np.random.default_rng(n)
+        dig = rng.integers(0, 256, size=n).astype(np.uint8)
+        res = dec.sync_raster(dig, lpm)
+        peaks, ph, img, err = _oracle_sync_image(dig.astype(np.int64), lpm)
+        assert res.peaks[0] == peaks, n
+        if err is None:
+            assert res.status[0] == 0 and np.array_equal(res.image(0), img)
+        else:
+            assert type(res.error(0)).__name__ == err[0], n
+
+
+# --------------------------------------------------------------------------- whole path vs golden
+def _check_end_to_end(res, i, ref, n_ref_image=None):
+    """Common end-to-end assertions against a reference-decoder result dict."""
+    assert rel_err(res.audio[i], ref["audio_data"]) < FLOAT_TOL
+    assert rel_err(res.demodulated[i], ref["demodulated_data"]) < FLOAT_TOL
+    frac, worst = frac_within_one(res.digitalized[i], ref["digitalized_data"])
+    assert frac >= PIXEL_FRACTION and worst <= 2, (frac, worst)
+
+
+@pytest.mark.parametrize("name", golden_full_names())
+def test_decode_matches_reference_golden(dec, name):
+    g = load_golden_full(name)
+    res = dec.decode(g["pcm"], g["sample_rate_in"], g["lpm"],
+                     want=("audio", "demodulated", "digitalized", "raster"))
+    _check_end_to_end(res, 0, g)
+    if g["error"] is None:
+        assert res.error(0) is None
+        assert res.phasing_signals[0] == [int(v) for v in g["phasing_signals"]]
+        assert int(res.start_frame[0]) == g["start_frame"]
+        img = res.image(0)
+        assert img.shape == g["output_image"].shape
+        frac, worst = frac_within_one(img, g["output_image"])
+        assert frac >= PIXEL_FRACTION, (frac, worst)
+    else:
+        err = res.error(0)
+        assert [type(err).__name__, str(err)] == list(g["error"])
+
+
+@pytest.mark.parametrize("name", sorted(load_digests()["cases"]))
+def test_decode_matches_oracle_and_digest(dec, name):
+    c = load_digests()["cases"][name]
+    pcm = synth.synth_recording(**c["synth"])
+    assert hashlib.sha256(pcm.tobytes()).hexdigest() == c["pcm_sha256"]
+    sr = c["synth"].get("sample_rate", 11025)
+    o = O.decode(pcm, sr, c["lpm"])
+    res = dec.decode(pcm, sr, c["lpm"], want=("audio", "demodulated", "digitalized", "raster"))
+    assert res.n_out == c["n_out"]
+    _check_end_to_end(res, 0, o)
+    # the float samples stored from the real reference
+    idx = np.linspace(0, c["n_out"] - 1, 4096).astype(np.int64)
+    assert np.abs(res.audio[0][idx] - np.asarray(c["audio_sample"])).max() / c["audio_absmax"] < FLOAT_TOL
+    assert np.abs(res.demodulated[0][idx] - np.asarray(c["demod_sample"])).max() / c["demod_absmax"] < FLOAT_TOL
+    if c["error"] is None:
+        assert res.error(0) is None
+        assert res.phasing_signals[0] == c["phasing_signals"]
+        assert int(res.start_frame[0]) == c["start_frame"]
+        img = res.image(0)
+        assert list(img.shape) == c["image_shape"]
+        frac, worst = frac_within_one(img, o["output_image"])
+        assert frac >= PIXEL_FRACTION, (frac, worst)
+
+
+def test_decode_batch_mixed_lpm(dec):
+    """A batch of equal-length recordings with different LPM (configs[3] in miniature)."""
+    specs = [synth.batch_spec(k, noisy=(k % 2 == 1)) for k in range(8)]
+    pcm = np.stack([synth.synth_recording(36.0, **s) for s in specs])
+    lpms = [s["lpm"] for s in specs]
+    res = dec.decode(pcm, 11025, lpms, want=("audio", "demodulated", "digitalized", "raster"))
+    for i, s in enumerate(specs):
+        o = O.decode(pcm[i], 11025, s["lpm"])
+        _check_end_to_end(res, i, o)
+        if o["error"] is None:
+            assert res.error(i) is None
+            # line starts on the CUDA path's own digitalized data: bit-exact against the oracle picker
+            consts = O.line_constants(s["lpm"])
+            assert res.peaks[i] == O.pattern_search(res.digitalized[i].astype(np.int64), consts)
+            if res.phasing_signals[i] == list(o["phasing_signals"]):
+                frac, worst = frac_within_one(res.image(i), o["output_image"])
+                assert frac >= PIXEL_FRACTION, (i, frac, worst)
+        else:
+            assert type(res.error(i)).__name__ == o["error"][0]
+
+
+def test_decode_device_resident(dec):
+    """Inputs and large outputs resident in HBM (torch tensors): same results as host buffers."""
+    import torch
+    pcm = np.stack([synth.synth_recording(20.0, seed=21 + k, noise_sigma=0.03) for k in range(3)])
+    host = dec.decode(pcm, 11025, 120, want=("audio", "demodulated", "digitalized", "raster"))
+    dev = dec.decode(torch.from_numpy(pcm).cuda(), 11025, 120,
+                     want=("audio", "demodulated", "digitalized", "raster"), device_outputs=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.digitalized.cpu().numpy(), host.digitalized)
+    assert np.array_equal(dev.audio.cpu().numpy(), host.audio)
+    assert np.array_equal(dev.start_frame, host.start_frame)
+    for i in range(3):
+        h, w = int(host.height[i]), host.width[i]
+        assert np.array_equal(dev.raster_flat[i, : h * w].cpu().numpy(), host.raster_flat[i][: h * w])
+
+
+def test_decode_waves_equal_single_wave(dec):
+    """A tiny workspace limit forces several waves; results must not change."""
+    from wefax_b200.decoder import Decoder
+    pcm = np.stack([synth.synth_recording(12.0, seed=40 + k, lpm=240, noise_sigma=0.02) for k in range(5)])
+    ref = dec.decode(pcm, 11025, 240)
+    small = Decoder(0, workspace_limit=8 << 20)
+    try:
+        res = small.decode(pcm, 11025, 240)
+    finally:
+        small.close()
+    assert np.array_equal(res.digitalized, ref.digitalized)
+    assert np.array_equal(res.start_frame, ref.start_frame) and np.array_equal(res.height, ref.height)
+    for i in range(5):
+        assert np.array_equal(res.image(i), ref.image(i))
+
+
+# --------------------------------------------------------------------------- the drop-in class
+def test_demodulator_drop_in(dec, tmp_path):
+    import json
+    from PIL import Image
+    from wefax_b200.wefax import Demodulator
+    g = load_golden_full("synth_12s_240")
+    wav = str(tmp_path / "rec.wav")
+    synth.write_wav(wav, g["pcm"], g["sample_rate_in"])
+    d = Demodulator(wav, lines_per_minute=240, tcp_stream=True, quiet=True)
+    assert d.file_info()["sample_rate"] == 11025
+    d.process()
+    assert d.sample_rate == 11025 and d.start_frame == g["start_frame"]
+    assert d.phasing_signals == [int(v) for v in g["phasing_signals"]]
+    assert isinstance(d.output_image, Image.Image) and d.output_image.mode == "L"
+    assert d.output_image.size == (g["output_image"].shape[1], g["output_image"].shape[0])
+    frac, _ = frac_within_one(np.asarray(d.output_image), g["output_image"])
+    assert frac >= PIXEL_FRACTION
+    assert rel_err(d.audio_data, g["audio_data"]) < FLOAT_TOL
+    assert rel_err(d.demodulated_data, g["demodulated_data"]) < FLOAT_TOL
+    titles = [m.get("progress_title", m.get("message_content")) for m in d.websocket_stack]
+    ref_titles = json.loads(str(g["progress_titles"]))
+    assert [t for i, t in enumerate(titles) if i == 0 or titles[i - 1] != t] == \
+           [t for i, t in enumerate(ref_titles) if i == 0 or ref_titles[i - 1] != t]
+    assert titles == ref_titles
+    assert d.websocket_stack[-1] == {"data_type": "message", "message_content": "convert_end"}
+    out = str(tmp_path / "out.png")
+    d.save_output_image(out)
+    assert np.array_equal(np.asarray(Image.open(out)), np.asarray(d.output_image))
+
+
+def test_demodulator_reference_errors(dec, tmp_path):
+    """The shipped 1-s fixtures make the reference raise ValueError from max([]) (wefax.py:294)."""
+    from wefax_b200.wefax import Demodulator
+    g = load_golden_full("fixture_start_tone")
+    wav = str(tmp_path / "start_tone.wav")
+    synth.write_wav(wav, g["pcm"], g["sample_rate_in"])
+    d = Demodulator(wav, lines_per_minute=120, tcp_stream=True, quiet=True)
+    with pytest.raises(ValueError, match=r"max\(\) iterable argument is empty"):
+        d.process()
+    assert rel_err(d.audio_data, g["audio_data"]) < FLOAT_TOL
+    assert d.digitalized_data.shape[0] == 11025 and d.sample_rate == 11025
+
+
+def test_demodulator_stereo(dec, tmp_path):
+    from wefax_b200.wefax import Demodulator
+    g = load_golden_full("synth_stereo_8s_240")
+    wav = str(tmp_path / "st.wav")
+    synth.write_wav(wav, g["pcm"], g["sample_rate_in"])
+    d = Demodulator(wav, lines_per_minute=240, tcp_stream=False, quiet=True)
+    assert d.file_info()["channels"] == 2
+    d.process()
+    assert d.start_frame == g["start_frame"]
+    assert rel_err(d.audio_data, g["audio_data"]) < FLOAT_TOL
+    frac, _ = frac_within_one(np.asarray(d.output_image), g["output_image"])
+    assert frac >= PIXEL_FRACTION

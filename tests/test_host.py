@@ -1,0 +1,167 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/wefax_b200.h
+declares, the host-side helpers agree with the oracle, the Python surface mirrors
+the reference's (constructor errors, file_info, config), and nothing silently
+falls back to the CPU when no GPU is present."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import wefax_oracle as O
+from wefax_b200 import _native as N
+from wefax_b200 import synth, wavio
+from wefax_b200.config import Config
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "wefax_b200.h")).read()
+    declared = set(re.findall(r"\b(wefax_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(N.EXPORTED_SYMBOLS), declared ^ set(N.EXPORTED_SYMBOLS)
+    lib = N.load()
+    for sym in N.EXPORTED_SYMBOLS:
+        assert hasattr(lib, sym), sym
+    out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (wefax_[a-z0-9_]+)", out))
+    assert set(N.EXPORTED_SYMBOLS) <= exported
+    assert lib.wefax_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler gives the public structs (LP64)
+    assert ctypes.sizeof(N.LineConstants) == 48
+    assert ctypes.sizeof(N.BatchDesc) == 48
+    assert ctypes.sizeof(N.BatchOut) == 13 * 8
+
+
+@pytest.mark.parametrize("lpm", [60, 90, 100, 120, 180, 240, 30, 45, 75, 110, 150, 200, 288, 360, 480])
+def test_line_constants_match_oracle(lpm):
+    c, o = N.line_constants(lpm), O.line_constants(lpm)
+    for key in ("frame_len", "n1", "n0", "template_len", "mindistance", "width", "dev_min", "dev_max"):
+        assert c[key] == o[key], (lpm, key)
+
+
+def test_resampled_length_matches_oracle():
+    rng = np.random.default_rng(0)
+    for sr in (8000, 12000, 22050, 44100, 48000, 96000):
+        for n in list(rng.integers(1000, 60_000_000, size=40)) + [48000, 960000, 57_600_000]:
+            assert N.resampled_length(int(n), sr) == O.resampled_length(int(n), sr)
+
+
+@pytest.mark.parametrize("f0,q", [(2600, 1), (2600, 2), (1900, 0.7), (3000, 5)])
+def test_notch_coefficients_match_oracle(f0, q):
+    b, a = N.notch_coefficients(f0, q, 11025)
+    bo, ao = O.notch_coefficients(f0, q, 11025)
+    assert np.array_equal(b, bo) and np.array_equal(a, ao)
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 4096, 11025, 100003, 330750, 275625, 6_615_000, 13_230_000,
+                               39_690_000, 57_600_000, 2 * 3 * 5 * 7 * 11 * 13, 13 ** 5, 999_983])
+def test_fft_plan_is_a_factorisation(n):
+    lens, blu = N.fft_plan_describe(n)
+    target = blu if blu else n
+    assert int(np.prod(lens, dtype=np.int64)) == target
+    if blu:
+        assert blu >= 2 * n - 1
+    for r in lens[:-1]:
+        assert r <= 1024           # strided passes keep >= 8 columns per 8192-element tile
+    assert lens[-1] <= 8192
+    for r in lens:
+        m = r
+        for p in (2, 3, 5, 7, 11, 13):
+            while m % p == 0:
+                m //= p
+        assert m == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    lib = N.load()
+    if lib.wefax_device_count() > 0:
+        pytest.skip("a GPU is present")
+    from wefax_b200.decoder import Decoder, WefaxNativeError
+    with pytest.raises(WefaxNativeError):
+        Decoder(0)
+
+
+def test_product_never_imports_oracle():
+    """The product path may not route through the oracle, scipy.signal or numpy.fft."""
+    pkg = os.path.join(ROOT, "wefax_b200")
+    banned = (r"^\s*(from|import)\s+oracle", r"^\s*(from|import)\s+scipy", r"\b(np|numpy)\.fft\.\w+\(")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                for pat in banned:
+                    assert not re.search(pat, text, flags=re.M), (f, pat)
+
+
+def test_demodulator_constructor_errors(tmp_path):
+    from wefax_b200.wefax import Demodulator
+    with pytest.raises(Exception) as e:
+        Demodulator(str(tmp_path / "missing.wav"))
+    assert str(e.value) == f"INVALID FILE: file at path: {tmp_path / 'missing.wav'} does not exist"
+    p = tmp_path / "x.txt"
+    p.write_text("hi")
+    with pytest.raises(Exception) as e:
+        Demodulator(str(p))
+    assert str(e.value) == "INVALID FILETYPE: only .wav files are supported at this moment"
+    w = tmp_path / "a.wav"
+    synth.write_wav(str(w), synth.synth_recording(1.0, seed=1), 11025)
+    d = Demodulator(str(w), lines_per_minute=90, quiet=True)
+    assert d.filename == "a.wav" and d.websocket_stack == []
+    assert d.time_for_one_frame == 1 / (90 / 60)
+    d.update_lines_per_minute(240)
+    assert d.lines_per_minute == 240 and d.time_for_one_frame == 0.25
+    info = d.file_info()
+    assert info == {"filename": "a.wav", "channels": 1, "sample_rate": 11025, "length": 1.0}
+
+
+def test_wav_reader_matches_scipy(tmp_path):
+    from scipy.io import wavfile
+    rng = np.random.default_rng(2)
+    mono = rng.integers(-32768, 32767, size=12345, dtype=np.int16)
+    stereo = rng.integers(-32768, 32767, size=(777, 2), dtype=np.int16)
+    for name, data, sr in (("m.wav", mono, 11025), ("s.wav", stereo, 48000)):
+        p = str(tmp_path / name)
+        wavfile.write(p, sr, data)
+        sr2, d2 = wavio.read(p)
+        assert sr2 == sr and d2.dtype == np.int16 and np.array_equal(d2, data)
+        p2 = str(tmp_path / ("w_" + name))
+        synth.write_wav(p2, data, sr)
+        sr3, d3 = wavfile.read(p2)
+        assert sr3 == sr and np.array_equal(d3, data)
+    u8 = rng.integers(0, 255, size=999, dtype=np.uint8)
+    p = str(tmp_path / "u8.wav")
+    wavfile.write(p, 8000, u8)
+    sr2, d2 = wavio.read(p)
+    assert sr2 == 8000 and d2.dtype == np.uint8 and np.array_equal(d2, u8)
+    f32 = rng.normal(size=100).astype(np.float32)
+    p = str(tmp_path / "f.wav")
+    wavfile.write(p, 8000, f32)
+    with pytest.raises(ValueError):
+        wavio.read(p)
+
+
+def test_config_reads_reference_format(tmp_path, monkeypatch):
+    cfgdir = tmp_path / "config"
+    cfgdir.mkdir()
+    (cfgdir / "config.json").write_text(
+        '{"host_settings": {"port": 1}, "notch_filter_settings": {"notch_filter_frequency": 2500, '
+        '"notch_filter_quality_factor": 2}}')
+    monkeypatch.chdir(tmp_path)
+    c = Config()
+    assert c.settings["notch_filter_settings"] == {"notch_filter_frequency": 2500, "notch_filter_quality_factor": 2}
+    monkeypatch.chdir(tmp_path / "config")          # no config/config.json here: package default
+    c = Config()
+    assert c.settings["notch_filter_settings"]["notch_filter_frequency"] == 2600
+    assert c.settings["notch_filter_settings"]["notch_filter_quality_factor"] == 1
+
+
+def test_synth_is_deterministic():
+    a = synth.synth_recording(3.0, seed=5, noise_sigma=0.05)
+    b = synth.synth_recording(3.0, seed=5, noise_sigma=0.05)
+    assert a.dtype == np.int16 and np.array_equal(a, b) and a.shape == (33075,)
+    assert synth.batch_spec(5) == {"lpm": 90, "ioc": 288, "seed": 1005}

@@ -1,0 +1,541 @@
+// extern "C" surface of libwefax_b200.so: context management, host helpers and
+// the batched decode that strings the kernels together (see include/wefax_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "stages.cuh"
+
+using namespace wefax;
+
+namespace {
+
+template <class F>
+int guarded(wefax_ctx *ctx, F &&f) {
+    try {
+        f();
+        return WEFAX_OK;
+    } catch (const Error &e) {
+        if (ctx) ctx->last_error = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        if (ctx) ctx->last_error = "host allocation failed";
+        return WEFAX_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        if (ctx) ctx->last_error = e.what();
+        return WEFAX_ERR_INVALID;
+    }
+}
+
+// scipy.signal.iirnotch (wefax.py:68-70)
+void notch_coefficients(double f0, double q, double fs, double b[3], double a[3]) {
+    double w0 = 2.0 * f0 / fs;
+    if (w0 > 1.0 || w0 < 0.0) WEFAX_THROW(WEFAX_ERR_INVALID, "w0 should be such that 0 < w0 < 1");
+    double bw = w0 / q * M_PI;
+    w0 = w0 * M_PI;
+    double beta = tan(bw / 2.0);
+    double gain = 1.0 / (1.0 + beta);
+    b[0] = gain;
+    b[1] = gain * (-2.0 * cos(w0));
+    b[2] = gain;
+    a[0] = 1.0;
+    a[1] = -2.0 * gain * cos(w0);
+    a[2] = 2.0 * gain - 1.0;
+}
+
+// impulse response of the biquad (direct form II transposed, as scipy's lfilter),
+// truncated where the remaining tail is below 3e-9 of the total
+FirParams make_fir(double f0, double q, double fs) {
+    double b[3], a[3];
+    notch_coefficients(f0, q, fs, b, a);
+    const int NMAX = 4096;
+    std::vector<double> h(NMAX);
+    double z0 = 0.0, z1 = 0.0, x = 1.0;
+    for (int i = 0; i < NMAX; ++i) {
+        double y = b[0] * x + z0;
+        z0 = b[1] * x - a[1] * y + z1;
+        z1 = b[2] * x - a[2] * y;
+        x = 0.0;
+        h[i] = y;
+    }
+    double total = 0.0;
+    for (double v : h) total += fabs(v);
+    double tail = 0.0;
+    int K = NMAX;
+    while (K > 1 && tail + fabs(h[K - 1]) < 3e-9 * total) tail += fabs(h[--K]);
+    if (K > kMaxFirTaps)
+        WEFAX_THROW(WEFAX_ERR_UNSUPPORTED,
+                    "notch impulse response needs %d taps (max %d): quality factor too high for the FIR path", K,
+                    kMaxFirTaps);
+    FirParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.K = K;
+    const int sizes[] = {16, 20, 24, 32, 48, 64};
+    for (int s : sizes)
+        if (K <= s) {
+            fp.KP = s;
+            break;
+        }
+    for (int i = 0; i < K; ++i) fp.h[i] = (float)h[i];
+    for (int j = 0; j < fp.KP; ++j) fp.hr[j] = fp.h[fp.KP - 1 - j];
+    return fp;
+}
+
+void line_constants(double lpm, int sr, wefax_line_constants *o) {
+    // Python: 1 / (lpm / 60); int(x * frame_len * sample_rate) evaluated left to right
+    volatile double frame_len = 1.0 / (lpm / 60.0);
+    volatile double t5 = 0.005 * frame_len;
+    volatile double t1 = 0.001 * frame_len;
+    volatile double f = frame_len * (double)sr;
+    o->frame_len = frame_len;
+    o->n1 = (int)(t5 * (double)sr);
+    o->n0 = (int)(t1 * (double)sr);
+    o->template_len = 2 * o->n1 + o->n0;
+    o->mindistance = (int)(f * 0.8);
+    o->width = (int)f;
+    o->dev_min = f - 500.0;
+    o->dev_max = f + 500.0;
+}
+
+void *pinned(wefax_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->pinned_cap) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+        CUDA_CHECK(cudaMallocHost(&ctx->pinned, bytes + 4096));
+        ctx->pinned_cap = bytes + 4096;
+    }
+    return ctx->pinned;
+}
+
+void use_device(wefax_ctx *ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
+
+struct LineSet {
+    std::vector<LineDev> lines;
+    int max_width = 0, min_width = 1 << 30, min_mind = 1 << 30;
+    long long raster_need = 0;
+};
+
+LineSet prepare_lines(const double *lpm, int nrec, long long n) {
+    LineSet ls;
+    ls.lines.resize(nrec);
+    for (int r = 0; r < nrec; ++r) {
+        if (!(lpm[r] > 0.0)) WEFAX_THROW(WEFAX_ERR_INVALID, "lines per minute must be positive");
+        wefax_line_constants lc;
+        line_constants(lpm[r], WEFAX_TARGET_RATE, &lc);
+        if (lc.width < 1 || lc.template_len < 1 || lc.template_len > 2048 || lc.mindistance < 1024)
+            WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "lines per minute %g outside the supported range (4..500)", lpm[r]);
+        ls.lines[r] = LineDev{lc.n1, lc.n0, lc.template_len, lc.mindistance, lc.width, lc.dev_min, lc.dev_max};
+        ls.max_width = std::max(ls.max_width, lc.width);
+        ls.min_width = std::min(ls.min_width, lc.width);
+        ls.min_mind = std::min(ls.min_mind, lc.mindistance);
+        ls.raster_need = std::max(ls.raster_need, 4 * (n / lc.width) * lc.width);
+    }
+    return ls;
+}
+
+// small per-recording results -> the caller's host arrays; rasters of host-output calls
+void deliver_results(wefax_ctx *ctx, const RecResult *h_res, int g, int w0, const LineSet &ls,
+                     const wefax_batch_out *out, const uint8_t *d_raster, size_t rs, bool out_dev) {
+    bool copied = false;
+    for (int r = 0; r < g; ++r) {
+        const RecResult &rr = h_res[r];
+        const int R = w0 + r;
+        if (out->n_peaks) out->n_peaks[R] = rr.n_peaks;
+        if (out->peaks) memcpy(out->peaks + (size_t)R * WEFAX_MAX_PEAKS, rr.peaks, sizeof(rr.peaks));
+        if (out->n_phasing) out->n_phasing[R] = rr.n_phasing;
+        if (out->phasing) memcpy(out->phasing + (size_t)R * WEFAX_MAX_PEAKS, rr.phasing, sizeof(rr.phasing));
+        if (out->start_frame) out->start_frame[R] = rr.start_frame;
+        if (out->height) out->height[R] = rr.height;
+        if (out->status) out->status[R] = rr.status;
+        if (out->low_high) {
+            out->low_high[2 * R] = rr.low;
+            out->low_high[2 * R + 1] = rr.high;
+        }
+        if (out->raster && !out_dev && rr.height > 0) {
+            const size_t bytes = (size_t)rr.height * ls.lines[R].width;
+            CUDA_CHECK(cudaMemcpyAsync(out->raster + (size_t)R * out->raster_stride, d_raster + (size_t)r * rs, bytes,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+            copied = true;
+        }
+    }
+    if (copied) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+int wefax_abi_version(void) { return WEFAX_ABI_VERSION; }
+
+int wefax_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
+    if (!out) return WEFAX_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        (void)cudaGetLastError();
+        return WEFAX_ERR_CUDA;   // no CUDA device: there is no CPU fallback
+    }
+    wefax_ctx *ctx = new (std::nothrow) wefax_ctx();
+    if (!ctx) return WEFAX_ERR_NOMEM;
+    int rc = guarded(ctx, [&] {
+        ctx->device = device;
+        use_device(ctx);
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "built for sm_100a (Blackwell); device %d is sm_%d%d", device, prop.major,
+                        prop.minor);
+        ctx->sm_count = prop.multiProcessorCount;
+        if (stream) {
+            ctx->stream = (cudaStream_t)stream;
+        } else {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->own_stream = true;
+        }
+    });
+    if (rc != WEFAX_OK) {
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return WEFAX_OK;
+}
+
+void wefax_ctx_destroy(wefax_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->plans.clear();
+    ctx->bluestein.clear();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *wefax_last_error(const wefax_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int wefax_ctx_sync(wefax_ctx *ctx) {
+    return guarded(ctx, [&] {
+        use_device(ctx);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+void *wefax_ctx_stream(wefax_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+long long wefax_ctx_launch_count(const wefax_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int wefax_ctx_set_workspace_limit(wefax_ctx *ctx, long long bytes) {
+    if (!ctx || bytes < (1ll << 20)) return WEFAX_ERR_INVALID;
+    ctx->workspace_limit = bytes;
+    return WEFAX_OK;
+}
+
+int wefax_line_constants_for(double lpm, int sample_rate, wefax_line_constants *out) {
+    if (!out || !(lpm > 0.0) || sample_rate <= 0) return WEFAX_ERR_INVALID;
+    line_constants(lpm, sample_rate, out);
+    return WEFAX_OK;
+}
+
+long long wefax_resampled_length(long long n_frames, int sample_rate) {
+    volatile double length = (double)n_frames / (double)sample_rate;
+    return (long long)((double)WEFAX_TARGET_RATE * length);
+}
+
+int wefax_notch_coefficients(double f0, double q, double fs, double b[3], double a[3]) {
+    return guarded(nullptr, [&] { notch_coefficients(f0, q, fs, b, a); });
+}
+
+int wefax_fft_plan_describe(long long n, int *n_passes, int pass_len[8], long long *bluestein_len) {
+    if (n < 1 || !n_passes || !pass_len || !bluestein_len) return WEFAX_ERR_INVALID;
+    std::vector<int> Rs;
+    long long m = 0;
+    if (!plan_factors(n, Rs)) {
+        m = next_smooth_length(2 * n - 1);
+        if (m <= 0 || !plan_factors(m, Rs)) return WEFAX_ERR_UNSUPPORTED;
+    }
+    *bluestein_len = m;
+    *n_passes = (int)Rs.size();
+    for (int i = 0; i < 8; ++i) pass_len[i] = i < (int)Rs.size() ? Rs[i] : 0;
+    return WEFAX_OK;
+}
+
+// ---------------------------------------------------------------------------
+int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm, const double *lpm,
+                       const wefax_batch_out *out) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!desc || !pcm || !lpm || !out) WEFAX_THROW(WEFAX_ERR_INVALID, "null argument");
+        const int nrec = desc->n_recordings;
+        const long long n_in = desc->n_frames;
+        const int ch = desc->channels;
+        if (nrec < 1 || n_in < 1 || (ch != 1 && ch != 2) || desc->sample_rate <= 0)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "bad batch description");
+        const bool resample = desc->sample_rate != WEFAX_TARGET_RATE;
+        const long long n = resample ? wefax_resampled_length(n_in, desc->sample_rate) : n_in;
+        if (n <= 9)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is 9.");
+        if (n_in >= (1ll << 31) - 4096 || n >= (1ll << 31) - 4096) WEFAX_THROW(WEFAX_ERR_INVALID, "recording too long");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const bool pcm_dev = desc->flags & WEFAX_F_PCM_ON_DEVICE;
+        const bool out_dev = desc->flags & WEFAX_F_OUT_ON_DEVICE;
+
+        // wefax.py:63: the frequency goes through int()
+        const FirParams fp = make_fir((double)(long long)desc->notch_freq, desc->notch_q, (double)WEFAX_TARGET_RATE);
+
+        const LineSet ls = prepare_lines(lpm, nrec, n);
+        const std::vector<LineDev> &lines = ls.lines;
+        const int max_width = ls.max_width, min_width = ls.min_width, min_mind = ls.min_mind;
+        const long long raster_cap = 4 * n;   // >= 4 * (n / w) * w for every w
+        const long long rstride_user = out->raster_stride;
+        if (out->raster && rstride_user < ls.raster_need)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "raster_stride %lld too small (need %lld)", rstride_user, ls.raster_need);
+
+        // transform scratch per recording
+        FftPlan *plan = get_plan(ctx, n);
+        long long zlen = n;
+        if (!plan) {
+            std::vector<int> tmp;
+            zlen = next_smooth_length(2 * n - 1);
+            if (zlen <= 0) WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "no transform length for n=%lld", n);
+        }
+        long long zlen_rs = 0;
+        if (resample) {
+            std::vector<int> tmp;
+            long long a = plan_factors(n_in, tmp) ? n_in : next_smooth_length(2 * n_in - 1);
+            zlen_rs = std::max(a, zlen);
+        }
+        const long long per_rec = (pcm_dev ? 0 : n_in * ch * 2) + (resample ? n_in * 4 + (n_in + n) * 8 : 0) +
+                                  std::max(zlen, zlen_rs) * 8 + n * (4 + 4 + 4 + 1 + 4) + 4096;
+        int wave = (int)std::max<long long>(1, std::min<long long>(nrec, ctx->workspace_limit / per_rec));
+        wave = std::min(wave, 32768);
+
+        LineDev *d_lines = (LineDev *)ctx->out_small.reserve((sizeof(LineDev) + sizeof(RecResult)) * (size_t)wave +
+                                                             sizeof(SelState) * (size_t)wave + 256);
+        RecResult *d_res = (RecResult *)(d_lines + wave);
+        SelState *d_sel = (SelState *)(((uintptr_t)(d_res + wave) + 255) & ~(uintptr_t)255);
+        RecResult *h_res = (RecResult *)pinned(ctx, sizeof(RecResult) * (size_t)wave + sizeof(LineDev) * (size_t)wave);
+        LineDev *h_lines = (LineDev *)(h_res + wave);
+
+        for (int w0 = 0; w0 < nrec; w0 += wave) {
+            const int g = std::min(wave, nrec - w0);
+            // ---- inputs ------------------------------------------------------------
+            const int16_t *d_pcm = pcm + (size_t)w0 * n_in * ch;
+            if (!pcm_dev) {
+                int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)g * n_in * ch * sizeof(int16_t));
+                CUDA_CHECK(cudaMemcpyAsync(buf, d_pcm, (size_t)g * n_in * ch * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+                d_pcm = buf;
+            }
+            memcpy(h_lines, lines.data() + w0, sizeof(LineDev) * g);
+            CUDA_CHECK(cudaMemcpyAsync(d_lines, h_lines, sizeof(LineDev) * g, cudaMemcpyHostToDevice, st));
+            CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * g, st));
+
+            float *d_audio = (out_dev && out->audio) ? out->audio + (size_t)w0 * n
+                                                      : (float *)ctx->work_a.reserve((size_t)g * n * sizeof(float));
+            float *d_env = (float *)ctx->work_e.reserve((size_t)g * n * sizeof(float));
+            uint8_t *d_dig = (out_dev && out->digitalized) ? out->digitalized + (size_t)w0 * n
+                                                           : (uint8_t *)ctx->out_dig.reserve((size_t)g * n);
+            const size_t rs = out_dev ? (size_t)rstride_user : (size_t)raster_cap;
+            uint8_t *d_raster = nullptr;
+            if (out->raster)
+                d_raster = out_dev ? out->raster + (size_t)w0 * rs : (uint8_t *)ctx->out_raster.reserve((size_t)g * rs);
+
+            // ---- resample (wefax.py:60-62) + zero-phase notch (wefax.py:63-72) -------
+            if (resample) {
+                float *xin = (float *)ctx->resample_in.reserve(((size_t)g * n_in + (size_t)g * n) * sizeof(float));
+                float *xrs = xin + (size_t)g * n_in;
+                launch_ingest_float(ctx, d_pcm, (size_t)n_in, ch, xin, (size_t)n_in, n_in, g);
+                resample_real(ctx, n_in, n, xin, (size_t)n_in, xrs, (size_t)n, g);
+                launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, d_audio, (size_t)n, n, fp, g);
+            } else {
+                launch_filtfilt(ctx, ch == 2 ? kInStereoI16 : kInMonoI16, d_pcm, (size_t)n_in, d_audio, (size_t)n, n, fp, g);
+            }
+            // ---- analytic-signal envelope (wefax.py:174) ------------------------------
+            if (plan) {
+                float2 *z = (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2));
+                hilbert_envelope(ctx, plan, d_audio, (size_t)n, z, (size_t)n, d_env, (size_t)n, g);
+            } else {
+                hilbert_envelope_bluestein(ctx, n, d_audio, (size_t)n, d_env, (size_t)n, g);
+            }
+            // ---- median-5, percentiles, grey map (wefax.py:175,196-200) ---------------
+            launch_percentiles(ctx, d_env, (size_t)n, n, g, d_sel, d_res);
+            launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res);
+            // ---- phasing search (wefax.py:218-294) and raster (wefax.py:296-327) -----
+            launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind);
+            if (d_raster)
+                launch_raster(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, d_raster, rs, max_width, (int)(n / min_width));
+            float *d_demod = nullptr;
+            if (out->demodulated) {
+                d_demod = out_dev ? out->demodulated + (size_t)w0 * n
+                                  : (float *)ctx->work_z.reserve((size_t)g * n * sizeof(float));
+                launch_median5(ctx, d_env, (size_t)n, d_demod, (size_t)n, n, g);
+            }
+
+            // ---- results ---------------------------------------------------------------
+            CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult) * g, cudaMemcpyDeviceToHost, st));
+            if (!out_dev) {
+                if (out->audio)
+                    CUDA_CHECK(cudaMemcpyAsync(out->audio + (size_t)w0 * n, d_audio, (size_t)g * n * sizeof(float),
+                                               cudaMemcpyDeviceToHost, st));
+                if (out->demodulated)
+                    CUDA_CHECK(cudaMemcpyAsync(out->demodulated + (size_t)w0 * n, d_demod, (size_t)g * n * sizeof(float),
+                                               cudaMemcpyDeviceToHost, st));
+                if (out->digitalized)
+                    CUDA_CHECK(cudaMemcpyAsync(out->digitalized + (size_t)w0 * n, d_dig, (size_t)g * n,
+                                               cudaMemcpyDeviceToHost, st));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            deliver_results(ctx, h_res, g, w0, ls, out, d_raster, rs, out_dev);
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------
+// stage-level entry points (host pointers)
+// ---------------------------------------------------------------------------
+int wefax_fft_c2c(wefax_ctx *ctx, long long n, int batch, const float *in, float *out, int inverse) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (n < 1 || batch < 1 || !in || !out) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        use_device(ctx);
+        FftPlan *plan = get_plan(ctx, n);
+        if (!plan) WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "n=%lld has a prime factor > 13 (Bluestein is used on the decode path)", n);
+        const size_t bytes = (size_t)n * batch * sizeof(float2);
+        float2 *a = (float2 *)ctx->work_z.reserve(bytes * 2);
+        float2 *scratch = a + (size_t)n * batch;
+        float2 *o = (float2 *)ctx->work_misc.reserve(bytes);
+        CUDA_CHECK(cudaMemcpyAsync(a, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        fft_c2c_natural(ctx, plan, a, o, scratch, batch, inverse != 0);
+        CUDA_CHECK(cudaMemcpyAsync(out, o, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int wefax_hilbert_envelope(wefax_ctx *ctx, long long n, int batch, const float *x, float *env) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (n < 1 || batch < 1 || !x || !env) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        use_device(ctx);
+        const size_t bytes = (size_t)n * batch * sizeof(float);
+        float *dx = (float *)ctx->work_a.reserve(bytes);
+        float *de = (float *)ctx->work_e.reserve(bytes);
+        CUDA_CHECK(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        FftPlan *plan = get_plan(ctx, n);
+        if (plan) {
+            float2 *z = (float2 *)ctx->work_z.reserve((size_t)n * batch * sizeof(float2));
+            hilbert_envelope(ctx, plan, dx, (size_t)n, z, (size_t)n, de, (size_t)n, batch);
+        } else {
+            hilbert_envelope_bluestein(ctx, n, dx, (size_t)n, de, (size_t)n, batch);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(env, de, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int wefax_resample(wefax_ctx *ctx, long long n, long long num, int batch, const float *x, float *y) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (n < 1 || num < 1 || batch < 1 || !x || !y) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        use_device(ctx);
+        float *dx = (float *)ctx->work_a.reserve((size_t)n * batch * sizeof(float));
+        float *dy = (float *)ctx->work_e.reserve((size_t)num * batch * sizeof(float));
+        CUDA_CHECK(cudaMemcpyAsync(dx, x, (size_t)n * batch * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        resample_real(ctx, n, num, dx, (size_t)n, dy, (size_t)num, batch);
+        CUDA_CHECK(cudaMemcpyAsync(y, dy, (size_t)num * batch * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int wefax_filtfilt(wefax_ctx *ctx, long long n, int batch, double notch_freq, double notch_q, const float *x,
+                   float *y) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (n < 1 || batch < 1 || !x || !y) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        if (n <= 9)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is 9.");
+        use_device(ctx);
+        const FirParams fp = make_fir(notch_freq, notch_q, (double)WEFAX_TARGET_RATE);
+        const size_t bytes = (size_t)n * batch * sizeof(float);
+        float *dx = (float *)ctx->work_a.reserve(bytes);
+        float *dy = (float *)ctx->work_e.reserve(bytes);
+        CUDA_CHECK(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        launch_filtfilt(ctx, kInFloat, dx, (size_t)n, dy, (size_t)n, n, fp, batch);
+        CUDA_CHECK(cudaMemcpyAsync(y, dy, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int wefax_digitalize(wefax_ctx *ctx, long long n, int batch, const float *envelope, float *demodulated,
+                     uint8_t *digitalized, double *low_high, int32_t *status) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (n < 1 || batch < 1 || !envelope) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const size_t bytes = (size_t)n * batch * sizeof(float);
+        float *de = (float *)ctx->work_e.reserve(bytes);
+        float *dm = (float *)ctx->work_a.reserve(bytes);
+        uint8_t *dd = (uint8_t *)ctx->out_dig.reserve((size_t)n * batch);
+        RecResult *d_res = (RecResult *)ctx->out_small.reserve((sizeof(RecResult) + sizeof(SelState)) * (size_t)batch + 256);
+        SelState *d_sel = (SelState *)(((uintptr_t)(d_res + batch) + 255) & ~(uintptr_t)255);
+        RecResult *h_res = (RecResult *)pinned(ctx, sizeof(RecResult) * (size_t)batch);
+        CUDA_CHECK(cudaMemcpyAsync(de, envelope, bytes, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * batch, st));
+        launch_percentiles(ctx, de, (size_t)n, n, batch, d_sel, d_res);
+        launch_quantise(ctx, de, (size_t)n, dd, (size_t)n, n, batch, d_res);
+        if (demodulated) {
+            launch_median5(ctx, de, (size_t)n, dm, (size_t)n, n, batch);
+            CUDA_CHECK(cudaMemcpyAsync(demodulated, dm, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        if (digitalized) CUDA_CHECK(cudaMemcpyAsync(digitalized, dd, (size_t)n * batch, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult) * batch, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int r = 0; r < batch; ++r) {
+            if (low_high) {
+                low_high[2 * r] = h_res[r].low;
+                low_high[2 * r + 1] = h_res[r].high;
+            }
+            if (status) status[r] = h_res[r].status;
+        }
+    });
+}
+
+int wefax_sync_raster(wefax_ctx *ctx, long long n, int batch, const uint8_t *digitalized, const double *lpm,
+                      const wefax_batch_out *out) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (n < 1 || batch < 1 || !digitalized || !lpm || !out) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const LineSet ls = prepare_lines(lpm, batch, n);
+        if (out->raster && out->raster_stride < ls.raster_need)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "raster_stride %lld too small (need %lld)", out->raster_stride, ls.raster_need);
+        uint8_t *dd = (uint8_t *)ctx->out_dig.reserve((size_t)n * batch);
+        LineDev *d_lines = (LineDev *)ctx->out_small.reserve((sizeof(LineDev) + sizeof(RecResult)) * (size_t)batch);
+        RecResult *d_res = (RecResult *)(d_lines + batch);
+        RecResult *h_res = (RecResult *)pinned(ctx, sizeof(RecResult) * (size_t)batch);
+        const size_t rs = (size_t)(4 * n);
+        uint8_t *d_raster = out->raster ? (uint8_t *)ctx->out_raster.reserve((size_t)batch * rs) : nullptr;
+        CUDA_CHECK(cudaMemcpyAsync(dd, digitalized, (size_t)n * batch, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_lines, ls.lines.data(), sizeof(LineDev) * batch, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * batch, st));
+        launch_sync_search(ctx, dd, (size_t)n, n, batch, d_lines, d_res, ls.min_mind);
+        if (d_raster)
+            launch_raster(ctx, dd, (size_t)n, n, batch, d_lines, d_res, d_raster, rs, ls.max_width, (int)(n / ls.min_width));
+        CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult) * batch, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        deliver_results(ctx, h_res, batch, 0, ls, out, d_raster, rs, false);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// The context behind the C-ABI handle: device, stream, cached FFT plans, scratch.
+#pragma once
+
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace wefax {
+// chirp-z (Bluestein) data for a transform length with a prime factor > 13
+struct Bluestein {
+    long long n = 0, m = 0;
+    FftPlan *plan = nullptr;   // length m (owned by the context's plan cache)
+    DevBuf chirp;              // c[i] = exp(-i*pi*i^2/n), i < n
+    DevBuf vhat;               // FFT_m of the wrapped conj(chirp), engine order, scaled by 1/m
+};
+}  // namespace wefax
+
+struct wefax_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string last_error;
+    long long launches = 0;
+    long long workspace_limit = 24ll << 30;
+    int sm_count = 148;
+    std::map<long long, std::unique_ptr<wefax::FftPlan>> plans;
+    std::map<long long, std::unique_ptr<wefax::Bluestein>> bluestein;
+    std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
+    // scratch (grown on demand, reused between calls)
+    wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in;
+    // pinned staging for small results
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+namespace wefax {
+
+FftPlan *get_plan(wefax_ctx *ctx, long long n);   // nullptr when n needs Bluestein
+
+template <class LoadOp, class StoreOp>
+void launch_pass(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const StoreOp &st, int batch) {
+    const void *fn = (const void *)fft_pass_kernel<LoadOp, StoreOp>;
+    if (!ctx->smem_configured.count(fn)) {
+        CUDA_CHECK(cudaFuncSetAttribute(fft_pass_kernel<LoadOp, StoreOp>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ctx->smem_configured[fn] = 1;
+    }
+    dim3 grid(p.ntiles, batch);
+    fft_pass_kernel<LoadOp, StoreOp><<<grid, kFftThreads, p.smem_bytes, ctx->stream>>>(p, ld, st);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// |hilbert(x)| for `batch` real sequences of length plan->n (no median filter).
+// x: real input (stride xs), z: complex scratch (stride zs >= n), env: output (stride es).
+void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, float2 *z, size_t zs,
+                      float *env, size_t es, int batch);
+
+// natural-order complex DFT (test entry / Bluestein building block)
+void fft_c2c_natural(wefax_ctx *ctx, FftPlan *plan, const float2 *in, float2 *out, float2 *scratch,
+                     int batch, bool inverse);
+
+// Bluestein path for lengths with a large prime factor
+void hilbert_envelope_bluestein(wefax_ctx *ctx, long long n, const float *x, size_t xs, float *env,
+                                size_t es, int batch);
+
+// scipy.signal.resample(x, num) on real float input (any n, num)
+void resample_real(wefax_ctx *ctx, long long n, long long num, const float *x, size_t xs, float *y,
+                   size_t ys, int batch);
+
+}  // namespace wefax

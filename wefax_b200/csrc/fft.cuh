@@ -1,0 +1,385 @@
+// Mixed-radix, multi-pass, in-place complex FFT for one long 1-D sequence (or a
+// batch of them).  Replaces the pocketfft calls under scipy.signal.hilbert /
+// scipy.signal.resample on the reference's path (wefax.py:174,384).
+//
+// n = R_0 * R_1 * ... * R_{P-1}.  Element index i = sum_i n_i * S_i with
+// S_i = prod_{j>i} R_j.  The forward transform is P decimation-in-frequency
+// passes: pass i transforms, for every "column" (all other digits fixed), the R_i
+// elements spaced S_i apart, multiplies by w_{L_i}^{k_i * m} (L_i = R_i*S_i, m the
+// column offset inside its length-L_i sub-problem) and stores in place.  After the
+// last pass the value of frequency k = k_0 + R_0*k_1 + R_0*R_1*k_2 + ... sits at
+// position sum_i k_i*S_i ("engine order").  The inverse runs the mirrored
+// decimation-in-time passes P-1..0 (twiddle on load) and ends in natural order,
+// so a forward/inverse pair needs no transposition at all; point-wise spectral
+// work (Hilbert mask, Bluestein products) is fused into the stores and only needs
+// the position -> frequency map.
+//
+// One CTA owns a tile of C adjacent columns x R rows in shared memory, runs the
+// radix-{8,4,2,3,5,7,11,13} stages there (in-place DIF, digit-reversed read-out),
+// and touches global memory exactly once per element per pass: coalesced C*8-byte
+// row segments for strided passes, one contiguous C*R*8-byte chunk for the last
+// (stride-1) pass.
+#pragma once
+
+#include "common.cuh"
+
+namespace wefax {
+
+constexpr int kMaxStages = 14;
+constexpr int kMaxPasses = 4;
+constexpr int kFftThreads = 256;
+constexpr int kTwLoBits = 11;   // two-level inter-pass twiddle table: 2^11 "lo" entries
+
+struct PassDev {
+    int R, S, ncols;          // transform length, element stride, number of columns (= n / R)
+    int C, log2C;             // columns per tile (power of two)
+    int contiguous;           // S == 1
+    int nstages;
+    int radix[kMaxStages];
+    FastDiv divM[kMaxStages];     // M = L / r of each stage
+    FastDiv divNbf[kMaxStages];   // R / r of each stage
+    FastDiv divR, divS;
+    const float2 *twR;            // w_R^e, e < R
+    const uint16_t *perm;         // smem position of output k after the in-place DIF stages
+    const float2 *tw_lo, *tw_hi;  // w_L^e = tw_lo[e & mask] * tw_hi[e >> bits]
+    int tw_mode;                  // 0 none, 1 multiply on store (forward), 2 multiply on load (inverse)
+    int smem_bytes;
+    int ntiles;
+};
+
+// ----------------------------- load / store functors -----------------------
+struct LoadComplex {
+    const float2 *src;
+    size_t bstride;
+    int conj;
+    __device__ __forceinline__ float2 operator()(size_t i, int b) const {
+        float2 v = __ldg(src + (size_t)b * bstride + i);
+        if (conj) v.y = -v.y;
+        return v;
+    }
+};
+struct LoadReal {
+    const float *src;
+    size_t bstride;
+    size_t n_valid;   // elements >= n_valid read as zero (zero padding)
+    __device__ __forceinline__ float2 operator()(size_t i, int b) const {
+        return make_float2(i < n_valid ? __ldg(src + (size_t)b * bstride + i) : 0.f, 0.f);
+    }
+};
+
+struct StoreComplex {
+    float2 *dst;
+    size_t bstride;
+    float scale;
+    int conj;
+    __device__ __forceinline__ int column_aux(int) const { return 0; }
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+        v.x *= scale;
+        v.y *= conj ? -scale : scale;
+        dst[(size_t)b * bstride + i] = v;
+    }
+};
+
+// position -> frequency for the LAST forward pass (stride 1): the column index o
+// encodes the digits k_0..k_{P-2} (most significant first); k = rev(o) + ncols*k_last.
+struct OuterDigits {
+    int nouter;
+    int Rout[kMaxPasses];
+    __device__ __forceinline__ int rev(int o) const {
+        int d[kMaxPasses];
+#pragma unroll
+        for (int i = kMaxPasses - 1; i >= 0; --i)
+            if (i < nouter) {
+                d[i] = o % Rout[i];
+                o /= Rout[i];
+            }
+        int k = 0, mult = 1;
+#pragma unroll
+        for (int i = 0; i < kMaxPasses; ++i)
+            if (i < nouter) {
+                k += d[i] * mult;
+                mult *= Rout[i];
+            }
+        return k;
+    }
+};
+
+// scipy.signal.hilbert's spectral mask (wefax.py:174), the 1/n of the inverse
+// transform and the conjugation that lets the inverse reuse the forward kernels.
+struct StoreHilbert {
+    float2 *dst;
+    size_t bstride;
+    OuterDigits od;
+    uint32_t n;
+    int ncols;
+    float inv_n;
+    __device__ __forceinline__ int column_aux(int col) const { return od.rev(col); }
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int k, int aux) const {
+        uint32_t kf = (uint32_t)aux + (uint32_t)ncols * (uint32_t)k;
+        uint64_t k2 = 2ull * kf;
+        float h = kf == 0 ? 1.f : (k2 < n ? 2.f : (k2 == n ? 1.f : 0.f));
+        h *= inv_n;
+        dst[(size_t)b * bstride + i] = make_float2(v.x * h, -v.y * h);
+    }
+};
+
+// |z| of the analytic signal (numpy.abs in wefax.py:175), only the first n_valid
+struct StoreAbs {
+    float *dst;
+    size_t bstride;
+    size_t n_valid;
+    float scale;
+    __device__ __forceinline__ int column_aux(int) const { return 0; }
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+        if (i < n_valid) dst[(size_t)b * bstride + i] = scale * sqrtf(fmaf(v.x, v.x, v.y * v.y));
+    }
+};
+
+struct StoreRealPart {
+    float *dst;
+    size_t bstride;
+    size_t n_valid;
+    float scale;
+    __device__ __forceinline__ int column_aux(int) const { return 0; }
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+        if (i < n_valid) dst[(size_t)b * bstride + i] = scale * v.x;
+    }
+};
+
+// ----------------------------- butterflies ---------------------------------
+template <int r> struct Bfly;
+
+template <> struct Bfly<2> {
+    __device__ __forceinline__ static void run(float2 *v, const float2 *) {
+        float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+template <> struct Bfly<4> {
+    __device__ __forceinline__ static void run(float2 *v, const float2 *) {
+        float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        float2 t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
+        v[0] = cadd(t0, t2);
+        v[2] = csub(t0, t2);
+        v[1] = make_float2(t1.x + t3.y, t1.y - t3.x);
+        v[3] = make_float2(t1.x - t3.y, t1.y + t3.x);
+    }
+};
+template <> struct Bfly<8> {
+    __device__ __forceinline__ static void run(float2 *v, const float2 *) {
+        float2 e[4] = {v[0], v[2], v[4], v[6]};
+        float2 o[4] = {v[1], v[3], v[5], v[7]};
+        Bfly<4>::run(e, nullptr);
+        Bfly<4>::run(o, nullptr);
+        const float h = 0.70710678118654752440f;
+        float2 o1 = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));    // * (1-i)/sqrt2
+        float2 o2 = make_float2(o[2].y, -o[2].x);                                  // * -i
+        float2 o3 = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));   // * (-1-i)/sqrt2
+        v[0] = cadd(e[0], o[0]);
+        v[4] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], o1);
+        v[5] = csub(e[1], o1);
+        v[2] = cadd(e[2], o2);
+        v[6] = csub(e[2], o2);
+        v[3] = cadd(e[3], o3);
+        v[7] = csub(e[3], o3);
+    }
+};
+// odd prime radix: pair (t, r-t); cs[j] = (cos, sin)(2*pi*(j+1)/r)
+template <int r> struct Bfly {
+    static constexpr int h = (r - 1) / 2;
+    __device__ __forceinline__ static void run(float2 *v, const float2 *cs) {
+        float2 a[h], b[h];
+#pragma unroll
+        for (int t = 1; t <= h; ++t) {
+            a[t - 1] = cadd(v[t], v[r - t]);
+            b[t - 1] = csub(v[t], v[r - t]);
+        }
+        float2 v0 = v[0];
+        float2 s = v0;
+#pragma unroll
+        for (int t = 0; t < h; ++t) s = cadd(s, a[t]);
+        v[0] = s;
+#pragma unroll
+        for (int u = 1; u <= h; ++u) {
+            float2 p = v0, q = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 1; t <= h; ++t) {
+                int j = (t * u) % r;
+                float c = j <= h ? cs[j - 1].x : cs[r - j - 1].x;
+                float sn = j <= h ? cs[j - 1].y : -cs[r - j - 1].y;
+                p.x = fmaf(c, a[t - 1].x, p.x);
+                p.y = fmaf(c, a[t - 1].y, p.y);
+                q.x = fmaf(sn, b[t - 1].x, q.x);
+                q.y = fmaf(sn, b[t - 1].y, q.y);
+            }
+            v[u] = make_float2(p.x + q.y, p.y - q.x);
+            v[r - u] = make_float2(p.x - q.y, p.y + q.x);
+        }
+    }
+};
+
+// One in-place DIF stage of radix r over the whole tile.
+template <int r>
+__device__ __forceinline__ void dif_stage(float2 *tile, const float2 *twR, const PassDev &p, int s, int L) {
+    const int M = L / r;
+    const int nb = p.R / L;
+    const int nbf = p.R / r;
+    const int total = nbf * p.C;
+    float2 cs[(r - 1) / 2 + 1];
+    if (r & 1) {
+#pragma unroll
+        for (int j = 1; j <= (r - 1) / 2; ++j) {
+            float2 w = twR[j * (p.R / r)];
+            cs[j - 1] = make_float2(w.x, -w.y);
+        }
+    }
+    for (int b = threadIdx.x; b < total; b += blockDim.x) {
+        int cc, qp, base, step;
+        if (p.contiguous) {
+            cc = p.divNbf[s].div(b);
+            qp = b - cc * nbf;
+        } else {
+            cc = b & (p.C - 1);
+            qp = b >> p.log2C;
+        }
+        const int blk = p.divM[s].div(qp);
+        const int q = qp - blk * M;
+        const int j0 = blk * L + q;
+        if (p.contiguous) {
+            base = cc * p.R + j0;
+            step = M;
+        } else {
+            base = j0 * p.C + cc;
+            step = M * p.C;
+        }
+        float2 v[r];
+#pragma unroll
+        for (int t = 0; t < r; ++t) v[t] = tile[base + t * step];
+        Bfly<r>::run(v, cs);
+        if (M > 1) {
+            const int e1 = q * nb;
+#pragma unroll
+            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], twR[e1 * u]);
+        }
+#pragma unroll
+        for (int t = 0; t < r; ++t) tile[base + t * step] = v[t];
+    }
+}
+
+__device__ __forceinline__ float2 pass_twiddle(const PassDev &p, uint32_t e) {
+    float2 lo = __ldg(p.tw_lo + (e & ((1u << kTwLoBits) - 1)));
+    float2 hi = __ldg(p.tw_hi + (e >> kTwLoBits));
+    return cmul(lo, hi);
+}
+
+template <class LoadOp, class StoreOp>
+__global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tile = reinterpret_cast<float2 *>(smem_raw);
+    float2 *twR = tile + (size_t)p.C * p.R;
+    uint16_t *perm = reinterpret_cast<uint16_t *>(twR + p.R);
+    int *aux = reinterpret_cast<int *>(perm + ((p.R + 1) & ~1));
+
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int batch = blockIdx.y;
+    const int c0 = blockIdx.x * p.C;
+
+    for (int i = tid; i < p.R; i += nt) {
+        twR[i] = __ldg(p.twR + i);
+        perm[i] = __ldg(p.perm + i);
+    }
+    if (tid < p.C) aux[tid] = (c0 + tid < p.ncols) ? st.column_aux(c0 + tid) : 0;
+
+    const int tile_elems = p.C * p.R;
+    // column geometry of this thread (strided passes): fixed for the whole kernel
+    const int cc_s = tid & (p.C - 1);
+    const int col_s = c0 + cc_s;
+    const bool valid_s = col_s < p.ncols;
+    const uint32_t o_s = p.divS.div((uint32_t)col_s);
+    const uint32_t m_s = (uint32_t)col_s - o_s * (uint32_t)p.S;
+    const size_t cbase = (size_t)o_s * (size_t)p.R * (size_t)p.S + m_s;
+    const int jstep = nt >> p.log2C;
+
+    if (p.contiguous) {
+        const size_t gbase = (size_t)c0 * p.R;
+        const int nvalid = min(p.C, p.ncols - c0) * p.R;
+#pragma unroll 4
+        for (int e = tid; e < tile_elems; e += nt)
+            tile[e] = e < nvalid ? ld(gbase + e, batch) : make_float2(0.f, 0.f);
+    } else {
+#pragma unroll 4
+        for (int j = tid >> p.log2C; j < p.R; j += jstep) {
+            float2 v = make_float2(0.f, 0.f);
+            if (valid_s) {
+                v = ld(cbase + (size_t)j * p.S, batch);
+                if (p.tw_mode == 2) v = cmul(v, pass_twiddle(p, (uint32_t)j * m_s));
+            }
+            tile[j * p.C + cc_s] = v;
+        }
+    }
+    __syncthreads();
+
+    int L = p.R;
+    for (int s = 0; s < p.nstages; ++s) {
+        const int r = p.radix[s];
+        switch (r) {
+            case 2: dif_stage<2>(tile, twR, p, s, L); break;
+            case 3: dif_stage<3>(tile, twR, p, s, L); break;
+            case 4: dif_stage<4>(tile, twR, p, s, L); break;
+            case 5: dif_stage<5>(tile, twR, p, s, L); break;
+            case 7: dif_stage<7>(tile, twR, p, s, L); break;
+            case 8: dif_stage<8>(tile, twR, p, s, L); break;
+            case 11: dif_stage<11>(tile, twR, p, s, L); break;
+            default: dif_stage<13>(tile, twR, p, s, L); break;
+        }
+        L /= r;
+        __syncthreads();
+    }
+
+    if (p.contiguous) {
+        const size_t gbase = (size_t)c0 * p.R;
+        const int nvalid = min(p.C, p.ncols - c0) * p.R;
+#pragma unroll 4
+        for (int e = tid; e < nvalid; e += nt) {
+            const int cc = p.divR.div(e);
+            const int k = e - cc * p.R;
+            st(gbase + e, batch, tile[cc * p.R + perm[k]], k, aux[cc]);
+        }
+    } else if (valid_s) {
+        const int a = aux[cc_s];
+#pragma unroll 4
+        for (int k = tid >> p.log2C; k < p.R; k += jstep) {
+            float2 v = tile[(int)perm[k] * p.C + cc_s];
+            if (p.tw_mode == 1) v = cmul(v, pass_twiddle(p, (uint32_t)k * m_s));
+            st(cbase + (size_t)k * p.S, batch, v, k, a);
+        }
+    }
+}
+
+// ----------------------------- host-side plan ------------------------------
+struct FftPlan {
+    long long n = 0;
+    int npass = 0;
+    int Rs[kMaxPasses] = {0, 0, 0, 0};
+    long long S[kMaxPasses] = {0, 0, 0, 0};
+    PassDev fwd[kMaxPasses];   // tw_mode 1 on all but the last pass
+    PassDev inv[kMaxPasses];   // tw_mode 2 on all but the last pass
+    DevBuf tables;             // twR / perm / tw_lo / tw_hi of every pass
+    OuterDigits outer() const {
+        OuterDigits od{};
+        od.nouter = npass - 1;
+        for (int i = 0; i < npass - 1; ++i) od.Rout[i] = Rs[i];
+        return od;
+    }
+};
+
+// Factor n into pass lengths; returns false when n has a prime factor > 13 or no
+// feasible split exists (the caller then uses Bluestein).
+bool plan_factors(long long n, std::vector<int> &Rs);
+// smallest 2^a 3^b 5^c 7^d >= m that plan_factors accepts
+long long next_smooth_length(long long m);
+std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream);
+
+}  // namespace wefax

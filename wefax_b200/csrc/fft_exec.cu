@@ -1,0 +1,373 @@
+// Transform drivers on top of the pass kernel: Hilbert envelope (smooth lengths
+// and Bluestein), natural-order DFT for tests, FFT-domain resampling.
+#include "ctx.cuh"
+
+namespace wefax {
+
+// ----------------------------- generic functors (cold paths) ---------------
+struct LoadGeneric {
+    int mode;               // 0 complex, 1 real zero-padded, 2 real*chirp zero-padded, 3 complex*chirp zero-padded
+    const void *src;
+    const float2 *chirp;
+    size_t bstride;
+    size_t n_valid;
+    int conj;
+    __device__ __forceinline__ float2 operator()(size_t i, int b) const {
+        switch (mode) {
+            case 0: {
+                float2 v = __ldg((const float2 *)src + (size_t)b * bstride + i);
+                if (conj) v.y = -v.y;
+                return v;
+            }
+            case 1:
+                return make_float2(i < n_valid ? __ldg((const float *)src + (size_t)b * bstride + i) : 0.f, 0.f);
+            case 2: {
+                if (i >= n_valid) return make_float2(0.f, 0.f);
+                float x = __ldg((const float *)src + (size_t)b * bstride + i);
+                float2 c = __ldg(chirp + i);
+                return make_float2(x * c.x, x * c.y);
+            }
+            default: {
+                if (i >= n_valid) return make_float2(0.f, 0.f);
+                float2 v = __ldg((const float2 *)src + (size_t)b * bstride + i);
+                if (conj) v.y = -v.y;
+                return cmul(v, __ldg(chirp + i));
+            }
+        }
+    }
+};
+
+struct StoreGeneric {
+    int mode;   // 0 complex, 1 mul-table+conj, 2 bluestein hilbert mid, 3 abs, 4 real part,
+                // 5 bluestein spectrum (natural), 6 bluestein real part
+    void *dst;
+    const float2 *table;    // mode 1: by position; modes 5/6: chirp
+    size_t bstride;
+    size_t n_valid;
+    uint32_t n;             // transform length of the Hilbert mask
+    float scale;
+    int conj;
+    __device__ __forceinline__ int column_aux(int) const { return 0; }
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+        switch (mode) {
+            case 0:
+                v.x *= scale;
+                v.y *= conj ? -scale : scale;
+                ((float2 *)dst)[(size_t)b * bstride + i] = v;
+                break;
+            case 1: {
+                float2 w = cmul(v, __ldg(table + i));
+                ((float2 *)dst)[(size_t)b * bstride + i] = make_float2(w.x, -w.y);
+                break;
+            }
+            case 2: {
+                float h = 0.f;
+                if (i < n) {
+                    uint64_t k2 = 2ull * i;
+                    h = i == 0 ? 1.f : (k2 < n ? 2.f : (k2 == n ? 1.f : 0.f));
+                }
+                h *= scale;
+                ((float2 *)dst)[(size_t)b * bstride + i] = make_float2(v.x * h, v.y * h);
+                break;
+            }
+            case 3:
+                if (i < n_valid) ((float *)dst)[(size_t)b * bstride + i] = scale * sqrtf(fmaf(v.x, v.x, v.y * v.y));
+                break;
+            case 4:
+                if (i < n_valid) ((float *)dst)[(size_t)b * bstride + i] = scale * v.x;
+                break;
+            case 5:
+                if (i < n_valid) {
+                    float2 w = cmul(make_float2(v.x, -v.y), __ldg(table + i));
+                    ((float2 *)dst)[(size_t)b * bstride + i] = make_float2(w.x * scale, w.y * scale);
+                }
+                break;
+            default:
+                if (i < n_valid) {
+                    float2 w = cmul(make_float2(v.x, -v.y), __ldg(table + i));
+                    ((float *)dst)[(size_t)b * bstride + i] = scale * w.x;
+                }
+                break;
+        }
+    }
+};
+
+// ----------------------------- position <-> frequency ----------------------
+struct PosMap {
+    int npass;
+    int R[kMaxPasses];
+    uint32_t S[kMaxPasses];
+    __device__ __forceinline__ uint32_t freq(uint32_t pos) const {
+        uint32_t k = 0, mult = 1;
+#pragma unroll
+        for (int i = 0; i < kMaxPasses; ++i)
+            if (i < npass) {
+                uint32_t d = (pos / S[i]) % (uint32_t)R[i];
+                k += d * mult;
+                mult *= (uint32_t)R[i];
+            }
+        return k;
+    }
+    __device__ __forceinline__ uint32_t pos(uint32_t k) const {
+        uint32_t p = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxPasses; ++i)
+            if (i < npass) {
+                uint32_t d = k % (uint32_t)R[i];
+                k /= (uint32_t)R[i];
+                p += d * S[i];
+            }
+        return p;
+    }
+};
+
+static PosMap pos_map(const FftPlan *plan) {
+    PosMap m{};
+    m.npass = plan->npass;
+    for (int i = 0; i < plan->npass; ++i) {
+        m.R[i] = plan->Rs[i];
+        m.S[i] = (uint32_t)plan->S[i];
+    }
+    return m;
+}
+
+// engine order -> natural order (first `keep` frequencies), or the reverse with zero fill
+__global__ void engine_to_natural_kernel(const float2 *z, size_t zs, float2 *out, size_t os, uint32_t keep, PosMap pm) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= keep) return;
+    out[(size_t)blockIdx.y * os + k] = z[(size_t)blockIdx.y * zs + pm.pos(k)];
+}
+__global__ void natural_to_engine_kernel(const float2 *in, size_t is, uint32_t have, float2 *z, size_t zs, uint32_t n,
+                                         PosMap pm, int conj) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t k = pm.freq(p);
+    float2 v = make_float2(0.f, 0.f);
+    if (k < have) {
+        v = in[(size_t)blockIdx.y * is + k];
+        if (conj) v.y = -v.y;
+    }
+    z[(size_t)blockIdx.y * zs + p] = v;
+}
+
+// ----------------------------- plans ---------------------------------------
+FftPlan *get_plan(wefax_ctx *ctx, long long n) {
+    auto it = ctx->plans.find(n);
+    if (it != ctx->plans.end()) return it->second.get();
+    std::unique_ptr<FftPlan> plan = make_plan(n, ctx->stream);
+    FftPlan *raw = plan.get();
+    ctx->plans[n] = std::move(plan);   // nullptr is cached too: "needs Bluestein"
+    return raw;
+}
+
+static LoadComplex load_c(const float2 *p, size_t bs, int conj = 0) { return LoadComplex{p, bs, conj}; }
+
+// forward passes 0..P-1 with `ld` feeding pass 0 and `st` finishing pass P-1
+template <class LoadFirst, class StoreLast>
+static void run_forward(wefax_ctx *ctx, FftPlan *plan, const LoadFirst &ld, const StoreLast &st, float2 *z, size_t zs,
+                        int batch) {
+    const int P = plan->npass;
+    if (P == 1) {
+        launch_pass(ctx, plan->fwd[0], ld, st, batch);
+        return;
+    }
+    launch_pass(ctx, plan->fwd[0], ld, StoreComplex{z, zs, 1.f, 0}, batch);
+    for (int i = 1; i < P - 1; ++i) launch_pass(ctx, plan->fwd[i], load_c(z, zs), StoreComplex{z, zs, 1.f, 0}, batch);
+    launch_pass(ctx, plan->fwd[P - 1], load_c(z, zs), st, batch);
+}
+
+// inverse-structure passes P-1..0 (engine order in, natural order out); the data
+// must already be conjugated/scaled by whoever produced it
+template <class LoadFirst, class StoreLast>
+static void run_inverse(wefax_ctx *ctx, FftPlan *plan, const LoadFirst &ld, const StoreLast &st, float2 *z, size_t zs,
+                        int batch) {
+    const int P = plan->npass;
+    if (P == 1) {
+        launch_pass(ctx, plan->inv[0], ld, st, batch);
+        return;
+    }
+    launch_pass(ctx, plan->inv[P - 1], ld, StoreComplex{z, zs, 1.f, 0}, batch);
+    for (int i = P - 2; i >= 1; --i) launch_pass(ctx, plan->inv[i], load_c(z, zs), StoreComplex{z, zs, 1.f, 0}, batch);
+    launch_pass(ctx, plan->inv[0], load_c(z, zs), st, batch);
+}
+
+void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, float2 *z, size_t zs, float *env,
+                      size_t es, int batch) {
+    const size_t n = (size_t)plan->n;
+    StoreHilbert sh{z, zs, plan->outer(), (uint32_t)n, (int)(n / plan->Rs[plan->npass - 1]), (float)(1.0 / (double)n)};
+    run_forward(ctx, plan, LoadReal{x, xs, n}, sh, z, zs, batch);
+    run_inverse(ctx, plan, load_c(z, zs), StoreAbs{env, es, n, 1.f}, z, zs, batch);
+}
+
+void fft_c2c_natural(wefax_ctx *ctx, FftPlan *plan, const float2 *in, float2 *out, float2 *scratch, int batch,
+                     bool inverse) {
+    const size_t n = (size_t)plan->n;
+    PosMap pm = pos_map(plan);
+    dim3 grid((unsigned)((n + 255) / 256), batch);
+    if (!inverse) {
+        run_forward(ctx, plan, load_c(in, n), StoreComplex{scratch, n, 1.f, 0}, scratch, n, batch);
+        engine_to_natural_kernel<<<grid, 256, 0, ctx->stream>>>(scratch, n, out, n, (uint32_t)n, pm);
+        ctx->launches++;
+    } else {
+        natural_to_engine_kernel<<<grid, 256, 0, ctx->stream>>>(in, n, (uint32_t)n, scratch, n, (uint32_t)n, pm, 1);
+        ctx->launches++;
+        run_inverse(ctx, plan, load_c(scratch, n), StoreComplex{out, n, (float)(1.0 / (double)n), 1}, scratch, n, batch);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ----------------------------- Bluestein -----------------------------------
+__global__ void chirp_kernel(float2 *c, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long e = ((unsigned long long)i * i) % (2ull * n);
+    double s, co;
+    sincospi(-(double)e / (double)n, &s, &co);
+    c[i] = make_float2((float)co, (float)s);
+}
+__global__ void chirp_wrap_kernel(const float2 *c, float2 *v, uint32_t n, uint32_t m) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    float2 out = make_float2(0.f, 0.f);
+    if (j < n) out = make_float2(c[j].x, -c[j].y);
+    else if (m - j < n) out = make_float2(c[m - j].x, -c[m - j].y);
+    v[j] = out;
+}
+
+static Bluestein *get_bluestein(wefax_ctx *ctx, long long n) {
+    auto it = ctx->bluestein.find(n);
+    if (it != ctx->bluestein.end()) return it->second.get();
+    auto b = std::make_unique<Bluestein>();
+    b->n = n;
+    b->m = next_smooth_length(2 * n - 1);
+    if (b->m <= 0) WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "no FFT length found for Bluestein n=%lld", n);
+    b->plan = get_plan(ctx, b->m);
+    if (!b->plan) WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "Bluestein length %lld not plannable", b->m);
+    float2 *c = (float2 *)b->chirp.reserve((size_t)n * sizeof(float2));
+    float2 *vh = (float2 *)b->vhat.reserve((size_t)b->m * sizeof(float2));
+    DevBuf tmp;
+    float2 *v = (float2 *)tmp.reserve((size_t)b->m * sizeof(float2));
+    chirp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(c, (uint32_t)n);
+    chirp_wrap_kernel<<<(unsigned)((b->m + 255) / 256), 256, 0, ctx->stream>>>(c, v, (uint32_t)n, (uint32_t)b->m);
+    ctx->launches += 2;
+    run_forward(ctx, b->plan, load_c(v, (size_t)b->m), StoreComplex{vh, (size_t)b->m, (float)(1.0 / (double)b->m), 0},
+                vh, (size_t)b->m, 1);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    Bluestein *raw = b.get();
+    ctx->bluestein[n] = std::move(b);
+    return raw;
+}
+
+static LoadGeneric lg(int mode, const void *src, const float2 *chirp, size_t bs, size_t n_valid, int conj = 0) {
+    return LoadGeneric{mode, src, chirp, bs, n_valid, conj};
+}
+static StoreGeneric sg(int mode, void *dst, const float2 *table, size_t bs, size_t n_valid, uint32_t n, float scale,
+                       int conj = 0) {
+    return StoreGeneric{mode, dst, table, bs, n_valid, n, scale, conj};
+}
+
+void hilbert_envelope_bluestein(wefax_ctx *ctx, long long n, const float *x, size_t xs, float *env, size_t es,
+                                int batch) {
+    Bluestein *b = get_bluestein(ctx, n);
+    const size_t m = (size_t)b->m;
+    float2 *z = (float2 *)ctx->work_z.reserve(m * sizeof(float2) * batch);
+    const float2 *c = b->chirp.as<float2>();
+    const float2 *vh = b->vhat.as<float2>();
+    // DFT_n(x) by chirp convolution; r = conj(conv)
+    run_forward(ctx, b->plan, lg(2, x, c, xs, (size_t)n), sg(1, z, vh, m, m, 0, 1.f), z, m, batch);
+    // u2 = (h/n) * r for k < n, zero beyond (|chirp| = 1 cancels)
+    run_inverse(ctx, b->plan, lg(0, z, nullptr, m, m), sg(2, z, nullptr, m, m, (uint32_t)n, (float)(1.0 / (double)n)),
+                z, m, batch);
+    run_forward(ctx, b->plan, lg(0, z, nullptr, m, m), sg(1, z, vh, m, m, 0, 1.f), z, m, batch);
+    run_inverse(ctx, b->plan, lg(0, z, nullptr, m, m), sg(3, env, nullptr, es, (size_t)n, 0, 1.f), z, m, batch);
+}
+
+// ----------------------------- resample ------------------------------------
+// scipy.signal.resample(x, num) for real x (wefax.py:384): X = rfft(x); keep
+// m2 = min(num, n)//2 + 1 bins; unpaired bin m/2 doubled (down) or halved (up)
+// when m is even and num != n; y = irfft(X * num/n, num).
+__global__ void resample_spectrum_kernel(const float2 *X, size_t xs, float2 *Zc, size_t zs, uint32_t m2, uint32_t m,
+                                         uint32_t n, uint32_t num, float scale) {
+    // Zc[k] = conj of the one-sided inverse-transform input (irfft as Re(IDFT) of a one-sided spectrum)
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m2) return;
+    float2 v = X[(size_t)blockIdx.y * xs + k];
+    if ((m & 1u) == 0 && num != n && k == m / 2) {
+        float f = num < n ? 2.f : 0.5f;
+        v.x *= f;
+        v.y *= f;
+    }
+    float w = 2.f;
+    if (k == 0) {
+        w = 1.f;
+        v.y = 0.f;   // irfft ignores the imaginary part of DC
+    } else if ((num & 1u) == 0 && k == num / 2) {
+        w = 1.f;
+        v.y = 0.f;   // ... and of the Nyquist bin
+    }
+    w *= scale;
+    Zc[(size_t)blockIdx.y * zs + k] = make_float2(v.x * w, -v.y * w);
+}
+
+// forward DFT of real x, first `keep` bins in natural order into X (stride xs_out)
+static void spectrum_natural(wefax_ctx *ctx, long long n, const float *x, size_t xs, float2 *X, size_t xs_out,
+                             uint32_t keep, int batch) {
+    FftPlan *plan = get_plan(ctx, n);
+    if (plan) {
+        float2 *z = (float2 *)ctx->work_z.reserve((size_t)n * sizeof(float2) * batch);
+        run_forward(ctx, plan, LoadReal{x, xs, (size_t)n}, StoreComplex{z, (size_t)n, 1.f, 0}, z, (size_t)n, batch);
+        dim3 grid((keep + 255) / 256, batch);
+        engine_to_natural_kernel<<<grid, 256, 0, ctx->stream>>>(z, (size_t)n, X, xs_out, keep, pos_map(plan));
+        ctx->launches++;
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    Bluestein *b = get_bluestein(ctx, n);
+    const size_t m = (size_t)b->m;
+    float2 *z = (float2 *)ctx->work_z.reserve(m * sizeof(float2) * batch);
+    run_forward(ctx, b->plan, lg(2, x, b->chirp.as<float2>(), xs, (size_t)n), sg(1, z, b->vhat.as<float2>(), m, m, 0, 1.f),
+                z, m, batch);
+    run_inverse(ctx, b->plan, lg(0, z, nullptr, m, m), sg(5, X, b->chirp.as<float2>(), xs_out, keep, 0, 1.f), z, m, batch);
+}
+
+// y = Re(DFT_num(Zc)) where Zc (natural order, `have` bins, zero beyond) is the
+// conjugated one-sided spectrum
+static void real_from_onesided(wefax_ctx *ctx, long long num, const float2 *Zc, size_t zcs, uint32_t have, float *y,
+                               size_t ys, int batch) {
+    FftPlan *plan = get_plan(ctx, num);
+    if (plan) {
+        float2 *z = (float2 *)ctx->work_z.reserve((size_t)num * sizeof(float2) * batch);
+        dim3 grid((unsigned)((num + 255) / 256), batch);
+        natural_to_engine_kernel<<<grid, 256, 0, ctx->stream>>>(Zc, zcs, have, z, (size_t)num, (uint32_t)num,
+                                                                pos_map(plan), 0);
+        ctx->launches++;
+        CUDA_CHECK(cudaGetLastError());
+        run_inverse(ctx, plan, load_c(z, (size_t)num), StoreRealPart{y, ys, (size_t)num, 1.f}, z, (size_t)num, batch);
+        return;
+    }
+    Bluestein *b = get_bluestein(ctx, num);
+    const size_t m = (size_t)b->m;
+    float2 *z = (float2 *)ctx->work_z.reserve(m * sizeof(float2) * batch);
+    run_forward(ctx, b->plan, lg(3, Zc, b->chirp.as<float2>(), zcs, have), sg(1, z, b->vhat.as<float2>(), m, m, 0, 1.f), z,
+                m, batch);
+    run_inverse(ctx, b->plan, lg(0, z, nullptr, m, m), sg(6, y, b->chirp.as<float2>(), ys, (size_t)num, 0, 1.f), z, m,
+                batch);
+}
+
+void resample_real(wefax_ctx *ctx, long long n, long long num, const float *x, size_t xs, float *y, size_t ys,
+                   int batch) {
+    const uint32_t m = (uint32_t)std::min(n, num);
+    const uint32_t m2 = m / 2 + 1;
+    float2 *X = (float2 *)ctx->work_misc.reserve((size_t)m2 * sizeof(float2) * 2 * batch);
+    float2 *Zc = X + (size_t)m2 * batch;
+    spectrum_natural(ctx, n, x, xs, X, m2, m2, batch);
+    dim3 grid((m2 + 255) / 256, batch);
+    // X * (num/n) and the 1/num of irfft combine to 1/n
+    resample_spectrum_kernel<<<grid, 256, 0, ctx->stream>>>(X, m2, Zc, m2, m2, m, (uint32_t)n, (uint32_t)num,
+                                                           (float)(1.0 / (double)n));
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    real_from_onesided(ctx, num, Zc, m2, m2, y, ys, batch);
+}
+
+}  // namespace wefax

@@ -1,0 +1,695 @@
+// Non-FFT stages: ingest, zero-phase notch, median-5, percentile selection,
+// grey-level quantisation, phasing search, line raster with x4 bicubic.
+#include <algorithm>
+#include <cmath>
+
+#include "stages.cuh"
+
+namespace wefax {
+
+// ===========================================================================
+// ingest (only needed in front of the resampler; the notch reads PCM directly)
+// ===========================================================================
+template <int MODE>
+__device__ __forceinline__ float load_sample(const void *in, size_t base, long long i) {
+    if (MODE == kInMonoI16) return (float)__ldg((const int16_t *)in + base + i);
+    if (MODE == kInStereoI16) {
+        // wefax.py:372: np.add on two int16 scalars wraps, then /2 in float64
+        const int16_t *p = (const int16_t *)in + 2 * (base + i);
+        int16_t s = (int16_t)(__ldg(p) + __ldg(p + 1));
+        return 0.5f * (float)s;
+    }
+    return __ldg((const float *)in + base + i);
+}
+
+template <int MODE>
+__global__ void ingest_kernel(const void *in, size_t in_stride, float *x, size_t xs, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[(size_t)blockIdx.y * xs + i] = load_sample<MODE>(in, (size_t)blockIdx.y * in_stride, i);
+}
+
+void launch_ingest_float(wefax_ctx *ctx, const int16_t *pcm, size_t pcm_stride, int channels, float *x, size_t xs,
+                         long long n, int batch) {
+    dim3 grid((unsigned)((n + 255) / 256), batch);
+    if (channels == 2)
+        ingest_kernel<kInStereoI16><<<grid, 256, 0, ctx->stream>>>(pcm, pcm_stride, x, xs, n);
+    else
+        ingest_kernel<kInMonoI16><<<grid, 256, 0, ctx->stream>>>(pcm, pcm_stride, x, xs, n);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// ===========================================================================
+// zero-phase notch == scipy.signal.filtfilt(b, a, x)   (wefax.py:72)
+// ===========================================================================
+constexpr int kFirTile = 2048;
+constexpr int kFirThreads = 256;
+constexpr int kPadLen = 9;   // 3 * max(len(a), len(b))
+
+template <int MODE, int KP>
+__global__ void __launch_bounds__(kFirThreads)
+filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride, long long n, const FirParams fp) {
+    constexpr int TS = kFirTile;
+    constexpr int NEXT = TS + 2 * (KP - 1);          // extended-signal samples a tile needs
+    constexpr int NEXT_AL = (NEXT + 16 + 3) & ~3;
+    constexpr int NYF = TS + KP - 1;                 // forward-filtered samples a tile needs
+    constexpr int NYF_AL = (NYF + 16 + 7) & ~7;
+    constexpr int W = KP + 8;                        // register window: 8 outputs + KP - 1 history
+    __shared__ __align__(16) float s_ext[NEXT_AL];
+    __shared__ __align__(16) float s_yf[NYF_AL];
+
+    const int tid = threadIdx.x;
+    const size_t base = (size_t)blockIdx.y * in_stride;
+    const long long E = n + 2 * kPadLen;                              // length of the odd-extended signal
+    const long long e0 = kPadLen + (long long)blockIdx.x * TS;        // first output of this tile, extended coords
+
+    for (int j = tid; j < NEXT_AL; j += kFirThreads) {
+        long long e = e0 - (KP - 1) + j;
+        float v = 0.f;
+        if (j < NEXT) {
+            if (e < 0) e = 0;   // steady-state initial condition: constant ext[0] to the left
+            if (e < E) {
+                if (e < kPadLen)
+                    v = 2.f * load_sample<MODE>(in, base, 0) - load_sample<MODE>(in, base, kPadLen - e);
+                else if (e >= n + kPadLen)
+                    v = 2.f * load_sample<MODE>(in, base, n - 1) - load_sample<MODE>(in, base, 2 * n + 7 - e);
+                else
+                    v = load_sample<MODE>(in, base, e - kPadLen);
+            }
+        }
+        s_ext[j] = v;
+    }
+    __syncthreads();
+
+    // forward (causal) section: yf_rel[i] = sum_j hr[j] * ext_rel[i + j]
+    for (int i0 = 8 * tid; i0 < NYF; i0 += 8 * kFirThreads) {
+        float w[W];
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+            float4 t = *reinterpret_cast<const float4 *>(&s_ext[i0 + 4 * q]);
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            const float c = fp.hr[j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[i + j], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_yf[i0 + i] = acc[i];
+    }
+    __syncthreads();
+
+    // backward section starts from the steady state of the last forward sample
+    const long long last_rel = (E - 1) - e0;
+    if (last_rel < NYF - 1) {
+        const float vlast = s_yf[last_rel];
+        for (int j = (int)last_rel + 1 + tid; j < NYF_AL; j += kFirThreads) s_yf[j] = vlast;
+    }
+    __syncthreads();
+
+    // backward (anti-causal) section: out[i] = sum_m h[m] * yf_rel[i + m]
+    {
+        const int i0 = 8 * tid;
+        float w[W];
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+            float4 t = *reinterpret_cast<const float4 *>(&s_yf[i0 + 4 * q]);
+            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+        }
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int m = 0; m < KP; ++m) {
+            const float c = fp.h[m];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[i + m], acc[i]);
+        }
+        __syncthreads();   // everyone is done reading s_ext (stage 1) long ago; reuse it for the coalesced store
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_ext[i0 + i] = acc[i];
+    }
+    __syncthreads();
+    const long long n0 = (long long)blockIdx.x * TS;
+    float *o = out + (size_t)blockIdx.y * out_stride;
+    for (int i = tid; i < TS; i += kFirThreads)
+        if (n0 + i < n) o[n0 + i] = s_ext[i];
+}
+
+template <int MODE>
+static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_stride, float *out, size_t out_stride,
+                                 long long n, const FirParams &fp, int batch) {
+    dim3 grid((unsigned)((n + kFirTile - 1) / kFirTile), batch);
+#define WEFAX_FIR_CASE(KP_)                                                                                   \
+    if (fp.KP == KP_) {                                                                                       \
+        filtfilt_kernel<MODE, KP_><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, n, fp); \
+        CUDA_CHECK(cudaGetLastError());                                                                       \
+        ctx->launches++;                                                                                      \
+        return;                                                                                               \
+    }
+    WEFAX_FIR_CASE(16)
+    WEFAX_FIR_CASE(20)
+    WEFAX_FIR_CASE(24)
+    WEFAX_FIR_CASE(32)
+    WEFAX_FIR_CASE(48)
+    WEFAX_FIR_CASE(64)
+#undef WEFAX_FIR_CASE
+    WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "notch impulse response needs %d taps (max %d)", fp.K, kMaxFirTaps);
+}
+
+void launch_filtfilt(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_stride, float *out, size_t out_stride,
+                     long long n, const FirParams &fp, int batch) {
+    switch (mode) {
+        case kInMonoI16: launch_filtfilt_mode<kInMonoI16>(ctx, in, in_stride, out, out_stride, n, fp, batch); break;
+        case kInStereoI16: launch_filtfilt_mode<kInStereoI16>(ctx, in, in_stride, out, out_stride, n, fp, batch); break;
+        default: launch_filtfilt_mode<kInFloat>(ctx, in, in_stride, out, out_stride, n, fp, batch); break;
+    }
+}
+
+// ===========================================================================
+// median of 5 with zero padding == scipy.signal.medfilt(v, 5)   (wefax.py:175)
+// ===========================================================================
+__device__ __forceinline__ float med3(float a, float b, float c) {
+    return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c));
+}
+__device__ __forceinline__ float med5(float a, float b, float c, float d, float e) {
+    float f = fmaxf(fminf(a, b), fminf(c, d));   // the two middle values of {a,b,c,d}
+    float g = fminf(fmaxf(a, b), fmaxf(c, d));
+    return med3(e, f, g);
+}
+
+// medians of elements i0..i0+3 of one recording (zero outside [0, n))
+__device__ __forceinline__ void load_med4(const float *e, long long i0, long long n, float out[4]) {
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        long long i = i0 - 2 + j;
+        w[j] = (i >= 0 && i < n) ? __ldg(e + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]);
+}
+
+__global__ void median5_kernel(const float *env, size_t es, float *out, size_t os, long long n) {
+    const float *e = env + (size_t)blockIdx.y * es;
+    float *o = out + (size_t)blockIdx.y * os;
+    long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    float m[4];
+    load_med4(e, i0, n, m);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (i0 + j < n) o[i0 + j] = m[j];
+}
+
+void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, size_t os, long long n, int batch) {
+    dim3 grid((unsigned)((n + 1023) / 1024), batch);
+    median5_kernel<<<grid, 256, 0, ctx->stream>>>(env, es, out, os, n);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// ===========================================================================
+// numpy.percentile(env, (0.5, 99.5))  (wefax.py:196): exact order statistics by a
+// 3-level radix select on the float bit pattern (11 + 11 + 10 bits), then numpy's
+// linear interpolation in double.
+// ===========================================================================
+__device__ __forceinline__ int level_shift(int level) { return level == 0 ? 21 : (level == 1 ? 10 : 0); }
+__device__ __forceinline__ uint32_t level_mask(int level) { return level == 2 ? 0x3FFu : 0x7FFu; }
+
+template <int LEVEL>
+__global__ void __launch_bounds__(256) hist_kernel(const float *env, size_t es, long long n, SelState *sel_all) {
+    constexpr int NH = LEVEL == 0 ? 1 : 4;
+    __shared__ uint32_t s_hist[NH][2048];
+    SelState *sel = sel_all + blockIdx.y;
+    const float *e = env + (size_t)blockIdx.y * es;
+    for (int i = threadIdx.x; i < NH * 2048; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    uint32_t prefix[4];
+    if (LEVEL > 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) prefix[t] = sel->prefix[t];
+    }
+    __syncthreads();
+
+    const long long stride = 4ll * blockDim.x * gridDim.x;
+    for (long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i0 < ((n + stride - 1) / stride) * stride;
+         i0 += stride) {
+        float m[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i0 < n) load_med4(e, i0, n, m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool valid = i0 + j < n;
+            const uint32_t key = __float_as_uint(m[j]);
+            if (LEVEL == 0) {
+                // warp-aggregated: the envelope is concentrated in a few exponent bins
+                const uint32_t bin = valid ? (key >> 21) : 0xFFFFFFFFu;
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+                if (valid && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[0][bin], __popc(peers));
+            } else if (valid) {
+                const uint32_t hi = key >> (LEVEL == 1 ? 21 : 10);
+                const uint32_t bin = (key >> level_shift(LEVEL)) & level_mask(LEVEL);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (hi == prefix[t]) atomicAdd(&s_hist[t % NH][bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NH * 2048; i += blockDim.x) {
+        uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&sel->hist[LEVEL][i >> 11][i & 2047], c);
+    }
+}
+
+__global__ void select_init_kernel(SelState *sel_all, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    SelState *sel = sel_all + blockIdx.x;
+    if (threadIdx.x == 0) {
+        sel->rank[0] = r0; sel->rank[1] = r1; sel->rank[2] = r2; sel->rank[3] = r3;
+        sel->prefix[0] = sel->prefix[1] = sel->prefix[2] = sel->prefix[3] = 0;
+    }
+}
+
+// one block (256 threads) per recording: locate, for each of the 4 target ranks, the
+// histogram bin that contains it
+__global__ void __launch_bounds__(256)
+select_kernel(SelState *sel_all, int level, RecResult *res_all, double t_lo, double t_hi) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_bin[4], s_before[4];
+    SelState *sel = sel_all + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int bits = level == 2 ? 10 : 11;
+    for (int t = 0; t < 4; ++t) {
+        const uint32_t *hist = sel->hist[level][level == 0 ? 0 : t];
+        const uint32_t rank = sel->rank[t];
+        uint32_t c[8], local = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = hist[8 * tid + j];
+            local += c[j];
+        }
+        uint32_t incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < wid; ++w) woff += s_warp[w];
+        uint32_t before = woff + incl - local;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (rank >= before && rank < before + c[j]) {
+                s_bin[t] = 8 * tid + j;
+                s_before[t] = before;
+            }
+            before += c[j];
+        }
+        __syncthreads();
+    }
+    if (tid < 4) {
+        sel->prefix[tid] = (sel->prefix[tid] << bits) | s_bin[tid];
+        sel->rank[tid] -= s_before[tid];
+    }
+    __syncthreads();
+    if (level == 2 && tid == 0) {
+        // numpy _lerp: a + (b-a)*t for t < 0.5, b - (b-a)*(1-t) otherwise (no FMA contraction)
+        double v[4];
+        for (int t = 0; t < 4; ++t) v[t] = (double)__uint_as_float(sel->prefix[t]);
+        double d0 = __dsub_rn(v[1], v[0]), d1 = __dsub_rn(v[3], v[2]);
+        double low = t_lo >= 0.5 ? __dsub_rn(v[1], __dmul_rn(d0, __dsub_rn(1.0, t_lo))) : __dadd_rn(v[0], __dmul_rn(d0, t_lo));
+        double high = t_hi >= 0.5 ? __dsub_rn(v[3], __dmul_rn(d1, __dsub_rn(1.0, t_hi))) : __dadd_rn(v[2], __dmul_rn(d1, t_hi));
+        RecResult *res = res_all + blockIdx.x;
+        res->low = low;
+        res->high = high;
+        double delta = __dsub_rn(high, low);
+        if (!(delta > 0.0) || isinf(delta)) res->status |= WEFAX_REC_NAN;
+    }
+}
+
+void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
+                        RecResult *res) {
+    // numpy 'linear' method: virtual index (n-1)*q, q = 0.5/100 and 99.5/100
+    const double v_lo = (double)(n - 1) * (0.5 / 100), v_hi = (double)(n - 1) * (99.5 / 100);
+    const long long i_lo = (long long)floor(v_lo), i_hi = (long long)floor(v_hi);
+    const double t_lo = v_lo - (double)i_lo, t_hi = v_hi - (double)i_hi;
+    auto clip = [&](long long r) { return (uint32_t)std::min(r, n - 1); };
+    CUDA_CHECK(cudaMemsetAsync(sel, 0, sizeof(SelState) * batch, ctx->stream));
+    select_init_kernel<<<batch, 32, 0, ctx->stream>>>(sel, clip(i_lo), clip(i_lo + 1), clip(i_hi), clip(i_hi + 1));
+    ctx->launches++;
+    long long per_block = 4 * 256;
+    int blocks = (int)std::min<long long>((n + per_block - 1) / per_block, (long long)ctx->sm_count * 8);
+    blocks = std::max(1, blocks / std::max(1, std::min(batch, 8)));
+    dim3 grid(blocks, batch);
+    hist_kernel<0><<<grid, 256, 0, ctx->stream>>>(env, es, n, sel);
+    select_kernel<<<batch, 256, 0, ctx->stream>>>(sel, 0, res, t_lo, t_hi);
+    hist_kernel<1><<<grid, 256, 0, ctx->stream>>>(env, es, n, sel);
+    select_kernel<<<batch, 256, 0, ctx->stream>>>(sel, 1, res, t_lo, t_hi);
+    hist_kernel<2><<<grid, 256, 0, ctx->stream>>>(env, es, n, sel);
+    select_kernel<<<batch, 256, 0, ctx->stream>>>(sel, 2, res, t_lo, t_hi);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches += 6;
+}
+
+// ===========================================================================
+// grey map  (wefax.py:197-200,216): round(255*(env-low)/(high-low)), clip, int
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long n, const RecResult *res_all) {
+    const RecResult *res = res_all + blockIdx.y;
+    const float *e = env + (size_t)blockIdx.y * es;
+    uint8_t *d = dig + (size_t)blockIdx.y * ds;
+    const double low = res->low;
+    const double delta = __dsub_rn(res->high, low);
+    long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    float m[4];
+    load_med4(e, i0, n, m);
+    uint8_t q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // numpy: round(255 * (env - low) / delta), evaluated in that order in float64;
+        // rint = round half to even = numpy.round
+        double v = rint(__ddiv_rn(__dmul_rn(255.0, __dsub_rn((double)m[j], low)), delta));
+        v = fmin(fmax(v, 0.0), 255.0);
+        q[j] = (uint8_t)(int)v;
+    }
+    if (i0 + 3 < n && ((reinterpret_cast<uintptr_t>(d + i0) & 3) == 0)) {
+        *reinterpret_cast<uchar4 *>(d + i0) = make_uchar4(q[0], q[1], q[2], q[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < n) d[i0 + j] = q[j];
+    }
+}
+
+void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
+                     const RecResult *res) {
+    dim3 grid((unsigned)((n + 1023) / 1024), batch);
+    quantise_kernel<<<grid, 256, 0, ctx->stream>>>(env, es, dig, ds, n, res);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// ===========================================================================
+// phasing search  (wefax.py:218-294)
+// ===========================================================================
+constexpr int kSyncThreads = 1024;
+constexpr int kSyncMaxL = 2048;
+
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long *s_red) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        v = o > v ? o : v;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();   // protect s_red from the previous reduction's readers
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    unsigned long long r = s_red[lane];   // kSyncThreads / 32 == 32 partials
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, r, d);
+        r = o > r ? o : r;
+    }
+    return r;
+}
+
+// key orders by correlation, ties by smallest index (the picker's strict '>')
+__device__ __forceinline__ unsigned long long sync_key(int corr, int idx) {
+    return ((unsigned long long)((uint32_t)corr ^ 0x80000000u) << 32) | (uint32_t)(0x7FFFFFFF - idx);
+}
+__device__ __forceinline__ int key_corr(unsigned long long k) { return (int)((uint32_t)(k >> 32) ^ 0x80000000u); }
+__device__ __forceinline__ int key_idx(unsigned long long k) { return 0x7FFFFFFF - (int)(uint32_t)k; }
+
+template <int PER>
+__global__ void __launch_bounds__(kSyncThreads)
+sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, RecResult *res_all) {
+    constexpr int CH = kSyncThreads * PER;            // positions handled per iteration
+    constexpr int TOTMAX = CH + kSyncMaxL;
+    constexpr int EPT = (TOTMAX + kSyncThreads - 1) / kSyncThreads;
+    __shared__ int s_p[TOTMAX + 1];                   // exclusive prefix sums of (d - 128)
+    __shared__ int s_wsum[32];
+    __shared__ unsigned long long s_red[32];
+    __shared__ int s_peaks[WEFAX_MAX_PEAKS];
+
+    const LineDev ln = lines[blockIdx.x];
+    RecResult *res = res_all + blockIdx.x;
+    const uint8_t *dig = dig_all + (size_t)blockIdx.x * ds;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int L = ln.L, n1 = ln.n1, n0 = ln.n0, mind = ln.mindistance;
+    const long long m = n - L;                        // range(len(data) - len(sync))
+
+    long long p = 0;       // position of the newest peak
+    int v = 0;             // its correlation
+    int npeaks = 1;        // peaks = [(0, 0)]
+    bool done = false;
+    if (tid == 0) s_peaks[0] = 0;
+
+    for (long long base = 0; base < m && !done; base += CH) {
+        const int valid = (int)min((long long)CH, m - base);
+        const int tot = valid + L;
+        // ---- exclusive prefix sums of (d - 128) over [base, base + tot) -----------------
+        int vals[EPT], run = 0;
+        const int j0 = tid * EPT;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            int idx = j0 + j;
+            int x = idx < tot ? (int)__ldg(dig + base + idx) - 128 : 0;
+            run += x;
+            vals[j] = run;
+        }
+        int incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        __syncthreads();   // previous iteration's readers of s_p / s_wsum are done
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        int woff = 0;
+        {
+            int t = lane < wid ? s_wsum[lane] : 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
+            woff = t;
+        }
+        const int excl = woff + incl - run;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            int idx = j0 + j;
+            if (idx < TOTMAX) s_p[idx + 1] = excl + vals[j];
+        }
+        if (tid == 0) s_p[0] = 0;
+        __syncthreads();
+
+        // ---- correlation of this thread's positions -------------------------------------
+        int corr[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            int i = tid + u * kSyncThreads;
+            int c = 0;
+            if (i < valid) {
+                int a = s_p[i], b = s_p[i + n1], cc = s_p[i + n1 + n0], d = s_p[i + L];
+                c = -127 * (b - a) - 128 * (cc - b) - 127 * (d - cc);
+            }
+            corr[u] = c;
+        }
+        auto range_max = [&](int lo, int hi) -> unsigned long long {   // max over positions [lo, hi)
+            unsigned long long k = 0;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                int i = tid + u * kSyncThreads;
+                if (i >= lo && i < hi) {
+                    unsigned long long kk = sync_key(corr[u], i);
+                    k = kk > k ? kk : k;
+                }
+            }
+            return block_max_u64(k, s_red);
+        };
+
+        const long long i_exp = p + mind + 1;          // first i with i - p > mindistance
+        if (i_exp < base + valid) {
+            const int a_exp = (int)(i_exp - base);
+            unsigned long long k1 = a_exp > 0 ? range_max(0, a_exp) : 0ull;
+            if (k1 != 0ull && key_corr(k1) > v) {
+                // a replacement happens first: the peak moves into this chunk, no opening here
+                unsigned long long k = range_max(0, valid);
+                p = base + key_idx(k);
+                v = key_corr(k);
+            } else {
+                // open a new peak at i_exp
+                int a = s_p[a_exp], b = s_p[a_exp + n1], cc = s_p[a_exp + n1 + n0], d = s_p[a_exp + L];
+                p = i_exp;
+                v = -127 * (b - a) - 128 * (cc - b) - 127 * (d - cc);
+                npeaks++;
+                if (npeaks == WEFAX_MAX_PEAKS) {
+                    done = true;
+                } else if (a_exp + 1 < valid) {
+                    unsigned long long k2 = range_max(a_exp + 1, valid);
+                    if (k2 != 0ull && key_corr(k2) > v) {
+                        p = base + key_idx(k2);
+                        v = key_corr(k2);
+                    }
+                }
+            }
+        } else {
+            unsigned long long k = range_max(0, valid);
+            if (k != 0ull && key_corr(k) > v) {
+                p = base + key_idx(k);
+                v = key_corr(k);
+            }
+        }
+        if (tid == 0) s_peaks[npeaks - 1] = (int)p;
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        // wefax.py:263-294 (find_sync_pulses / find_peak_groups, quirks included)
+        const int np = npeaks;
+        auto regular = [&](int x) { return ln.dev_max > (double)x && (double)x > ln.dev_min; };
+        int nclear = 0;
+        for (int i = 1; i < np - 1; ++i)
+            if (regular(s_peaks[i] - s_peaks[i - 1])) nclear++;
+        int best_start = 0, best_len = -1, cur_start = 1, cur_len = 0;
+        for (int i = 1; i < nclear - 1; ++i) {
+            if (regular(s_peaks[i] - s_peaks[i - 1])) {
+                if (cur_len == 0) cur_start = i;
+                cur_len++;
+            } else {
+                if (cur_len > best_len) {
+                    best_len = cur_len;
+                    best_start = cur_start;
+                }
+                cur_len = 0;
+            }
+        }
+        res->n_peaks = np;
+        for (int i = 0; i < np; ++i) res->peaks[i] = s_peaks[i];
+        int status = res->status;
+        long long start = 0;
+        if (best_len < 0) {
+            status |= WEFAX_REC_NO_GROUPS;
+            res->n_phasing = 0;
+        } else {
+            res->n_phasing = best_len;
+            for (int i = 0; i < best_len; ++i) res->phasing[i] = s_peaks[best_start + i];
+            if (best_len > 0) start = s_peaks[best_start + best_len - 1];
+        }
+        res->start_frame = start;
+        long long h = (n - start) / ln.width;
+        if (!(status & WEFAX_REC_NO_GROUPS) && h == 0) status |= WEFAX_REC_NO_LINES;
+        res->height = (status == WEFAX_REC_OK) ? (int32_t)(4 * h) : 0;
+        res->status = status;
+    }
+}
+
+void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
+                        RecResult *res, int min_mindistance) {
+    if (min_mindistance >= 4096)
+        sync_search_kernel<4><<<batch, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, lines, res);
+    else if (min_mindistance >= 2048)
+        sync_search_kernel<2><<<batch, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, lines, res);
+    else
+        sync_search_kernel<1><<<batch, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, lines, res);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// ===========================================================================
+// line raster + x4 vertical bicubic == Image.new/putpixel/resize  (wefax.py:296-327)
+// Pillow Resample.c: BICUBIC (a = -0.5), support 2, coefficients normalised per
+// output row, fixed point with PRECISION_BITS = 22.
+// ===========================================================================
+constexpr int kRasterRows = 32;     // input lines per tile (-> 128 output rows)
+constexpr int kRasterCols = 256;
+
+__device__ __forceinline__ double bicubic_filter(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+
+__global__ void __launch_bounds__(kRasterCols)
+raster_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, const RecResult *res_all,
+              uint8_t *raster_all, size_t rs) {
+    __shared__ uint8_t s_lum[kRasterRows + 4][kRasterCols];
+    __shared__ int s_k[4 * kRasterRows][5];
+    __shared__ int s_xmin[4 * kRasterRows], s_cnt[4 * kRasterRows];
+
+    const RecResult *res = res_all + blockIdx.z;
+    const int w = lines[blockIdx.z].width;
+    const int h = res->height / 4;
+    const int r0 = blockIdx.y * kRasterRows;
+    const int x0 = blockIdx.x * kRasterCols;
+    if (res->status != WEFAX_REC_OK || r0 >= h || x0 >= w) return;
+    const int tid = threadIdx.x;
+    const int x = x0 + tid;
+    const uint8_t *dig = dig_all + (size_t)blockIdx.z * ds + res->start_frame;
+    uint8_t *out = raster_all + (size_t)blockIdx.z * rs;
+
+    // luminance 255 - value of lines r0-2 .. r0+33 (wefax.py:303)
+#pragma unroll 4
+    for (int rr = 0; rr < kRasterRows + 4; ++rr) {
+        int r = r0 - 2 + rr;
+        uint8_t lum = 0;
+        if (r >= 0 && r < h && x < w) lum = 255 - __ldg(dig + (size_t)r * w + x);
+        s_lum[rr][tid] = lum;
+    }
+    // Pillow precompute_coeffs + normalize_coeffs_8bpc for this tile's output rows
+    if (tid < 4 * kRasterRows) {
+        const int yy = 4 * r0 + tid;
+        const double scale = 0.25, support = 2.0;
+        const double center = (yy + 0.5) * scale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > h) xmax = h;
+        xmax -= xmin;
+        double kw[5], ww = 0.0;
+        for (int t = 0; t < 5; ++t) {
+            kw[t] = t < xmax ? bicubic_filter((t + xmin - center + 0.5)) : 0.0;
+            ww += kw[t];
+        }
+        for (int t = 0; t < 5; ++t) {
+            double kv = (ww != 0.0) ? kw[t] / ww : kw[t];
+            s_k[tid][t] = t < xmax ? (kv < 0 ? (int)(-0.5 + kv * 4194304.0) : (int)(0.5 + kv * 4194304.0)) : 0;
+        }
+        s_xmin[tid] = xmin;
+        s_cnt[tid] = xmax;
+    }
+    __syncthreads();
+    if (x >= w) return;
+    const int rows_out = min(4 * kRasterRows, 4 * h - 4 * r0);
+    for (int j = 0; j < rows_out; ++j) {
+        const int rb = s_xmin[j] - (r0 - 2);
+        const int cnt = s_cnt[j];
+        int acc = 1 << 21;
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+            if (t < cnt) acc += (int)s_lum[rb + t][tid] * s_k[j][t];
+        acc >>= 22;
+        acc = min(max(acc, 0), 255);
+        out[(size_t)(4 * r0 + j) * w + x] = (uint8_t)acc;
+    }
+}
+
+void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
+                   const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines) {
+    if (max_lines <= 0) return;
+    dim3 grid((max_width + kRasterCols - 1) / kRasterCols, (max_lines + kRasterRows - 1) / kRasterRows, batch);
+    raster_kernel<<<grid, kRasterCols, 0, ctx->stream>>>(dig, ds, n, lines, res, raster, rs);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+}  // namespace wefax

@@ -1,0 +1,63 @@
+// Non-FFT stages of the decode path: declarations shared by stages.cu and api.cu.
+#pragma once
+
+#include "ctx.cuh"
+
+namespace wefax {
+
+constexpr int kMaxFirTaps = 64;
+
+// Truncated impulse response of the notch section (wefax.py:68-72): filtfilt is
+// evaluated as a causal FIR h followed by an anti-causal FIR h with scipy's exact
+// edge treatment (odd extension by 9, steady-state initial conditions).
+struct FirParams {
+    int K;                    // taps actually used (<= kMaxFirTaps), padded to KP
+    int KP;                   // K rounded up to a multiple of 4
+    float h[kMaxFirTaps];     // h[m], zero padded
+    float hr[kMaxFirTaps];    // reversed: hr[j] = h[KP-1-j]
+};
+
+// per-recording line geometry (wefax_line_constants, device copy)
+struct LineDev {
+    int n1, n0, L, mindistance, width;
+    double dev_min, dev_max;
+};
+
+// per-recording results produced on the device
+struct RecResult {
+    int32_t n_peaks;
+    int32_t peaks[WEFAX_MAX_PEAKS];
+    int32_t n_phasing;
+    int32_t phasing[WEFAX_MAX_PEAKS];
+    long long start_frame;
+    int32_t height;      // raster rows (4 * image lines)
+    int32_t status;
+    double low, high;
+};
+
+// percentile selection state, one per recording
+struct SelState {
+    uint32_t rank[4];      // remaining rank of each target inside its prefix class
+    uint32_t prefix[4];    // key prefix found so far
+    uint32_t hist[3][4][2048];
+};
+
+enum IngestMode { kInMonoI16 = 0, kInStereoI16 = 1, kInFloat = 2 };
+
+void launch_ingest_float(wefax_ctx *ctx, const int16_t *pcm, size_t pcm_stride, int channels, float *x, size_t xs,
+                         long long n, int batch);
+void launch_filtfilt(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_stride, float *out, size_t out_stride,
+                     long long n, const FirParams &fp, int batch);
+void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, size_t os, long long n, int batch);
+// 0.5 / 99.5 percentiles of median5(env) -> RecResult.low/high (+ WEFAX_REC_NAN)
+void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
+                        RecResult *res);
+void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
+                     const RecResult *res);
+// min_mindistance: smallest LineDev.mindistance of the batch (sizes the scan chunk; must be >= 1024)
+void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
+                        RecResult *res, int min_mindistance);
+void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
+                   const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines);
+
+}  // namespace wefax

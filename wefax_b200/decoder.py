@@ -1,0 +1,306 @@
+"""Batched decode on one GPU: thin Python over ``wefax_decode_batch`` (C-ABI).
+
+``Decoder`` owns one native context (one GPU, one stream).  ``decode`` takes a
+batch of equal-length recordings — host ``numpy`` int16 (pageable or pinned) or
+a CUDA ``torch`` int16 tensor — and returns the reference decoder's
+post-``process()`` quantities for each of them (wefax.py:55-84).  PyTorch is
+used only to allocate pinned / device buffers and to hand over a stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native as N
+
+ALL_OUTPUTS = ("audio", "demodulated", "digitalized", "raster")
+
+
+class WefaxNativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"wefax_b200 native error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+@dataclass
+class BatchResult:
+    """Outputs of one ``Decoder.decode`` call; arrays are indexed by recording."""
+    n_out: int                      # samples per recording at 11025 Hz
+    sample_rate: int                # always 11025 after the call (wefax.py:392)
+    lpm: list
+    width: list                     # image width per recording (wefax.py:298)
+    status: np.ndarray              # WEFAX_REC_* bits
+    peaks: list                     # pattern_search() positions (wefax.py:261)
+    phasing_signals: list           # wefax.py:78
+    start_frame: np.ndarray         # wefax.py:80
+    height: np.ndarray              # raster rows
+    low_high: np.ndarray            # (B, 2) the 0.5 / 99.5 percentiles
+    audio: object = None            # (B, n_out) float32   wefax.py:72
+    demodulated: object = None      # (B, n_out) float32   wefax.py:74
+    digitalized: object = None      # (B, n_out) uint8     wefax.py:76
+    raster_flat: object = None      # (B, raster_stride) uint8
+    on_device: bool = False
+    _keepalive: list = field(default_factory=list, repr=False)
+
+    def image(self, i: int):
+        """Raster of recording ``i`` as a ``(height, width)`` uint8 array (a view)."""
+        if self.raster_flat is None:
+            raise ValueError("decode() was called without 'raster' in want")
+        h, w = int(self.height[i]), int(self.width[i])
+        return self.raster_flat[i][: h * w].reshape(h, w)
+
+    def error(self, i: int):
+        """The exception the reference's process() would raise for recording ``i`` (or None)."""
+        s = int(self.status[i])
+        if s & N.REC_NAN:
+            return ValueError("cannot convert float NaN to integer")       # wefax.py:216
+        if s & N.REC_NO_GROUPS:
+            return ValueError("max() iterable argument is empty")           # wefax.py:294
+        if s & N.REC_NO_LINES:
+            return IndexError("image index out of range")                   # wefax.py:304
+        return None
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class Decoder:
+    """One native context = one GPU + one stream.  Not thread-safe; use one per thread."""
+
+    def __init__(self, device: int = 0, stream: int | None = None, workspace_limit: int | None = None):
+        lib = N.load()
+        if lib.wefax_abi_version() != 1:
+            raise RuntimeError("libwefax_b200.so ABI mismatch; rebuild")
+        handle = C.c_void_p()
+        rc = lib.wefax_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(handle))
+        if rc != N.OK:
+            raise WefaxNativeError(rc, "cannot create a CUDA context on device %d "
+                                       "(wefax_b200 needs a Blackwell GPU; there is no CPU fallback)" % device)
+        self._lib = lib
+        self._h = handle
+        self.device = int(device)
+        if workspace_limit:
+            lib.wefax_ctx_set_workspace_limit(self._h, int(workspace_limit))
+
+    # -- plumbing -----------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.wefax_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != N.OK:
+            msg = self._lib.wefax_last_error(self._h).decode(errors="replace")
+            if rc == N.ERR_INVALID:
+                raise ValueError(msg)
+            raise WefaxNativeError(rc, msg)
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.wefax_ctx_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.wefax_ctx_launch_count(self._h))
+
+    def synchronize(self) -> None:
+        self._check(self._lib.wefax_ctx_sync(self._h))
+
+    # -- the decode path ------------------------------------------------------
+    def decode(self, pcm, sample_rate: int, lpm=120, notch_freq=2600, notch_q=1,
+               want=("digitalized", "raster"), device_outputs: bool = False, pinned: bool = False,
+               out: BatchResult | None = None) -> BatchResult:
+        """Decode a batch.
+
+        pcm: int16, shape ``(n,)``, ``(n, 2)``, ``(B, n)`` or ``(B, n, 2)`` (numpy / CUDA torch
+        tensor; a 2-D array whose last dim is 2 is taken as one stereo recording).
+        lpm: one value or one per recording.  want: which large outputs to produce.
+        device_outputs: leave the large outputs on the GPU (torch tensors).
+        pinned: allocate host outputs in pinned memory (faster D2H).
+        out: a previous result with the same shapes whose buffers are reused.
+        """
+        on_dev_in = _is_torch(pcm) and pcm.is_cuda
+        shape = tuple(pcm.shape)
+        if len(shape) == 1:
+            B, n, ch = 1, shape[0], 1
+        elif len(shape) == 2 and shape[1] == 2 and shape[0] != 2:
+            B, n, ch = 1, shape[0], 2
+        elif len(shape) == 2:
+            B, n, ch = shape[0], shape[1], 1
+        elif len(shape) == 3 and shape[2] == 2:
+            B, n, ch = shape[0], shape[1], 2
+        else:
+            raise ValueError(f"unsupported pcm shape {shape}")
+        if on_dev_in:
+            import torch
+            if pcm.dtype != torch.int16 or not pcm.is_contiguous():
+                raise ValueError("device pcm must be a contiguous int16 tensor")
+            pcm_ptr = pcm.data_ptr()
+        else:
+            if _is_torch(pcm):
+                pcm = pcm.numpy()
+            if pcm.dtype != np.int16:
+                raise TypeError(f"pcm must be int16 (got {pcm.dtype}); other WAV sample formats are not supported")
+            pcm = np.ascontiguousarray(pcm)
+            pcm_ptr = pcm.ctypes.data
+        lpms = [float(lpm)] * B if np.isscalar(lpm) else [float(v) for v in lpm]
+        if len(lpms) != B:
+            raise ValueError("need one lpm per recording")
+        sample_rate = int(sample_rate)
+        n_out = n if sample_rate == N.TARGET_RATE else N.resampled_length(n, sample_rate)
+        widths = [N.line_constants(v)["width"] for v in lpms]
+        rstride = max(4 * (n_out // w) * w for w in widths) if n_out > 0 else 0
+        for name in want:
+            if name not in ALL_OUTPUTS:
+                raise ValueError(f"unknown output {name!r}")
+
+        keep = [pcm]
+        bufs = {}
+
+        def alloc(name, shape_, dtype):
+            if out is not None and getattr(out, name if name != "raster" else "raster_flat") is not None:
+                return getattr(out, name if name != "raster" else "raster_flat")
+            if device_outputs:
+                import torch
+                tdt = {np.float32: torch.float32, np.uint8: torch.uint8}[dtype]
+                return torch.empty(shape_, dtype=tdt, device=f"cuda:{self.device}")
+            if pinned:
+                import torch
+                tdt = {np.float32: torch.float32, np.uint8: torch.uint8}[dtype]
+                t = torch.empty(shape_, dtype=tdt, pin_memory=True)
+                keep.append(t)
+                return t.numpy()
+            return np.empty(shape_, dtype=dtype)
+
+        def ptr(a):
+            return a.data_ptr() if _is_torch(a) else a.ctypes.data
+
+        o = N.BatchOut()
+        for name, dtype in (("audio", np.float32), ("demodulated", np.float32), ("digitalized", np.uint8)):
+            if name in want:
+                bufs[name] = alloc(name, (B, n_out), dtype)
+                setattr(o, name, ptr(bufs[name]))
+        if "raster" in want:
+            bufs["raster"] = alloc("raster", (B, max(rstride, 1)), np.uint8)
+            o.raster = ptr(bufs["raster"])
+        o.raster_stride = max(rstride, 1)
+        peaks = np.zeros((B, N.MAX_PEAKS), dtype=np.int32)
+        n_peaks = np.zeros(B, dtype=np.int32)
+        phasing = np.zeros((B, N.MAX_PEAKS), dtype=np.int32)
+        n_phasing = np.zeros(B, dtype=np.int32)
+        start = np.zeros(B, dtype=np.int64)
+        height = np.zeros(B, dtype=np.int32)
+        status = np.zeros(B, dtype=np.int32)
+        low_high = np.zeros((B, 2), dtype=np.float64)
+        o.peaks, o.n_peaks = peaks.ctypes.data, n_peaks.ctypes.data
+        o.phasing, o.n_phasing = phasing.ctypes.data, n_phasing.ctypes.data
+        o.start_frame, o.height = start.ctypes.data, height.ctypes.data
+        o.status, o.low_high = status.ctypes.data, low_high.ctypes.data
+
+        desc = N.BatchDesc(B, n, ch, sample_rate, float(notch_freq), float(notch_q),
+                           (N.F_PCM_ON_DEVICE if on_dev_in else 0) | (N.F_OUT_ON_DEVICE if device_outputs else 0))
+        lpm_arr = (C.c_double * B)(*lpms)
+        self._check(self._lib.wefax_decode_batch(self._h, C.byref(desc), C.c_void_p(pcm_ptr),
+                                                 C.cast(lpm_arr, C.c_void_p), C.byref(o)))
+        return BatchResult(
+            n_out=n_out, sample_rate=N.TARGET_RATE, lpm=lpms, width=widths, status=status,
+            peaks=[peaks[i, : n_peaks[i]].tolist() for i in range(B)],
+            phasing_signals=[phasing[i, : n_phasing[i]].tolist() for i in range(B)],
+            start_frame=start, height=height, low_high=low_high,
+            audio=bufs.get("audio"), demodulated=bufs.get("demodulated"),
+            digitalized=bufs.get("digitalized"), raster_flat=bufs.get("raster"),
+            on_device=device_outputs, _keepalive=keep)
+
+    # -- stage-level entry points (parity tests) --------------------------------
+    def fft(self, x: np.ndarray, inverse: bool = False) -> np.ndarray:
+        """Complex DFT along the last axis (complex64 in/out); numpy.fft conventions."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        batch = int(np.prod(x.shape[:-1])) if x.ndim > 1 else 1
+        y = np.empty_like(x)
+        self._check(self._lib.wefax_fft_c2c(self._h, x.shape[-1], batch, x.ctypes.data, y.ctypes.data, int(inverse)))
+        return y
+
+    def hilbert_envelope(self, x: np.ndarray) -> np.ndarray:
+        """``abs(scipy.signal.hilbert(x))`` along the last axis (float32)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        batch = int(np.prod(x.shape[:-1])) if x.ndim > 1 else 1
+        y = np.empty_like(x)
+        self._check(self._lib.wefax_hilbert_envelope(self._h, x.shape[-1], batch, x.ctypes.data, y.ctypes.data))
+        return y
+
+    def resample(self, x: np.ndarray, num: int) -> np.ndarray:
+        """``scipy.signal.resample(x, num)`` along the last axis (float32)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        batch = int(np.prod(x.shape[:-1])) if x.ndim > 1 else 1
+        y = np.empty(x.shape[:-1] + (int(num),), dtype=np.float32)
+        self._check(self._lib.wefax_resample(self._h, x.shape[-1], int(num), batch, x.ctypes.data, y.ctypes.data))
+        return y
+
+    def filtfilt(self, x: np.ndarray, notch_freq=2600, notch_q=1) -> np.ndarray:
+        """``scipy.signal.filtfilt(*iirnotch(f0, Q, 11025), x)`` along the last axis (float32)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        batch = int(np.prod(x.shape[:-1])) if x.ndim > 1 else 1
+        y = np.empty_like(x)
+        self._check(self._lib.wefax_filtfilt(self._h, x.shape[-1], batch, float(notch_freq), float(notch_q),
+                                             x.ctypes.data, y.ctypes.data))
+        return y
+
+    def digitalize(self, envelope: np.ndarray):
+        """median-5 + percentile stretch + rounding of a raw |hilbert| envelope
+        (wefax.py:175,196-216).  Returns ``(demodulated, digitalized, low_high, status)``."""
+        e = np.ascontiguousarray(envelope, dtype=np.float32)
+        batch = int(np.prod(e.shape[:-1])) if e.ndim > 1 else 1
+        dem = np.empty_like(e)
+        dig = np.empty(e.shape, dtype=np.uint8)
+        lh = np.zeros((batch, 2), dtype=np.float64)
+        st = np.zeros(batch, dtype=np.int32)
+        self._check(self._lib.wefax_digitalize(self._h, e.shape[-1], batch, e.ctypes.data, dem.ctypes.data,
+                                               dig.ctypes.data, lh.ctypes.data, st.ctypes.data))
+        return dem, dig, lh, st
+
+    def sync_raster(self, digitalized: np.ndarray, lpm) -> BatchResult:
+        """Phasing search + raster on given digitalized data ``(B, n)`` uint8 (wefax.py:218-327)."""
+        dig = np.ascontiguousarray(digitalized, dtype=np.uint8)
+        if dig.ndim == 1:
+            dig = dig[None]
+        B, n = dig.shape
+        lpms = [float(lpm)] * B if np.isscalar(lpm) else [float(v) for v in lpm]
+        widths = [N.line_constants(v)["width"] for v in lpms]
+        rstride = max(max(4 * (n // w) * w for w in widths), 1)
+        raster = np.zeros((B, rstride), dtype=np.uint8)
+        peaks = np.zeros((B, N.MAX_PEAKS), dtype=np.int32)
+        n_peaks = np.zeros(B, dtype=np.int32)
+        phasing = np.zeros((B, N.MAX_PEAKS), dtype=np.int32)
+        n_phasing = np.zeros(B, dtype=np.int32)
+        start = np.zeros(B, dtype=np.int64)
+        height = np.zeros(B, dtype=np.int32)
+        status = np.zeros(B, dtype=np.int32)
+        o = N.BatchOut()
+        o.raster, o.raster_stride = raster.ctypes.data, rstride
+        o.peaks, o.n_peaks = peaks.ctypes.data, n_peaks.ctypes.data
+        o.phasing, o.n_phasing = phasing.ctypes.data, n_phasing.ctypes.data
+        o.start_frame, o.height, o.status = start.ctypes.data, height.ctypes.data, status.ctypes.data
+        lpm_arr = (C.c_double * B)(*lpms)
+        self._check(self._lib.wefax_sync_raster(self._h, n, B, dig.ctypes.data, C.cast(lpm_arr, C.c_void_p),
+                                                C.byref(o)))
+        return BatchResult(
+            n_out=n, sample_rate=N.TARGET_RATE, lpm=lpms, width=widths, status=status,
+            peaks=[peaks[i, : n_peaks[i]].tolist() for i in range(B)],
+            phasing_signals=[phasing[i, : n_phasing[i]].tolist() for i in range(B)],
+            start_frame=start, height=height, low_high=np.zeros((B, 2)), digitalized=dig, raster_flat=raster)
