@@ -69,6 +69,12 @@ long long wefax_ctx_launch_count(const wefax_ctx *ctx);
 /* cap on the scratch memory one decode wave may use (default 24 GiB); recordings
  * of a batch are processed in waves that fit. */
 int wefax_ctx_set_workspace_limit(wefax_ctx *ctx, long long bytes);
+/* Per-stage device timing with CUDA events on the context's stream.  After
+ * wefax_ctx_enable_timing(ctx, 1) every stage launch is bracketed by an event pair;
+ * wefax_ctx_timings() synchronises, accumulates and writes one line per stage
+ * ("name total_ms launches\n") into buf; reset != 0 clears the accumulators. */
+int wefax_ctx_enable_timing(wefax_ctx *ctx, int enable);
+int wefax_ctx_timings(wefax_ctx *ctx, char *buf, long long buf_len, int reset);
 int wefax_abi_version(void);
 int wefax_device_count(void);
 

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "wefax_line_constants_for", "wefax_resampled_length", "wefax_notch_coefficients",
     "wefax_fft_plan_describe", "wefax_decode_batch", "wefax_fft_c2c", "wefax_hilbert_envelope",
     "wefax_resample", "wefax_filtfilt", "wefax_digitalize", "wefax_sync_raster",
+    "wefax_ctx_enable_timing", "wefax_ctx_timings",
 )
 
 
@@ -80,6 +81,10 @@ def load():
     lib.wefax_ctx_launch_count.restype = ll
     lib.wefax_ctx_set_workspace_limit.argtypes = [vp, ll]
     lib.wefax_ctx_set_workspace_limit.restype = i
+    lib.wefax_ctx_enable_timing.argtypes = [vp, i]
+    lib.wefax_ctx_enable_timing.restype = i
+    lib.wefax_ctx_timings.argtypes = [vp, C.c_char_p, ll, i]
+    lib.wefax_ctx_timings.restype = i
     lib.wefax_abi_version.argtypes = []
     lib.wefax_abi_version.restype = i
     lib.wefax_device_count.argtypes = []

@@ -218,6 +218,11 @@ void wefax_ctx_destroy(wefax_ctx *ctx) {
     ctx->plans.clear();
     ctx->bluestein.clear();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &sp : ctx->spans) {
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -238,6 +243,41 @@ int wefax_ctx_set_workspace_limit(wefax_ctx *ctx, long long bytes) {
     if (!ctx || bytes < (1ll << 20)) return WEFAX_ERR_INVALID;
     ctx->workspace_limit = bytes;
     return WEFAX_OK;
+}
+
+int wefax_ctx_enable_timing(wefax_ctx *ctx, int enable) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    ctx->timing = enable != 0;
+    return WEFAX_OK;
+}
+
+// Resolves the pending event pairs and writes "name total_ms launches\n" lines
+// (accumulated since the last reset) into buf.
+int wefax_ctx_timings(wefax_ctx *ctx, char *buf, long long buf_len, int reset) {
+    if (!ctx || !buf || buf_len < 1) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        use_device(ctx);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (auto &sp : ctx->spans) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+            auto &acc = ctx->stage_ms[sp.name];
+            acc.first += ms;
+            acc.second += 1;
+            ctx->event_pool.push_back(sp.e0);
+            ctx->event_pool.push_back(sp.e1);
+        }
+        ctx->spans.clear();
+        std::string out;
+        for (auto &kv : ctx->stage_ms) {
+            char line[128];
+            snprintf(line, sizeof(line), "%s %.6f %lld\n", kv.first.c_str(), kv.second.first, kv.second.second);
+            out += line;
+        }
+        if ((long long)out.size() + 1 > buf_len) WEFAX_THROW(WEFAX_ERR_INVALID, "timing buffer too small");
+        memcpy(buf, out.c_str(), out.size() + 1);
+        if (reset) ctx->stage_ms.clear();
+    });
 }
 
 int wefax_line_constants_for(double lpm, int sample_rate, wefax_line_constants *out) {
@@ -333,6 +373,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             const int16_t *d_pcm = pcm + (size_t)w0 * n_in * ch;
             if (!pcm_dev) {
                 int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)g * n_in * ch * sizeof(int16_t));
+                StageTimer timer(ctx, "h2d_pcm");
                 CUDA_CHECK(cudaMemcpyAsync(buf, d_pcm, (size_t)g * n_in * ch * sizeof(int16_t), cudaMemcpyHostToDevice, st));
                 d_pcm = buf;
             }
@@ -384,6 +425,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             // ---- results ---------------------------------------------------------------
             CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult) * g, cudaMemcpyDeviceToHost, st));
             if (!out_dev) {
+                StageTimer timer(ctx, "d2h_outputs");
                 if (out->audio)
                     CUDA_CHECK(cudaMemcpyAsync(out->audio + (size_t)w0 * n, d_audio, (size_t)g * n * sizeof(float),
                                                cudaMemcpyDeviceToHost, st));

@@ -30,11 +30,45 @@ struct wefax_ctx {
     // pinned staging for small results
     void *pinned = nullptr;
     size_t pinned_cap = 0;
+    // optional per-stage device timing (CUDA events on the context's stream)
+    bool timing = false;
+    struct Span {
+        const char *name;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    std::map<std::string, std::pair<double, long long>> stage_ms;   // name -> (total ms, launches)
 };
 
 namespace wefax {
 
 FftPlan *get_plan(wefax_ctx *ctx, long long n);   // nullptr when n needs Bluestein
+
+// Brackets one stage with CUDA events when ctx->timing is on (no host sync here;
+// wefax_ctx_timings() resolves them).
+struct StageTimer {
+    wefax_ctx *ctx;
+    cudaEvent_t e1 = nullptr;
+    StageTimer(wefax_ctx *c, const char *name) : ctx(c) {
+        if (!ctx->timing) return;
+        cudaEvent_t ev[2];
+        for (auto &e : ev) {
+            if (!ctx->event_pool.empty()) {
+                e = ctx->event_pool.back();
+                ctx->event_pool.pop_back();
+            } else {
+                CUDA_CHECK(cudaEventCreate(&e));
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(ev[0], ctx->stream));
+        e1 = ev[1];
+        ctx->spans.push_back({name, ev[0], ev[1]});
+    }
+    ~StageTimer() {
+        if (e1) cudaEventRecord(e1, ctx->stream);
+    }
+};
 
 template <class LoadOp, class StoreOp>
 void launch_pass(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const StoreOp &st, int batch) {
@@ -44,6 +78,7 @@ void launch_pass(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const Store
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->smem_configured[fn] = 1;
     }
+    StageTimer timer(ctx, p.tag);
     dim3 grid(p.ntiles, batch);
     fft_pass_kernel<LoadOp, StoreOp><<<grid, kFftThreads, p.smem_bytes, ctx->stream>>>(p, ld, st);
     CUDA_CHECK(cudaGetLastError());

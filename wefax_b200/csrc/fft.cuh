@@ -45,6 +45,7 @@ struct PassDev {
     int tw_mode;                  // 0 none, 1 multiply on store (forward), 2 multiply on load (inverse)
     int smem_bytes;
     int ntiles;
+    char tag[16];                 // "fft_fwd_0", "fft_inv_2", ... (stage timing label)
 };
 
 // ----------------------------- load / store functors -----------------------

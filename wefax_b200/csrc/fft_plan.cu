@@ -219,8 +219,10 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
         CUDA_CHECK(cudaGetLastError());
 
         d.tw_mode = d.contiguous ? 0 : 1;
+        snprintf(d.tag, sizeof(d.tag), "fft_fwd_%d", i);
         plan->fwd[i] = d;
         d.tw_mode = d.contiguous ? 0 : 2;
+        snprintf(d.tag, sizeof(d.tag), "fft_inv_%d", i);
         plan->inv[i] = d;
     }
     CUDA_CHECK(cudaStreamSynchronize(stream));

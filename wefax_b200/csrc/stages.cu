@@ -30,6 +30,7 @@ __global__ void ingest_kernel(const void *in, size_t in_stride, float *x, size_t
 
 void launch_ingest_float(wefax_ctx *ctx, const int16_t *pcm, size_t pcm_stride, int channels, float *x, size_t xs,
                          long long n, int batch) {
+    StageTimer timer(ctx, "ingest");
     dim3 grid((unsigned)((n + 255) / 256), batch);
     if (channels == 2)
         ingest_kernel<kInStereoI16><<<grid, 256, 0, ctx->stream>>>(pcm, pcm_stride, x, xs, n);
@@ -143,6 +144,7 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
 template <int MODE>
 static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_stride, float *out, size_t out_stride,
                                  long long n, const FirParams &fp, int batch) {
+    StageTimer timer(ctx, "filtfilt");
     dim3 grid((unsigned)((n + kFirTile - 1) / kFirTile), batch);
 #define WEFAX_FIR_CASE(KP_)                                                                                   \
     if (fp.KP == KP_) {                                                                                       \
@@ -207,6 +209,7 @@ __global__ void median5_kernel(const float *env, size_t es, float *out, size_t o
 }
 
 void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, size_t os, long long n, int batch) {
+    StageTimer timer(ctx, "median5");
     dim3 grid((unsigned)((n + 1023) / 1024), batch);
     median5_kernel<<<grid, 256, 0, ctx->stream>>>(env, es, out, os, n);
     CUDA_CHECK(cudaGetLastError());
@@ -334,6 +337,7 @@ select_kernel(SelState *sel_all, int level, RecResult *res_all, double t_lo, dou
 
 void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
                         RecResult *res) {
+    StageTimer timer(ctx, "percentiles");
     // numpy 'linear' method: virtual index (n-1)*q, q = 0.5/100 and 99.5/100
     const double v_lo = (double)(n - 1) * (0.5 / 100), v_hi = (double)(n - 1) * (99.5 / 100);
     const long long i_lo = (long long)floor(v_lo), i_hi = (long long)floor(v_hi);
@@ -390,6 +394,7 @@ quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long 
 
 void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
                      const RecResult *res) {
+    StageTimer timer(ctx, "quantise");
     dim3 grid((unsigned)((n + 1023) / 1024), batch);
     quantise_kernel<<<grid, 256, 0, ctx->stream>>>(env, es, dig, ds, n, res);
     CUDA_CHECK(cudaGetLastError());
@@ -593,6 +598,7 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
 
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                         RecResult *res, int min_mindistance) {
+    StageTimer timer(ctx, "sync_search");
     if (min_mindistance >= 4096)
         sync_search_kernel<4><<<batch, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, lines, res);
     else if (min_mindistance >= 2048)
@@ -685,6 +691,7 @@ raster_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lin
 
 void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                    const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines) {
+    StageTimer timer(ctx, "raster");
     if (max_lines <= 0) return;
     dim3 grid((max_width + kRasterCols - 1) / kRasterCols, (max_lines + kRasterRows - 1) / kRasterRows, batch);
     raster_kernel<<<grid, kRasterCols, 0, ctx->stream>>>(dig, ds, n, lines, res, raster, rs);

@@ -122,6 +122,20 @@ class Decoder:
     def synchronize(self) -> None:
         self._check(self._lib.wefax_ctx_sync(self._h))
 
+    def enable_timing(self, enable: bool = True) -> None:
+        """Bracket every stage launch with CUDA events on the context's stream."""
+        self._check(self._lib.wefax_ctx_enable_timing(self._h, int(enable)))
+
+    def timings(self, reset: bool = True) -> dict:
+        """``{stage: (total_ms, launches)}`` accumulated since the last reset."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._lib.wefax_ctx_timings(self._h, buf, len(buf), int(reset)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split()
+            out[name] = (float(ms), int(cnt))
+        return out
+
     # -- the decode path ------------------------------------------------------
     def decode(self, pcm, sample_rate: int, lpm=120, notch_freq=2600, notch_q=1,
                want=("digitalized", "raster"), device_outputs: bool = False, pinned: bool = False,
