@@ -15,7 +15,8 @@
 // the position -> frequency map.
 //
 // One CTA owns a tile of C adjacent columns x R rows in shared memory, runs the
-// radix-{8,4,2,3,5,7,11,13} stages there (in-place DIF, digit-reversed read-out),
+// radix-2..32 stages there (prime radices 2,3,5,7,11,13 and in-register composites
+// such as 14, 15, 16, 25, 28; in-place DIF, digit-reversed read-out),
 // and touches global memory exactly once per element per pass: coalesced C*8-byte
 // row segments for strided passes, one contiguous C*R*8-byte chunk for the last
 // (stride-1) pass.
@@ -221,21 +222,59 @@ template <int r> struct Bfly {
     }
 };
 
-// One in-place DIF stage of radix r over the whole tile.
-template <int r>
+// Length-(A*B) DFT held in registers: B radix-A butterflies over stride B, the
+// inner twiddles w_{AB}^{t_b*u_a} (from the w_R table), then A radix-B butterflies.
+// Output u = u_a + A*u_b ends up in v[u_a*B + u_b].
+template <int A, int B> struct Composite {
+    static constexpr int r = A * B;
+    __device__ __forceinline__ static void run(float2 *v, const float2 *twR, int tw_stride, const float2 *csA,
+                                               const float2 *csB) {
+        if constexpr (B == 1) {
+            Bfly<A>::run(v, csA);
+        } else {
+#pragma unroll
+        for (int tb = 0; tb < B; ++tb) {
+            float2 x[A];
+#pragma unroll
+            for (int ta = 0; ta < A; ++ta) x[ta] = v[ta * B + tb];
+            Bfly<A>::run(x, csA);
+#pragma unroll
+            for (int ua = 0; ua < A; ++ua) v[ua * B + tb] = x[ua];
+        }
+#pragma unroll
+        for (int ua = 1; ua < A; ++ua)
+#pragma unroll
+            for (int tb = 1; tb < B; ++tb) v[ua * B + tb] = cmul(v[ua * B + tb], twR[(ua * tb) * tw_stride]);
+#pragma unroll
+        for (int ua = 0; ua < A; ++ua) Bfly<B>::run(&v[ua * B], csB);
+        }
+    }
+};
+
+template <int r> __device__ __forceinline__ void load_cs(float2 *cs, const float2 *twR, int R) {
+    if constexpr ((r & 1) && r > 1) {
+#pragma unroll
+        for (int j = 1; j <= (r - 1) / 2; ++j) {
+            float2 w = twR[j * (R / r)];
+            cs[j - 1] = make_float2(w.x, -w.y);
+        }
+    }
+}
+
+// One in-place DIF stage of radix A*B over the whole tile: each thread takes A*B
+// elements spaced M = L/(A*B) apart into registers, transforms them, applies the
+// stage twiddles w_L^{q*u} and writes them back to the same places.
+template <int A, int B>
 __device__ __forceinline__ void dif_stage(float2 *tile, const float2 *twR, const PassDev &p, int s, int L) {
+    constexpr int r = A * B;
     const int M = L / r;
     const int nb = p.R / L;
     const int nbf = p.R / r;
     const int total = nbf * p.C;
-    float2 cs[(r - 1) / 2 + 1];
-    if (r & 1) {
-#pragma unroll
-        for (int j = 1; j <= (r - 1) / 2; ++j) {
-            float2 w = twR[j * (p.R / r)];
-            cs[j - 1] = make_float2(w.x, -w.y);
-        }
-    }
+    float2 csA[(A - 1) / 2 + 1], csB[(B - 1) / 2 + 1];
+    load_cs<A>(csA, twR, p.R);
+    load_cs<B>(csB, twR, p.R);
+    const int tw_stride = p.R / r;
     for (int b = threadIdx.x; b < total; b += blockDim.x) {
         int cc, qp, base, step;
         if (p.contiguous) {
@@ -258,14 +297,17 @@ __device__ __forceinline__ void dif_stage(float2 *tile, const float2 *twR, const
         float2 v[r];
 #pragma unroll
         for (int t = 0; t < r; ++t) v[t] = tile[base + t * step];
-        Bfly<r>::run(v, cs);
-        if (M > 1) {
-            const int e1 = q * nb;
+        Composite<A, B>::run(v, twR, tw_stride, csA, csB);
+        const int e1 = q * nb;
 #pragma unroll
-            for (int u = 1; u < r; ++u) v[u] = cmul(v[u], twR[e1 * u]);
-        }
+        for (int ua = 0; ua < A; ++ua)
 #pragma unroll
-        for (int t = 0; t < r; ++t) tile[base + t * step] = v[t];
+            for (int ub = 0; ub < B; ++ub) {
+                const int u = ua + A * ub;
+                float2 x = v[ua * B + ub];
+                if (M > 1 && u > 0) x = cmul(x, twR[e1 * u]);
+                tile[base + u * step] = x;
+            }
     }
 }
 
@@ -276,7 +318,7 @@ __device__ __forceinline__ float2 pass_twiddle(const PassDev &p, uint32_t e) {
 }
 
 template <class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st) {
+__global__ void __launch_bounds__(kFftThreads, 2) fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *tile = reinterpret_cast<float2 *>(smem_raw);
     float2 *twR = tile + (size_t)p.C * p.R;
@@ -326,14 +368,27 @@ __global__ void __launch_bounds__(kFftThreads) fft_pass_kernel(const PassDev p, 
     for (int s = 0; s < p.nstages; ++s) {
         const int r = p.radix[s];
         switch (r) {
-            case 2: dif_stage<2>(tile, twR, p, s, L); break;
-            case 3: dif_stage<3>(tile, twR, p, s, L); break;
-            case 4: dif_stage<4>(tile, twR, p, s, L); break;
-            case 5: dif_stage<5>(tile, twR, p, s, L); break;
-            case 7: dif_stage<7>(tile, twR, p, s, L); break;
-            case 8: dif_stage<8>(tile, twR, p, s, L); break;
-            case 11: dif_stage<11>(tile, twR, p, s, L); break;
-            default: dif_stage<13>(tile, twR, p, s, L); break;
+            case 2: dif_stage<2, 1>(tile, twR, p, s, L); break;
+            case 3: dif_stage<3, 1>(tile, twR, p, s, L); break;
+            case 4: dif_stage<4, 1>(tile, twR, p, s, L); break;
+            case 5: dif_stage<5, 1>(tile, twR, p, s, L); break;
+            case 7: dif_stage<7, 1>(tile, twR, p, s, L); break;
+            case 8: dif_stage<8, 1>(tile, twR, p, s, L); break;
+            case 11: dif_stage<11, 1>(tile, twR, p, s, L); break;
+            case 13: dif_stage<13, 1>(tile, twR, p, s, L); break;
+            case 6: dif_stage<2, 3>(tile, twR, p, s, L); break;
+            case 9: dif_stage<3, 3>(tile, twR, p, s, L); break;
+            case 10: dif_stage<2, 5>(tile, twR, p, s, L); break;
+            case 12: dif_stage<4, 3>(tile, twR, p, s, L); break;
+            case 14: dif_stage<2, 7>(tile, twR, p, s, L); break;
+            case 15: dif_stage<3, 5>(tile, twR, p, s, L); break;
+            case 16: dif_stage<4, 4>(tile, twR, p, s, L); break;
+            case 20: dif_stage<4, 5>(tile, twR, p, s, L); break;
+            case 21: dif_stage<3, 7>(tile, twR, p, s, L); break;
+            case 24: dif_stage<8, 3>(tile, twR, p, s, L); break;
+            case 25: dif_stage<5, 5>(tile, twR, p, s, L); break;
+            case 28: dif_stage<4, 7>(tile, twR, p, s, L); break;
+            default: dif_stage<8, 4>(tile, twR, p, s, L); break;   // 32
         }
         L /= r;
         __syncthreads();

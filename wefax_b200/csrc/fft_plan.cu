@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 
 #include "fft.cuh"
 
@@ -39,18 +40,76 @@ std::vector<long long> divisors_upto(long long n, long long cap) {
     return out;
 }
 
+// stage radices the kernel implements (primes and two-factor in-register composites)
+const int kRadixMenu[] = {2, 3, 4, 5, 7, 8, 11, 13, 6, 9, 10, 12, 14, 15, 16, 20, 21, 24, 25, 28, 32};
+
+// rough thread-instructions per element of one shared-memory stage of radix r
+double stage_cost(int r) { return 14.0 + 30.0 / r + 2.5 * std::log2((double)r); }
+constexpr double kPassCost = 40.0;   // global load/store + inter-pass twiddle, per element
+
+// cheapest split of R into menu radices (memoised); cost < 0 when impossible
+struct StagePlan {
+    double cost = -1.0;
+    std::vector<int> radices;
+};
+const StagePlan &stage_plan(int R) {
+    static std::map<int, StagePlan> memo;
+    auto it = memo.find(R);
+    if (it != memo.end()) return it->second;
+    StagePlan best;
+    if (R == 1) {
+        best.cost = 0.0;
+    } else {
+        for (int r : kRadixMenu) {
+            if (R % r) continue;
+            const StagePlan &sub = stage_plan(R / r);
+            if (sub.cost < 0) continue;
+            double c = stage_cost(r) + sub.cost;
+            if (best.cost < 0 || c < best.cost - 1e-9) {
+                best.cost = c;
+                best.radices = sub.radices;
+                best.radices.push_back(r);   // larger radices tend to come last: the last stage has no twiddles
+            }
+        }
+    }
+    return memo[R] = best;
+}
+
+int tile_cols(int R, int ncols) {
+    int C = 1;
+    while (C * 2 * R <= tile_max() && C * 2 <= 64) C *= 2;
+    while (C > 1 && C / 2 >= ncols) C /= 2;
+    return C;
+}
+
+// per-element cost of one pass of length R: its stages, each divided by the fraction
+// of the 256 threads that have a butterfly in the last round, plus the global traffic
+double pass_cost(int R, long long n) {
+    const StagePlan &sp = stage_plan(R);
+    if (sp.cost < 0) return -1.0;
+    const int C = tile_cols(R, (int)std::min<long long>(n / R, 1 << 30));
+    double c = kPassCost;
+    for (int r : sp.radices) {
+        const int total = C * (R / r);
+        const int rounds = (total + kFftThreads - 1) / kFftThreads;
+        c += stage_cost(r) * (double)(rounds * kFftThreads) / (double)total;
+    }
+    return c;
+}
+
 struct Search {
-    long long cap_s, cap_l;
+    long long n, cap_s, cap_l, min_r;
     double best_cost = 1e300;
     std::vector<int> best;
     std::vector<int> cur;
     // strided factors are chosen non-decreasing; the remainder is the last pass
-    void go(long long rem, int left, long long min_r) {
+    void go(long long rem, int left, long long lo) {
         if (left == 0) {
-            if (rem > cap_l || rem < 2) return;
-            double cost = (double)rem;
-            for (int r : cur) cost = std::max(cost, 4.0 * r);
-            if (cost < best_cost) {
+            if (rem > cap_l || rem < 2 || (!cur.empty() && rem < min_r)) return;
+            double cost = pass_cost((int)rem, n);
+            if (cost < 0) return;
+            for (int r : cur) cost += pass_cost(r, n);
+            if (cost < best_cost - 1e-9) {
                 best_cost = cost;
                 best = cur;
                 best.push_back((int)rem);
@@ -58,7 +117,8 @@ struct Search {
             return;
         }
         for (long long d : divisors_upto(rem, cap_s)) {
-            if (d < min_r || d < 2) continue;
+            if (d < lo || d < 2 || d < min_r) continue;
+            if (stage_plan((int)d).cost < 0) continue;
             cur.push_back((int)d);
             go(rem / d, left - 1, d);
             cur.pop_back();
@@ -66,15 +126,7 @@ struct Search {
     }
 };
 
-std::vector<int> stage_radices(int R) {
-    std::vector<int> r;
-    for (int p : {8, 4, 2, 3, 5, 7, 11, 13})
-        while (R % p == 0) {
-            r.push_back(p);
-            R /= p;
-        }
-    return r;
-}
+std::vector<int> stage_radices(int R) { return stage_plan(R).radices; }
 
 __global__ void twiddle_table_kernel(float2 *dst, int count, double L, double mult) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,18 +152,21 @@ bool plan_factors(long long n, std::vector<int> &Rs) {
     const long long cap_l = tmax;
     const long long cap_s = std::max(2, tmax / min_cols());
     int forced = env_int("WEFAX_FFT_PASSES", 0);
+    double best_cost = 1e300;
     for (int P = 1; P <= kMaxPasses; ++P) {
         if (forced && P != forced) continue;
         Search s;
+        s.n = n;
         s.cap_s = cap_s;
         s.cap_l = cap_l;
+        s.min_r = n >= 64 * 64 ? 64 : 2;   // no degenerate passes on long transforms
         s.go(n, P - 1, 2);
-        if (!s.best.empty()) {
+        if (!s.best.empty() && s.best_cost < best_cost - 1e-9) {
+            best_cost = s.best_cost;
             Rs = s.best;
-            return true;
         }
     }
-    return false;
+    return !Rs.empty();
 }
 
 long long next_smooth_length(long long m) {
@@ -159,7 +214,6 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
     }
     char *base = (char *)plan->tables.reserve(off);
 
-    const int tmax = tile_max();
     for (int i = 0; i < P; ++i) {
         PassDev d;
         memset(&d, 0, sizeof(d));
@@ -168,9 +222,7 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
         d.S = (int)plan->S[i];
         d.ncols = (int)(n / R);
         d.contiguous = (i == P - 1);
-        int C = 1;
-        while (C * 2 * R <= tmax && C * 2 <= 64) C *= 2;
-        while (C > 1 && C / 2 >= d.ncols) C /= 2;
+        const int C = tile_cols(R, d.ncols);
         d.C = C;
         d.log2C = 0;
         while ((1 << d.log2C) < C) ++d.log2C;
