@@ -2,6 +2,7 @@
 // the batched decode that strings the kernels together (see include/wefax_b200.h).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "stages.cuh"
@@ -196,6 +197,8 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
             WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "built for sm_100a (Blackwell); device %d is sm_%d%d", device, prop.major,
                         prop.minor);
         ctx->sm_count = prop.multiProcessorCount;
+        const char *tma = getenv("WEFAX_FFT_TMA");
+        ctx->use_tma = !(tma && tma[0] == '0');
         if (stream) {
             ctx->stream = (cudaStream_t)stream;
         } else {
@@ -381,8 +384,6 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             CUDA_CHECK(cudaMemcpyAsync(d_lines, h_lines, sizeof(LineDev) * g, cudaMemcpyHostToDevice, st));
             CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * g, st));
 
-            float *d_audio = (out_dev && out->audio) ? out->audio + (size_t)w0 * n
-                                                      : (float *)ctx->work_a.reserve((size_t)g * n * sizeof(float));
             float *d_env = (float *)ctx->work_e.reserve((size_t)g * n * sizeof(float));
             uint8_t *d_dig = (out_dev && out->digitalized) ? out->digitalized + (size_t)w0 * n
                                                            : (uint8_t *)ctx->out_dig.reserve((size_t)g * n);
@@ -392,22 +393,30 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                 d_raster = out_dev ? out->raster + (size_t)w0 * rs : (uint8_t *)ctx->out_raster.reserve((size_t)g * rs);
 
             // ---- resample (wefax.py:60-62) + zero-phase notch (wefax.py:63-72) -------
+            // The notch writes the complex copy (x, 0) the transform reads; the float audio_data
+            // only when the caller asked for it (or the Bluestein path needs a real input).
+            float2 *z = plan ? (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2)) : nullptr;
+            const bool need_audio = out->audio != nullptr || !plan;
+            float *d_audio = nullptr;
+            if (need_audio)
+                d_audio = (out_dev && out->audio) ? out->audio + (size_t)w0 * n
+                                                  : (float *)ctx->work_a.reserve((size_t)g * n * sizeof(float));
             if (resample) {
                 float *xin = (float *)ctx->resample_in.reserve(((size_t)g * n_in + (size_t)g * n) * sizeof(float));
                 float *xrs = xin + (size_t)g * n_in;
                 launch_ingest_float(ctx, d_pcm, (size_t)n_in, ch, xin, (size_t)n_in, n_in, g);
                 resample_real(ctx, n_in, n, xin, (size_t)n_in, xrs, (size_t)n, g);
-                launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, d_audio, (size_t)n, n, fp, g);
+                if (plan) z = (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2));   // resample used work_z
+                launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, d_audio, (size_t)n, z, (size_t)n, n, fp, g);
             } else {
-                launch_filtfilt(ctx, ch == 2 ? kInStereoI16 : kInMonoI16, d_pcm, (size_t)n_in, d_audio, (size_t)n, n, fp, g);
+                launch_filtfilt(ctx, ch == 2 ? kInStereoI16 : kInMonoI16, d_pcm, (size_t)n_in, d_audio, (size_t)n, z,
+                                (size_t)n, n, fp, g);
             }
             // ---- analytic-signal envelope (wefax.py:174) ------------------------------
-            if (plan) {
-                float2 *z = (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2));
-                hilbert_envelope(ctx, plan, d_audio, (size_t)n, z, (size_t)n, d_env, (size_t)n, g);
-            } else {
+            if (plan)
+                hilbert_envelope(ctx, plan, nullptr, 0, z, (size_t)n, d_env, (size_t)n, g);
+            else
                 hilbert_envelope_bluestein(ctx, n, d_audio, (size_t)n, d_env, (size_t)n, g);
-            }
             // ---- median-5, percentiles, grey map (wefax.py:175,196-200) ---------------
             launch_percentiles(ctx, d_env, (size_t)n, n, g, d_sel, d_res);
             launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res);
@@ -511,7 +520,7 @@ int wefax_filtfilt(wefax_ctx *ctx, long long n, int batch, double notch_freq, do
         float *dx = (float *)ctx->work_a.reserve(bytes);
         float *dy = (float *)ctx->work_e.reserve(bytes);
         CUDA_CHECK(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        launch_filtfilt(ctx, kInFloat, dx, (size_t)n, dy, (size_t)n, n, fp, batch);
+        launch_filtfilt(ctx, kInFloat, dx, (size_t)n, dy, (size_t)n, nullptr, 0, n, fp, batch);
         CUDA_CHECK(cudaMemcpyAsync(y, dy, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     });

@@ -1,6 +1,8 @@
 // The context behind the C-ABI handle: device, stream, cached FFT plans, scratch.
 #pragma once
 
+#include <cstring>
+
 #include "common.cuh"
 #include "fft.cuh"
 
@@ -22,6 +24,7 @@ struct wefax_ctx {
     long long launches = 0;
     long long workspace_limit = 24ll << 30;
     int sm_count = 148;
+    bool use_tma = true;   // WEFAX_FFT_TMA=0 forces the LDG tile loads
     std::map<long long, std::unique_ptr<wefax::FftPlan>> plans;
     std::map<long long, std::unique_ptr<wefax::Bluestein>> bluestein;
     std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
@@ -33,7 +36,7 @@ struct wefax_ctx {
     // optional per-stage device timing (CUDA events on the context's stream)
     bool timing = false;
     struct Span {
-        const char *name;
+        char name[24];   // copied: pass tags live in short-lived PassDev copies
         cudaEvent_t e0, e1;
     };
     std::vector<Span> spans;
@@ -63,7 +66,12 @@ struct StageTimer {
         }
         CUDA_CHECK(cudaEventRecord(ev[0], ctx->stream));
         e1 = ev[1];
-        ctx->spans.push_back({name, ev[0], ev[1]});
+        wefax_ctx::Span sp;
+        strncpy(sp.name, name, sizeof(sp.name) - 1);
+        sp.name[sizeof(sp.name) - 1] = 0;
+        sp.e0 = ev[0];
+        sp.e1 = ev[1];
+        ctx->spans.push_back(sp);
     }
     ~StageTimer() {
         if (e1) cudaEventRecord(e1, ctx->stream);
@@ -71,22 +79,30 @@ struct StageTimer {
 };
 
 template <class LoadOp, class StoreOp>
-void launch_pass(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const StoreOp &st, int batch) {
+void launch_pass(wefax_ctx *ctx, const PassDev &p_in, const LoadOp &ld, const StoreOp &st, int batch) {
     const void *fn = (const void *)fft_pass_kernel<LoadOp, StoreOp>;
     if (!ctx->smem_configured.count(fn)) {
         CUDA_CHECK(cudaFuncSetAttribute(fft_pass_kernel<LoadOp, StoreOp>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->smem_configured[fn] = 1;
     }
+    PassDev p = p_in;
+    alignas(64) CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const float2 *base = nullptr;
+    size_t bstride = 0;
+    p.load_mode = 0;
+    if (ctx->use_tma && ld.tma_source(&base, &bstride)) p.load_mode = choose_load_mode(p, base, bstride, batch, &map);
     StageTimer timer(ctx, p.tag);
     dim3 grid(p.ntiles, batch);
-    fft_pass_kernel<LoadOp, StoreOp><<<grid, kFftThreads, p.smem_bytes, ctx->stream>>>(p, ld, st);
+    fft_pass_kernel<LoadOp, StoreOp><<<grid, p.nthreads, p.smem_bytes, ctx->stream>>>(p, ld, st, map, base, bstride);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
 
 // |hilbert(x)| for `batch` real sequences of length plan->n (no median filter).
-// x: real input (stride xs), z: complex scratch (stride zs >= n), env: output (stride es).
+// x: real input (stride xs) or nullptr when z already holds (x, 0); z: complex scratch
+// (stride zs >= n); env: output (stride es).
 void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, float2 *z, size_t zs,
                       float *env, size_t es, int batch);
 

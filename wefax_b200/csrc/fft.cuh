@@ -22,6 +22,8 @@
 // (stride-1) pass.
 #pragma once
 
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace wefax {
@@ -39,11 +41,16 @@ struct PassDev {
     int radix[kMaxStages];
     FastDiv divM[kMaxStages];     // M = L / r of each stage
     FastDiv divNbf[kMaxStages];   // R / r of each stage
-    FastDiv divR, divS;
+    FastDiv divR, divTpo;
     const float2 *twR;            // w_R^e, e < R
     const uint16_t *perm;         // smem position of output k after the in-place DIF stages
-    const float2 *tw_lo, *tw_hi;  // w_L^e = tw_lo[e & mask] * tw_hi[e >> bits]
-    int tw_mode;                  // 0 none, 1 multiply on store (forward), 2 multiply on load (inverse)
+    const float2 *tw_lo, *tw_hi;  // inter-pass twiddle w_L^e = tw_lo[e & mask] * tw_hi[e >> bits]
+    int tw_mode;                  // applied on store: 0 none, 1 forward e = k*m, 2 inverse e = ko*(k*S + m)
+    int ko_R;                     // inverse: length of the pass that runs next (ko = o % ko_R)
+    int tiles_per_o;              // strided passes: ceil(S / C) tiles per outer index
+    int load_mode;                // 0 functor (LDG), 1 TMA tensor tile (strided), 2 TMA bulk copy (contiguous)
+    int rbox, nbox;               // TMA box rows / boxes per tile
+    int nthreads;
     int smem_bytes;
     int ntiles;
     char tag[16];                 // "fft_fwd_0", "fft_inv_2", ... (stage timing label)
@@ -54,6 +61,12 @@ struct LoadComplex {
     const float2 *src;
     size_t bstride;
     int conj;
+    // a plain (unconjugated) complex load can be replaced by a TMA tile copy
+    bool tma_source(const float2 **base, size_t *stride) const {
+        *base = src;
+        *stride = bstride;
+        return conj == 0;
+    }
     __device__ __forceinline__ float2 operator()(size_t i, int b) const {
         float2 v = __ldg(src + (size_t)b * bstride + i);
         if (conj) v.y = -v.y;
@@ -64,6 +77,7 @@ struct LoadReal {
     const float *src;
     size_t bstride;
     size_t n_valid;   // elements >= n_valid read as zero (zero padding)
+    bool tma_source(const float2 **, size_t *) const { return false; }
     __device__ __forceinline__ float2 operator()(size_t i, int b) const {
         return make_float2(i < n_valid ? __ldg(src + (size_t)b * bstride + i) : 0.f, 0.f);
     }
@@ -317,52 +331,134 @@ __device__ __forceinline__ float2 pass_twiddle(const PassDev &p, uint32_t e) {
     return cmul(lo, hi);
 }
 
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG / UBLKCP / SYNCS) -------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One pass over one tile.  Global memory is touched once per element: the tile comes
+// in through TMA (one tensor box per <=256 rows for strided passes, one bulk copy for
+// the stride-1 pass) or, for fused prologues, through the load functor; it leaves
+// through coalesced stores with the inter-pass twiddle and the store functor applied.
 template <class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(kFftThreads, 2) fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kFftThreads, 2)
+fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid_constant__ CUtensorMap tmap,
+                const float2 *bulk_src, size_t bulk_bstride) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     float2 *tile = reinterpret_cast<float2 *>(smem_raw);
     float2 *twR = tile + (size_t)p.C * p.R;
     uint16_t *perm = reinterpret_cast<uint16_t *>(twR + p.R);
     int *aux = reinterpret_cast<int *>(perm + ((p.R + 1) & ~1));
+    int *aux2 = aux + p.C;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(aux2 + p.C) + 7) & ~uintptr_t(7));
 
     const int tid = threadIdx.x, nt = blockDim.x;
     const int batch = blockIdx.y;
-    const int c0 = blockIdx.x * p.C;
+
+    // tile geometry
+    int o, m0, c0;                       // strided: outer index and first column offset; contiguous: first row
+    if (p.contiguous) {
+        c0 = blockIdx.x * p.C;
+        o = 0;
+        m0 = 0;
+    } else {
+        o = p.divTpo.div(blockIdx.x);
+        m0 = (blockIdx.x - o * p.tiles_per_o) * p.C;
+        c0 = 0;
+    }
+    const int rows_valid = p.contiguous ? min(p.C, p.ncols - c0) : 0;
+
+    if (p.load_mode != 0 && tid == 0) {
+        mbar_init(mbar, 1);
+    }
+    if (p.load_mode != 0) __syncthreads();
+    if (p.load_mode == 1 && tid == 0) {
+        mbar_expect_tx(mbar, (uint32_t)(p.R * p.C * sizeof(float2)));
+        for (int b = 0; b < p.nbox; ++b)
+            tma_load_4d(tile + (size_t)b * p.rbox * p.C, &tmap, mbar, 2 * m0, b * p.rbox, o, batch);
+    } else if (p.load_mode == 2 && tid == 0) {
+        const uint32_t bytes = (uint32_t)(rows_valid * p.R * sizeof(float2));
+        mbar_expect_tx(mbar, bytes);
+        tma_load_bulk(tile, bulk_src + (size_t)batch * bulk_bstride + (size_t)c0 * p.R, bytes, mbar);
+    }
 
     for (int i = tid; i < p.R; i += nt) {
         twR[i] = __ldg(p.twR + i);
         perm[i] = __ldg(p.perm + i);
     }
-    if (tid < p.C) aux[tid] = (c0 + tid < p.ncols) ? st.column_aux(c0 + tid) : 0;
-
-    const int tile_elems = p.C * p.R;
-    // column geometry of this thread (strided passes): fixed for the whole kernel
+    // per-column constants: store-functor aux, inter-pass twiddle exponent e = e0 + k*de
     const int cc_s = tid & (p.C - 1);
-    const int col_s = c0 + cc_s;
-    const bool valid_s = col_s < p.ncols;
-    const uint32_t o_s = p.divS.div((uint32_t)col_s);
-    const uint32_t m_s = (uint32_t)col_s - o_s * (uint32_t)p.S;
-    const size_t cbase = (size_t)o_s * (size_t)p.R * (size_t)p.S + m_s;
+    const uint32_t m_s = (uint32_t)(m0 + cc_s);
+    const bool valid_s = !p.contiguous && m_s < (uint32_t)p.S;
+    const size_t cbase = (size_t)o * (size_t)p.R * (size_t)p.S + m_s;
     const int jstep = nt >> p.log2C;
-
-    if (p.contiguous) {
-        const size_t gbase = (size_t)c0 * p.R;
-        const int nvalid = min(p.C, p.ncols - c0) * p.R;
-#pragma unroll 4
-        for (int e = tid; e < tile_elems; e += nt)
-            tile[e] = e < nvalid ? ld(gbase + e, batch) : make_float2(0.f, 0.f);
-    } else {
-#pragma unroll 4
-        for (int j = tid >> p.log2C; j < p.R; j += jstep) {
-            float2 v = make_float2(0.f, 0.f);
-            if (valid_s) {
-                v = ld(cbase + (size_t)j * p.S, batch);
-                if (p.tw_mode == 2) v = cmul(v, pass_twiddle(p, (uint32_t)j * m_s));
-            }
-            tile[j * p.C + cc_s] = v;
+    uint32_t tw_e0 = 0, tw_de = 0;
+    if (!p.contiguous) {
+        if (p.tw_mode == 1) {
+            tw_de = m_s;
+        } else if (p.tw_mode == 2) {
+            const uint32_t ko = (uint32_t)o % (uint32_t)p.ko_R;
+            tw_e0 = ko * m_s;
+            tw_de = ko * (uint32_t)p.S;
         }
     }
-    __syncthreads();
+    if (tid < p.C) {
+        const int col = p.contiguous ? c0 + tid : o * p.S + m0 + tid;
+        const bool ok = p.contiguous ? (tid < rows_valid) : (m0 + tid < p.S);
+        aux[tid] = ok ? st.column_aux(col) : 0;
+        aux2[tid] = (p.contiguous && p.tw_mode == 2) ? (c0 + tid) % p.ko_R : 0;
+    }
+
+    const int tile_elems = p.C * p.R;
+    if (p.load_mode == 0) {
+        if (p.contiguous) {
+            const size_t gbase = (size_t)c0 * p.R;
+            const int nvalid = rows_valid * p.R;
+#pragma unroll 8
+            for (int e = tid; e < tile_elems; e += nt)
+                tile[e] = e < nvalid ? ld(gbase + e, batch) : make_float2(0.f, 0.f);
+        } else {
+#pragma unroll 8
+            for (int j = tid >> p.log2C; j < p.R; j += jstep)
+                tile[j * p.C + cc_s] = valid_s ? ld(cbase + (size_t)j * p.S, batch) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+    } else {
+        __syncthreads();          // tables visible to everyone
+        mbar_wait(mbar, 0);       // tile has landed (async proxy writes are visible after the wait)
+    }
 
     int L = p.R;
     for (int s = 0; s < p.nstages; ++s) {
@@ -396,19 +492,21 @@ __global__ void __launch_bounds__(kFftThreads, 2) fft_pass_kernel(const PassDev 
 
     if (p.contiguous) {
         const size_t gbase = (size_t)c0 * p.R;
-        const int nvalid = min(p.C, p.ncols - c0) * p.R;
+        const int nvalid = rows_valid * p.R;
 #pragma unroll 4
         for (int e = tid; e < nvalid; e += nt) {
             const int cc = p.divR.div(e);
             const int k = e - cc * p.R;
-            st(gbase + e, batch, tile[cc * p.R + perm[k]], k, aux[cc]);
+            float2 v = tile[cc * p.R + perm[k]];
+            if (p.tw_mode == 2) v = cmul(v, pass_twiddle(p, (uint32_t)aux2[cc] * (uint32_t)k));
+            st(gbase + e, batch, v, k, aux[cc]);
         }
     } else if (valid_s) {
         const int a = aux[cc_s];
 #pragma unroll 4
         for (int k = tid >> p.log2C; k < p.R; k += jstep) {
             float2 v = tile[(int)perm[k] * p.C + cc_s];
-            if (p.tw_mode == 1) v = cmul(v, pass_twiddle(p, (uint32_t)k * m_s));
+            if (p.tw_mode != 0) v = cmul(v, pass_twiddle(p, tw_e0 + (uint32_t)k * tw_de));
             st(cbase + (size_t)k * p.S, batch, v, k, a);
         }
     }
@@ -421,7 +519,7 @@ struct FftPlan {
     int Rs[kMaxPasses] = {0, 0, 0, 0};
     long long S[kMaxPasses] = {0, 0, 0, 0};
     PassDev fwd[kMaxPasses];   // tw_mode 1 on all but the last pass
-    PassDev inv[kMaxPasses];   // tw_mode 2 on all but the last pass
+    PassDev inv[kMaxPasses];   // tw_mode 2 on all but pass 0 (the last one to run)
     DevBuf tables;             // twR / perm / tw_lo / tw_hi of every pass
     OuterDigits outer() const {
         OuterDigits od{};
@@ -437,5 +535,8 @@ bool plan_factors(long long n, std::vector<int> &Rs);
 // smallest 2^a 3^b 5^c 7^d >= m that plan_factors accepts
 long long next_smooth_length(long long m);
 std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream);
+// Chooses how a pass reads its tile from `base` (see PassDev::load_mode) and, for
+// strided passes, encodes the 4-D tensor map {2S floats, R, outer, batch}.
+int choose_load_mode(const PassDev &p, const float2 *base, size_t bstride, int batch, CUtensorMap *map);
 
 }  // namespace wefax

@@ -12,6 +12,11 @@ struct LoadGeneric {
     size_t bstride;
     size_t n_valid;
     int conj;
+    bool tma_source(const float2 **base, size_t *stride) const {
+        *base = (const float2 *)src;
+        *stride = bstride;
+        return mode == 0 && conj == 0;
+    }
     __device__ __forceinline__ float2 operator()(size_t i, int b) const {
         switch (mode) {
             case 0: {
@@ -195,7 +200,10 @@ void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, 
                       size_t es, int batch) {
     const size_t n = (size_t)plan->n;
     StoreHilbert sh{z, zs, plan->outer(), (uint32_t)n, (int)(n / plan->Rs[plan->npass - 1]), (float)(1.0 / (double)n)};
-    run_forward(ctx, plan, LoadReal{x, xs, n}, sh, z, zs, batch);
+    if (x)
+        run_forward(ctx, plan, LoadReal{x, xs, n}, sh, z, zs, batch);
+    else   // z already holds (x, 0): every pass can take its tile through TMA
+        run_forward(ctx, plan, load_c(z, zs), sh, z, zs, batch);
     run_inverse(ctx, plan, load_c(z, zs), StoreAbs{env, es, n, 1.f}, z, zs, batch);
 }
 

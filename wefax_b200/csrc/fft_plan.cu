@@ -237,14 +237,29 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
             L /= rad[s];
         }
         d.divR.init(R);
-        d.divS.init(d.S);
+        const long long nouter = n / ((long long)R * d.S);
+        if (d.contiguous) {
+            d.tiles_per_o = 1;
+            d.ntiles = (d.ncols + C - 1) / C;
+        } else {
+            d.tiles_per_o = (d.S + C - 1) / C;
+            d.ntiles = (int)(nouter * d.tiles_per_o);
+        }
+        d.divTpo.init(d.tiles_per_o);
+        // TMA box: the most rows (<= 256) that divide R and keep every box 128-byte aligned in smem
+        d.rbox = 0;
+        for (int rb = std::min(R, 256); rb >= 1; --rb)
+            if (R % rb == 0 && ((size_t)rb * C * sizeof(float2)) % 128 == 0) {
+                d.rbox = rb;
+                break;
+            }
+        d.nbox = d.rbox ? R / d.rbox : 0;
+        if (d.nbox > 16) d.rbox = d.nbox = 0;
+        d.nthreads = std::max(C, env_int("WEFAX_FFT_THREADS", kFftThreads));
         d.twR = (const float2 *)(base + o_twR[i]);
         d.perm = (const uint16_t *)(base + o_perm[i]);
-        d.tw_lo = (const float2 *)(base + o_lo[i]);
-        d.tw_hi = (const float2 *)(base + o_hi[i]);
         d.smem_bytes = (int)((size_t)C * R * sizeof(float2) + (size_t)R * sizeof(float2) +
-                             (size_t)((R + 1) & ~1) * sizeof(uint16_t) + (size_t)C * sizeof(int));
-        d.ntiles = (d.ncols + C - 1) / C;
+                             (size_t)((R + 1) & ~1) * sizeof(uint16_t) + (size_t)2 * C * sizeof(int) + 32);
 
         // digit-reversal: smem position of output k after the in-place DIF stages
         std::vector<uint16_t> perm(R);
@@ -270,15 +285,74 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
             (float2 *)(base + o_hi[i]), (int)n_hi[i], Lp, (double)(1 << kTwLoBits));
         CUDA_CHECK(cudaGetLastError());
 
-        d.tw_mode = d.contiguous ? 0 : 1;
+        // forward: multiply by w_{L_i}^{k*m} on store (all but the last pass)
+        d.tw_mode = (i < P - 1) ? 1 : 0;
+        d.ko_R = 1;
+        d.tw_lo = (const float2 *)(base + o_lo[i]);
+        d.tw_hi = (const float2 *)(base + o_hi[i]);
         snprintf(d.tag, sizeof(d.tag), "fft_fwd_%d", i);
         plan->fwd[i] = d;
-        d.tw_mode = d.contiguous ? 0 : 2;
+        // inverse (passes run P-1 .. 0): the twiddle the NEXT pass (i-1) needs on its input,
+        // w_{L_{i-1}}^{k_{i-1} * (position inside its sub-problem)}, is applied on this pass's store
+        d.tw_mode = (i > 0) ? 2 : 0;
+        d.ko_R = (i > 0) ? Rs[i - 1] : 1;
+        d.tw_lo = (const float2 *)(base + o_lo[i > 0 ? i - 1 : 0]);
+        d.tw_hi = (const float2 *)(base + o_hi[i > 0 ? i - 1 : 0]);
         snprintf(d.tag, sizeof(d.tag), "fft_inv_%d", i);
         plan->inv[i] = d;
     }
     CUDA_CHECK(cudaStreamSynchronize(stream));
     return plan;
+}
+
+}  // namespace wefax
+
+namespace wefax {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+int choose_load_mode(const PassDev &p, const float2 *base, size_t bstride, int batch, CUtensorMap *map) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return 0;
+    if (batch > 1 && (bstride & 1)) return 0;               // every batch element must stay 16-byte aligned
+    if (p.contiguous) {
+        // one bulk copy per tile: source and size must be multiples of 16 bytes
+        const bool full_ok = (((size_t)p.C * p.R) & 1) == 0 || p.ntiles == 1;
+        const int tail = p.ncols % p.C;
+        const bool tail_ok = ((size_t)(tail ? tail : p.C) * p.R & 1) == 0;
+        const bool first_ok = p.ntiles > 1 || tail_ok;
+        return (full_ok && tail_ok && first_ok) ? 2 : 0;
+    }
+    if ((p.S & 1) || !p.rbox) return 0;                      // row pitch S*8 bytes must be a multiple of 16
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return 0;
+    const unsigned long long nouter = (unsigned long long)p.ncols / (unsigned long long)p.S;
+    cuuint64_t dims[4] = {2ull * (unsigned long long)p.S, (cuuint64_t)p.R, nouter, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)p.S * 8ull, (cuuint64_t)p.R * (cuuint64_t)p.S * 8ull,
+                             (cuuint64_t)(batch > 1 ? bstride : (size_t)p.R * p.S * nouter) * 8ull};
+    cuuint32_t box[4] = {2u * (cuuint32_t)p.C, (cuuint32_t)p.rbox, 1u, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS ? 1 : 0;
 }
 
 }  // namespace wefax

@@ -49,7 +49,8 @@ constexpr int kPadLen = 9;   // 3 * max(len(a), len(b))
 
 template <int MODE, int KP>
 __global__ void __launch_bounds__(kFirThreads)
-filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride, long long n, const FirParams fp) {
+filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout, size_t z_stride,
+                long long n, const FirParams fp) {
     constexpr int TS = kFirTile;
     constexpr int NEXT = TS + 2 * (KP - 1);          // extended-signal samples a tile needs
     constexpr int NEXT_AL = (NEXT + 16 + 3) & ~3;
@@ -136,19 +137,27 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
     }
     __syncthreads();
     const long long n0 = (long long)blockIdx.x * TS;
-    float *o = out + (size_t)blockIdx.y * out_stride;
-    for (int i = tid; i < TS; i += kFirThreads)
-        if (n0 + i < n) o[n0 + i] = s_ext[i];
+    // real output (audio_data) and / or the complex copy (x, 0) the transform reads through TMA
+    if (out) {
+        float *o = out + (size_t)blockIdx.y * out_stride;
+        for (int i = tid; i < TS; i += kFirThreads)
+            if (n0 + i < n) o[n0 + i] = s_ext[i];
+    }
+    if (zout) {
+        float2 *z = zout + (size_t)blockIdx.y * z_stride;
+        for (int i = tid; i < TS; i += kFirThreads)
+            if (n0 + i < n) z[n0 + i] = make_float2(s_ext[i], 0.f);
+    }
 }
 
 template <int MODE>
 static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_stride, float *out, size_t out_stride,
-                                 long long n, const FirParams &fp, int batch) {
+                                 float2 *zout, size_t z_stride, long long n, const FirParams &fp, int batch) {
     StageTimer timer(ctx, "filtfilt");
     dim3 grid((unsigned)((n + kFirTile - 1) / kFirTile), batch);
 #define WEFAX_FIR_CASE(KP_)                                                                                   \
     if (fp.KP == KP_) {                                                                                       \
-        filtfilt_kernel<MODE, KP_><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, n, fp); \
+        filtfilt_kernel<MODE, KP_><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp); \
         CUDA_CHECK(cudaGetLastError());                                                                       \
         ctx->launches++;                                                                                      \
         return;                                                                                               \
@@ -164,11 +173,17 @@ static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_strid
 }
 
 void launch_filtfilt(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_stride, float *out, size_t out_stride,
-                     long long n, const FirParams &fp, int batch) {
+                     float2 *zout, size_t z_stride, long long n, const FirParams &fp, int batch) {
     switch (mode) {
-        case kInMonoI16: launch_filtfilt_mode<kInMonoI16>(ctx, in, in_stride, out, out_stride, n, fp, batch); break;
-        case kInStereoI16: launch_filtfilt_mode<kInStereoI16>(ctx, in, in_stride, out, out_stride, n, fp, batch); break;
-        default: launch_filtfilt_mode<kInFloat>(ctx, in, in_stride, out, out_stride, n, fp, batch); break;
+        case kInMonoI16:
+            launch_filtfilt_mode<kInMonoI16>(ctx, in, in_stride, out, out_stride, zout, z_stride, n, fp, batch);
+            break;
+        case kInStereoI16:
+            launch_filtfilt_mode<kInStereoI16>(ctx, in, in_stride, out, out_stride, zout, z_stride, n, fp, batch);
+            break;
+        default:
+            launch_filtfilt_mode<kInFloat>(ctx, in, in_stride, out, out_stride, zout, z_stride, n, fp, batch);
+            break;
     }
 }
 

@@ -46,8 +46,9 @@ enum IngestMode { kInMonoI16 = 0, kInStereoI16 = 1, kInFloat = 2 };
 
 void launch_ingest_float(wefax_ctx *ctx, const int16_t *pcm, size_t pcm_stride, int channels, float *x, size_t xs,
                          long long n, int batch);
+// out (float, may be null) and / or zout (complex (x, 0), may be null)
 void launch_filtfilt(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_stride, float *out, size_t out_stride,
-                     long long n, const FirParams &fp, int batch);
+                     float2 *zout, size_t z_stride, long long n, const FirParams &fp, int batch);
 void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, size_t os, long long n, int batch);
 // 0.5 / 99.5 percentiles of median5(env) -> RecResult.low/high (+ WEFAX_REC_NAN)
 void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
