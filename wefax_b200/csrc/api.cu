@@ -383,6 +383,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             memcpy(h_lines, lines.data() + w0, sizeof(LineDev) * g);
             CUDA_CHECK(cudaMemcpyAsync(d_lines, h_lines, sizeof(LineDev) * g, cudaMemcpyHostToDevice, st));
             CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * g, st));
+            const SyncPlan splan = prepare_sync(ctx, lines.data() + w0, g, n);   // (synchronises: done while the stream is idle)
 
             float *d_env = (float *)ctx->work_e.reserve((size_t)g * n * sizeof(float));
             uint8_t *d_dig = (out_dev && out->digitalized) ? out->digitalized + (size_t)w0 * n
@@ -421,7 +422,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             launch_percentiles(ctx, d_env, (size_t)n, n, g, d_sel, d_res);
             launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res);
             // ---- phasing search (wefax.py:218-294) and raster (wefax.py:296-327) -----
-            launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind);
+            launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan);
             if (d_raster)
                 launch_raster(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, d_raster, rs, max_width, (int)(n / min_width));
             float *d_demod = nullptr;
@@ -580,7 +581,8 @@ int wefax_sync_raster(wefax_ctx *ctx, long long n, int batch, const uint8_t *dig
         CUDA_CHECK(cudaMemcpyAsync(dd, digitalized, (size_t)n * batch, cudaMemcpyHostToDevice, st));
         CUDA_CHECK(cudaMemcpyAsync(d_lines, ls.lines.data(), sizeof(LineDev) * batch, cudaMemcpyHostToDevice, st));
         CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * batch, st));
-        launch_sync_search(ctx, dd, (size_t)n, n, batch, d_lines, d_res, ls.min_mind);
+        const SyncPlan splan = prepare_sync(ctx, ls.lines.data(), batch, n);
+        launch_sync_search(ctx, dd, (size_t)n, n, batch, d_lines, d_res, ls.min_mind, splan);
         if (d_raster)
             launch_raster(ctx, dd, (size_t)n, n, batch, d_lines, d_res, d_raster, rs, ls.max_width, (int)(n / ls.min_width));
         CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult) * batch, cudaMemcpyDeviceToHost, st));

@@ -448,9 +448,50 @@ __device__ __forceinline__ unsigned long long sync_key(int corr, int idx) {
 __device__ __forceinline__ int key_corr(unsigned long long k) { return (int)((uint32_t)(k >> 32) ^ 0x80000000u); }
 __device__ __forceinline__ int key_idx(unsigned long long k) { return 0x7FFFFFFF - (int)(uint32_t)k; }
 
+// wefax.py:263-294 (find_sync_pulses / find_peak_groups, quirks included), then
+// start_frame (wefax.py:80) and the image height (wefax.py:299).  One thread.
+__device__ void finish_sync(const int *peaks, int np, const LineDev &ln, long long n, RecResult *res) {
+    auto regular = [&](int x) { return ln.dev_max > (double)x && (double)x > ln.dev_min; };
+    int nclear = 0;
+    for (int i = 1; i < np - 1; ++i)
+        if (regular(peaks[i] - peaks[i - 1])) nclear++;
+    int best_start = 0, best_len = -1, cur_start = 1, cur_len = 0;
+    for (int i = 1; i < nclear - 1; ++i) {
+        if (regular(peaks[i] - peaks[i - 1])) {
+            if (cur_len == 0) cur_start = i;
+            cur_len++;
+        } else {
+            if (cur_len > best_len) {
+                best_len = cur_len;
+                best_start = cur_start;
+            }
+            cur_len = 0;
+        }
+    }
+    res->n_peaks = np;
+    for (int i = 0; i < np; ++i) res->peaks[i] = peaks[i];
+    int status = res->status;
+    long long start = 0;
+    if (best_len < 0) {
+        status |= WEFAX_REC_NO_GROUPS;
+        res->n_phasing = 0;
+    } else {
+        res->n_phasing = best_len;
+        for (int i = 0; i < best_len; ++i) res->phasing[i] = peaks[best_start + i];
+        if (best_len > 0) start = peaks[best_start + best_len - 1];
+    }
+    res->start_frame = start;
+    long long h = (n - start) / ln.width;
+    if (!(status & WEFAX_REC_NO_GROUPS) && h == 0) status |= WEFAX_REC_NO_LINES;
+    res->height = (status == WEFAX_REC_OK) ? (int32_t)(4 * h) : 0;
+    res->status = status;
+}
+
 template <int PER>
 __global__ void __launch_bounds__(kSyncThreads)
-sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, RecResult *res_all) {
+sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, RecResult *res_all,
+                   const int *need_scan) {
+    if (need_scan && !need_scan[blockIdx.x]) return;   // the windowed-maximum path already finished this recording
     constexpr int CH = kSyncThreads * PER;            // positions handled per iteration
     constexpr int TOTMAX = CH + kSyncMaxL;
     constexpr int EPT = (TOTMAX + kSyncThreads - 1) / kSyncThreads;
@@ -571,55 +612,279 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
     }
     __syncthreads();
 
-    if (tid == 0) {
-        // wefax.py:263-294 (find_sync_pulses / find_peak_groups, quirks included)
-        const int np = npeaks;
-        auto regular = [&](int x) { return ln.dev_max > (double)x && (double)x > ln.dev_min; };
-        int nclear = 0;
-        for (int i = 1; i < np - 1; ++i)
-            if (regular(s_peaks[i] - s_peaks[i - 1])) nclear++;
-        int best_start = 0, best_len = -1, cur_start = 1, cur_len = 0;
-        for (int i = 1; i < nclear - 1; ++i) {
-            if (regular(s_peaks[i] - s_peaks[i - 1])) {
-                if (cur_len == 0) cur_start = i;
-                cur_len++;
-            } else {
-                if (cur_len > best_len) {
-                    best_len = cur_len;
-                    best_start = cur_start;
+    if (tid == 0) finish_sync(s_peaks, npeaks, ln, n, res);
+}
+
+// ---------------------------------------------------------------------------
+// Parallel form of the greedy picker.  Let corr[i] be the correlation and
+// W[i] = max corr over (i, min(i + mindistance, m-1)].  Position i is "settled"
+// when corr[i] >= W[i]: once the picker's newest peak sits there, nothing replaces it
+// before the next peak opens.  The picker's trajectory is then
+//     P_k = first settled position >= a_k,     a_{k+1} = P_k + mindistance + 1,
+// with a_0 = first i <= mindistance with corr[i] > 0 (the initial peak (0, 0) only
+// moves to a strictly positive correlation; if there is none, P_0 = 0).  corr, W
+// (van Herk prefix/suffix maxima over blocks of mindistance) and the settled bits
+// are data-parallel; only the <= 100-step chain over a bitmask in shared memory is
+// sequential.  Equivalence with wefax.py:234-259 is checked bit for bit in the tests.
+// ---------------------------------------------------------------------------
+constexpr int kCorrTile = 4096;
+
+__global__ void __launch_bounds__(kSyncThreads)
+sync_corr_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, const SyncDev *sd_all,
+                 int *corr_all, size_t cs, int *first_pos) {
+    constexpr int TOTMAX = kCorrTile + kSyncMaxL;
+    constexpr int EPT = (TOTMAX + kSyncThreads - 1) / kSyncThreads;
+    __shared__ int s_p[TOTMAX + 1];
+    __shared__ int s_wsum[32];
+    const LineDev ln = lines[blockIdx.y];
+    const SyncDev sd = sd_all[blockIdx.y];
+    const long long base = (long long)blockIdx.x * kCorrTile;
+    if (!sd.fast || base >= sd.limc) return;
+    const uint8_t *dig = dig_all + (size_t)blockIdx.y * ds;
+    int *corr = corr_all + (size_t)blockIdx.y * cs;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int L = ln.L, n1 = ln.n1, n0 = ln.n0;
+    const int valid = (int)min((long long)kCorrTile, sd.limc - base);
+    const int tot = valid + L;
+    int vals[EPT], run = 0;
+    const int j0 = tid * EPT;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx = j0 + j;
+        int x = idx < tot ? (int)__ldg(dig + base + idx) - 128 : 0;
+        run += x;
+        vals[j] = run;
+    }
+    int incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    int woff;
+    {
+        int t = lane < wid ? s_wsum[lane] : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
+        woff = t;
+    }
+    const int excl = woff + incl - run;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx = j0 + j;
+        if (idx < TOTMAX) s_p[idx + 1] = excl + vals[j];
+    }
+    if (tid == 0) s_p[0] = 0;
+    __syncthreads();
+    int first = 0x7FFFFFFF;
+    for (int i = tid; i < valid; i += kSyncThreads) {
+        int a = s_p[i], b = s_p[i + n1], cc = s_p[i + n1 + n0], d = s_p[i + L];
+        int c = -127 * (b - a) - 128 * (cc - b) - 127 * (d - cc);
+        corr[base + i] = c;
+        if (c > 0 && base + i <= ln.mindistance) first = min(first, (int)(base + i));
+    }
+    if (base <= ln.mindistance) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, d));
+        if (lane == 0 && first != 0x7FFFFFFF) atomicMin(first_pos + blockIdx.y, first);
+    }
+}
+
+// prefix / suffix maxima inside blocks of `mindistance` positions (van Herk / Gil-Werman)
+__global__ void __launch_bounds__(kSyncThreads)
+sync_window_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr_all, int *pre_all, int *suf_all,
+                   size_t cs) {
+    extern __shared__ int s_c[];
+    __shared__ int s_w[32];
+    const LineDev ln = lines[blockIdx.y];
+    const SyncDev sd = sd_all[blockIdx.y];
+    const int w = ln.mindistance;
+    const long long b0 = (long long)blockIdx.x * w;
+    if (!sd.fast || b0 >= sd.limc) return;
+    const int len = (int)min((long long)w, sd.limc - b0);
+    const int *corr = corr_all + (size_t)blockIdx.y * cs + b0;
+    int *pre = pre_all + (size_t)blockIdx.y * cs + b0;
+    int *suf = suf_all + (size_t)blockIdx.y * cs + b0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < len; i += kSyncThreads) s_c[i] = corr[i];
+    __syncthreads();
+    const int per = (len + kSyncThreads - 1) / kSyncThreads;
+    const int NEG = (int)0x80000000;
+    for (int dir = 0; dir < 2; ++dir) {
+        // dir 0: prefix maxima left to right; dir 1: suffix maxima (same scan on the mirrored index)
+        const int lo = tid * per, hi = min(lo + per, len);
+        int run = NEG;
+        for (int i = lo; i < hi; ++i) {
+            int v = s_c[dir ? len - 1 - i : i];
+            run = max(run, v);
+        }
+        int incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl = max(incl, o);
+        }
+        __syncthreads();
+        if (lane == 31) s_w[wid] = incl;
+        __syncthreads();
+        int carry = NEG;
+        for (int k = 0; k < wid; ++k) carry = max(carry, s_w[k]);
+        int prev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane > 0) carry = max(carry, prev);
+        run = carry;
+        int *dst = dir ? suf : pre;
+        for (int i = lo; i < hi; ++i) {
+            const int idx = dir ? len - 1 - i : i;
+            run = max(run, s_c[idx]);
+            dst[idx] = run;
+        }
+    }
+}
+
+// settled bits: corr[i] >= max corr over (i, min(i + w, m - 1)]
+__global__ void __launch_bounds__(256)
+sync_settled_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr_all, const int *pre_all,
+                    const int *suf_all, size_t cs, uint32_t *bits_all, size_t bs) {
+    const LineDev ln = lines[blockIdx.y];
+    const SyncDev sd = sd_all[blockIdx.y];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!sd.fast || i >= ((sd.lim + 31) & ~31ll)) return;
+    const int *corr = corr_all + (size_t)blockIdx.y * cs;
+    const int *pre = pre_all + (size_t)blockIdx.y * cs;
+    const int *suf = suf_all + (size_t)blockIdx.y * cs;
+    bool settled = false;
+    if (i < sd.lim) {
+        const long long w = ln.mindistance;
+        const long long a = i + 1, e = min(i + w, sd.m - 1);
+        int wmax = (int)0x80000000;
+        if (a <= e) {
+            const long long ba = a / w, be = e / w;
+            if (ba == be)
+                wmax = (a % w == 0) ? pre[e] : suf[a];   // a whole block, or the tail of the last (truncated) block
+            else
+                wmax = max(suf[a], pre[e]);
+        }
+        settled = corr[i] >= wmax;
+    }
+    const unsigned word = __ballot_sync(0xFFFFFFFFu, settled);
+    if ((threadIdx.x & 31) == 0) bits_all[(size_t)blockIdx.y * bs + (i >> 5)] = word;
+}
+
+// the sequential part: <= 100 jumps over the settled-bit mask held in shared memory
+__global__ void __launch_bounds__(256)
+sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, const uint32_t *bits_all, size_t bs,
+                  const int *first_pos, RecResult *res_all, int *need_scan) {
+    extern __shared__ uint32_t s_bits[];
+    __shared__ int s_peaks[WEFAX_MAX_PEAKS];
+    __shared__ int s_np, s_ok;
+    const LineDev ln = lines[blockIdx.x];
+    const SyncDev sd = sd_all[blockIdx.x];
+    if (!sd.fast) {
+        if (threadIdx.x == 0) need_scan[blockIdx.x] = 1;
+        return;
+    }
+    const int nwords = (int)((sd.lim + 31) >> 5);
+    const uint32_t *bits = bits_all + (size_t)blockIdx.x * bs;
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_bits[i] = bits[i];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const long long w = ln.mindistance;
+        // first settled position >= x inside [0, lim); -1 when the mask ends first
+        auto next_settled = [&](long long x) -> long long {
+            int wi = (int)(x >> 5);
+            uint32_t head = ~0u << (x & 31);
+            while (wi < nwords) {
+                uint32_t v = (wi + lane < nwords) ? s_bits[wi + lane] : 0u;
+                if (lane == 0) v &= head;
+                head = ~0u;
+                const unsigned any = __ballot_sync(0xFFFFFFFFu, v != 0u);
+                if (any) {
+                    const int l = __ffs(any) - 1;
+                    const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, l);
+                    return ((long long)(wi + l) << 5) + (__ffs(vv) - 1);
                 }
-                cur_len = 0;
+                wi += 32;
             }
+            return -1;
+        };
+        int np = 0, ok = 1;
+        long long P = 0;
+        const int j0 = first_pos[blockIdx.x];
+        if (sd.m > 0 && j0 != 0x7F7F7F7F) {
+            P = next_settled(j0);
+            if (P < 0) ok = 0;
         }
-        res->n_peaks = np;
-        for (int i = 0; i < np; ++i) res->peaks[i] = s_peaks[i];
-        int status = res->status;
-        long long start = 0;
-        if (best_len < 0) {
-            status |= WEFAX_REC_NO_GROUPS;
-            res->n_phasing = 0;
+        if (lane == 0) s_peaks[0] = (int)P;
+        np = 1;
+        while (ok && sd.m > 0) {
+            const long long a = P + w + 1;
+            if (a > sd.m - 1) break;
+            np++;
+            if (np == WEFAX_MAX_PEAKS) {
+                if (lane == 0) s_peaks[np - 1] = (int)a;   // the 100th peak is never refined (wefax.py:251)
+                break;
+            }
+            if (a >= sd.lim) {
+                ok = 0;
+                break;
+            }
+            P = next_settled(a);
+            if (P < 0) {
+                ok = 0;
+                break;
+            }
+            if (lane == 0) s_peaks[np - 1] = (int)P;
+        }
+        if (lane == 0) {
+            s_np = np;
+            s_ok = ok;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_ok) {
+            need_scan[blockIdx.x] = 0;
+            finish_sync(s_peaks, s_np, ln, n, res_all + blockIdx.x);
         } else {
-            res->n_phasing = best_len;
-            for (int i = 0; i < best_len; ++i) res->phasing[i] = s_peaks[best_start + i];
-            if (best_len > 0) start = s_peaks[best_start + best_len - 1];
+            need_scan[blockIdx.x] = 1;   // ran out of precomputed region: let the sequential scan do it
         }
-        res->start_frame = start;
-        long long h = (n - start) / ln.width;
-        if (!(status & WEFAX_REC_NO_GROUPS) && h == 0) status |= WEFAX_REC_NO_LINES;
-        res->height = (status == WEFAX_REC_OK) ? (int32_t)(4 * h) : 0;
-        res->status = status;
     }
 }
 
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
-                        RecResult *res, int min_mindistance) {
+                        RecResult *res, int min_mindistance, const SyncPlan &sp) {
     StageTimer timer(ctx, "sync_search");
+    cudaStream_t st = ctx->stream;
+    if (sp.any_fast) {
+        CUDA_CHECK(cudaMemsetAsync(sp.first_pos, 0x7F, sizeof(int) * batch, st));   // 0x7F7F7F7F = no positive correlation yet
+        dim3 g1((unsigned)std::max<long long>(1, (sp.max_limc + kCorrTile - 1) / kCorrTile), batch);
+        sync_corr_kernel<<<g1, kSyncThreads, 0, st>>>(dig, ds, n, lines, sp.sd, sp.corr, sp.cs, sp.first_pos);
+        dim3 g2((unsigned)std::max(1, sp.max_wblocks), batch);
+        const void *fn = (const void *)sync_window_kernel;
+        if (!ctx->smem_configured.count(fn)) {
+            CUDA_CHECK(cudaFuncSetAttribute(sync_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(sync_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ctx->smem_configured[fn] = 1;
+        }
+        sync_window_kernel<<<g2, kSyncThreads, (size_t)sp.max_w * sizeof(int), st>>>(lines, sp.sd, sp.corr, sp.pre, sp.suf,
+                                                                                   sp.cs);
+        dim3 g3((unsigned)std::max<long long>(1, (sp.max_lim + 255) / 256), batch);
+        sync_settled_kernel<<<g3, 256, 0, st>>>(lines, sp.sd, sp.corr, sp.pre, sp.suf, sp.cs, sp.bits, sp.bs);
+        sync_chain_kernel<<<batch, 256, (size_t)((sp.max_lim + 31) / 32) * sizeof(uint32_t), st>>>(
+            n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan);
+        ctx->launches += 4;
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(sp.need_scan, 1, sizeof(int) * batch, st));
+    }
     if (min_mindistance >= 4096)
-        sync_search_kernel<4><<<batch, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, lines, res);
+        sync_search_kernel<4><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
     else if (min_mindistance >= 2048)
-        sync_search_kernel<2><<<batch, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, lines, res);
+        sync_search_kernel<2><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
     else
-        sync_search_kernel<1><<<batch, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, lines, res);
+        sync_search_kernel<1><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -712,6 +977,53 @@ void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, i
     raster_kernel<<<grid, kRasterCols, 0, ctx->stream>>>(dig, ds, n, lines, res, raster, rs);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
+}
+
+}  // namespace wefax
+
+namespace wefax {
+
+SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long long n) {
+    SyncPlan sp;
+    std::vector<SyncDev> sd(count);
+    for (int r = 0; r < count; ++r) {
+        const LineDev &ln = host_lines[r];
+        SyncDev d;
+        d.m = n - ln.L;
+        d.fast = ln.mindistance * (long long)sizeof(int) <= 200 * 1024;
+        if (d.m <= 0) {
+            d.m = d.m < 0 ? 0 : d.m;
+            d.lim = d.limc = 0;
+        } else {
+            const long long w = ln.mindistance;
+            d.lim = std::min<long long>(d.m, std::min<long long>(160ll * ln.width, 1500000ll));
+            d.limc = std::min<long long>(d.m, ((d.lim + w + 1 + w - 1) / w) * w);
+        }
+        if (d.fast) {
+            sp.any_fast = true;
+            sp.max_lim = std::max(sp.max_lim, d.lim);
+            sp.max_limc = std::max(sp.max_limc, d.limc);
+            sp.max_w = std::max(sp.max_w, ln.mindistance);
+            if (d.limc > 0)
+                sp.max_wblocks = std::max(sp.max_wblocks, (int)((d.limc + ln.mindistance - 1) / ln.mindistance));
+        }
+        sd[r] = d;
+    }
+    sp.cs = (size_t)((sp.max_limc + 63) & ~63ll);
+    sp.bs = (size_t)((sp.max_lim + 31) / 32 + 1);
+    const size_t ints = 3 * sp.cs * count;
+    const size_t bytes = ints * sizeof(int) + sp.bs * count * sizeof(uint32_t) + (size_t)count * (sizeof(SyncDev) + 8) + 256;
+    char *base = (char *)ctx->sync_buf.reserve(bytes);
+    sp.corr = (int *)base;
+    sp.pre = sp.corr + sp.cs * count;
+    sp.suf = sp.pre + sp.cs * count;
+    sp.bits = (uint32_t *)(sp.suf + sp.cs * count);
+    sp.first_pos = (int *)(sp.bits + sp.bs * count);
+    sp.need_scan = sp.first_pos + count;
+    sp.sd = (SyncDev *)(((uintptr_t)(sp.need_scan + count) + 15) & ~(uintptr_t)15);
+    CUDA_CHECK(cudaMemcpyAsync(sp.sd, sd.data(), sizeof(SyncDev) * count, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // sd is a stack temporary
+    return sp;
 }
 
 }  // namespace wefax

@@ -35,6 +35,27 @@ struct RecResult {
     double low, high;
 };
 
+// per-recording geometry of the parallel phasing search (host-computed)
+struct SyncDev {
+    long long m;      // number of correlation positions = n - L
+    long long lim;    // settled bits are computed for [0, lim)
+    long long limc;   // correlation / window maxima are computed for [0, limc)
+    int fast;         // 0: this recording only runs the sequential scan
+};
+
+// device scratch of the parallel phasing search for one wave
+struct SyncPlan {
+    bool any_fast = false;
+    SyncDev *sd = nullptr;
+    int *corr = nullptr, *pre = nullptr, *suf = nullptr;
+    size_t cs = 0;             // ints per recording in corr / pre / suf
+    uint32_t *bits = nullptr;
+    size_t bs = 0;             // words per recording in bits
+    int *first_pos = nullptr, *need_scan = nullptr;
+    long long max_lim = 0, max_limc = 0;
+    int max_w = 0, max_wblocks = 0;
+};
+
 // percentile selection state, one per recording
 struct SelState {
     uint32_t rank[4];      // remaining rank of each target inside its prefix class
@@ -57,7 +78,9 @@ void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, 
                      const RecResult *res);
 // min_mindistance: smallest LineDev.mindistance of the batch (sizes the scan chunk; must be >= 1024)
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
-                        RecResult *res, int min_mindistance);
+                        RecResult *res, int min_mindistance, const SyncPlan &sp);
+// sizes the parallel search for recordings [first, first+count) and uploads its geometry
+SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long long n);
 void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                    const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines);
 
