@@ -894,8 +894,8 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
 // Pillow Resample.c: BICUBIC (a = -0.5), support 2, coefficients normalised per
 // output row, fixed point with PRECISION_BITS = 22.
 // ===========================================================================
-constexpr int kRasterRows = 32;     // input lines per tile (-> 128 output rows)
-constexpr int kRasterCols = 256;
+constexpr int kRasterRows = 16;      // input lines per tile (-> 64 output rows)
+constexpr int kRasterThreads = 256;  // x 4 columns per thread
 
 __device__ __forceinline__ double bicubic_filter(double x) {
     const double a = -0.5;
@@ -905,35 +905,27 @@ __device__ __forceinline__ double bicubic_filter(double x) {
     return 0.0;
 }
 
-__global__ void __launch_bounds__(kRasterCols)
+// Each thread owns 4 adjacent columns and walks down kRasterRows input lines with a
+// 5-line luminance window (lines r-2 .. r+2) in registers; every input line yields 4
+// output rows whose Pillow coefficients sit in shared memory as 5 "window slot" weights.
+__global__ void __launch_bounds__(kRasterThreads)
 raster_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, const RecResult *res_all,
               uint8_t *raster_all, size_t rs) {
-    __shared__ uint8_t s_lum[kRasterRows + 4][kRasterCols];
     __shared__ int s_k[4 * kRasterRows][5];
-    __shared__ int s_xmin[4 * kRasterRows], s_cnt[4 * kRasterRows];
 
     const RecResult *res = res_all + blockIdx.z;
     const int w = lines[blockIdx.z].width;
     const int h = res->height / 4;
     const int r0 = blockIdx.y * kRasterRows;
-    const int x0 = blockIdx.x * kRasterCols;
-    if (res->status != WEFAX_REC_OK || r0 >= h || x0 >= w) return;
-    const int tid = threadIdx.x;
-    const int x = x0 + tid;
+    const int x0 = (blockIdx.x * kRasterThreads + threadIdx.x) * 4;
+    if (res->status != WEFAX_REC_OK || r0 >= h || blockIdx.x * kRasterThreads * 4 >= w) return;
     const uint8_t *dig = dig_all + (size_t)blockIdx.z * ds + res->start_frame;
     uint8_t *out = raster_all + (size_t)blockIdx.z * rs;
 
-    // luminance 255 - value of lines r0-2 .. r0+33 (wefax.py:303)
-#pragma unroll 4
-    for (int rr = 0; rr < kRasterRows + 4; ++rr) {
-        int r = r0 - 2 + rr;
-        uint8_t lum = 0;
-        if (r >= 0 && r < h && x < w) lum = 255 - __ldg(dig + (size_t)r * w + x);
-        s_lum[rr][tid] = lum;
-    }
     // Pillow precompute_coeffs + normalize_coeffs_8bpc for this tile's output rows
-    if (tid < 4 * kRasterRows) {
-        const int yy = 4 * r0 + tid;
+    if (threadIdx.x < 4 * kRasterRows) {
+        const int yy = 4 * r0 + threadIdx.x;
+        const int r = yy >> 2;
         const double scale = 0.25, support = 2.0;
         const double center = (yy + 0.5) * scale;
         int xmin = (int)(center - support + 0.5);
@@ -946,26 +938,63 @@ raster_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lin
             kw[t] = t < xmax ? bicubic_filter((t + xmin - center + 0.5)) : 0.0;
             ww += kw[t];
         }
+        int slot[5] = {0, 0, 0, 0, 0};
         for (int t = 0; t < 5; ++t) {
+            if (t >= xmax) break;
             double kv = (ww != 0.0) ? kw[t] / ww : kw[t];
-            s_k[tid][t] = t < xmax ? (kv < 0 ? (int)(-0.5 + kv * 4194304.0) : (int)(0.5 + kv * 4194304.0)) : 0;
+            int ki = kv < 0 ? (int)(-0.5 + kv * 4194304.0) : (int)(0.5 + kv * 4194304.0);
+            int sl = xmin + t - (r - 2);          // window slot of input line xmin + t
+            if (sl >= 0 && sl < 5) slot[sl] = ki;
         }
-        s_xmin[tid] = xmin;
-        s_cnt[tid] = xmax;
+        for (int t = 0; t < 5; ++t) s_k[threadIdx.x][t] = slot[t];
     }
     __syncthreads();
-    if (x >= w) return;
-    const int rows_out = min(4 * kRasterRows, 4 * h - 4 * r0);
-    for (int j = 0; j < rows_out; ++j) {
-        const int rb = s_xmin[j] - (r0 - 2);
-        const int cnt = s_cnt[j];
-        int acc = 1 << 21;
+    if (x0 >= w) return;
+
+    auto load_line = [&](int r, int *l) {
+        // luminance 255 - value (wefax.py:303); lines outside the image only meet zero weights
+        if (r < 0 || r >= h) {
+            l[0] = l[1] = l[2] = l[3] = 0;
+            return;
+        }
+        const uint8_t *p = dig + (size_t)r * w + x0;
 #pragma unroll
-        for (int t = 0; t < 5; ++t)
-            if (t < cnt) acc += (int)s_lum[rb + t][tid] * s_k[j][t];
-        acc >>= 22;
-        acc = min(max(acc, 0), 255);
-        out[(size_t)(4 * r0 + j) * w + x] = (uint8_t)acc;
+        for (int c = 0; c < 4; ++c) l[c] = (x0 + c < w) ? 255 - (int)__ldg(p + c) : 0;
+    };
+    int win[5][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) load_line(r0 - 2 + j, win[j]);
+    const bool full = x0 + 3 < w;
+#pragma unroll
+    for (int rr = 0; rr < kRasterRows; ++rr) {
+        const int r = r0 + rr;
+        if (r >= h) break;
+        load_line(r + 2, win[4]);
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            const int k0 = s_k[4 * rr + ph][0], k1 = s_k[4 * rr + ph][1], k2 = s_k[4 * rr + ph][2],
+                      k3 = s_k[4 * rr + ph][3], k4 = s_k[4 * rr + ph][4];
+            int v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int acc = (1 << 21) + win[0][c] * k0 + win[1][c] * k1 + win[2][c] * k2 + win[3][c] * k3 + win[4][c] * k4;
+                acc >>= 22;
+                v[c] = min(max(acc, 0), 255);
+            }
+            uint8_t *o = out + (size_t)(4 * r + ph) * w + x0;
+            if (full && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+                *reinterpret_cast<uint32_t *>(o) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) |
+                                                   ((uint32_t)v[3] << 24);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (x0 + c < w) o[c] = (uint8_t)v[c];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) win[j][c] = win[j + 1][c];
     }
 }
 
@@ -973,8 +1002,9 @@ void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, i
                    const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines) {
     StageTimer timer(ctx, "raster");
     if (max_lines <= 0) return;
-    dim3 grid((max_width + kRasterCols - 1) / kRasterCols, (max_lines + kRasterRows - 1) / kRasterRows, batch);
-    raster_kernel<<<grid, kRasterCols, 0, ctx->stream>>>(dig, ds, n, lines, res, raster, rs);
+    const int cols_per_block = kRasterThreads * 4;
+    dim3 grid((max_width + cols_per_block - 1) / cols_per_block, (max_lines + kRasterRows - 1) / kRasterRows, batch);
+    raster_kernel<<<grid, kRasterThreads, 0, ctx->stream>>>(dig, ds, n, lines, res, raster, rs);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
