@@ -345,9 +345,10 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             WEFAX_THROW(WEFAX_ERR_INVALID, "raster_stride %lld too small (need %lld)", rstride_user, ls.raster_need);
 
         // transform scratch per recording
-        FftPlan *plan = get_plan(ctx, n);
-        long long zlen = n;
-        if (!plan) {
+        FftPlan *half = (n % 2 == 0 && !getenv("WEFAX_NO_REAL_FFT")) ? get_plan(ctx, n / 2) : nullptr;
+        FftPlan *plan = half ? nullptr : get_plan(ctx, n);
+        long long zlen = half ? n / 2 : n;
+        if (!plan && !half) {
             std::vector<int> tmp;
             zlen = next_smooth_length(2 * n - 1);
             if (zlen <= 0) WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "no transform length for n=%lld", n);
@@ -394,27 +395,39 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                 d_raster = out_dev ? out->raster + (size_t)w0 * rs : (uint8_t *)ctx->out_raster.reserve((size_t)g * rs);
 
             // ---- resample (wefax.py:60-62) + zero-phase notch (wefax.py:63-72) -------
-            // The notch writes the complex copy (x, 0) the transform reads; the float audio_data
-            // only when the caller asked for it (or the Bluestein path needs a real input).
-            float2 *z = plan ? (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2)) : nullptr;
-            const bool need_audio = out->audio != nullptr || !plan;
+            // Even n: the notch writes the float audio_data and the envelope comes from a
+            // half-length transform of the packed real signal.  Odd n: the notch also writes
+            // the complex copy (x, 0) a full-length transform reads (or Bluestein's real input).
+            float2 *z = nullptr;
+            if (half)
+                z = (float2 *)ctx->work_z.reserve((size_t)g * (n / 2) * sizeof(float2));
+            else if (plan)
+                z = (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2));
+            const bool need_audio = out->audio != nullptr || half || !plan;
             float *d_audio = nullptr;
             if (need_audio)
                 d_audio = (out_dev && out->audio) ? out->audio + (size_t)w0 * n
                                                   : (float *)ctx->work_a.reserve((size_t)g * n * sizeof(float));
+            float2 *zcopy = half ? nullptr : z;
             if (resample) {
                 float *xin = (float *)ctx->resample_in.reserve(((size_t)g * n_in + (size_t)g * n) * sizeof(float));
                 float *xrs = xin + (size_t)g * n_in;
                 launch_ingest_float(ctx, d_pcm, (size_t)n_in, ch, xin, (size_t)n_in, n_in, g);
                 resample_real(ctx, n_in, n, xin, (size_t)n_in, xrs, (size_t)n, g);
-                if (plan) z = (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2));   // resample used work_z
-                launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, d_audio, (size_t)n, z, (size_t)n, n, fp, g);
+                // the resampler used work_z: take the (possibly re-allocated) buffer again
+                if (half)
+                    z = (float2 *)ctx->work_z.reserve((size_t)g * (n / 2) * sizeof(float2));
+                else if (plan)
+                    z = zcopy = (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2));
+                launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, d_audio, (size_t)n, zcopy, (size_t)n, n, fp, g);
             } else {
-                launch_filtfilt(ctx, ch == 2 ? kInStereoI16 : kInMonoI16, d_pcm, (size_t)n_in, d_audio, (size_t)n, z,
+                launch_filtfilt(ctx, ch == 2 ? kInStereoI16 : kInMonoI16, d_pcm, (size_t)n_in, d_audio, (size_t)n, zcopy,
                                 (size_t)n, n, fp, g);
             }
             // ---- analytic-signal envelope (wefax.py:174) ------------------------------
-            if (plan)
+            if (half)
+                hilbert_envelope_real(ctx, half, d_audio, (size_t)n, z, (size_t)(n / 2), d_env, (size_t)n, g);
+            else if (plan)
                 hilbert_envelope(ctx, plan, nullptr, 0, z, (size_t)n, d_env, (size_t)n, g);
             else
                 hilbert_envelope_bluestein(ctx, n, d_audio, (size_t)n, d_env, (size_t)n, g);
@@ -482,8 +495,12 @@ int wefax_hilbert_envelope(wefax_ctx *ctx, long long n, int batch, const float *
         float *dx = (float *)ctx->work_a.reserve(bytes);
         float *de = (float *)ctx->work_e.reserve(bytes);
         CUDA_CHECK(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        FftPlan *plan = get_plan(ctx, n);
-        if (plan) {
+        FftPlan *half = (n % 2 == 0 && !getenv("WEFAX_NO_REAL_FFT")) ? get_plan(ctx, n / 2) : nullptr;
+        FftPlan *plan = half ? nullptr : get_plan(ctx, n);
+        if (half) {
+            float2 *z = (float2 *)ctx->work_z.reserve((size_t)(n / 2) * batch * sizeof(float2));
+            hilbert_envelope_real(ctx, half, dx, (size_t)n, z, (size_t)(n / 2), de, (size_t)n, batch);
+        } else if (plan) {
             float2 *z = (float2 *)ctx->work_z.reserve((size_t)n * batch * sizeof(float2));
             hilbert_envelope(ctx, plan, dx, (size_t)n, z, (size_t)n, de, (size_t)n, batch);
         } else {

@@ -106,6 +106,11 @@ void launch_pass(wefax_ctx *ctx, const PassDev &p_in, const LoadOp &ld, const St
 void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, float2 *z, size_t zs,
                       float *env, size_t es, int batch);
 
+// Same result for even n through a half-length transform of the packed real input
+// (half = plan of n/2; x and env strides even).  x must stay intact until the end.
+void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t xs, float2 *z, size_t zs, float *env,
+                           size_t es, int batch);
+
 // natural-order complex DFT (test entry / Bluestein building block)
 void fft_c2c_natural(wefax_ctx *ctx, FftPlan *plan, const float2 *in, float2 *out, float2 *scratch,
                      int batch, bool inverse);

@@ -151,6 +151,20 @@ struct StoreAbs {
     }
 };
 
+// Real-input path: the last inverse pass yields conj(y[2m] + i*y[2m+1]) with y the
+// Hilbert transform of x; the envelope is sqrt(x^2 + y^2) for the sample pair (2m, 2m+1).
+struct StoreEnvPairs {
+    float2 *env;            // envelope viewed as pairs
+    const float2 *x;        // the real input viewed as pairs
+    size_t ebstride, xbstride;
+    __device__ __forceinline__ int column_aux(int) const { return 0; }
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+        const float2 xs = __ldg(x + (size_t)b * xbstride + i);
+        env[(size_t)b * ebstride + i] =
+            make_float2(sqrtf(fmaf(xs.x, xs.x, v.x * v.x)), sqrtf(fmaf(xs.y, xs.y, v.y * v.y)));
+    }
+};
+
 struct StoreRealPart {
     float *dst;
     size_t bstride;
@@ -521,6 +535,7 @@ struct FftPlan {
     PassDev fwd[kMaxPasses];   // tw_mode 1 on all but the last pass
     PassDev inv[kMaxPasses];   // tw_mode 2 on all but pass 0 (the last one to run)
     DevBuf tables;             // twR / perm / tw_lo / tw_hi of every pass
+    const float2 *tw2_lo = nullptr, *tw2_hi = nullptr;   // w_{2n}^e (real-input packing), two-level like tw_lo/hi
     OuterDigits outer() const {
         OuterDigits od{};
         od.nouter = npass - 1;

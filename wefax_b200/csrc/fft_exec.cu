@@ -207,6 +207,60 @@ void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, 
     run_inverse(ctx, plan, load_c(z, zs), StoreAbs{env, es, n, 1.f}, z, zs, batch);
 }
 
+// ----------------------------- real-input Hilbert envelope ------------------
+// x real, n = 2M.  z[m] = x[2m] + i*x[2m+1]; Z = DFT_M(z).  With E/O the spectra of the
+// even/odd samples (E = (Z[k] + conj Z[M-k])/2, O = (Z[k] - conj Z[M-k])/(2i)) the
+// spectrum of x is X[k] = E + w^k O, w = exp(-2*pi*i/n).  The Hilbert transform
+// y = H[x] has Y[k] = -i X[k] (0 < k < M), Y[0] = Y[M] = 0; packing y the same way,
+// Z'[k] = conj(w^k) (Z[k] + conj Z[M-k])/2 - w^k (Z[k] - conj Z[M-k])/2,  Z'[0] = 0,
+// and IDFT_M(Z') = y[2m] + i*y[2m+1].  This kernel turns Z into conj(Z')/M in place
+// (conjugated so the inverse can run on the forward kernels); engine order throughout.
+__global__ void hilbert_pairs_kernel(float2 *z_all, size_t zs, uint32_t M, PosMap pm, const float2 *tw_lo,
+                                     const float2 *tw_hi, float inv_m) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= M) return;
+    float2 *z = z_all + (size_t)blockIdx.y * zs;
+    const uint32_t k = pm.freq(p);
+    if (k == 0) {
+        z[p] = make_float2(0.f, 0.f);
+        return;
+    }
+    const uint32_t km = M - k;
+    if (k > km) return;                       // the partner thread handles the pair
+    const uint32_t pmir = pm.pos(km);
+    const float2 zk = z[p], zm = z[pmir];
+    const float2 lo = __ldg(tw_lo + (k & ((1u << kTwLoBits) - 1))), hi = __ldg(tw_hi + (k >> kTwLoBits));
+    const float2 w = cmul(lo, hi);            // w_n^k
+    // s = (zk + conj zm)/2, d = (zk - conj zm)/2
+    const float2 s = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+    // Z'[k] = conj(w) s - w d
+    const float2 a = cmul(make_float2(w.x, -w.y), s), b = cmul(w, d);
+    z[p] = make_float2((a.x - b.x) * inv_m, -(a.y - b.y) * inv_m);
+    if (k != km) {
+        // Z'[M-k] = conj(w') s' - w' d' with w' = w^(M-k) = -conj(w), s' = conj(s), d' = -conj(d)
+        // = -w conj(s) - conj(w) conj(d)
+        const float2 a2 = cmul(w, make_float2(s.x, -s.y)), b2 = cmul(make_float2(w.x, -w.y), make_float2(d.x, -d.y));
+        z[pmir] = make_float2(-(a2.x + b2.x) * inv_m, (a2.y + b2.y) * inv_m);
+    }
+}
+
+void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t xs, float2 *z, size_t zs, float *env,
+                           size_t es, int batch) {
+    const size_t M = (size_t)half->n;
+    // x / env strides are in floats and must be even so that pair views stay aligned
+    run_forward(ctx, half, load_c((const float2 *)x, xs / 2), StoreComplex{z, zs, 1.f, 0}, z, zs, batch);
+    {
+        StageTimer timer(ctx, "hilbert_pairs");
+        dim3 grid((unsigned)((M + 255) / 256), batch);
+        hilbert_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(z, zs, (uint32_t)M, pos_map(half), half->tw2_lo, half->tw2_hi,
+                                                           (float)(1.0 / (double)M));
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    }
+    run_inverse(ctx, half, load_c(z, zs), StoreEnvPairs{(float2 *)env, (const float2 *)x, es / 2, xs / 2}, z, zs, batch);
+}
+
 void fft_c2c_natural(wefax_ctx *ctx, FftPlan *plan, const float2 *in, float2 *out, float2 *scratch, int batch,
                      bool inverse) {
     const size_t n = (size_t)plan->n;

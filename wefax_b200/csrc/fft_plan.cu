@@ -212,7 +212,15 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
         o_lo[i] = take(sizeof(float2) << kTwLoBits);
         o_hi[i] = take((size_t)n_hi[i] * sizeof(float2));
     }
+    const long long n2_hi = ((2 * n) >> kTwLoBits) + 1;
+    const size_t o2_lo = take(sizeof(float2) << kTwLoBits), o2_hi = take((size_t)n2_hi * sizeof(float2));
     char *base = (char *)plan->tables.reserve(off);
+    plan->tw2_lo = (const float2 *)(base + o2_lo);
+    plan->tw2_hi = (const float2 *)(base + o2_hi);
+    twiddle_table_kernel<<<((1 << kTwLoBits) + 255) / 256, 256, 0, stream>>>((float2 *)(base + o2_lo), 1 << kTwLoBits,
+                                                                           2.0 * (double)n, 1.0);
+    twiddle_table_kernel<<<(unsigned)((n2_hi + 255) / 256), 256, 0, stream>>>((float2 *)(base + o2_hi), (int)n2_hi,
+                                                                           2.0 * (double)n, (double)(1 << kTwLoBits));
 
     for (int i = 0; i < P; ++i) {
         PassDev d;
