@@ -133,6 +133,33 @@ def test_digitalize_stage_bit_exact(dec, n):
         assert np.array_equal(dig[r].astype(np.int64), d)
 
 
+@pytest.mark.parametrize("mode", ["bracket", "radix"])
+@pytest.mark.parametrize("kind", ["noise", "ramp", "duplicates", "two_level", "periodic"])
+def test_percentile_paths_agree_with_numpy(dec, mode, kind, monkeypatch):
+    """Both selection strategies (sample-bracketed single pass with exact fallback, and the
+    3-level radix select) must return numpy's percentiles exactly, also on data that defeats
+    the systematic sample (monotone ramps, a period equal to the sampling stride)."""
+    monkeypatch.setenv("WEFAX_PCT_MODE", mode)
+    n = 1_300_007
+    rng = np.random.default_rng(7)
+    if kind == "noise":
+        env = np.abs(rng.normal(size=n)) * 2000
+    elif kind == "ramp":
+        env = np.linspace(1.0, 9000.0, n)
+    elif kind == "duplicates":
+        env = rng.integers(0, 40, size=n).astype(np.float64) * 100.0
+    elif kind == "two_level":
+        env = np.where(rng.random(n) < 0.004, 50.0, 3000.0) + rng.random(n)
+    else:
+        env = 1000.0 + 900.0 * np.sin(2 * np.pi * np.arange(n) / 127.0) + rng.random(n)
+    env = env.astype(np.float32)
+    dem, dig, lh, st = dec.digitalize(env[None])
+    m = O.medfilt5(env.astype(np.float64))
+    d, low, high = O.digitalize(m)
+    assert lh[0, 0] == low and lh[0, 1] == high, (mode, kind)
+    assert st[0] == 0 and np.array_equal(dig[0].astype(np.int64), d)
+
+
 def test_digitalize_constant_envelope_flags_nan(dec):
     env = np.full((1, 5000), 7.0, dtype=np.float32)
     _, _, lh, st = dec.digitalize(env)

@@ -29,7 +29,7 @@ struct wefax_ctx {
     std::map<long long, std::unique_ptr<wefax::Bluestein>> bluestein;
     std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
     // scratch (grown on demand, reused between calls)
-    wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in, sync_buf;
+    wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in, sync_buf, pct_buf;
     // pinned staging for small results
     void *pinned = nullptr;
     size_t pinned_cap = 0;

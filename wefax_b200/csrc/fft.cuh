@@ -517,7 +517,7 @@ fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid
         }
     } else if (valid_s) {
         const int a = aux[cc_s];
-#pragma unroll 4
+#pragma unroll 8
         for (int k = tid >> p.log2C; k < p.R; k += jstep) {
             float2 v = tile[(int)perm[k] * p.C + cc_s];
             if (p.tw_mode != 0) v = cmul(v, pass_twiddle(p, tw_e0 + (uint32_t)k * tw_de));

@@ -215,33 +215,70 @@ void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, 
 // Z'[k] = conj(w^k) (Z[k] + conj Z[M-k])/2 - w^k (Z[k] - conj Z[M-k])/2,  Z'[0] = 0,
 // and IDFT_M(Z') = y[2m] + i*y[2m+1].  This kernel turns Z into conj(Z')/M in place
 // (conjugated so the inverse can run on the forward kernels); engine order throughout.
-__global__ void hilbert_pairs_kernel(float2 *z_all, size_t zs, uint32_t M, PosMap pm, const float2 *tw_lo,
-                                     const float2 *tw_hi, float inv_m) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= M) return;
+// One CTA per engine-order row (all digits but the last fixed): frequency
+// k = kb + ncols*j for j = 0..R_last-1; its mirror M-k lives in the row of
+// kb' = (ncols - kb) mod ncols at j' = R_last-1-j (kb > 0) or (R_last-j) mod R_last
+// (kb = 0): both rows are walked contiguously, one forwards and one backwards.
+struct PairGeom {
+    int nouter;                 // passes - 1
+    int Rout[kMaxPasses];       // R_0 .. R_{P-2}
+    int R_last, ncols;
+};
+
+__global__ void __launch_bounds__(256)
+hilbert_pairs_kernel(float2 *z_all, size_t zs, uint32_t M, PairGeom g, const float2 *tw_lo, const float2 *tw_hi,
+                     float inv_m) {
     float2 *z = z_all + (size_t)blockIdx.y * zs;
-    const uint32_t k = pm.freq(p);
-    if (k == 0) {
-        z[p] = make_float2(0.f, 0.f);
-        return;
+    const int o = blockIdx.x;
+    // digits of this row (most significant first in o), its base frequency and the mirrored row
+    int kb = 0, o2 = 0;
+    {
+        int d[kMaxPasses], rem = o;
+#pragma unroll
+        for (int i = kMaxPasses - 1; i >= 0; --i)
+            if (i < g.nouter) {
+                d[i] = rem % g.Rout[i];
+                rem /= g.Rout[i];
+            }
+        int mult = 1;
+#pragma unroll
+        for (int i = 0; i < kMaxPasses; ++i)
+            if (i < g.nouter) {
+                kb += d[i] * mult;
+                mult *= g.Rout[i];
+            }
+        int kb2 = kb ? g.ncols - kb : 0, rem2 = kb2;
+#pragma unroll
+        for (int i = 0; i < kMaxPasses; ++i)
+            if (i < g.nouter) {
+                o2 = o2 * g.Rout[i] + rem2 % g.Rout[i];
+                rem2 /= g.Rout[i];
+            }
     }
-    const uint32_t km = M - k;
-    if (k > km) return;                       // the partner thread handles the pair
-    const uint32_t pmir = pm.pos(km);
-    const float2 zk = z[p], zm = z[pmir];
-    const float2 lo = __ldg(tw_lo + (k & ((1u << kTwLoBits) - 1))), hi = __ldg(tw_hi + (k >> kTwLoBits));
-    const float2 w = cmul(lo, hi);            // w_n^k
-    // s = (zk + conj zm)/2, d = (zk - conj zm)/2
-    const float2 s = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-    const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
-    // Z'[k] = conj(w) s - w d
-    const float2 a = cmul(make_float2(w.x, -w.y), s), b = cmul(w, d);
-    z[p] = make_float2((a.x - b.x) * inv_m, -(a.y - b.y) * inv_m);
-    if (k != km) {
-        // Z'[M-k] = conj(w') s' - w' d' with w' = w^(M-k) = -conj(w), s' = conj(s), d' = -conj(d)
-        // = -w conj(s) - conj(w) conj(d)
-        const float2 a2 = cmul(w, make_float2(s.x, -s.y)), b2 = cmul(make_float2(w.x, -w.y), make_float2(d.x, -d.y));
-        z[pmir] = make_float2(-(a2.x + b2.x) * inv_m, (a2.y + b2.y) * inv_m);
+    if (o2 < o) return;                                   // the mirrored row's CTA owns these pairs
+    float2 *row = z + (size_t)o * g.R_last;
+    float2 *row2 = z + (size_t)o2 * g.R_last;
+    for (int j = threadIdx.x; j < g.R_last; j += blockDim.x) {
+        const int j2 = kb ? g.R_last - 1 - j : (j ? g.R_last - j : 0);
+        if (o2 == o && j2 < j) continue;                  // self-mirrored row: each pair once
+        const uint32_t k = (uint32_t)kb + (uint32_t)g.ncols * (uint32_t)j;
+        if (k == 0) {
+            row[0] = make_float2(0.f, 0.f);
+            continue;
+        }
+        const float2 zk = row[j], zm = row2[j2];
+        const float2 lo = __ldg(tw_lo + (k & ((1u << kTwLoBits) - 1))), hi = __ldg(tw_hi + (k >> kTwLoBits));
+        const float2 w = cmul(lo, hi);                    // w_n^k
+        const float2 s = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));   // (zk + conj zm)/2
+        const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));   // (zk - conj zm)/2
+        const float2 a = cmul(make_float2(w.x, -w.y), s), b = cmul(w, d);           // Z'[k] = conj(w) s - w d
+        row[j] = make_float2((a.x - b.x) * inv_m, -(a.y - b.y) * inv_m);
+        if (!(o2 == o && j2 == j)) {
+            // Z'[M-k] = -w conj(s) - conj(w) conj(d)
+            const float2 a2 = cmul(w, make_float2(s.x, -s.y)),
+                         b2 = cmul(make_float2(w.x, -w.y), make_float2(d.x, -d.y));
+            row2[j2] = make_float2(-(a2.x + b2.x) * inv_m, (a2.y + b2.y) * inv_m);
+        }
     }
 }
 
@@ -252,8 +289,13 @@ void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t
     run_forward(ctx, half, load_c((const float2 *)x, xs / 2), StoreComplex{z, zs, 1.f, 0}, z, zs, batch);
     {
         StageTimer timer(ctx, "hilbert_pairs");
-        dim3 grid((unsigned)((M + 255) / 256), batch);
-        hilbert_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(z, zs, (uint32_t)M, pos_map(half), half->tw2_lo, half->tw2_hi,
+        PairGeom g{};
+        g.nouter = half->npass - 1;
+        for (int i = 0; i < g.nouter; ++i) g.Rout[i] = half->Rs[i];
+        g.R_last = half->Rs[half->npass - 1];
+        g.ncols = (int)(M / g.R_last);
+        dim3 grid((unsigned)g.ncols, batch);
+        hilbert_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(z, zs, (uint32_t)M, g, half->tw2_lo, half->tw2_hi,
                                                            (float)(1.0 / (double)M));
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;

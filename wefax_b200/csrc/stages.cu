@@ -2,6 +2,8 @@
 // grey-level quantisation, phasing search, line raster with x4 bicubic.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "stages.cuh"
 
@@ -65,21 +67,39 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
     const long long E = n + 2 * kPadLen;                              // length of the odd-extended signal
     const long long e0 = kPadLen + (long long)blockIdx.x * TS;        // first output of this tile, extended coords
 
-    for (int j = tid; j < NEXT_AL; j += kFirThreads) {
-        long long e = e0 - (KP - 1) + j;
-        float v = 0.f;
-        if (j < NEXT) {
-            if (e < 0) e = 0;   // steady-state initial condition: constant ext[0] to the left
-            if (e < E) {
-                if (e < kPadLen)
-                    v = 2.f * load_sample<MODE>(in, base, 0) - load_sample<MODE>(in, base, kPadLen - e);
-                else if (e >= n + kPadLen)
-                    v = 2.f * load_sample<MODE>(in, base, n - 1) - load_sample<MODE>(in, base, 2 * n + 7 - e);
-                else
-                    v = load_sample<MODE>(in, base, e - kPadLen);
-            }
+    const long long e_first = e0 - (KP - 1);                          // extended index of s_ext[0]
+    if (e_first >= kPadLen && e_first + NEXT <= n + kPadLen) {
+        // interior tile: every sample is a plain input sample; keep all loads in flight
+        const long long g0 = e_first - kPadLen;
+        constexpr int ITER = (NEXT_AL + kFirThreads - 1) / kFirThreads;
+        float v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int j = tid + it * kFirThreads;
+            v[it] = j < NEXT ? load_sample<MODE>(in, base, g0 + j) : 0.f;
         }
-        s_ext[j] = v;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int j = tid + it * kFirThreads;
+            if (j < NEXT_AL) s_ext[j] = v[it];
+        }
+    } else {
+        for (int j = tid; j < NEXT_AL; j += kFirThreads) {
+            long long e = e_first + j;
+            float v = 0.f;
+            if (j < NEXT) {
+                if (e < 0) e = 0;   // steady-state initial condition: constant ext[0] to the left
+                if (e < E) {
+                    if (e < kPadLen)
+                        v = 2.f * load_sample<MODE>(in, base, 0) - load_sample<MODE>(in, base, kPadLen - e);
+                    else if (e >= n + kPadLen)
+                        v = 2.f * load_sample<MODE>(in, base, n - 1) - load_sample<MODE>(in, base, 2 * n + 7 - e);
+                    else
+                        v = load_sample<MODE>(in, base, e - kPadLen);
+                }
+            }
+            s_ext[j] = v;
+        }
     }
     __syncthreads();
 
@@ -350,29 +370,425 @@ select_kernel(SelState *sel_all, int level, RecResult *res_all, double t_lo, dou
     }
 }
 
+// ---------------------------------------------------------------------------
+// Bracketed selection for long recordings: one light pass over the data instead of
+// three histogram passes.
+//   1. every 61st median-filtered sample goes into a small array;
+//   2. one CTA selects, exactly, four order statistics of that sample: values that
+//      bracket the 0.5 and 99.5 percentile with a wide safety margin;
+//   3. one pass over the data counts the elements below each bracket and copies the
+//      (few) elements inside into a list;
+//   4. one CTA selects the exact order statistics inside the lists and checks that
+//      the wanted ranks really fell inside the brackets.  If not (or a list
+//      overflowed) a flag makes the fallback kernel redo the selection exactly over
+//      the whole data, so the result is always the exact numpy.percentile value.
+// ---------------------------------------------------------------------------
+constexpr int kPctStride = 127;
+constexpr int kSelThreads = 1024;
+
+struct PctGeom {
+    long long n, ns;               // samples, sub-sampled count
+    uint32_t s_rank[4];            // sample ranks of the bracket ends: lo_a, lo_b, hi_a, hi_b
+    int open_lo, open_hi;          // bracket reaches the end of the sample: extend to -inf / +inf
+    uint32_t r[4];                 // wanted ranks: i_lo, i_lo+1, i_hi, i_hi+1 (clipped)
+    double t_lo, t_hi;             // numpy lerp weights
+    uint32_t cap;                  // capacity of each candidate list
+};
+
+struct PctState {                  // per recording, device
+    uint32_t key[4];               // bracket keys lo_a, lo_b, hi_a, hi_b
+    unsigned long long below[2];   // elements with key < lo_a / < hi_a
+    uint32_t len[2];               // candidates collected in each list (may exceed cap: overflow)
+    int fallback;
+};
+
+// Exact selection of NT order statistics among `count` keys produced by key_at(i),
+// by the `ncta` co-resident CTAs (kSelThreads threads each) that serve one
+// recording: 3 radix levels (11 + 11 + 10 bits); every CTA histograms its slice in
+// shared memory, adds it to the recording's global histogram, the CTAs meet at a
+// barrier and each of them locates the targets' bins (so all hold the same state).
+// ranks[] in (s_rank), keys out (s_prefix).  ghist: 3 levels x NT x 2048 zeroed words.
+struct CoopSync {
+    unsigned int arrived;   // monotonically increasing barrier counter
+};
+
+__device__ __forceinline__ void coop_barrier(CoopSync *cs, unsigned ncta, unsigned &phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++phase;
+        if (ncta > 1) {
+            __threadfence();
+            atomicAdd(&cs->arrived, 1u);
+            while (*((volatile unsigned int *)&cs->arrived) < phase * ncta) {
+            }
+            __threadfence();
+        }
+    }
+    __syncthreads();
+}
+
+template <int NT, class KeyAt>
+__device__ void coop_select(KeyAt key_at, long long count, int cta, unsigned ncta, CoopSync *cs, unsigned &phase,
+                            uint32_t *ghist, uint32_t *s_hist /* NT*2048 */, uint32_t *s_rank, uint32_t *s_prefix,
+                            uint32_t *s_scan /* 32 */) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < NT) s_prefix[tid] = 0;
+    for (int level = 0; level < 3; ++level) {
+        const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+        const uint32_t mask = level == 2 ? 0x3FFu : 0x7FFu;
+        const int nh = level == 0 ? 1 : NT;           // level 0: all targets share one histogram
+        uint32_t *gh = ghist + (size_t)level * NT * 2048;
+        for (int i = tid; i < nh * 2048; i += kSelThreads) s_hist[i] = 0;
+        __syncthreads();
+        uint32_t pre[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) pre[t] = s_prefix[t];
+        // 8 independent loads per thread are issued before any of them is consumed
+        constexpr int U = 8;
+        const long long span = (long long)U * kSelThreads;
+        const long long rounds = (count + span * ncta - 1) / (span * ncta);
+        for (long long it = 0; it < rounds; ++it) {
+            uint32_t key[U];
+            bool valid[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = ((it * ncta + cta) * U + u) * kSelThreads + tid;
+                valid[u] = i < count;
+                key[u] = valid[u] ? key_at(i) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (level == 0) {
+                    // keys are concentrated in a few bins: lanes with equal bins share one atomic
+                    const uint32_t bin = valid[u] ? (key[u] >> 21) : 0xFFFFFFFFu;
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+                    if (valid[u] && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
+                } else if (valid[u]) {
+                    const uint32_t hi = key[u] >> (level == 1 ? 21 : 10);
+                    const uint32_t bin = (key[u] >> shift) & mask;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t)
+                        if (hi == pre[t]) atomicAdd(&s_hist[t * 2048 + bin], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nh * 2048; i += kSelThreads) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(&gh[i], c);
+        }
+        coop_barrier(cs, ncta, phase);
+        // locate each target in the recording-wide histogram: thread tid owns bins 2*tid, 2*tid+1
+        for (int t = 0; t < NT; ++t) {
+            const int hsel = level == 0 ? 0 : t;
+            const uint32_t c0 = __ldcg(&gh[hsel * 2048 + 2 * tid]), c1 = __ldcg(&gh[hsel * 2048 + 2 * tid + 1]);
+            uint32_t incl = c0 + c1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) s_scan[wid] = incl;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int w = 0; w < wid; ++w) woff += s_scan[w];
+            uint32_t before = woff + incl - (c0 + c1);
+            const uint32_t rank = s_rank[t];
+            uint32_t found_bin = 0xFFFFFFFFu, found_before = 0;
+            if (rank >= before && rank < before + c0) {
+                found_bin = 2 * tid;
+                found_before = before;
+            } else if (rank >= before + c0 && rank < before + c0 + c1) {
+                found_bin = 2 * tid + 1;
+                found_before = before + c0;
+            }
+            __syncthreads();
+            if (found_bin != 0xFFFFFFFFu) {
+                s_prefix[t] = (pre[t] << (level == 2 ? 10 : 11)) | found_bin;
+                s_rank[t] = rank - found_before;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pct_sample_kernel(const float *env, size_t es, PctGeom g, float *samp, size_t ss) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.ns) return;
+    const float *e = env + (size_t)blockIdx.y * es;
+    const long long i = s * kPctStride;
+    float w[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const long long k = i - 2 + j;
+        w[j] = (k >= 0 && k < g.n) ? __ldg(e + k) : 0.f;
+    }
+    samp[(size_t)blockIdx.y * ss + s] = med5(w[0], w[1], w[2], w[3], w[4]);
+}
+
+// scratch of the cooperative selections of one recording (zeroed before every use)
+struct PctCoop {
+    CoopSync sync[2];                // bracket kernel, final kernel
+    uint32_t hist[3][3 * 4 * 2048];  // [sample | low list | high list][level][target][bin]
+};
+
+__global__ void __launch_bounds__(kSelThreads)
+pct_bracket_kernel(const float *samp, size_t ss, PctGeom g, PctState *st_all, PctCoop *coop_all, int ncta) {
+    __shared__ uint32_t s_hist[4 * 2048];
+    __shared__ uint32_t s_rank[4], s_prefix[4], s_scan[32];
+    const int rec = blockIdx.x / ncta, cta = blockIdx.x % ncta;
+    const float *sp = samp + (size_t)rec * ss;
+    PctCoop *coop = coop_all + rec;
+    if (threadIdx.x < 4) s_rank[threadIdx.x] = g.s_rank[threadIdx.x];
+    __syncthreads();
+    unsigned phase = 0;
+    coop_select<4>([&](long long i) { return __float_as_uint(__ldg(sp + i)); }, g.ns, cta, (unsigned)ncta, &coop->sync[0],
+                   phase, coop->hist[0], s_hist, s_rank, s_prefix, s_scan);
+    if (cta == 0 && threadIdx.x == 0) {
+        PctState *st = st_all + rec;
+        st->key[0] = g.open_lo ? 0u : s_prefix[0];
+        st->key[1] = s_prefix[1];
+        st->key[2] = s_prefix[2];
+        st->key[3] = g.open_hi ? 0xFFFFFFFFu : s_prefix[3];
+        st->below[0] = st->below[1] = 0;
+        st->len[0] = st->len[1] = 0;
+        st->fallback = 0;
+    }
+}
+
+constexpr int kPctStage = 1024;   // per-CTA staging of candidates before one global append
+
+__global__ void __launch_bounds__(256)
+pct_collect_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, float *lists, size_t ls) {
+    __shared__ unsigned long long s_below[2];
+    __shared__ float s_cand[2][kPctStage];
+    __shared__ uint32_t s_cnt[2], s_base[2];
+    PctState *st = st_all + blockIdx.y;
+    const float *e = env + (size_t)blockIdx.y * es;
+    float *list[2] = {lists + (size_t)blockIdx.y * ls, lists + (size_t)blockIdx.y * ls + g.cap};
+    const uint32_t k0 = st->key[0], k1 = st->key[1], k2 = st->key[2], k3 = st->key[3];
+    if (threadIdx.x < 2) {
+        s_below[threadIdx.x] = 0;
+        s_cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    auto append = [&](int h, float v) {
+        const uint32_t slot = atomicAdd(&s_cnt[h], 1u);
+        if (slot < kPctStage) {
+            s_cand[h][slot] = v;
+        } else {                                    // staging full (pathological data): append directly
+            const uint32_t gslot = atomicAdd(&st->len[h], 1u);
+            if (gslot < g.cap) list[h][gslot] = v;
+        }
+    };
+    uint32_t below0 = 0, below1 = 0;
+    const long long stride = 4ll * blockDim.x * gridDim.x;
+    for (long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i0 < g.n; i0 += stride) {
+        float m[4];
+        load_med4(e, i0, g.n, m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j >= g.n) break;
+            const uint32_t key = __float_as_uint(m[j]);
+            below0 += key < k0;
+            below1 += key < k2;
+            if (key >= k0 && key <= k1) append(0, m[j]);
+            if (key >= k2 && key <= k3) append(1, m[j]);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        below0 += __shfl_xor_sync(0xFFFFFFFFu, below0, d);
+        below1 += __shfl_xor_sync(0xFFFFFFFFu, below1, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_below[0], (unsigned long long)below0);
+        atomicAdd(&s_below[1], (unsigned long long)below1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        atomicAdd(&st->below[threadIdx.x], s_below[threadIdx.x]);
+        const uint32_t c = min(s_cnt[threadIdx.x], (uint32_t)kPctStage);
+        s_cnt[threadIdx.x] = c;
+        s_base[threadIdx.x] = c ? atomicAdd(&st->len[threadIdx.x], c) : 0u;
+    }
+    __syncthreads();
+    for (int h = 0; h < 2; ++h)
+        for (uint32_t i = threadIdx.x; i < s_cnt[h]; i += blockDim.x)
+            if (s_base[h] + i < g.cap) list[h][s_base[h] + i] = s_cand[h][i];
+}
+
+__device__ void write_percentiles(RecResult *res, const uint32_t key[4], double t_lo, double t_hi) {
+    // numpy _lerp: a + (b-a)*t for t < 0.5, b - (b-a)*(1-t) otherwise (no FMA contraction)
+    double v[4];
+    for (int t = 0; t < 4; ++t) v[t] = (double)__uint_as_float(key[t]);
+    double d0 = __dsub_rn(v[1], v[0]), d1 = __dsub_rn(v[3], v[2]);
+    double low = t_lo >= 0.5 ? __dsub_rn(v[1], __dmul_rn(d0, __dsub_rn(1.0, t_lo))) : __dadd_rn(v[0], __dmul_rn(d0, t_lo));
+    double high = t_hi >= 0.5 ? __dsub_rn(v[3], __dmul_rn(d1, __dsub_rn(1.0, t_hi))) : __dadd_rn(v[2], __dmul_rn(d1, t_hi));
+    res->low = low;
+    res->high = high;
+    double delta = __dsub_rn(high, low);
+    if (!(delta > 0.0) || isinf(delta)) res->status |= WEFAX_REC_NAN;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, RecResult *res_all, PctCoop *coop_all,
+                 int ncta) {
+    __shared__ uint32_t s_hist[2 * 2048];
+    __shared__ uint32_t s_rank[2], s_prefix[2], s_scan[32], s_key[4];
+    const int rec = blockIdx.x / ncta, cta = blockIdx.x % ncta;
+    PctState *st = st_all + rec;
+    PctCoop *coop = coop_all + rec;
+    const float *list_lo = lists + (size_t)rec * ls, *list_hi = list_lo + g.cap;
+    // every CTA of the recording takes the same decision from the same data
+    bool ok = st->len[0] <= g.cap && st->len[1] <= g.cap;
+    for (int h = 0; h < 2 && ok; ++h) {
+        const unsigned long long b = st->below[h];
+        ok = b <= g.r[2 * h] && (unsigned long long)g.r[2 * h + 1] < b + st->len[h];
+    }
+    if (!ok) {
+        if (cta == 0 && threadIdx.x == 0) st->fallback = 1;
+        return;
+    }
+    unsigned phase = 0;
+    for (int h = 0; h < 2; ++h) {
+        const float *lst = h ? list_hi : list_lo;
+        if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)st->below[h];
+        __syncthreads();
+        coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], cta,
+                       (unsigned)ncta, &coop->sync[1], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
+        if (threadIdx.x < 2) s_key[2 * h + threadIdx.x] = s_prefix[threadIdx.x];
+        __syncthreads();
+    }
+    if (cta == 0 && threadIdx.x == 0) write_percentiles(res_all + rec, s_key, g.t_lo, g.t_hi);
+}
+
+// exact selection over the whole recording by one CTA (only when a bracket failed)
+__global__ void __launch_bounds__(kSelThreads)
+pct_fallback_kernel(const float *env, size_t es, PctGeom g, const PctState *st_all, RecResult *res_all,
+                    PctCoop *coop_all) {
+    __shared__ uint32_t s_hist[4 * 2048];
+    __shared__ uint32_t s_rank[4], s_prefix[4], s_scan[32];
+    if (!st_all[blockIdx.x].fallback) return;
+    const float *e = env + (size_t)blockIdx.x * es;
+    PctCoop *coop = coop_all + blockIdx.x;
+    // reuse the sample histogram space (its selection is long finished): clear it first
+    for (int i = threadIdx.x; i < 3 * 4 * 2048; i += kSelThreads) coop->hist[0][i] = 0;
+    if (threadIdx.x < 4) s_rank[threadIdx.x] = g.r[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    const long long n = g.n;
+    unsigned phase = 0;
+    coop_select<4>(
+        [&](long long i) {
+            float w[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const long long k = i - 2 + j;
+                w[j] = (k >= 0 && k < n) ? __ldg(e + k) : 0.f;
+            }
+            return __float_as_uint(med5(w[0], w[1], w[2], w[3], w[4]));
+        },
+        n, 0, 1u, &coop->sync[0], phase, coop->hist[0], s_hist, s_rank, s_prefix, s_scan);
+    if (threadIdx.x == 0) write_percentiles(res_all + blockIdx.x, s_prefix, g.t_lo, g.t_hi);
+}
+
 void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
                         RecResult *res) {
     StageTimer timer(ctx, "percentiles");
+    cudaStream_t st = ctx->stream;
     // numpy 'linear' method: virtual index (n-1)*q, q = 0.5/100 and 99.5/100
     const double v_lo = (double)(n - 1) * (0.5 / 100), v_hi = (double)(n - 1) * (99.5 / 100);
     const long long i_lo = (long long)floor(v_lo), i_hi = (long long)floor(v_hi);
     const double t_lo = v_lo - (double)i_lo, t_hi = v_hi - (double)i_hi;
     auto clip = [&](long long r) { return (uint32_t)std::min(r, n - 1); };
-    CUDA_CHECK(cudaMemsetAsync(sel, 0, sizeof(SelState) * batch, ctx->stream));
-    select_init_kernel<<<batch, 32, 0, ctx->stream>>>(sel, clip(i_lo), clip(i_lo + 1), clip(i_hi), clip(i_hi + 1));
-    ctx->launches++;
-    long long per_block = 4 * 256;
-    int blocks = (int)std::min<long long>((n + per_block - 1) / per_block, (long long)ctx->sm_count * 8);
+    const char *force = getenv("WEFAX_PCT_MODE");   // "radix" | "bracket" (tests); default by length
+    const bool bracket = force ? (force[0] == 'b') : (n >= (1ll << 20));
+    if (!bracket) {
+        CUDA_CHECK(cudaMemsetAsync(sel, 0, sizeof(SelState) * batch, st));
+        select_init_kernel<<<batch, 32, 0, st>>>(sel, clip(i_lo), clip(i_lo + 1), clip(i_hi), clip(i_hi + 1));
+        long long per_block = 4 * 256;
+        int blocks = (int)std::min<long long>((n + per_block - 1) / per_block, (long long)ctx->sm_count * 8);
+        blocks = std::max(1, blocks / std::max(1, std::min(batch, 8)));
+        dim3 grid(blocks, batch);
+        hist_kernel<0><<<grid, 256, 0, st>>>(env, es, n, sel);
+        select_kernel<<<batch, 256, 0, st>>>(sel, 0, res, t_lo, t_hi);
+        hist_kernel<1><<<grid, 256, 0, st>>>(env, es, n, sel);
+        select_kernel<<<batch, 256, 0, st>>>(sel, 1, res, t_lo, t_hi);
+        hist_kernel<2><<<grid, 256, 0, st>>>(env, es, n, sel);
+        select_kernel<<<batch, 256, 0, st>>>(sel, 2, res, t_lo, t_hi);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches += 7;
+        return;
+    }
+    PctGeom g;
+    memset(&g, 0, sizeof(g));
+    g.n = n;
+    g.ns = (n + kPctStride - 1) / kPctStride;
+    g.r[0] = clip(i_lo); g.r[1] = clip(i_lo + 1); g.r[2] = clip(i_hi); g.r[3] = clip(i_hi + 1);
+    g.t_lo = t_lo;
+    g.t_hi = t_hi;
+    // bracket half-width in sample ranks: 12 sigma of a binomial tail count, at least 64
+    const double q = 0.005;
+    const long long delta = std::max<long long>(64, (long long)std::ceil(12.0 * std::sqrt((double)g.ns * q)));
+    const long long a_lo = (long long)(g.r[0] / kPctStride) - delta, b_lo = (long long)(g.r[1] / kPctStride) + 1 + delta;
+    const long long a_hi = (long long)(g.r[2] / kPctStride) - delta, b_hi = (long long)(g.r[3] / kPctStride) + 1 + delta;
+    g.open_lo = a_lo <= 0;
+    g.open_hi = b_hi >= g.ns - 1;
+    auto sclip = [&](long long r) { return (uint32_t)std::min<long long>(std::max<long long>(r, 0), g.ns - 1); };
+    g.s_rank[0] = sclip(a_lo); g.s_rank[1] = sclip(b_lo); g.s_rank[2] = sclip(a_hi); g.s_rank[3] = sclip(b_hi);
+    g.cap = (uint32_t)std::min<long long>(n, 4 * (2 * delta + 2) * kPctStride + 4096);
+    const size_t ss = (size_t)((g.ns + 63) & ~63ll), ls = 2 * (size_t)g.cap;
+    char *base = (char *)ctx->pct_buf.reserve((ss + ls) * sizeof(float) * batch +
+                                              (sizeof(PctState) + sizeof(PctCoop)) * batch + 512);
+    float *samp = (float *)base;
+    float *lists = samp + ss * batch;
+    PctState *pst = (PctState *)(((uintptr_t)(lists + ls * batch) + 15) & ~(uintptr_t)15);
+    PctCoop *coop = (PctCoop *)(((uintptr_t)(pst + batch) + 255) & ~(uintptr_t)255);
+    CUDA_CHECK(cudaMemsetAsync(coop, 0, sizeof(PctCoop) * batch, st));
+    // CTAs of one recording spin at a barrier, so all of them must be resident at once:
+    // 1024-thread CTAs, two per SM
+    const int ncta = std::max(1, std::min(32, ctx->sm_count / batch));
+
+    dim3 g1((unsigned)((g.ns + 255) / 256), batch);
+    {
+        StageTimer t1(ctx, "pct_sample");
+        pct_sample_kernel<<<g1, 256, 0, st>>>(env, es, g, samp, ss);
+    }
+    {
+        StageTimer t1(ctx, "pct_bracket");
+        // cooperative launch: the runtime only starts the grid when all its CTAs fit at once
+        int ncta_arg = ncta;
+        size_t ss_arg = ss;
+        void *args[] = {(void *)&samp, (void *)&ss_arg, (void *)&g, (void *)&pst, (void *)&coop, (void *)&ncta_arg};
+        if (ncta > 1)
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pct_bracket_kernel, dim3(batch * ncta),
+                                                   dim3(kSelThreads), args, 0, st));
+        else   // one CTA per recording: no cross-CTA barrier, any grid size
+            pct_bracket_kernel<<<batch, kSelThreads, 0, st>>>(samp, ss, g, pst, coop, 1);
+    }
+    int blocks = (int)std::min<long long>((n + 1023) / 1024, (long long)ctx->sm_count * 8);
     blocks = std::max(1, blocks / std::max(1, std::min(batch, 8)));
-    dim3 grid(blocks, batch);
-    hist_kernel<0><<<grid, 256, 0, ctx->stream>>>(env, es, n, sel);
-    select_kernel<<<batch, 256, 0, ctx->stream>>>(sel, 0, res, t_lo, t_hi);
-    hist_kernel<1><<<grid, 256, 0, ctx->stream>>>(env, es, n, sel);
-    select_kernel<<<batch, 256, 0, ctx->stream>>>(sel, 1, res, t_lo, t_hi);
-    hist_kernel<2><<<grid, 256, 0, ctx->stream>>>(env, es, n, sel);
-    select_kernel<<<batch, 256, 0, ctx->stream>>>(sel, 2, res, t_lo, t_hi);
+    {
+        StageTimer t1(ctx, "pct_collect");
+        pct_collect_kernel<<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
+    }
+    {
+        StageTimer t1(ctx, "pct_final");
+        int ncta_arg = ncta;
+        size_t ls_arg = ls;
+        void *args[] = {(void *)&g, (void *)&pst, (void *)&lists, (void *)&ls_arg, (void *)&res, (void *)&coop,
+                        (void *)&ncta_arg};
+        if (ncta > 1)
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pct_final_kernel, dim3(batch * ncta), dim3(kSelThreads),
+                                                   args, 0, st));
+        else
+            pct_final_kernel<<<batch, kSelThreads, 0, st>>>(g, pst, lists, ls, res, coop, 1);
+        pct_fallback_kernel<<<batch, kSelThreads, 0, st>>>(env, es, g, pst, res, coop);
+    }
     CUDA_CHECK(cudaGetLastError());
-    ctx->launches += 6;
+    ctx->launches += 5;
 }
 
 // ===========================================================================
