@@ -22,6 +22,8 @@
 // (stride-1) pass.
 #pragma once
 
+#include <type_traits>
+
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "common.cuh"
@@ -83,13 +85,17 @@ struct LoadReal {
     }
 };
 
+struct NoSide {};   // store functors without a side input
+
 struct StoreComplex {
     float2 *dst;
     size_t bstride;
     float scale;
     int conj;
+    using Side = NoSide;
+    __device__ __forceinline__ Side side_load(size_t, int) const { return Side{}; }
     __device__ __forceinline__ int column_aux(int) const { return 0; }
-    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int, Side = Side{}) const {
         v.x *= scale;
         v.y *= conj ? -scale : scale;
         dst[(size_t)b * bstride + i] = v;
@@ -129,8 +135,10 @@ struct StoreHilbert {
     uint32_t n;
     int ncols;
     float inv_n;
+    using Side = NoSide;
+    __device__ __forceinline__ Side side_load(size_t, int) const { return Side{}; }
     __device__ __forceinline__ int column_aux(int col) const { return od.rev(col); }
-    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int k, int aux) const {
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int k, int aux, Side = Side{}) const {
         uint32_t kf = (uint32_t)aux + (uint32_t)ncols * (uint32_t)k;
         uint64_t k2 = 2ull * kf;
         float h = kf == 0 ? 1.f : (k2 < n ? 2.f : (k2 == n ? 1.f : 0.f));
@@ -145,8 +153,10 @@ struct StoreAbs {
     size_t bstride;
     size_t n_valid;
     float scale;
+    using Side = NoSide;
+    __device__ __forceinline__ Side side_load(size_t, int) const { return Side{}; }
     __device__ __forceinline__ int column_aux(int) const { return 0; }
-    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int, Side = Side{}) const {
         if (i < n_valid) dst[(size_t)b * bstride + i] = scale * sqrtf(fmaf(v.x, v.x, v.y * v.y));
     }
 };
@@ -157,9 +167,10 @@ struct StoreEnvPairs {
     float2 *env;            // envelope viewed as pairs
     const float2 *x;        // the real input viewed as pairs
     size_t ebstride, xbstride;
+    using Side = float2;    // the x pair, fetched a few iterations ahead of its use
+    __device__ __forceinline__ Side side_load(size_t i, int b) const { return __ldg(x + (size_t)b * xbstride + i); }
     __device__ __forceinline__ int column_aux(int) const { return 0; }
-    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
-        const float2 xs = __ldg(x + (size_t)b * xbstride + i);
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int, Side xs) const {
         env[(size_t)b * ebstride + i] =
             make_float2(sqrtf(fmaf(xs.x, xs.x, v.x * v.x)), sqrtf(fmaf(xs.y, xs.y, v.y * v.y)));
     }
@@ -170,8 +181,10 @@ struct StoreRealPart {
     size_t bstride;
     size_t n_valid;
     float scale;
+    using Side = NoSide;
+    __device__ __forceinline__ Side side_load(size_t, int) const { return Side{}; }
     __device__ __forceinline__ int column_aux(int) const { return 0; }
-    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int, Side = Side{}) const {
         if (i < n_valid) dst[(size_t)b * bstride + i] = scale * v.x;
     }
 };
@@ -504,24 +517,52 @@ fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid
         __syncthreads();
     }
 
+    // Functors with a side input (e.g. the x pair of the envelope store) get their side
+    // loads of SU elements requested before any is used; the others keep the plain loop.
+    constexpr bool kHasSide = !std::is_empty<typename StoreOp::Side>::value;
+    constexpr int SU = kHasSide ? 8 : 1;
     if (p.contiguous) {
         const size_t gbase = (size_t)c0 * p.R;
         const int nvalid = rows_valid * p.R;
-#pragma unroll 4
-        for (int e = tid; e < nvalid; e += nt) {
-            const int cc = p.divR.div(e);
-            const int k = e - cc * p.R;
-            float2 v = tile[cc * p.R + perm[k]];
-            if (p.tw_mode == 2) v = cmul(v, pass_twiddle(p, (uint32_t)aux2[cc] * (uint32_t)k));
-            st(gbase + e, batch, v, k, aux[cc]);
+#pragma unroll(kHasSide ? 1 : 4)
+        for (int e0 = tid; e0 < nvalid; e0 += SU * nt) {
+            typename StoreOp::Side side[SU];
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int e = e0 + u * nt;
+                if (e < nvalid) side[u] = st.side_load(gbase + e, batch);
+            }
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int e = e0 + u * nt;
+                if (e < nvalid) {
+                    const int cc = p.divR.div(e);
+                    const int k = e - cc * p.R;
+                    float2 v = tile[cc * p.R + perm[k]];
+                    if (p.tw_mode == 2) v = cmul(v, pass_twiddle(p, (uint32_t)aux2[cc] * (uint32_t)k));
+                    st(gbase + e, batch, v, k, aux[cc], side[u]);
+                }
+            }
         }
     } else if (valid_s) {
         const int a = aux[cc_s];
-#pragma unroll 8
-        for (int k = tid >> p.log2C; k < p.R; k += jstep) {
-            float2 v = tile[(int)perm[k] * p.C + cc_s];
-            if (p.tw_mode != 0) v = cmul(v, pass_twiddle(p, tw_e0 + (uint32_t)k * tw_de));
-            st(cbase + (size_t)k * p.S, batch, v, k, a);
+#pragma unroll(kHasSide ? 1 : 4)
+        for (int k0 = tid >> p.log2C; k0 < p.R; k0 += SU * jstep) {
+            typename StoreOp::Side side[SU];
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int k = k0 + u * jstep;
+                if (k < p.R) side[u] = st.side_load(cbase + (size_t)k * p.S, batch);
+            }
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int k = k0 + u * jstep;
+                if (k < p.R) {
+                    float2 v = tile[(int)perm[k] * p.C + cc_s];
+                    if (p.tw_mode != 0) v = cmul(v, pass_twiddle(p, tw_e0 + (uint32_t)k * tw_de));
+                    st(cbase + (size_t)k * p.S, batch, v, k, a, side[u]);
+                }
+            }
         }
     }
 }

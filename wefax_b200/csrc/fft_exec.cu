@@ -52,8 +52,10 @@ struct StoreGeneric {
     uint32_t n;             // transform length of the Hilbert mask
     float scale;
     int conj;
+    using Side = NoSide;
+    __device__ __forceinline__ Side side_load(size_t, int) const { return Side{}; }
     __device__ __forceinline__ int column_aux(int) const { return 0; }
-    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int) const {
+    __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int, Side = Side{}) const {
         switch (mode) {
             case 0:
                 v.x *= scale;
