@@ -231,6 +231,30 @@ __device__ __forceinline__ void load_med4(const float *e, long long i0, long lon
     for (int j = 0; j < 4; ++j) out[j] = med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]);
 }
 
+// medians of elements i0..i0+7 (i0 a multiple of 8); interior 16-byte aligned runs
+// come in as four 128-bit loads
+__device__ __forceinline__ void load_med8(const float *e, long long i0, long long n, float out[8]) {
+    float w[12];   // elements i0-2 .. i0+9
+    if (i0 >= 4 && i0 + 12 <= n && (reinterpret_cast<uintptr_t>(e + i0) & 15) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(e + i0 - 4));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(e + i0));
+        const float4 c = __ldg(reinterpret_cast<const float4 *>(e + i0 + 4));
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(e + i0 + 8));
+        w[0] = a.z; w[1] = a.w;
+        w[2] = b.x; w[3] = b.y; w[4] = b.z; w[5] = b.w;
+        w[6] = c.x; w[7] = c.y; w[8] = c.z; w[9] = c.w;
+        w[10] = d.x; w[11] = d.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const long long i = i0 - 2 + j;
+            w[j] = (i >= 0 && i < n) ? __ldg(e + i) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]);
+}
+
 __global__ void median5_kernel(const float *env, size_t es, float *out, size_t os, long long n) {
     const float *e = env + (size_t)blockIdx.y * es;
     float *o = out + (size_t)blockIdx.y * os;
@@ -583,12 +607,12 @@ pct_collect_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, flo
         }
     };
     uint32_t below0 = 0, below1 = 0;
-    const long long stride = 4ll * blockDim.x * gridDim.x;
-    for (long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i0 < g.n; i0 += stride) {
-        float m[4];
-        load_med4(e, i0, g.n, m);
+    const long long stride = 8ll * blockDim.x * gridDim.x;
+    for (long long i0 = 8 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i0 < g.n; i0 += stride) {
+        float m[8];
+        load_med8(e, i0, g.n, m);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             if (i0 + j >= g.n) break;
             const uint32_t key = __float_as_uint(m[j]);
             below0 += key < k0;
@@ -768,7 +792,7 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
         else   // one CTA per recording: no cross-CTA barrier, any grid size
             pct_bracket_kernel<<<batch, kSelThreads, 0, st>>>(samp, ss, g, pst, coop, 1);
     }
-    int blocks = (int)std::min<long long>((n + 1023) / 1024, (long long)ctx->sm_count * 8);
+    int blocks = (int)std::min<long long>((n + 2047) / 2048, (long long)ctx->sm_count * 8);
     blocks = std::max(1, blocks / std::max(1, std::min(batch, 8)));
     {
         StageTimer t1(ctx, "pct_collect");
@@ -801,32 +825,43 @@ quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long 
     uint8_t *d = dig + (size_t)blockIdx.y * ds;
     const double low = res->low;
     const double delta = __dsub_rn(res->high, low);
-    long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    long long i0 = 8 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
     if (i0 >= n) return;
-    float m[4];
-    load_med4(e, i0, n, m);
-    uint8_t q[4];
+    float m[8];
+    load_med8(e, i0, n, m);
+    // numpy: round(255 * (env - low) / delta) in float64 (rint = half to even = numpy.round).
+    // The float64 divide is only needed when the value is close to a rounding boundary: an
+    // fp32 estimate (error << 1e-3 grey levels) decides every other element.
+    const float low_f = (float)low, scale_f = (float)(255.0 / delta);
+    // estimate error ~ |low|*scale*2^-24 + |est|*3*2^-24: must stay far below the 2e-3 guard band
+    const bool fast_ok = delta > 0.0 && isfinite(scale_f) && fabs(low) * (255.0 / delta) * 1.2e-7 < 5e-4;
+    uint32_t packed[2] = {0u, 0u};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        // numpy: round(255 * (env - low) / delta), evaluated in that order in float64;
-        // rint = round half to even = numpy.round
-        double v = rint(__ddiv_rn(__dmul_rn(255.0, __dsub_rn((double)m[j], low)), delta));
-        v = fmin(fmax(v, 0.0), 255.0);
-        q[j] = (uint8_t)(int)v;
+    for (int j = 0; j < 8; ++j) {
+        const float est = (m[j] - low_f) * scale_f;
+        const float fr = est - floorf(est);
+        float v;
+        if (fast_ok && fabsf(fr - 0.5f) > 2e-3f && fabsf(est) < 1e6f) {
+            v = rintf(est);
+        } else {
+            v = (float)rint(__ddiv_rn(__dmul_rn(255.0, __dsub_rn((double)m[j], low)), delta));
+        }
+        v = fminf(fmaxf(v, 0.f), 255.f);
+        packed[j >> 2] |= (uint32_t)(int)v << (8 * (j & 3));
     }
-    if (i0 + 3 < n && ((reinterpret_cast<uintptr_t>(d + i0) & 3) == 0)) {
-        *reinterpret_cast<uchar4 *>(d + i0) = make_uchar4(q[0], q[1], q[2], q[3]);
+    if (i0 + 7 < n && ((reinterpret_cast<uintptr_t>(d + i0) & 7) == 0)) {
+        *reinterpret_cast<uint2 *>(d + i0) = make_uint2(packed[0], packed[1]);
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (i0 + j < n) d[i0 + j] = q[j];
+        for (int j = 0; j < 8; ++j)
+            if (i0 + j < n) d[i0 + j] = (uint8_t)(packed[j >> 2] >> (8 * (j & 3)));
     }
 }
 
 void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
                      const RecResult *res) {
     StageTimer timer(ctx, "quantise");
-    dim3 grid((unsigned)((n + 1023) / 1024), batch);
+    dim3 grid((unsigned)((n + 2047) / 2048), batch);
     quantise_kernel<<<grid, 256, 0, ctx->stream>>>(env, es, dig, ds, n, res);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
