@@ -47,10 +47,16 @@ def parse_args():
     ap.add_argument("--duration", type=float, default=3600.0, help="seconds of audio per recording")
     ap.add_argument("--lpm", type=int, default=120)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=1,
+                    help="recordings per GPU per step; > 1 selects the batch workload (BASELINE.json configs[3] shape: "
+                         "--duration 600 --batch 64, LPM cycling 60/90/120/240)")
     return ap.parse_args()
 
 
 def workload_name(args) -> str:
+    if args.batch > 1:
+        return (f"batch of {args.batch} synthetic {args.duration / 60:g}-min mono 11025 Hz recordings per GPU, mixed LPM "
+                f"60/90/120/240 (BASELINE.json configs[3] shape)")
     return (f"synthetic {args.duration / 60:g}-min mono 11025 Hz WEFAX recording, IOC576/{args.lpm} LPM, "
             f"one per GPU (BASELINE.json configs[1])")
 
@@ -199,30 +205,41 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    pcm = synth.synth_recording(args.duration, lpm=args.lpm, seed=rank)
-    n = int(pcm.shape[0])
+    if args.batch > 1:
+        # a pool of distinct recordings (one per LPM), replicated to the batch size: every copy is
+        # decoded in full, nothing is cached between copies
+        pool = {l: synth.synth_recording(args.duration, lpm=l, seed=1000 * rank + l, noise_sigma=0.02)
+                for l in synth.BATCH_LPMS}
+        lpms = [synth.BATCH_LPMS[k % 4] for k in range(args.batch)]
+        pcm = np.stack([pool[l] for l in lpms])
+        lpm_arg = lpms
+    else:
+        pcm = synth.synth_recording(args.duration, lpm=args.lpm, seed=rank)
+        lpm_arg = args.lpm
+    n = int(pcm.shape[-1]) * (args.batch if args.batch > 1 else 1)   # samples per GPU per step
+    n_rec = int(pcm.shape[-1])
     stream = torch.cuda.Stream(device=local_rank)
     dec = Decoder(local_rank, stream=stream.cuda_stream)
     pcm_dev = torch.from_numpy(pcm).cuda()
-    pcm_pin = torch.empty(n, dtype=torch.int16, pin_memory=True)
-    pcm_pin.numpy()[:] = pcm
+    pcm_pin = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
+    pcm_pin.numpy()[...] = pcm
     want = ("digitalized", "raster")
     sampler = ClockSampler(local_rank)
     sampler.start()
 
     # ---- value: everything resident in HBM -------------------------------------------
-    res = dec.decode(pcm_dev, 11025, args.lpm, want=want, device_outputs=True)
+    res = dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True)
     if res.error(0) is not None:
         raise RuntimeError(f"decode failed: {res.error(0)!r}")
     for _ in range(args.warmup):
-        dec.decode(pcm_dev, 11025, args.lpm, want=want, device_outputs=True, out=res)
+        dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True, out=res)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = dec.launch_count
     sampler.region(True)
     ev0.record(stream)
     for _ in range(args.steps):
-        dec.decode(pcm_dev, 11025, args.lpm, want=want, device_outputs=True, out=res)
+        dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True, out=res)
     ev1.record(stream)
     barrier()
     sampler.region(False)
@@ -236,27 +253,27 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     dec.timings(reset=True)
     sampler.region(True)
     for _ in range(args.steps):
-        dec.decode(pcm_dev, 11025, args.lpm, want=want, device_outputs=True, out=res)
+        dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True, out=res)
     sampler.region(False)
     stage_ms = dec.timings(reset=True)
     dec.enable_timing(False)
 
     # ---- e2e: host buffers through the C-ABI -------------------------------------------
-    host = dec.decode(pcm_pin.numpy(), 11025, args.lpm, want=want, pinned=True)
+    host = dec.decode(pcm_pin.numpy(), 11025, lpm_arg, want=want, pinned=True)
     for _ in range(max(1, args.warmup // 2)):
-        dec.decode(pcm_pin.numpy(), 11025, args.lpm, want=want, pinned=True, out=host)
+        dec.decode(pcm_pin.numpy(), 11025, lpm_arg, want=want, pinned=True, out=host)
     barrier()
     sampler.region(True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dec.decode(pcm_pin.numpy(), 11025, args.lpm, want=want, pinned=True, out=host)
+        dec.decode(pcm_pin.numpy(), 11025, lpm_arg, want=want, pinned=True, out=host)
     dec.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.region(False)
     barrier()
     e2e_value = world * n * args.steps / e2e_s / 1e6
     h2d = n * 2
-    d2h = n + int(host.height[0]) * int(host.width[0])
+    d2h = n + int(sum(int(h) * int(w) for h, w in zip(host.height, host.width)))
     clocks = sampler.stop()
 
     if rank != 0:
@@ -265,11 +282,11 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         return
 
     peak, peak_src = hbm_peak()
-    half = n % 2 == 0 and not os.environ.get("WEFAX_NO_REAL_FFT")
-    lens, blu = N.fft_plan_describe(n // 2 if half else n)
+    half = n_rec % 2 == 0 and not os.environ.get("WEFAX_NO_REAL_FFT")
+    lens, blu = N.fft_plan_describe(n_rec // 2 if half else n_rec)
     if half and blu:                 # n/2 not smooth: the library falls back to the full-length transform
         half = False
-        lens, blu = N.fft_plan_describe(n)
+        lens, blu = N.fft_plan_describe(n_rec)
     kernels = {}
     for name, (ms, cnt) in stage_ms.items():
         avg = ms / max(cnt, 1)
@@ -305,8 +322,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "samples_per_recording": n, "recordings_per_step": world,
-                   "fft_passes": lens, "fft_length": n // 2 if half else n,
+        "config": {"workload": workload_name(args), "samples_per_recording": n_rec, "recordings_per_step": world * max(1, args.batch),
+                   "fft_passes": lens, "fft_length": n_rec // 2 if half else n_rec,
                    "real_input_transform": bool(half), "bluestein": bool(blu), "outputs": list(want),
                    "l2": "no explicit flush: one step streams ~1.3 GB (>> 126 MB L2) through HBM",
                    "parallelism": f"{world} independent recordings, no collective"},
@@ -323,7 +340,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                                     "frac": round(path_gbs / peak, 4)}},
         "stages": kernels, "percentile_parts": sub,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.batch == 1:
         from oracle import wefax_oracle as O
         t0 = time.perf_counter()
         o = O.decode(pcm, 11025, args.lpm)

@@ -68,7 +68,7 @@ def test_fft_plan_is_a_factorisation(n):
         assert blu >= 2 * n - 1
     for r in lens[:-1]:
         assert r <= 1024           # strided passes keep >= 8 columns per 8192-element tile
-    assert lens[-1] <= 8192
+    assert lens[-1] <= 12000         # tile + tables of the stride-1 pass fit 227 KiB of shared memory
     for r in lens:
         m = r
         for p in (2, 3, 5, 7, 11, 13):

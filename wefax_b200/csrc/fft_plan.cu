@@ -75,25 +75,34 @@ const StagePlan &stage_plan(int R) {
     return memo[R] = best;
 }
 
-int tile_cols(int R, int ncols) {
+// Columns per tile of a pass of length R.  Strided passes want >= 32 adjacent columns
+// (256-byte row segments); the budget is 8192 complex (64 KiB, 2-3 CTAs per SM) and is
+// raised to 16384 (one CTA per SM) only when that is what it takes to get there.
+int tile_cols(int R, int ncols, bool strided) {
+    const int tmax = tile_max();
     int C = 1;
-    while (C * 2 * R <= tile_max() && C * 2 <= 64) C *= 2;
+    while (C * 2 * R <= tmax && C * 2 <= 64) C *= 2;
+    if (strided && C < 32 && !getenv("WEFAX_FFT_TILE"))
+        while (C * 2 * R <= 2 * tmax && C < 32) C *= 2;
     while (C > 1 && C / 2 >= ncols) C /= 2;
     return C;
 }
 
 // per-element cost of one pass of length R: its stages, each divided by the fraction
-// of the 256 threads that have a butterfly in the last round, plus the global traffic
-double pass_cost(int R, long long n) {
+// of the 256 threads that have a butterfly in the last round, plus the global traffic,
+// scaled by how badly short row segments and single-CTA occupancy hurt (measured on B200)
+double pass_cost(int R, long long n, bool strided) {
     const StagePlan &sp = stage_plan(R);
     if (sp.cost < 0) return -1.0;
-    const int C = tile_cols(R, (int)std::min<long long>(n / R, 1 << 30));
+    const int C = tile_cols(R, (int)std::min<long long>(n / R, 1 << 30), strided);
     double c = kPassCost;
     for (int r : sp.radices) {
         const int total = C * (R / r);
         const int rounds = (total + kFftThreads - 1) / kFftThreads;
         c += stage_cost(r) * (double)(rounds * kFftThreads) / (double)total;
     }
+    if (strided && C < 32) c *= 1.0 + 0.5 * (32.0 / C - 1.0);     // 64-byte segments cost ~2.5x
+    if ((long long)C * R > tile_max()) c *= 1.25;                  // one CTA per SM
     return c;
 }
 
@@ -106,9 +115,11 @@ struct Search {
     void go(long long rem, int left, long long lo) {
         if (left == 0) {
             if (rem > cap_l || rem < 2 || (!cur.empty() && rem < min_r)) return;
-            double cost = pass_cost((int)rem, n);
+            // an even last pass keeps every stride even: TMA tensor loads need 16-byte row pitches
+            if (!cur.empty() && n % 2 == 0 && rem % 2 != 0) return;
+            double cost = pass_cost((int)rem, n, false);
             if (cost < 0) return;
-            for (int r : cur) cost += pass_cost(r, n);
+            for (int r : cur) cost += pass_cost(r, n, true);
             if (cost < best_cost - 1e-9) {
                 best_cost = cost;
                 best = cur;
@@ -149,7 +160,8 @@ bool plan_factors(long long n, std::vector<int> &Rs) {
     }
     if (!smooth13(n)) return false;
     const int tmax = tile_max();
-    const long long cap_l = tmax;
+    // the stride-1 pass keeps tile + w_R table + permutation (18 bytes per point) within 227 KiB
+    const long long cap_l = getenv("WEFAX_FFT_TILE") ? tmax : 12000;
     const long long cap_s = std::max(2, tmax / min_cols());
     int forced = env_int("WEFAX_FFT_PASSES", 0);
     double best_cost = 1e300;
@@ -230,7 +242,7 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
         d.S = (int)plan->S[i];
         d.ncols = (int)(n / R);
         d.contiguous = (i == P - 1);
-        const int C = tile_cols(R, d.ncols);
+        const int C = tile_cols(R, d.ncols, !d.contiguous);
         d.C = C;
         d.log2C = 0;
         while ((1 << d.log2C) < C) ++d.log2C;
