@@ -227,59 +227,72 @@ struct PairGeom {
     int R_last, ncols;
 };
 
+constexpr int kPairRows = 8;   // engine-order rows per CTA
+
 __global__ void __launch_bounds__(256)
 hilbert_pairs_kernel(float2 *z_all, size_t zs, uint32_t M, PairGeom g, const float2 *tw_lo, const float2 *tw_hi,
                      float inv_m) {
+    __shared__ int s_kb[kPairRows], s_o2[kPairRows];
     float2 *z = z_all + (size_t)blockIdx.y * zs;
-    const int o = blockIdx.x;
-    // digits of this row (most significant first in o), its base frequency and the mirrored row
-    int kb = 0, o2 = 0;
-    {
-        int d[kMaxPasses], rem = o;
+    const int o0 = blockIdx.x * kPairRows;
+    if (threadIdx.x < kPairRows) {
+        // digits of this row (most significant first in o), its base frequency and the mirrored row
+        const int o = o0 + threadIdx.x;
+        int kb = 0, o2 = -1;
+        if (o < g.ncols) {
+            int d[kMaxPasses], rem = o;
 #pragma unroll
-        for (int i = kMaxPasses - 1; i >= 0; --i)
-            if (i < g.nouter) {
-                d[i] = rem % g.Rout[i];
-                rem /= g.Rout[i];
-            }
-        int mult = 1;
+            for (int i = kMaxPasses - 1; i >= 0; --i)
+                if (i < g.nouter) {
+                    d[i] = rem % g.Rout[i];
+                    rem /= g.Rout[i];
+                }
+            int mult = 1;
 #pragma unroll
-        for (int i = 0; i < kMaxPasses; ++i)
-            if (i < g.nouter) {
-                kb += d[i] * mult;
-                mult *= g.Rout[i];
-            }
-        int kb2 = kb ? g.ncols - kb : 0, rem2 = kb2;
+            for (int i = 0; i < kMaxPasses; ++i)
+                if (i < g.nouter) {
+                    kb += d[i] * mult;
+                    mult *= g.Rout[i];
+                }
+            int rem2 = kb ? g.ncols - kb : 0;
+            o2 = 0;
 #pragma unroll
-        for (int i = 0; i < kMaxPasses; ++i)
-            if (i < g.nouter) {
-                o2 = o2 * g.Rout[i] + rem2 % g.Rout[i];
-                rem2 /= g.Rout[i];
-            }
-    }
-    if (o2 < o) return;                                   // the mirrored row's CTA owns these pairs
-    float2 *row = z + (size_t)o * g.R_last;
-    float2 *row2 = z + (size_t)o2 * g.R_last;
-    for (int j = threadIdx.x; j < g.R_last; j += blockDim.x) {
-        const int j2 = kb ? g.R_last - 1 - j : (j ? g.R_last - j : 0);
-        if (o2 == o && j2 < j) continue;                  // self-mirrored row: each pair once
-        const uint32_t k = (uint32_t)kb + (uint32_t)g.ncols * (uint32_t)j;
-        if (k == 0) {
-            row[0] = make_float2(0.f, 0.f);
-            continue;
+            for (int i = 0; i < kMaxPasses; ++i)
+                if (i < g.nouter) {
+                    o2 = o2 * g.Rout[i] + rem2 % g.Rout[i];
+                    rem2 /= g.Rout[i];
+                }
         }
-        const float2 zk = row[j], zm = row2[j2];
-        const float2 lo = __ldg(tw_lo + (k & ((1u << kTwLoBits) - 1))), hi = __ldg(tw_hi + (k >> kTwLoBits));
-        const float2 w = cmul(lo, hi);                    // w_n^k
-        const float2 s = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));   // (zk + conj zm)/2
-        const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));   // (zk - conj zm)/2
-        const float2 a = cmul(make_float2(w.x, -w.y), s), b = cmul(w, d);           // Z'[k] = conj(w) s - w d
-        row[j] = make_float2((a.x - b.x) * inv_m, -(a.y - b.y) * inv_m);
-        if (!(o2 == o && j2 == j)) {
-            // Z'[M-k] = -w conj(s) - conj(w) conj(d)
-            const float2 a2 = cmul(w, make_float2(s.x, -s.y)),
-                         b2 = cmul(make_float2(w.x, -w.y), make_float2(d.x, -d.y));
-            row2[j2] = make_float2(-(a2.x + b2.x) * inv_m, (a2.y + b2.y) * inv_m);
+        s_kb[threadIdx.x] = kb;
+        s_o2[threadIdx.x] = o2;
+    }
+    __syncthreads();
+    for (int r = 0; r < kPairRows; ++r) {
+        const int o = o0 + r, o2 = s_o2[r], kb = s_kb[r];
+        if (o >= g.ncols || o2 < o) continue;             // the mirrored row's CTA owns these pairs
+        float2 *row = z + (size_t)o * g.R_last;
+        float2 *row2 = z + (size_t)o2 * g.R_last;
+        for (int j = threadIdx.x; j < g.R_last; j += blockDim.x) {
+            const int j2 = kb ? g.R_last - 1 - j : (j ? g.R_last - j : 0);
+            if (o2 == o && j2 < j) continue;              // self-mirrored row: each pair once
+            const uint32_t k = (uint32_t)kb + (uint32_t)g.ncols * (uint32_t)j;
+            if (k == 0) {
+                row[0] = make_float2(0.f, 0.f);
+                continue;
+            }
+            const float2 zk = row[j], zm = row2[j2];
+            const float2 lo = __ldg(tw_lo + (k & ((1u << kTwLoBits) - 1))), hi = __ldg(tw_hi + (k >> kTwLoBits));
+            const float2 w = cmul(lo, hi);                // w_n^k
+            const float2 s = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));   // (zk + conj zm)/2
+            const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));   // (zk - conj zm)/2
+            const float2 a = cmul(make_float2(w.x, -w.y), s), b = cmul(w, d);           // Z'[k] = conj(w) s - w d
+            row[j] = make_float2((a.x - b.x) * inv_m, -(a.y - b.y) * inv_m);
+            if (!(o2 == o && j2 == j)) {
+                // Z'[M-k] = -w conj(s) - conj(w) conj(d)
+                const float2 a2 = cmul(w, make_float2(s.x, -s.y)),
+                             b2 = cmul(make_float2(w.x, -w.y), make_float2(d.x, -d.y));
+                row2[j2] = make_float2(-(a2.x + b2.x) * inv_m, (a2.y + b2.y) * inv_m);
+            }
         }
     }
 }
@@ -296,7 +309,7 @@ void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t
         for (int i = 0; i < g.nouter; ++i) g.Rout[i] = half->Rs[i];
         g.R_last = half->Rs[half->npass - 1];
         g.ncols = (int)(M / g.R_last);
-        dim3 grid((unsigned)g.ncols, batch);
+        dim3 grid((unsigned)((g.ncols + kPairRows - 1) / kPairRows), batch);
         hilbert_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(z, zs, (uint32_t)M, g, half->tw2_lo, half->tw2_hi,
                                                            (float)(1.0 / (double)M));
         CUDA_CHECK(cudaGetLastError());

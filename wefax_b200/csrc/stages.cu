@@ -1224,7 +1224,7 @@ sync_settled_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr
 }
 
 // the sequential part: <= 100 jumps over the settled-bit mask held in shared memory
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, const uint32_t *bits_all, size_t bs,
                   const int *first_pos, RecResult *res_all, int *need_scan) {
     extern __shared__ uint32_t s_bits[];
@@ -1238,7 +1238,14 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
     }
     const int nwords = (int)((sd.lim + 31) >> 5);
     const uint32_t *bits = bits_all + (size_t)blockIdx.x * bs;
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_bits[i] = bits[i];
+    {
+        // 128-bit loads, several in flight per thread (bs is a multiple of 4 words)
+        const int nvec = (nwords + 3) >> 2;
+        const uint4 *src = reinterpret_cast<const uint4 *>(bits);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_bits);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
     __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
@@ -1324,7 +1331,7 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
                                                                                    sp.cs);
         dim3 g3((unsigned)std::max<long long>(1, (sp.max_lim + 255) / 256), batch);
         sync_settled_kernel<<<g3, 256, 0, st>>>(lines, sp.sd, sp.corr, sp.pre, sp.suf, sp.cs, sp.bits, sp.bs);
-        sync_chain_kernel<<<batch, 256, (size_t)((sp.max_lim + 31) / 32) * sizeof(uint32_t), st>>>(
+        sync_chain_kernel<<<batch, 1024, (size_t)((sp.max_lim + 31) / 32 + 4) * sizeof(uint32_t), st>>>(
             n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan);
         ctx->launches += 4;
     } else {
@@ -1491,7 +1498,7 @@ SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long
         sd[r] = d;
     }
     sp.cs = (size_t)((sp.max_limc + 63) & ~63ll);
-    sp.bs = (size_t)((sp.max_lim + 31) / 32 + 1);
+    sp.bs = (size_t)(((sp.max_lim + 31) / 32 + 4) & ~3ll);   // whole uint4s, 16-byte aligned rows
     const size_t ints = 3 * sp.cs * count;
     const size_t bytes = ints * sizeof(int) + sp.bs * count * sizeof(uint32_t) + (size_t)count * (sizeof(SyncDev) + 8) + 256;
     char *base = (char *)ctx->sync_buf.reserve(bytes);
