@@ -33,7 +33,8 @@ namespace wefax {
 constexpr int kMaxStages = 14;
 constexpr int kMaxPasses = 4;
 constexpr int kFftThreads = 256;
-constexpr int kTwLoBits = 11;   // two-level inter-pass twiddle table: 2^11 "lo" entries
+constexpr int kTwLoBits = 11;
+constexpr int kTwStep = 16;     // rows between two exact inter-pass twiddle anchors   // two-level inter-pass twiddle table: 2^11 "lo" entries
 
 struct PassDev {
     int R, S, ncols;          // transform length, element stride, number of columns (= n / R)
@@ -410,6 +411,10 @@ fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid
     int *aux = reinterpret_cast<int *>(perm + ((p.R + 1) & ~1));
     int *aux2 = aux + p.C;
     uint64_t *mbar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(aux2 + p.C) + 7) & ~uintptr_t(7));
+    // inter-pass twiddles of this tile, factored as anchor[k / 16] * step[k % 16] per column / row
+    float2 *twA = reinterpret_cast<float2 *>(mbar + 2);
+    const int NA = (p.R + kTwStep - 1) / kTwStep;
+    float2 *twS = twA + p.C * NA;
 
     const int tid = threadIdx.x, nt = blockDim.x;
     const int batch = blockIdx.y;
@@ -466,6 +471,42 @@ fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid
         const bool ok = p.contiguous ? (tid < rows_valid) : (m0 + tid < p.S);
         aux[tid] = ok ? st.column_aux(col) : 0;
         aux2[tid] = (p.contiguous && p.tw_mode == 2) ? (c0 + tid) % p.ko_R : 0;
+    }
+
+    if (p.tw_mode != 0) {
+        // exact two-level lookups once per (column, anchor) and (column, step) while the tile is in flight
+        if (p.contiguous) __syncthreads();   // aux2 (ko per row) is needed below
+        const int total = p.C * (NA + kTwStep);
+        for (int idx = tid; idx < total; idx += nt) {
+            int cc, x;
+            uint32_t e0, de;
+            if (p.contiguous) {               // layout [cc][x]; e = ko * k
+                cc = idx / (NA + kTwStep);
+                x = idx - cc * (NA + kTwStep);
+                e0 = 0;
+                de = (uint32_t)aux2[cc];
+            } else {                          // layout [x][cc]; e = e0 + k * de of column cc
+                x = idx >> p.log2C;
+                cc = idx & (p.C - 1);
+                const uint32_t m = (uint32_t)(m0 + cc);
+                if (p.tw_mode == 1) {
+                    e0 = 0;
+                    de = m;
+                } else {
+                    const uint32_t ko = (uint32_t)o % (uint32_t)p.ko_R;
+                    e0 = ko * m;
+                    de = ko * (uint32_t)p.S;
+                }
+                if (m >= (uint32_t)p.S) e0 = de = 0;   // padding column
+            }
+            const bool anchor = x < NA;
+            const uint32_t e = anchor ? e0 + (uint32_t)(x * kTwStep) * de : (uint32_t)(x - NA) * de;
+            const float2 w = pass_twiddle(p, e);
+            if (p.contiguous)
+                (anchor ? twA[cc * NA + x] : twS[cc * kTwStep + (x - NA)]) = w;
+            else
+                (anchor ? twA[x * p.C + cc] : twS[(x - NA) * p.C + cc]) = w;
+        }
     }
 
     const int tile_elems = p.C * p.R;
@@ -539,7 +580,8 @@ fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid
                     const int cc = p.divR.div(e);
                     const int k = e - cc * p.R;
                     float2 v = tile[cc * p.R + perm[k]];
-                    if (p.tw_mode == 2) v = cmul(v, pass_twiddle(p, (uint32_t)aux2[cc] * (uint32_t)k));
+                    if (p.tw_mode == 2)
+                        v = cmul(v, cmul(twA[cc * NA + (k >> 4)], twS[cc * kTwStep + (k & (kTwStep - 1))]));
                     st(gbase + e, batch, v, k, aux[cc], side[u]);
                 }
             }
@@ -559,7 +601,8 @@ fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid
                 const int k = k0 + u * jstep;
                 if (k < p.R) {
                     float2 v = tile[(int)perm[k] * p.C + cc_s];
-                    if (p.tw_mode != 0) v = cmul(v, pass_twiddle(p, tw_e0 + (uint32_t)k * tw_de));
+                    if (p.tw_mode != 0)
+                        v = cmul(v, cmul(twA[(k >> 4) * p.C + cc_s], twS[(k & (kTwStep - 1)) * p.C + cc_s]));
                     st(cbase + (size_t)k * p.S, batch, v, k, a, side[u]);
                 }
             }

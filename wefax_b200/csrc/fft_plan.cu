@@ -279,7 +279,8 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
         d.twR = (const float2 *)(base + o_twR[i]);
         d.perm = (const uint16_t *)(base + o_perm[i]);
         d.smem_bytes = (int)((size_t)C * R * sizeof(float2) + (size_t)R * sizeof(float2) +
-                             (size_t)((R + 1) & ~1) * sizeof(uint16_t) + (size_t)2 * C * sizeof(int) + 32);
+                             (size_t)((R + 1) & ~1) * sizeof(uint16_t) + (size_t)2 * C * sizeof(int) + 48 +
+                             (size_t)C * ((R + kTwStep - 1) / kTwStep + kTwStep) * sizeof(float2));
 
         // digit-reversal: smem position of output k after the in-place DIF stages
         std::vector<uint16_t> perm(R);
