@@ -78,14 +78,21 @@ struct StageTimer {
     }
 };
 
-template <class LoadOp, class StoreOp>
-void launch_pass(wefax_ctx *ctx, const PassDev &p_in, const LoadOp &ld, const StoreOp &st, int batch) {
-    const void *fn = (const void *)fft_pass_kernel<LoadOp, StoreOp>;
+template <class LoadOp, class StoreOp, int MINB>
+void launch_pass_variant(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const StoreOp &st, int batch,
+                         const CUtensorMap &map, const float2 *base, size_t bstride) {
+    const void *fn = (const void *)fft_pass_kernel<LoadOp, StoreOp, MINB>;
     if (!ctx->smem_configured.count(fn)) {
-        CUDA_CHECK(cudaFuncSetAttribute(fft_pass_kernel<LoadOp, StoreOp>,
+        CUDA_CHECK(cudaFuncSetAttribute(fft_pass_kernel<LoadOp, StoreOp, MINB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->smem_configured[fn] = 1;
     }
+    dim3 grid(p.ntiles, batch);
+    fft_pass_kernel<LoadOp, StoreOp, MINB><<<grid, p.nthreads, p.smem_bytes, ctx->stream>>>(p, ld, st, map, base, bstride);
+}
+
+template <class LoadOp, class StoreOp>
+void launch_pass(wefax_ctx *ctx, const PassDev &p_in, const LoadOp &ld, const StoreOp &st, int batch) {
     PassDev p = p_in;
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof(map));
@@ -94,8 +101,11 @@ void launch_pass(wefax_ctx *ctx, const PassDev &p_in, const LoadOp &ld, const St
     p.load_mode = 0;
     if (ctx->use_tma && ld.tma_source(&base, &bstride)) p.load_mode = choose_load_mode(p, base, bstride, batch, &map);
     StageTimer timer(ctx, p.tag);
-    dim3 grid(p.ntiles, batch);
-    fft_pass_kernel<LoadOp, StoreOp><<<grid, p.nthreads, p.smem_bytes, ctx->stream>>>(p, ld, st, map, base, bstride);
+    // three CTAs of this pass fit one SM (227 KiB shared memory, 1 KiB reserved per CTA)?
+    if ((size_t)p.smem_bytes + 1024 <= (size_t)(227 * 1024) / 3)
+        launch_pass_variant<LoadOp, StoreOp, 3>(ctx, p, ld, st, batch, map, base, bstride);
+    else
+        launch_pass_variant<LoadOp, StoreOp, 2>(ctx, p, ld, st, batch, map, base, bstride);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

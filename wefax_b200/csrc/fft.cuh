@@ -400,8 +400,10 @@ __device__ __forceinline__ void tma_load_bulk(void *dst, const void *src, uint32
 // in through TMA (one tensor box per <=256 rows for strided passes, one bulk copy for
 // the stride-1 pass) or, for fused prologues, through the load functor; it leaves
 // through coalesced stores with the inter-pass twiddle and the store functor applied.
-template <class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(kFftThreads, 2)
+// MINB = CTAs per SM the register allocation aims for: 3 when the tile is small enough for
+// three CTAs to share an SM (a few spills, better latency hiding), else 2.
+template <class LoadOp, class StoreOp, int MINB>
+__global__ void __launch_bounds__(kFftThreads, MINB)
 fft_pass_kernel(const PassDev p, const LoadOp ld, const StoreOp st, const __grid_constant__ CUtensorMap tmap,
                 const float2 *bulk_src, size_t bulk_bstride) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
