@@ -102,7 +102,11 @@ double pass_cost(int R, long long n, bool strided) {
         c += stage_cost(r) * (double)(rounds * kFftThreads) / (double)total;
     }
     if (strided && C < 32) c *= 1.0 + 0.5 * (32.0 / C - 1.0);     // 64-byte segments cost ~2.5x
-    if ((long long)C * R > tile_max()) c *= 1.25;                  // one CTA per SM
+    // CTAs per SM by shared memory (tile + w_R table + permutation): measured per-element
+    // pass times on B200 are ~5 ps with three resident CTAs, ~6 ps with two, ~10 ps with one
+    const double smem = (double)C * R * 8.0 + R * 10.0 + 8192.0;
+    const int ctas = (int)std::min(3.0, std::floor(227.0 * 1024.0 / smem));
+    c *= ctas >= 3 ? 1.0 : (ctas == 2 ? 1.15 : 1.9);
     return c;
 }
 
