@@ -294,6 +294,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         kernels[name] = {"ms": round(avg, 5), "launches_per_step": cnt / args.steps,
                          "algo_bytes": b, "gbs": round(b / (avg * 1e-3) / 1e9, 1) if avg > 0 and b else None}
     sub = {k: kernels.pop(k) for k in list(kernels) if k.startswith("pct_")}   # parts of "percentiles"
+    sub.update({k: kernels.pop(k) for k in list(kernels) if k.startswith("sync_") and k != "sync_search"})
     fft = {k: v for k, v in kernels.items() if k.startswith("fft_")}
     fft_ms = sum(v["ms"] * v["launches_per_step"] for v in fft.values())
     fft_launches = sum(v["launches_per_step"] for v in fft.values())
@@ -338,7 +339,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                      if stage_sum else None,
                      "whole_path": {"algo_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "achieved": round(path_gbs, 1),
                                     "frac": round(path_gbs / peak, 4)}},
-        "stages": kernels, "percentile_parts": sub,
+        "stages": kernels, "stage_parts": sub,
     }
     if world == 1 and not args.no_cpu_baseline and args.batch == 1:
         from oracle import wefax_oracle as O

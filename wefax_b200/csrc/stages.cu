@@ -1143,84 +1143,78 @@ sync_corr_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *
     }
 }
 
-// prefix / suffix maxima inside blocks of `mindistance` positions (van Herk / Gil-Werman)
+// inclusive running maximum of s[0..len) (dir 0: left to right, dir 1: right to left) by one CTA
+__device__ __forceinline__ void block_running_max(const int *src, int *dst, int len, int dir, int *s_w) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (len + kSyncThreads - 1) / kSyncThreads;
+    const int NEG = (int)0x80000000;
+    const int lo = tid * per, hi = min(lo + per, len);
+    int run = NEG;
+    for (int i = lo; i < hi; ++i) run = max(run, src[dir ? len - 1 - i : i]);
+    int incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl = max(incl, o);
+    }
+    __syncthreads();
+    if (lane == 31) s_w[wid] = incl;
+    __syncthreads();
+    int carry = NEG;
+    for (int k = 0; k < wid; ++k) carry = max(carry, s_w[k]);
+    int prev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane > 0) carry = max(carry, prev);
+    run = carry;
+    // src and dst may alias: a thread only rewrites its own chunk, after reading it
+    for (int i = lo; i < hi; ++i) {
+        const int idx = dir ? len - 1 - i : i;
+        run = max(run, src[idx]);
+        dst[idx] = run;
+    }
+    __syncthreads();
+}
+
+// settled bits: corr[i] >= max corr over (i, min(i + w, m - 1)], with the window maximum from
+// van Herk / Gil-Werman prefix and suffix maxima over blocks of w = mindistance positions.
+// CTA j holds block j and block j+1 of the correlation in shared memory: suffix maxima of
+// block j, prefix maxima of block j+1; nothing but the bit mask goes back to global memory.
 __global__ void __launch_bounds__(kSyncThreads)
-sync_window_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr_all, int *pre_all, int *suf_all,
-                   size_t cs) {
-    extern __shared__ int s_c[];
+sync_settled_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr_all, size_t cs, uint32_t *bits_all,
+                    size_t bs) {
+    extern __shared__ int s_dyn[];
     __shared__ int s_w[32];
     const LineDev ln = lines[blockIdx.y];
     const SyncDev sd = sd_all[blockIdx.y];
     const int w = ln.mindistance;
     const long long b0 = (long long)blockIdx.x * w;
-    if (!sd.fast || b0 >= sd.limc) return;
-    const int len = (int)min((long long)w, sd.limc - b0);
-    const int *corr = corr_all + (size_t)blockIdx.y * cs + b0;
-    int *pre = pre_all + (size_t)blockIdx.y * cs + b0;
-    int *suf = suf_all + (size_t)blockIdx.y * cs + b0;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < len; i += kSyncThreads) s_c[i] = corr[i];
-    __syncthreads();
-    const int per = (len + kSyncThreads - 1) / kSyncThreads;
-    const int NEG = (int)0x80000000;
-    for (int dir = 0; dir < 2; ++dir) {
-        // dir 0: prefix maxima left to right; dir 1: suffix maxima (same scan on the mirrored index)
-        const int lo = tid * per, hi = min(lo + per, len);
-        int run = NEG;
-        for (int i = lo; i < hi; ++i) {
-            int v = s_c[dir ? len - 1 - i : i];
-            run = max(run, v);
-        }
-        int incl = run;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl = max(incl, o);
-        }
-        __syncthreads();
-        if (lane == 31) s_w[wid] = incl;
-        __syncthreads();
-        int carry = NEG;
-        for (int k = 0; k < wid; ++k) carry = max(carry, s_w[k]);
-        int prev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-        if (lane > 0) carry = max(carry, prev);
-        run = carry;
-        int *dst = dir ? suf : pre;
-        for (int i = lo; i < hi; ++i) {
-            const int idx = dir ? len - 1 - i : i;
-            run = max(run, s_c[idx]);
-            dst[idx] = run;
-        }
-    }
-}
-
-// settled bits: corr[i] >= max corr over (i, min(i + w, m - 1)]
-__global__ void __launch_bounds__(256)
-sync_settled_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr_all, const int *pre_all,
-                    const int *suf_all, size_t cs, uint32_t *bits_all, size_t bs) {
-    const LineDev ln = lines[blockIdx.y];
-    const SyncDev sd = sd_all[blockIdx.y];
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (!sd.fast || i >= ((sd.lim + 31) & ~31ll)) return;
+    if (!sd.fast || b0 >= sd.lim) return;
+    int *s_c = s_dyn, *s_suf = s_dyn + w, *s_pre = s_dyn + 2 * w;
+    const int len0 = (int)min((long long)w, sd.limc - b0);
+    const int len1 = (int)max(0ll, min((long long)w, sd.limc - (b0 + w)));
     const int *corr = corr_all + (size_t)blockIdx.y * cs;
-    const int *pre = pre_all + (size_t)blockIdx.y * cs;
-    const int *suf = suf_all + (size_t)blockIdx.y * cs;
-    bool settled = false;
-    if (i < sd.lim) {
-        const long long w = ln.mindistance;
-        const long long a = i + 1, e = min(i + w, sd.m - 1);
-        int wmax = (int)0x80000000;
-        if (a <= e) {
-            const long long ba = a / w, be = e / w;
-            if (ba == be)
-                wmax = (a % w == 0) ? pre[e] : suf[a];   // a whole block, or the tail of the last (truncated) block
-            else
-                wmax = max(suf[a], pre[e]);
+    for (int i = threadIdx.x; i < len0; i += kSyncThreads) s_c[i] = corr[b0 + i];
+    for (int i = threadIdx.x; i < len1; i += kSyncThreads) s_pre[i] = corr[b0 + w + i];
+    __syncthreads();
+    block_running_max(s_c, s_suf, len0, 1, s_w);
+    if (len1 > 0) block_running_max(s_pre, s_pre, len1, 0, s_w);
+    uint32_t *bits = bits_all + (size_t)blockIdx.y * bs;
+    const long long p_first = b0 & ~31ll;
+    const long long p_end = min(b0 + len0, sd.lim);
+    for (long long p = p_first + threadIdx.x; p < ((p_end + 31) & ~31ll); p += kSyncThreads) {
+        bool settled = false;
+        if (p >= b0 && p < p_end) {
+            const int i = (int)(p - b0);
+            const long long a = p + 1, e = min(p + w, sd.m - 1);
+            int wmax = (int)0x80000000;
+            if (a <= e) {
+                if (a < b0 + w && i + 1 < len0) wmax = s_suf[i + 1];              // rest of block j
+                if (e >= b0 + w) wmax = max(wmax, s_pre[e - (b0 + w)]);           // head of block j+1
+            }
+            settled = s_c[i] >= wmax;
         }
-        settled = corr[i] >= wmax;
+        const unsigned word = __ballot_sync(0xFFFFFFFFu, settled);
+        if ((threadIdx.x & 31) == 0 && word) atomicOr(&bits[p >> 5], word);       // words straddle CTAs
     }
-    const unsigned word = __ballot_sync(0xFFFFFFFFu, settled);
-    if ((threadIdx.x & 31) == 0) bits_all[(size_t)blockIdx.y * bs + (i >> 5)] = word;
 }
 
 // the sequential part: <= 100 jumps over the settled-bit mask held in shared memory
@@ -1319,21 +1313,29 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
     if (sp.any_fast) {
         CUDA_CHECK(cudaMemsetAsync(sp.first_pos, 0x7F, sizeof(int) * batch, st));   // 0x7F7F7F7F = no positive correlation yet
         dim3 g1((unsigned)std::max<long long>(1, (sp.max_limc + kCorrTile - 1) / kCorrTile), batch);
-        sync_corr_kernel<<<g1, kSyncThreads, 0, st>>>(dig, ds, n, lines, sp.sd, sp.corr, sp.cs, sp.first_pos);
+        {
+            StageTimer t1(ctx, "sync_corr");
+            sync_corr_kernel<<<g1, kSyncThreads, 0, st>>>(dig, ds, n, lines, sp.sd, sp.corr, sp.cs, sp.first_pos);
+        }
         dim3 g2((unsigned)std::max(1, sp.max_wblocks), batch);
-        const void *fn = (const void *)sync_window_kernel;
+        const void *fn = (const void *)sync_settled_kernel;
         if (!ctx->smem_configured.count(fn)) {
-            CUDA_CHECK(cudaFuncSetAttribute(sync_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(sync_settled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CUDA_CHECK(cudaFuncSetAttribute(sync_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             ctx->smem_configured[fn] = 1;
         }
-        sync_window_kernel<<<g2, kSyncThreads, (size_t)sp.max_w * sizeof(int), st>>>(lines, sp.sd, sp.corr, sp.pre, sp.suf,
-                                                                                   sp.cs);
-        dim3 g3((unsigned)std::max<long long>(1, (sp.max_lim + 255) / 256), batch);
-        sync_settled_kernel<<<g3, 256, 0, st>>>(lines, sp.sd, sp.corr, sp.pre, sp.suf, sp.cs, sp.bits, sp.bs);
-        sync_chain_kernel<<<batch, 1024, (size_t)((sp.max_lim + 31) / 32 + 4) * sizeof(uint32_t), st>>>(
-            n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan);
-        ctx->launches += 4;
+        {
+            StageTimer t1(ctx, "sync_settled");
+            CUDA_CHECK(cudaMemsetAsync(sp.bits, 0, sp.bs * batch * sizeof(uint32_t), st));
+            sync_settled_kernel<<<g2, kSyncThreads, (size_t)3 * sp.max_w * sizeof(int), st>>>(lines, sp.sd, sp.corr, sp.cs,
+                                                                                           sp.bits, sp.bs);
+        }
+        {
+            StageTimer t1(ctx, "sync_chain");
+            sync_chain_kernel<<<batch, 1024, (size_t)((sp.max_lim + 31) / 32 + 4) * sizeof(uint32_t), st>>>(
+                n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan);
+        }
+        ctx->launches += 3;
     } else {
         CUDA_CHECK(cudaMemsetAsync(sp.need_scan, 1, sizeof(int) * batch, st));
     }
@@ -1478,7 +1480,7 @@ SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long
         const LineDev &ln = host_lines[r];
         SyncDev d;
         d.m = n - ln.L;
-        d.fast = ln.mindistance * (long long)sizeof(int) <= 200 * 1024;
+        d.fast = 3ll * ln.mindistance * (long long)sizeof(int) <= 200 * 1024;
         if (d.m <= 0) {
             d.m = d.m < 0 ? 0 : d.m;
             d.lim = d.limc = 0;
@@ -1499,13 +1501,11 @@ SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long
     }
     sp.cs = (size_t)((sp.max_limc + 63) & ~63ll);
     sp.bs = (size_t)(((sp.max_lim + 31) / 32 + 4) & ~3ll);   // whole uint4s, 16-byte aligned rows
-    const size_t ints = 3 * sp.cs * count;
+    const size_t ints = sp.cs * count;
     const size_t bytes = ints * sizeof(int) + sp.bs * count * sizeof(uint32_t) + (size_t)count * (sizeof(SyncDev) + 8) + 256;
     char *base = (char *)ctx->sync_buf.reserve(bytes);
     sp.corr = (int *)base;
-    sp.pre = sp.corr + sp.cs * count;
-    sp.suf = sp.pre + sp.cs * count;
-    sp.bits = (uint32_t *)(sp.suf + sp.cs * count);
+    sp.bits = (uint32_t *)(sp.corr + sp.cs * count);
     sp.first_pos = (int *)(sp.bits + sp.bs * count);
     sp.need_scan = sp.first_pos + count;
     sp.sd = (SyncDev *)(((uintptr_t)(sp.need_scan + count) + 15) & ~(uintptr_t)15);

@@ -47,8 +47,8 @@ struct SyncDev {
 struct SyncPlan {
     bool any_fast = false;
     SyncDev *sd = nullptr;
-    int *corr = nullptr, *pre = nullptr, *suf = nullptr;
-    size_t cs = 0;             // ints per recording in corr / pre / suf
+    int *corr = nullptr;
+    size_t cs = 0;             // ints per recording in corr
     uint32_t *bits = nullptr;
     size_t bs = 0;             // words per recording in bits
     int *first_pos = nullptr, *need_scan = nullptr;
