@@ -396,3 +396,84 @@ def test_demodulator_stereo(dec, tmp_path):
     assert rel_err(d.audio_data, g["audio_data"]) < FLOAT_TOL
     frac, _ = frac_within_one(np.asarray(d.output_image), g["output_image"])
     assert frac >= PIXEL_FRACTION
+
+
+# --------------------------------------------------------------------------- full size (BASELINE.json configs[1])
+@pytest.mark.slow
+def test_full_size_60min_stage_properties(dec):
+    """The 60-min / 39.69 M-sample recording the benchmark runs.  Every stage is checked
+    against the oracle's stage applied to the CUDA path's own upstream output, which is
+    size-independent and bit-exact for the integer stages; the fp32 stages are compared with
+    the float64 oracle on a 2 M-sample window around the middle and at both ends."""
+    lpm = 120
+    pcm = synth.synth_recording(3600.0, lpm=lpm, seed=0)
+    n = pcm.shape[0]
+    res = dec.decode(pcm, 11025, lpm, want=("audio", "demodulated", "digitalized", "raster"))
+    assert res.error(0) is None and res.n_out == n == 39_690_000
+    audio, dem, dig = res.audio[0], res.demodulated[0], res.digitalized[0]
+    # zero-phase notch: FIR of finite support -> windows are independent of the rest
+    b, a = O.notch_coefficients(2600, 1, 11025)
+    for lo in (0, n // 2 - 1_000_000, n - 2_000_000):
+        hi = lo + 2_000_000
+        pad_lo, pad_hi = max(lo - 200, 0), min(hi + 200, n)
+        ref = O.filtfilt(b, a, pcm[pad_lo:pad_hi].astype(np.float64))[lo - pad_lo: lo - pad_lo + (hi - lo)]
+        keep = slice(100 if lo else 0, (hi - lo) - (100 if hi < n else 0))
+        assert np.abs(audio[lo:hi][keep] - ref[keep]).max() / np.abs(ref).max() < FLOAT_TOL
+    # median-5 of an envelope cannot exceed the analytic-signal magnitude bound, and the envelope of
+    # this constant-amplitude FM signal stays near 0.25 FS * notch gain: sanity of the global transform
+    assert np.isfinite(dem).all() and dem.min() >= 0
+    # percentiles + rounding: exactly numpy on the CUDA path's own median-filtered envelope
+    d, low, high = O.digitalize(dem.astype(np.float64))
+    assert res.low_high[0, 0] == low and res.low_high[0, 1] == high
+    assert np.array_equal(dig, d.astype(np.uint8))
+    # order-statistic property of the two percentiles on the full data
+    assert (dem < low).sum() <= 0.005 * (n - 1) + 1 <= (dem <= low).sum() + 1
+    assert (dem > high).sum() <= 0.005 * (n - 1) + 1 <= (dem >= high).sum() + 1
+    # phasing search and raster: exactly the oracle on the CUDA path's own grey levels
+    consts = O.line_constants(lpm)
+    peaks = O.pattern_search(dig[: 200 * consts["width"]].astype(np.int64), consts)
+    assert res.peaks[0] == peaks and len(peaks) == 100
+    ph = O.find_phasing(peaks, consts)
+    assert res.phasing_signals[0] == list(ph)
+    sf = ph[-1] if ph else 0
+    assert int(res.start_frame[0]) == sf
+    img = res.image(0)
+    assert img.shape == (4 * ((n - sf) // consts["width"]), consts["width"])
+    for r0 in (0, img.shape[0] // 8 - 101, img.shape[0] // 4 - 300):       # top, middle and bottom bands
+        rows = slice(max(r0, 0), min(r0 + 300, img.shape[0] // 4))
+        band = dig[sf + rows.start * consts["width"]: sf + rows.stop * consts["width"]].astype(np.int64)
+        full_ref = O.convert_to_image(band, consts["width"])
+        inner = slice(8 if rows.start else 0, full_ref.shape[0] - (8 if rows.stop < img.shape[0] // 4 else 0))
+        assert np.array_equal(img[4 * rows.start: 4 * rows.stop][inner], full_ref[inner])
+
+
+def test_demodulator_with_a_polling_consumer(dec, tmp_path):
+    """What main.py does around the decoder (main.py:63-83, 270-291): one thread runs process()
+    and save_output_image(), another pops websocket_stack until it sees convert_end."""
+    import threading
+    from wefax_b200.wefax import Demodulator
+    g = load_golden_full("synth_12s_240")
+    wav = str(tmp_path / "upload.wav")
+    synth.write_wav(wav, g["pcm"], g["sample_rate_in"])
+    d = Demodulator(wav, lines_per_minute=120, tcp_stream=True, quiet=True)     # /load_file
+    seen, done = [], threading.Event()
+
+    def poll():
+        while not done.is_set():
+            if d.websocket_stack:
+                msg = d.websocket_stack.pop(0)
+                seen.append(msg)
+                if msg.get("message_content") == "convert_end":
+                    done.set()
+
+    t = threading.Thread(target=poll, daemon=True)
+    t.start()
+    d.update_lines_per_minute(int("240"))                                          # /convert_file
+    d.process()
+    d.save_output_image(str(tmp_path / "upload.png"))
+    assert done.wait(timeout=30)
+    t.join(timeout=5)
+    titles = [m.get("progress_title") for m in seen if m["data_type"] == "progress_bar"]
+    assert titles[0] == "demodulating signal" and "converting signal to image" in titles
+    assert all(0 <= m["percentage"] <= 100 for m in seen if m["data_type"] == "progress_bar")
+    assert (tmp_path / "upload.png").stat().st_size > 1000
