@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--duration", type=float, default=3600.0, help="seconds of audio per recording")
     ap.add_argument("--lpm", type=int, default=120)
+    ap.add_argument("--sample-rate", type=int, default=11025,
+                    help="input sample rate; != 11025 exercises the FFT-domain resampler (configs[2]: 48000, 1200 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=1,
                     help="recordings per GPU per step; > 1 selects the batch workload (BASELINE.json configs[3] shape: "
@@ -54,6 +56,9 @@ def parse_args():
 
 
 def workload_name(args) -> str:
+    if args.sample_rate != 11025:
+        return (f"synthetic {args.duration / 60:g}-min mono {args.sample_rate} Hz recording resampled to 11025 Hz, "
+                f"{args.lpm} LPM, one per GPU (BASELINE.json configs[2] on one GPU)")
     if args.batch > 1:
         return (f"batch of {args.batch} synthetic {args.duration / 60:g}-min mono 11025 Hz recordings per GPU, mixed LPM "
                 f"60/90/120/240 (BASELINE.json configs[3] shape)")
@@ -214,7 +219,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         pcm = np.stack([pool[l] for l in lpms])
         lpm_arg = lpms
     else:
-        pcm = synth.synth_recording(args.duration, lpm=args.lpm, seed=rank)
+        pcm = synth.synth_recording(args.duration, sample_rate=args.sample_rate, lpm=args.lpm, seed=rank)
         lpm_arg = args.lpm
     n = int(pcm.shape[-1]) * (args.batch if args.batch > 1 else 1)   # samples per GPU per step
     n_rec = int(pcm.shape[-1])
@@ -228,18 +233,18 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     sampler.start()
 
     # ---- value: everything resident in HBM -------------------------------------------
-    res = dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True)
+    res = dec.decode(pcm_dev, args.sample_rate, lpm_arg, want=want, device_outputs=True)
     if res.error(0) is not None:
         raise RuntimeError(f"decode failed: {res.error(0)!r}")
     for _ in range(args.warmup):
-        dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True, out=res)
+        dec.decode(pcm_dev, args.sample_rate, lpm_arg, want=want, device_outputs=True, out=res)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = dec.launch_count
     sampler.region(True)
     ev0.record(stream)
     for _ in range(args.steps):
-        dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True, out=res)
+        dec.decode(pcm_dev, args.sample_rate, lpm_arg, want=want, device_outputs=True, out=res)
     ev1.record(stream)
     barrier()
     sampler.region(False)
@@ -253,27 +258,27 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     dec.timings(reset=True)
     sampler.region(True)
     for _ in range(args.steps):
-        dec.decode(pcm_dev, 11025, lpm_arg, want=want, device_outputs=True, out=res)
+        dec.decode(pcm_dev, args.sample_rate, lpm_arg, want=want, device_outputs=True, out=res)
     sampler.region(False)
     stage_ms = dec.timings(reset=True)
     dec.enable_timing(False)
 
     # ---- e2e: host buffers through the C-ABI -------------------------------------------
-    host = dec.decode(pcm_pin.numpy(), 11025, lpm_arg, want=want, pinned=True)
+    host = dec.decode(pcm_pin.numpy(), args.sample_rate, lpm_arg, want=want, pinned=True)
     for _ in range(max(1, args.warmup // 2)):
-        dec.decode(pcm_pin.numpy(), 11025, lpm_arg, want=want, pinned=True, out=host)
+        dec.decode(pcm_pin.numpy(), args.sample_rate, lpm_arg, want=want, pinned=True, out=host)
     barrier()
     sampler.region(True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dec.decode(pcm_pin.numpy(), 11025, lpm_arg, want=want, pinned=True, out=host)
+        dec.decode(pcm_pin.numpy(), args.sample_rate, lpm_arg, want=want, pinned=True, out=host)
     dec.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.region(False)
     barrier()
     e2e_value = world * n * args.steps / e2e_s / 1e6
     h2d = n * 2
-    d2h = n + int(sum(int(h) * int(w) for h, w in zip(host.height, host.width)))
+    d2h = int(host.n_out) * max(1, args.batch) + int(sum(int(h) * int(w) for h, w in zip(host.height, host.width)))
     clocks = sampler.stop()
 
     if rank != 0:
@@ -282,6 +287,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         return
 
     peak, peak_src = hbm_peak()
+    n_rec = int(res.n_out)            # samples per recording at 11025 Hz (after the resampler)
     half = n_rec % 2 == 0 and not os.environ.get("WEFAX_NO_REAL_FFT")
     lens, blu = N.fft_plan_describe(n_rec // 2 if half else n_rec)
     if half and blu:                 # n/2 not smooth: the library falls back to the full-length transform
@@ -341,7 +347,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                                     "frac": round(path_gbs / peak, 4)}},
         "stages": kernels, "stage_parts": sub,
     }
-    if world == 1 and not args.no_cpu_baseline and args.batch == 1:
+    if world == 1 and not args.no_cpu_baseline and args.batch == 1 and args.sample_rate == 11025:
         from oracle import wefax_oracle as O
         t0 = time.perf_counter()
         o = O.decode(pcm, 11025, args.lpm)
