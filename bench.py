@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--sample-rate", type=int, default=11025,
                     help="input sample rate; != 11025 exercises the FFT-domain resampler (configs[2]: 48000, 1200 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workspace-mb", type=int, default=0, help="cap on the scratch of one decode wave (0 = library default)")
     ap.add_argument("--batch", type=int, default=1,
                     help="recordings per GPU per step; > 1 selects the batch workload (BASELINE.json configs[3] shape: "
                          "--duration 600 --batch 64, LPM cycling 60/90/120/240)")
@@ -224,7 +225,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     n = int(pcm.shape[-1]) * (args.batch if args.batch > 1 else 1)   # samples per GPU per step
     n_rec = int(pcm.shape[-1])
     stream = torch.cuda.Stream(device=local_rank)
-    dec = Decoder(local_rank, stream=stream.cuda_stream)
+    dec = Decoder(local_rank, stream=stream.cuda_stream, workspace_limit=(args.workspace_mb << 20) or None)
     pcm_dev = torch.from_numpy(pcm).cuda()
     pcm_pin = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
     pcm_pin.numpy()[...] = pcm

@@ -165,3 +165,22 @@ def test_synth_is_deterministic():
     b = synth.synth_recording(3.0, seed=5, noise_sigma=0.05)
     assert a.dtype == np.int16 and np.array_equal(a, b) and a.shape == (33075,)
     assert synth.batch_spec(5) == {"lpm": 90, "ioc": 288, "seed": 1005}
+
+
+def test_parallel_png_writer_roundtrip(tmp_path):
+    from PIL import Image
+    from wefax_b200 import pngio
+    rng = np.random.default_rng(3)
+    for shape, band in (((1, 1), 4 << 20), ((37, 53), 64), ((900, 2756), 1 << 16), ((301, 5512), 1 << 18)):
+        img = (rng.integers(0, 256, size=shape) // 8 * 8).astype(np.uint8)
+        p = str(tmp_path / f"{shape[0]}x{shape[1]}.png")
+        pngio.write_png_gray8(p, img, band_bytes=band)
+        with Image.open(p) as im:
+            assert im.mode == "L" and im.size == (shape[1], shape[0])
+            assert np.array_equal(np.asarray(im), img)
+    with pytest.raises(ValueError):
+        pngio.write_png_gray8(str(tmp_path / "e.png"), np.zeros((0, 5), np.uint8))
+    # zlib's adler32_combine identity
+    a, b = rng.bytes(100003), rng.bytes(77)
+    import zlib
+    assert pngio._adler32_combine(zlib.adler32(a), zlib.adler32(b), len(b)) == zlib.adler32(a + b)

@@ -177,7 +177,14 @@ class Demodulator:
         plt.show()
 
     def save_output_image(self, filepath: str):
-        self.output_image.save(filepath)
+        """wefax.py:407-408.  Large greyscale PNGs go through the multi-threaded writer
+        (same pixels, ~10x faster than one zlib stream on one core); anything else through Pillow."""
+        img = self.output_image
+        if filepath.lower().endswith(".png") and img.mode == "L" and img.width * img.height >= (1 << 20):
+            from . import pngio
+            pngio.write_png_gray8(filepath, np.asarray(img))
+        else:
+            img.save(filepath)
 
 
 if __name__ == "__main__":
