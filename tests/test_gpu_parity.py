@@ -477,3 +477,49 @@ def test_demodulator_with_a_polling_consumer(dec, tmp_path):
     assert titles[0] == "demodulating signal" and "converting signal to image" in titles
     assert all(0 <= m["percentage"] <= 100 for m in seen if m["data_type"] == "progress_bar")
     assert (tmp_path / "upload.png").stat().st_size > 1000
+
+
+# --------------------------------------------------------------------------- edge shapes
+@pytest.mark.parametrize("n", [10, 11, 58, 59, 60, 100, 2000, 5511, 5512, 5513, 5600])
+def test_decode_tiny_recordings_match_oracle(dec, n):
+    """Shorter than a line / than the sync template: same outputs and the same exception as the oracle."""
+    rng = np.random.default_rng(n)
+    pcm = np.round(4000 * np.sin(2 * np.pi * 1900 * np.arange(n) / 11025) + rng.normal(size=n) * 500).astype(np.int16)
+    o = O.decode(pcm, 11025, 120)
+    res = dec.decode(pcm, 11025, 120, want=("audio", "demodulated", "digitalized", "raster"))
+    assert rel_err(res.audio[0], o["audio_data"]) < FLOAT_TOL
+    assert rel_err(res.demodulated[0], o["demodulated_data"]) < FLOAT_TOL
+    frac, worst = frac_within_one(res.digitalized[0], o["digitalized_data"])
+    assert frac >= 0.99 and worst <= 2
+    err = res.error(0)
+    if o["error"] is None:
+        assert err is None and res.image(0).shape == o["output_image"].shape
+    else:
+        assert err is not None and type(err).__name__ == o["error"][0]
+
+
+def test_decode_rejects_what_the_reference_rejects(dec):
+    with pytest.raises(ValueError, match="greater than padlen"):
+        dec.decode(np.zeros(9, dtype=np.int16), 11025, 120)
+    with pytest.raises(TypeError):
+        dec.decode(np.zeros(100, dtype=np.float32), 11025, 120)
+    with pytest.raises(Exception):
+        dec.decode(np.zeros(5000, dtype=np.int16), 11025, 0)
+
+
+def test_decode_batch_odd_length_and_stereo(dec):
+    """Odd n takes the full-length complex transform (and LDG tile loads for batch elements that
+    are not 16-byte aligned); stereo goes through the wrapping merge."""
+    n = 33075                                   # 3 s, odd
+    mono = np.stack([synth.synth_recording(3.0, lpm=240, seed=70 + k, noise_sigma=0.03) for k in range(3)])
+    res = dec.decode(mono, 11025, 240, want=("audio", "demodulated", "digitalized", "raster"))
+    for i in range(3):
+        o = O.decode(mono[i], 11025, 240)
+        _check_end_to_end(res, i, o)
+        assert (res.error(i) is None) == (o["error"] is None)
+    left = mono.astype(np.int32) * 3
+    stereo = np.stack([left, np.roll(left, 5, axis=1)], axis=2).astype(np.int16)      # sums wrap
+    res = dec.decode(stereo, 11025, 240, want=("audio", "demodulated", "digitalized", "raster"))
+    for i in range(3):
+        o = O.decode(stereo[i], 11025, 240)
+        _check_end_to_end(res, i, o)
