@@ -80,9 +80,10 @@ const StagePlan &stage_plan(int R) {
 // raised to 16384 (one CTA per SM) only when that is what it takes to get there.
 int tile_cols(int R, int ncols, bool strided) {
     const int tmax = tile_max();
+    const int maxc = env_int("WEFAX_FFT_MAXC", 64);
     int C = 1;
-    while (C * 2 * R <= tmax && C * 2 <= 64) C *= 2;
-    if (strided && C < 32 && !getenv("WEFAX_FFT_TILE"))
+    while (C * 2 * R <= tmax && C * 2 <= maxc) C *= 2;
+    if (strided && C < 32 && !getenv("WEFAX_FFT_TILE") && maxc >= 32)
         while (C * 2 * R <= 2 * tmax && C < 32) C *= 2;
     while (C > 1 && C / 2 >= ncols) C /= 2;
     return C;
