@@ -523,3 +523,35 @@ def test_decode_batch_odd_length_and_stereo(dec):
     for i in range(3):
         o = O.decode(stereo[i], 11025, 240)
         _check_end_to_end(res, i, o)
+
+
+@pytest.mark.slow
+def test_noisy_batch_at_scale(dec):
+    """BASELINE.json configs[4] in miniature: 32 noisy recordings (AWGN 0.02-0.1 FS, +-50 Hz carrier
+    offset, 5 ppm clock drift), LPM 60/90/120/240.  Phasing search, grouping and raster are checked
+    bit for bit against the oracle applied to the CUDA path's own grey levels for every recording;
+    the fp32 stages and the end-to-end image against the float64 oracle."""
+    specs = [synth.batch_spec(k, noisy=True) for k in range(32)]
+    pcm = np.stack([synth.synth_recording(45.0, **s) for s in specs])
+    lpms = [s["lpm"] for s in specs]
+    res = dec.decode(pcm, 11025, lpms, want=("audio", "demodulated", "digitalized", "raster"))
+    n_same_start = 0
+    for i, s in enumerate(specs):
+        consts = O.line_constants(s["lpm"])
+        dig = res.digitalized[i].astype(np.int64)
+        peaks, ph, img, err = _oracle_sync_image(dig, s["lpm"])
+        assert res.peaks[i] == peaks, i
+        if err is None:
+            assert res.error(i) is None and res.phasing_signals[i] == list(ph)
+            assert np.array_equal(res.image(i), img), i
+        else:
+            assert type(res.error(i)).__name__ == err[0]
+        o = O.decode(pcm[i], 11025, s["lpm"])
+        _check_end_to_end(res, i, o)
+        if err is None and o["error"] is None and int(res.start_frame[i]) == o["start_frame"]:
+            n_same_start += 1
+            frac, worst = frac_within_one(res.image(i), o["output_image"])
+            assert frac >= PIXEL_FRACTION, (i, frac, worst)
+    # the fp32 envelope may flip single grey levels, which the greedy picker can amplify into a
+    # different start line on noise; on this set every recording keeps the reference's start line
+    assert n_same_start >= 30, n_same_start
