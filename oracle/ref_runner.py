@@ -111,3 +111,32 @@ def run_reference(wav_path: str, lpm: int = 120) -> dict:
     out["progress_titles"] = [m.get("progress_title", m.get("message_content"))
                               for m in d.websocket_stack]
     return out
+
+
+def import_reference_data_packet():
+    """The reference's ``data_packet`` module (live-path packet DSP, tone detection)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not mounted at {REFERENCE_ROOT}")
+    if "data_packet" in sys.modules and getattr(sys.modules["data_packet"], "_is_reference", False):
+        return sys.modules["data_packet"]
+    try:
+        import matplotlib  # noqa: F401
+    except Exception:
+        _stub_matplotlib()
+    with _in_reference_root():
+        sys.path.insert(0, REFERENCE_ROOT)
+        try:
+            import data_packet
+        finally:
+            sys.path.remove(REFERENCE_ROOT)
+    data_packet._is_reference = True
+    return data_packet
+
+
+def run_reference_tones(samples: np.ndarray, sample_rate: int, lpm: int = 120) -> tuple:
+    """``(contain_start_tone, contain_stop_tone)`` of the unmodified reference for one packet
+    (data_packet.py:345-385)."""
+    dp = import_reference_data_packet()
+    with _in_reference_root():
+        packet = dp.DataPacket(sample_rate, np.asarray(samples), lpm, "/tmp/", len(samples) / sample_rate, 0)
+        return bool(packet.contain_start_tone()), bool(packet.contain_stop_tone())

@@ -138,5 +138,37 @@ def main() -> None:
         json.dump(digests, fh, indent=1)
 
 
+#: recordings whose 1-s packets are run through the reference's tone test
+TONE_CASES = {
+    "clean_30s_ioc576": dict(duration_s=30.0, lpm=120, ioc=576, seed=3),
+    "clean_30s_ioc288": dict(duration_s=30.0, lpm=120, ioc=288, seed=4),
+    "noisy_30s_ioc576": dict(duration_s=30.0, lpm=120, ioc=576, seed=5, noise_sigma=0.05),
+    "offset_30s_ioc576": dict(duration_s=30.0, lpm=60, ioc=576, seed=6, noise_sigma=0.02, carrier_offset_hz=40.0),
+}
+
+
+def make_tones() -> None:
+    """tests/golden/tones.json: contain_start_tone / contain_stop_tone of the reference's DataPacket."""
+    from scipy.io import wavfile
+    out = {"versions": versions(), "fixtures": {}, "synthetic": {}}
+    for name in ("image.wav", "stop_tone.wav", "start_tone.wav", "start_tone_noisy.wav", "start_tone_start.wav"):
+        sr, pcm = wavfile.read(os.path.join(FIXTURE_DIR, name))
+        start, stop = ref_runner.run_reference_tones(pcm, sr)
+        out["fixtures"][name] = dict(sample_rate=int(sr), start=start, stop=stop)
+        print(name, sr, start, stop)
+    for name, kw in TONE_CASES.items():
+        pcm = synth.synth_recording(**kw)
+        flags = [ref_runner.run_reference_tones(pcm[k * 11025:(k + 1) * 11025], 11025, kw["lpm"])
+                 for k in range(pcm.shape[0] // 11025)]
+        out["synthetic"][name] = dict(synth=kw, pcm_sha256=sha(pcm), start=[f[0] for f in flags],
+                                      stop=[f[1] for f in flags])
+        print(name, "start:", "".join("1" if f[0] else "." for f in flags), "stop:",
+              "".join("1" if f[1] else "." for f in flags))
+    with open(os.path.join(HERE, "tones.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if "--tones-only" not in sys.argv:
+        main()
+    make_tones()

@@ -96,3 +96,59 @@ def test_scipy_pillow_crosscheck():
         img = rng.integers(0, 256, size=(h, 7), dtype=np.uint8)
         ref = np.asarray(Image.fromarray(img, mode="L").resize((7, 4 * h)))
         assert np.array_equal(O.resize_rows_x4(img), ref)
+
+
+# ---- N2: start / stop tone test (oracle/tones_oracle.py vs the reference's DataPacket) ----------
+
+def _load_tones():
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "tones.json")) as fh:
+        return json.load(fh)
+
+
+def test_tone_find_peaks_matches_scipy():
+    import scipy.signal
+    from oracle import tones_oracle as T
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        n = int(rng.integers(50, 3000))
+        x = np.abs(rng.normal(size=n)) * (rng.random(n) < 0.3)
+        x = np.round(x / (x.max() + 1e-4), 2)          # many ties and plateaus
+        for distance in (1, 7, 250, 380):
+            ref = scipy.signal.find_peaks(x, distance=distance, height=0.05, prominence=0.2)[0]
+            assert np.array_equal(T.find_peaks(x, distance, 0.05, 0.2), ref), (trial, distance)
+
+
+@pytest.mark.parametrize("name", sorted(_load_tones()["synthetic"]))
+def test_tone_oracle_matches_reference_synthetic(name):
+    from oracle import tones_oracle as T
+    c = _load_tones()["synthetic"][name]
+    pcm = synth.synth_recording(**c["synth"])
+    assert _sha(pcm) == c["pcm_sha256"]
+    start, stop = T.scan(pcm, 11025)
+    assert start.tolist() == c["start"]
+    assert stop.tolist() == c["stop"]
+
+
+def test_tone_oracle_known_answers_of_the_survey():
+    """peaks of the start tone sit 300 Hz apart around 1900 Hz, of the stop tone
+    450 Hz apart; a synthetic IOC576 start tone reproduces the 300 Hz spacing."""
+    from oracle import tones_oracle as T
+    pcm = synth.synth_recording(30.0, seed=3)
+    freq, amp = T.fourier_transform(pcm[:11025], 11025)
+    pk = T.find_peaks(amp, 250, 0.05, 0.2)
+    assert 4 <= len(pk) <= 6
+    assert np.all(np.abs(np.diff(freq[pk]) - 600.0) < 2.0) or np.all(np.abs(np.diff(freq[pk]) - 300.0) < 2.0)
+
+
+@pytest.mark.parametrize("name", sorted(_load_tones()["fixtures"]))
+def test_tone_oracle_matches_reference_fixtures(name):
+    """The five shipped 1-s packets (their PCM travels inside the full_fixture_*.npz vectors)."""
+    from oracle import tones_oracle as T
+    c = _load_tones()["fixtures"][name]
+    g = load_golden_full("fixture_" + name[:-len(".wav")])
+    assert g["sample_rate_in"] == c["sample_rate"]
+    assert T.contain_start_tone(g["pcm"], c["sample_rate"]) == c["start"]
+    assert T.contain_stop_tone(g["pcm"], c["sample_rate"]) == c["stop"]
