@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WEFAX_ABI_VERSION 1
+#define WEFAX_ABI_VERSION 2
 #define WEFAX_TARGET_RATE 11025   /* wefax.py:60 */
 #define WEFAX_MAX_PEAKS 100       /* wefax.py:251 */
 
@@ -166,6 +166,30 @@ int wefax_digitalize(wefax_ctx *ctx, long long n, int batch, const float *envelo
  * uses out->peaks .. out->status and out->raster / raster_stride; other fields ignored. */
 int wefax_sync_raster(wefax_ctx *ctx, long long n, int batch, const uint8_t *digitalized, const double *lpm,
                       const wefax_batch_out *out);
+
+/* ---- start / stop tone test of packets ------------------- */
+
+/* config/config.json "tones_settings" as data_packet.py:43-57 reads them. */
+typedef struct {
+    double start_distance;   /* start_tone_peaks_minimum_distance (bins)  data_packet.py:352 */
+    double stop_distance;    /* stop_tone_peaks_minimum_distance (bins)   data_packet.py:362 */
+    double height;           /* tones_peaks_minimum_height                data_packet.py:374 */
+    double prominence;       /* tones_peaks_minimum_prominence            data_packet.py:375 */
+    double min_frequency;    /* tones_peaks_minimum_frequency (Hz)        data_packet.py:380-381 */
+    double max_frequency;    /* tones_peaks_maximum_frequency (Hz)                            */
+    int min_amount;          /* tones_peaks_minimum_amount                data_packet.py:383-384 */
+    int max_amount;          /* tones_peaks_maximum_amount                                    */
+} wefax_tone_settings;
+
+/* DataPacket.contain_start_tone() / contain_stop_tone() (data_packet.py:345-406) for every
+ * consecutive packet of packet_frames frames of ONE recording: n_packets = n_frames / packet_frames
+ * (a trailing partial packet is ignored).  pcm: int16, mono or interleaved stereo (merged as in
+ * wefax.py:372), host pointer unless flags has WEFAX_F_PCM_ON_DEVICE.  Outputs are HOST pointers
+ * of n_packets entries each; any may be NULL.  n_*_peaks = number of peaks find_peaks returned
+ * (after the distance / height / prominence filters). */
+int wefax_tone_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int channels, int sample_rate,
+                    long long packet_frames, unsigned flags, const wefax_tone_settings *settings,
+                    uint8_t *start_flags, uint8_t *stop_flags, int32_t *n_start_peaks, int32_t *n_stop_peaks);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,142 @@
+"""GPU parity of the start / stop tone test: wefax_tone_scan through the
+C-ABI against oracle/tones_oracle.py and against the answers of the unmodified reference's
+DataPacket (tests/golden/tones.json).
+
+Tolerance: the decision is a boolean taken on thresholded float quantities (height 0.05,
+prominence 0.2 of a max-normalised spectrum); the CUDA path computes the spectrum in fp32, the
+reference in float64.  Flags and peak counts must be IDENTICAL on every committed case; packets
+whose oracle peak heights / prominences come within 1e-4 of a threshold are excluded from the
+random-noise test (none of the golden cases is that close)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, load_golden_full
+from oracle import tones_oracle as T
+from wefax_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dec():
+    from wefax_b200.decoder import Decoder
+    d = Decoder(0)
+    yield d
+    d.close()
+
+
+def _golden():
+    with open(os.path.join(GOLDEN_DIR, "tones.json")) as fh:
+        return json.load(fh)
+
+
+def _oracle_counts(pcm, sr, plen):
+    out = []
+    for k in range(len(pcm) // plen):
+        _, amp = T.fourier_transform(pcm[k * plen:(k + 1) * plen], sr)
+        out.append((len(T.find_peaks(amp, 250, 0.05, 0.2)), len(T.find_peaks(amp, 380, 0.05, 0.2))))
+    return np.asarray(out, dtype=np.int64).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("name", sorted(_golden()["synthetic"]))
+def test_tone_scan_matches_reference_synthetic(dec, name):
+    from wefax_b200.tones import scan_tones
+    c = _golden()["synthetic"][name]
+    pcm = synth.synth_recording(**c["synth"])
+    start, stop, ns, nt = scan_tones(dec, pcm, 11025)
+    assert start.tolist() == c["start"]
+    assert stop.tolist() == c["stop"]
+    cnt = _oracle_counts(pcm, 11025, 11025)
+    assert ns.tolist() == cnt[:, 0].tolist()
+    assert nt.tolist() == cnt[:, 1].tolist()
+
+
+@pytest.mark.parametrize("name", sorted(_golden()["fixtures"]))
+def test_tone_scan_matches_reference_fixtures(dec, name):
+    """The five shipped 1-s packets: 11025 Hz and 48 kHz (24000 bins per packet)."""
+    from wefax_b200.tones import scan_tones
+    c = _golden()["fixtures"][name]
+    g = load_golden_full("fixture_" + name[:-len(".wav")])
+    sr = c["sample_rate"]
+    pcm = g["pcm"][: sr]
+    start, stop, ns, nt = scan_tones(dec, pcm, sr)
+    assert (bool(start[0]), bool(stop[0])) == (c["start"], c["stop"])
+    cnt = _oracle_counts(pcm, sr, sr)
+    assert (int(ns[0]), int(nt[0])) == (int(cnt[0, 0]), int(cnt[0, 1]))
+
+
+def test_tone_scan_device_input_and_stereo(dec):
+    import torch
+    from wefax_b200.tones import scan_tones
+    pcm = synth.synth_recording(30.0, seed=3)
+    ref = scan_tones(dec, pcm, 11025)
+    dev = scan_tones(dec, torch.from_numpy(pcm).cuda(), 11025)
+    for a, b in zip(ref, dev):
+        assert np.array_equal(a, b)
+    stereo = np.stack([pcm, pcm], axis=1)              # (L + R) / 2 == L
+    st = scan_tones(dec, stereo, 11025)
+    for a, b in zip(ref, st):
+        assert np.array_equal(a, b)
+
+
+def test_tone_scan_noise_and_odd_packet_lengths(dec):
+    """Random packets (thousands of candidate peaks, Bluestein packet lengths) against the oracle."""
+    from wefax_b200.tones import scan_tones
+    rng = np.random.default_rng(5)
+    for sr, seconds in ((11025, 1.0), (8000, 0.5), (10007, 1.0), (22050, 0.25)):
+        plen = int(sr * seconds)
+        npk = 12
+        t = np.arange(plen * npk) / sr
+        x = rng.normal(0, 2000, size=plen * npk)
+        for f0 in (1000, 1450, 1900, 2350, 2800):        # five lines, stop-tone spacing
+            x += 4000 * rng.uniform(0.2, 1.0) * np.sin(2 * np.pi * (f0 + rng.uniform(-3, 3)) * t)
+        pcm = np.clip(np.round(x), -32768, 32767).astype(np.int16)
+        start, stop, ns, nt = scan_tones(dec, pcm, sr, packet_seconds=seconds)
+        for k in range(npk):
+            seg = pcm[k * plen:(k + 1) * plen]
+            freq, amp = T.fourier_transform(seg, sr)
+            close = False
+            want = []
+            for dist in (250, 380):
+                pk = T.local_maxima_1d(amp)
+                pk = pk[amp[pk] >= 0.05 - 1e-4]
+                pk = pk[T.select_by_peak_distance(pk, amp[pk], dist)]
+                prom = T.peak_prominences(amp, pk)
+                close |= bool(np.any(np.abs(amp[pk] - 0.05) < 1e-4) or np.any(np.abs(prom - 0.2) < 1e-4))
+                want.append(len(T.find_peaks(amp, dist, 0.05, 0.2)))
+            if close:
+                continue
+            assert (int(ns[k]), int(nt[k])) == tuple(want), (sr, k)
+            assert bool(start[k]) == T.contain_start_tone(seg, sr), (sr, k)
+            assert bool(stop[k]) == T.contain_stop_tone(seg, sr), (sr, k)
+
+
+def test_tone_scan_full_hour_and_transmission_bounds(dec):
+    """BASELINE configs[1] size: every packet of the synthetic 60-min recording is scanned in one call;
+    a sample of packets (both ends + 150 random ones) is checked against the oracle, and the counting
+    logic of the live state machine finds the one transmission (start tone in the first 5 s, stop tone
+    15 s before the end)."""
+    from wefax_b200.tones import find_transmissions, scan_tones
+    pcm = synth.synth_recording(3600.0, seed=0)
+    start, stop, _, _ = scan_tones(dec, pcm, 11025)
+    assert start.shape == (3600,)
+    rng = np.random.default_rng(0)
+    picks = sorted(set(range(10)) | set(range(3570, 3600)) | set(rng.integers(10, 3570, size=150).tolist()))
+    for k in picks:
+        seg = pcm[k * 11025:(k + 1) * 11025]
+        assert bool(start[k]) == T.contain_start_tone(seg, 11025), k
+        assert bool(stop[k]) == T.contain_stop_tone(seg, 11025), k
+    assert find_transmissions(start, stop) == [(3, 3588)]
+
+
+def test_tone_scan_rejects_bad_arguments(dec):
+    from wefax_b200.tones import scan_tones
+    with pytest.raises(ValueError):
+        scan_tones(dec, np.zeros(100, dtype=np.int16), 2, packet_seconds=1.0)
+    out = scan_tones(dec, np.zeros(100, dtype=np.int16), 11025)     # shorter than one packet
+    assert all(len(a) == 0 for a in out)
+    start, stop, ns, nt = scan_tones(dec, np.zeros(11025, dtype=np.int16), 11025)   # silence: no peaks
+    assert not start[0] and not stop[0] and ns[0] == 0 and nt[0] == 0

@@ -26,8 +26,9 @@ EXPORTED_SYMBOLS = (
     "wefax_line_constants_for", "wefax_resampled_length", "wefax_notch_coefficients",
     "wefax_fft_plan_describe", "wefax_decode_batch", "wefax_fft_c2c", "wefax_hilbert_envelope",
     "wefax_resample", "wefax_filtfilt", "wefax_digitalize", "wefax_sync_raster",
-    "wefax_ctx_enable_timing", "wefax_ctx_timings",
+    "wefax_ctx_enable_timing", "wefax_ctx_timings", "wefax_tone_scan",
 )
+ABI_VERSION = 2
 
 
 class LineConstants(C.Structure):
@@ -47,6 +48,12 @@ class BatchOut(C.Structure):
                 ("n_phasing", C.c_void_p), ("start_frame", C.c_void_p), ("height", C.c_void_p),
                 ("status", C.c_void_p), ("low_high", C.c_void_p), ("raster", C.c_void_p),
                 ("raster_stride", C.c_longlong)]
+
+
+class ToneSettings(C.Structure):
+    _fields_ = [("start_distance", C.c_double), ("stop_distance", C.c_double), ("height", C.c_double),
+                ("prominence", C.c_double), ("min_frequency", C.c_double), ("max_frequency", C.c_double),
+                ("min_amount", C.c_int), ("max_amount", C.c_int)]
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -111,6 +118,8 @@ def load():
     lib.wefax_digitalize.restype = i
     lib.wefax_sync_raster.argtypes = [vp, ll, i, vp, vp, C.POINTER(BatchOut)]
     lib.wefax_sync_raster.restype = i
+    lib.wefax_tone_scan.argtypes = [vp, vp, ll, i, i, ll, C.c_uint, C.POINTER(ToneSettings), vp, vp, vp, vp]
+    lib.wefax_tone_scan.restype = i
     _lib = lib
     return lib
 

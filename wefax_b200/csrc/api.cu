@@ -608,4 +608,57 @@ int wefax_sync_raster(wefax_ctx *ctx, long long n, int batch, const uint8_t *dig
     });
 }
 
+int wefax_tone_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int channels, int sample_rate,
+                    long long packet_frames, unsigned flags, const wefax_tone_settings *settings,
+                    uint8_t *start_flags, uint8_t *stop_flags, int32_t *n_start_peaks, int32_t *n_stop_peaks) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!pcm || !settings || n_frames < 0 || packet_frames < 4 || sample_rate < 1 || (channels != 1 && channels != 2))
+            WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        const long long n_packets = n_frames / packet_frames;
+        if (n_packets == 0) return;
+        if (n_packets > 0x7fffffff) WEFAX_THROW(WEFAX_ERR_INVALID, "too many packets");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const size_t P = (size_t)packet_frames;
+        const uint32_t half = (uint32_t)(P / 2);
+        // packets per wave: float samples + complex transform scratch + kept bins within the workspace cap
+        const size_t per_packet = P * (sizeof(float) + sizeof(float2) * 4) + (size_t)half * sizeof(float2);
+        long long wave = (long long)((size_t)ctx->workspace_limit / per_packet);
+        if (wave < 1) wave = 1;
+        if (wave > n_packets) wave = n_packets;
+        if (wave > 65535) wave = 65535;   // grid.y of the transform passes
+        const bool on_dev = (flags & WEFAX_F_PCM_ON_DEVICE) != 0;
+        const size_t frame_elems = (size_t)channels;
+        uint8_t *h_flags = (uint8_t *)pinned(ctx, (size_t)n_packets * (2 + 2 * sizeof(int32_t)) + 16);
+        int32_t *h_counts = (int32_t *)(h_flags + (((size_t)n_packets * 2 + 15) & ~(size_t)15));
+        uint8_t *d_flags = (uint8_t *)ctx->out_small.reserve((size_t)n_packets * (2 + 2 * sizeof(int32_t)) + 16);
+        int32_t *d_counts = (int32_t *)(d_flags + (((size_t)n_packets * 2 + 15) & ~(size_t)15));
+        for (long long p0 = 0; p0 < n_packets; p0 += wave) {
+            const int np = (int)std::min(wave, n_packets - p0);
+            const int16_t *src = pcm + (size_t)p0 * P * frame_elems;
+            const int16_t *d_pcm = src;
+            if (!on_dev) {
+                int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)np * P * frame_elems * sizeof(int16_t));
+                CUDA_CHECK(cudaMemcpyAsync(buf, src, (size_t)np * P * frame_elems * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+                d_pcm = buf;
+            }
+            float *x = (float *)ctx->work_a.reserve((size_t)np * P * sizeof(float));
+            float2 *X = (float2 *)ctx->work_e.reserve((size_t)np * half * sizeof(float2));
+            launch_ingest_float(ctx, d_pcm, P * frame_elems, channels, x, P, (long long)P, np);
+            spectrum_natural(ctx, (long long)P, x, P, X, half, half, np);
+            launch_tone_peaks(ctx, X, half, (long long)P, sample_rate, np, *settings, d_flags + 2 * p0, d_counts + 2 * p0);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(h_flags, d_flags, (size_t)n_packets * 2, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(h_counts, d_counts, (size_t)n_packets * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (long long k = 0; k < n_packets; ++k) {
+            if (start_flags) start_flags[k] = h_flags[2 * k];
+            if (stop_flags) stop_flags[k] = h_flags[2 * k + 1];
+            if (n_start_peaks) n_start_peaks[k] = h_counts[2 * k];
+            if (n_stop_peaks) n_stop_peaks[k] = h_counts[2 * k + 1];
+        }
+    });
+}
+
 }  // extern "C"

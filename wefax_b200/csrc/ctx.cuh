@@ -129,6 +129,11 @@ void fft_c2c_natural(wefax_ctx *ctx, FftPlan *plan, const float2 *in, float2 *ou
 void hilbert_envelope_bluestein(wefax_ctx *ctx, long long n, const float *x, size_t xs, float *env,
                                 size_t es, int batch);
 
+// forward DFT of `batch` real sequences of length n (any n), first `keep` bins in natural
+// order into X (stride xs_out); scratch: ctx->work_z
+void spectrum_natural(wefax_ctx *ctx, long long n, const float *x, size_t xs, float2 *X, size_t xs_out,
+                      uint32_t keep, int batch);
+
 // scipy.signal.resample(x, num) on real float input (any n, num)
 void resample_real(wefax_ctx *ctx, long long n, long long num, const float *x, size_t xs, float *y,
                    size_t ys, int batch);

@@ -429,8 +429,8 @@ __global__ void resample_spectrum_kernel(const float2 *X, size_t xs, float2 *Zc,
 }
 
 // forward DFT of real x, first `keep` bins in natural order into X (stride xs_out)
-static void spectrum_natural(wefax_ctx *ctx, long long n, const float *x, size_t xs, float2 *X, size_t xs_out,
-                             uint32_t keep, int batch) {
+void spectrum_natural(wefax_ctx *ctx, long long n, const float *x, size_t xs, float2 *X, size_t xs_out,
+                      uint32_t keep, int batch) {
     FftPlan *plan = get_plan(ctx, n);
     if (plan) {
         float2 *z = (float2 *)ctx->work_z.reserve((size_t)n * sizeof(float2) * batch);

@@ -84,4 +84,9 @@ SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long
 void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                    const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines);
 
+// find_peaks-based start / stop tone decision on the spectra of n_packets packets (tones.cu);
+// flags / counts hold 2 entries per packet (start, stop), device pointers
+void launch_tone_peaks(wefax_ctx *ctx, const float2 *X, size_t xs, long long packet_len, int sample_rate,
+                       int n_packets, const wefax_tone_settings &s, uint8_t *flags, int32_t *counts);
+
 }  // namespace wefax

@@ -73,7 +73,7 @@ class Decoder:
 
     def __init__(self, device: int = 0, stream: int | None = None, workspace_limit: int | None = None):
         lib = N.load()
-        if lib.wefax_abi_version() != 1:
+        if lib.wefax_abi_version() != N.ABI_VERSION:
             raise RuntimeError("libwefax_b200.so ABI mismatch; rebuild")
         handle = C.c_void_p()
         rc = lib.wefax_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(handle))
