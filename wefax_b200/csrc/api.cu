@@ -199,6 +199,8 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
         ctx->sm_count = prop.multiProcessorCount;
         const char *tma = getenv("WEFAX_FFT_TMA");
         ctx->use_tma = !(tma && tma[0] == '0');
+        const char *fastk = getenv("WEFAX_FFT_FAST");
+        ctx->use_fast = !(fastk && fastk[0] == '0');
         if (stream) {
             ctx->stream = (cudaStream_t)stream;
         } else {
@@ -645,7 +647,7 @@ int wefax_tone_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int 
             }
             float *x = (float *)ctx->work_a.reserve((size_t)np * P * sizeof(float));
             float2 *X = (float2 *)ctx->work_e.reserve((size_t)np * half * sizeof(float2));
-            launch_ingest_float(ctx, d_pcm, P * frame_elems, channels, x, P, (long long)P, np);
+            launch_ingest_float(ctx, d_pcm, P, channels, x, P, (long long)P, np);   // stride in frames
             spectrum_natural(ctx, (long long)P, x, P, X, half, half, np);
             launch_tone_peaks(ctx, X, half, (long long)P, sample_rate, np, *settings, d_flags + 2 * p0, d_counts + 2 * p0);
         }

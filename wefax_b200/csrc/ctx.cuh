@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "fft.cuh"
+#include "fft_fast.cuh"
 
 namespace wefax {
 // chirp-z (Bluestein) data for a transform length with a prime factor > 13
@@ -25,6 +26,7 @@ struct wefax_ctx {
     long long workspace_limit = 24ll << 30;
     int sm_count = 148;
     bool use_tma = true;   // WEFAX_FFT_TMA=0 forces the LDG tile loads
+    bool use_fast = true;  // WEFAX_FFT_FAST=0 keeps every pass on the generic kernel
     std::map<long long, std::unique_ptr<wefax::FftPlan>> plans;
     std::map<long long, std::unique_ptr<wefax::Bluestein>> bluestein;
     std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
@@ -91,8 +93,63 @@ void launch_pass_variant(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, con
     fft_pass_kernel<LoadOp, StoreOp, MINB><<<grid, p.nthreads, p.smem_bytes, ctx->stream>>>(p, ld, st, map, base, bstride);
 }
 
+template <int R1, int R2, class StoreOp>
+void launch_fast_variant(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t bstride, const StoreOp &st,
+                         int batch) {
+    using K = fast::Cfg<R1, R2, fast::kFastC>;
+    auto kern = fast::fft_fast_strided_kernel<R1, R2, fast::kFastC, StoreOp>;
+    const void *fn = (const void *)kern;
+    auto it = ctx->smem_configured.find(fn);
+    int per_sm;
+    if (it == ctx->smem_configured.end()) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K::T, K::SMEM));
+        if (per_sm < 1) per_sm = 1;
+        ctx->smem_configured[fn] = per_sm;
+    } else {
+        per_sm = it->second;
+    }
+    const long long total = (long long)p.fast_ntiles * batch;
+    const int grid = (int)std::min<long long>(total, (long long)ctx->sm_count * per_sm);
+    kern<<<grid, K::T, K::SMEM, ctx->stream>>>(p, src, bstride, st, (int)total);
+}
+
+// Strided passes whose length has a compiled (R1, R2) pair go to the specialised kernel when the
+// tile comes from plain complex memory and the store functor is one of the hot-path ones.
+template <class LoadOp, class StoreOp>
+bool try_launch_fast(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const StoreOp &st, int batch) {
+    if constexpr (std::is_same<LoadOp, LoadComplex>::value &&
+                  (std::is_same<StoreOp, StoreComplex>::value || std::is_same<StoreOp, StoreEnvPairs>::value)) {
+        if (!ctx->use_fast || !p.fast_R1 || p.contiguous || ld.conj) return false;
+        if ((long long)p.fast_ntiles * batch > 0x7fffffffll) return false;
+        StageTimer timer(ctx, p.tag);
+        switch (p.fast_R1 * 100 + p.fast_R2) {
+#define WEFAX_FAST_CASE(a, b) \
+    case (a) * 100 + (b): launch_fast_variant<a, b, StoreOp>(ctx, p, ld.src, ld.bstride, st, batch); break;
+            WEFAX_FAST_CASE(12, 12)
+            WEFAX_FAST_CASE(14, 12)
+            WEFAX_FAST_CASE(15, 12)
+            WEFAX_FAST_CASE(16, 12)
+            WEFAX_FAST_CASE(14, 14)
+            WEFAX_FAST_CASE(15, 14)
+            WEFAX_FAST_CASE(16, 14)
+            WEFAX_FAST_CASE(15, 15)
+            WEFAX_FAST_CASE(16, 15)
+            WEFAX_FAST_CASE(16, 16)
+#undef WEFAX_FAST_CASE
+            default: return false;
+        }
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        return true;
+    } else {
+        return false;
+    }
+}
+
 template <class LoadOp, class StoreOp>
 void launch_pass(wefax_ctx *ctx, const PassDev &p_in, const LoadOp &ld, const StoreOp &st, int batch) {
+    if (try_launch_fast(ctx, p_in, ld, st, batch)) return;
     PassDev p = p_in;
     alignas(64) CUtensorMap map;
     memset(&map, 0, sizeof(map));

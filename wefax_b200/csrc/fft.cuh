@@ -57,6 +57,10 @@ struct PassDev {
     int smem_bytes;
     int ntiles;
     char tag[16];                 // "fft_fwd_0", "fft_inv_2", ... (stage timing label)
+    // specialised two-stage kernel (fft_fast.cuh) for strided passes with R = fast_R1 * fast_R2; 0 = none
+    int fast_R1, fast_R2;
+    int fast_tiles_per_o, fast_ntiles;
+    FastDiv fast_divTpo;
 };
 
 // ----------------------------- load / store functors -----------------------

@@ -7,6 +7,7 @@
 #include <map>
 
 #include "fft.cuh"
+#include "fft_fast.cuh"
 
 namespace wefax {
 
@@ -95,6 +96,8 @@ int tile_cols(int R, int ncols, bool strided) {
 double pass_cost(int R, long long n, bool strided) {
     const StagePlan &sp = stage_plan(R);
     if (sp.cost < 0) return -1.0;
+    // specialised two-stage kernel (fft_fast.cuh): ~45 instructions per point
+    if (strided && n >= (1 << 16) && env_int("WEFAX_FFT_FAST", 1) && fast::fast_pair(R, nullptr, nullptr)) return 50.0;
     const int C = tile_cols(R, (int)std::min<long long>(n / R, 1 << 30), strided);
     double c = kPassCost;
     for (int r : sp.radices) {
@@ -271,6 +274,13 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
             d.ntiles = (int)(nouter * d.tiles_per_o);
         }
         d.divTpo.init(d.tiles_per_o);
+        d.fast_R1 = d.fast_R2 = 0;
+        d.fast_tiles_per_o = d.fast_ntiles = 1;
+        if (!d.contiguous && fast::fast_pair(R, &d.fast_R1, &d.fast_R2)) {
+            d.fast_tiles_per_o = (d.S + fast::kFastC - 1) / fast::kFastC;
+            d.fast_ntiles = (int)(nouter * d.fast_tiles_per_o);
+        }
+        d.fast_divTpo.init(d.fast_tiles_per_o);
         // TMA box: the most rows (<= 256) that divide R and keep every box 128-byte aligned in smem
         d.rbox = 0;
         for (int rb = std::min(R, 256); rb >= 1; --rb)
