@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwefax_b200.so")
+LIB_PATH = os.environ.get("WEFAX_B200_LIB") or os.path.join(HERE, "libwefax_b200.so")   # override: A/B builds
 
 MAX_PEAKS = 100
 TARGET_RATE = 11025

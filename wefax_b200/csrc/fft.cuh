@@ -626,6 +626,9 @@ struct FftPlan {
     PassDev inv[kMaxPasses];   // tw_mode 2 on all but pass 0 (the last one to run)
     DevBuf tables;             // twR / perm / tw_lo / tw_hi of every pass
     const float2 *tw2_lo = nullptr, *tw2_hi = nullptr;   // w_{2n}^e (real-input packing), two-level like tw_lo/hi
+    // fused "last forward pass + pair untangling + first inverse pass" (fft_mid.cuh): row pairs and w_{2R}^j
+    DevBuf mid_tab;
+    int mid_npairs = 0;
     OuterDigits outer() const {
         OuterDigits od{};
         od.nouter = npass - 1;

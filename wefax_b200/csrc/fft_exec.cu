@@ -1,6 +1,7 @@
 // Transform drivers on top of the pass kernel: Hilbert envelope (smooth lengths
 // and Bluestein), natural-order DFT for tests, FFT-domain resampling.
 #include "ctx.cuh"
+#include "fft_mid.cuh"
 
 namespace wefax {
 
@@ -297,10 +298,107 @@ hilbert_pairs_kernel(float2 *z_all, size_t zs, uint32_t M, PairGeom g, const flo
     }
 }
 
+// row pairs (o, mirrored o, base frequency) and w_{2R}^j for the fused middle kernel, built once per plan
+static void ensure_mid_tables(wefax_ctx *ctx, FftPlan *half) {
+    if (half->mid_npairs) return;
+    const int P = half->npass;
+    const int nouter = P - 1;
+    const int R = half->Rs[P - 1];
+    const int ncols = (int)(half->n / R);
+    std::vector<fast::MidRow> rows;
+    rows.reserve(ncols / 2 + 2);
+    for (int o = 0; o < ncols; ++o) {
+        int d[kMaxPasses] = {0, 0, 0, 0}, rem = o;
+        for (int i = nouter - 1; i >= 0; --i) {
+            d[i] = rem % half->Rs[i];
+            rem /= half->Rs[i];
+        }
+        int kb = 0, mult = 1;
+        for (int i = 0; i < nouter; ++i) {
+            kb += d[i] * mult;
+            mult *= half->Rs[i];
+        }
+        int rem2 = kb ? ncols - kb : 0, o2 = 0;
+        for (int i = 0; i < nouter; ++i) {
+            o2 = o2 * half->Rs[i] + rem2 % half->Rs[i];
+            rem2 /= half->Rs[i];
+        }
+        if (o2 >= o) rows.push_back(fast::MidRow{o, o2, kb, 0});
+    }
+    std::vector<float2> twB(R);
+    for (int j = 0; j < R; ++j) {
+        const double ang = -M_PI * (double)j / (double)R;   // w_{2R}^j
+        twB[j] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    const size_t rows_bytes = (rows.size() * sizeof(fast::MidRow) + 255) & ~size_t(255);
+    char *base = (char *)half->mid_tab.reserve(rows_bytes + R * sizeof(float2));
+    CUDA_CHECK(cudaMemcpyAsync(base, rows.data(), rows.size() * sizeof(fast::MidRow), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(base + rows_bytes, twB.data(), R * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+    half->mid_npairs = (int)rows.size();
+}
+
+template <int R1, int R2>
+static void launch_mid(wefax_ctx *ctx, FftPlan *half, float2 *z, size_t zs, int batch) {
+    using K = fast::MidCfg<R1, R2>;
+    auto kern = fast::hilbert_mid_kernel<R1, R2>;
+    const void *fn = (const void *)kern;
+    auto it = ctx->smem_configured.find(fn);
+    int per_sm;
+    if (it == ctx->smem_configured.end()) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K::T, K::SMEM));
+        if (per_sm < 1) per_sm = 1;
+        ctx->smem_configured[fn] = per_sm;
+    } else {
+        per_sm = it->second;
+    }
+    const int P = half->npass;
+    const PassDev &pi = half->inv[P - 1];
+    fast::MidArgs a{};
+    a.z = z;
+    a.zs = zs;
+    const size_t rows_bytes = ((size_t)half->mid_npairs * sizeof(fast::MidRow) + 255) & ~size_t(255);
+    a.rows = half->mid_tab.as<fast::MidRow>();
+    a.twB = (const float2 *)(half->mid_tab.as<char>() + rows_bytes);
+    a.npairs = half->mid_npairs;
+    a.tiles_per_batch = (a.npairs + K::ROWS / 2 - 1) / (K::ROWS / 2);
+    a.total_tiles = a.tiles_per_batch * batch;
+    a.ncols = (int)(half->n / K::R);
+    a.twR = pi.twR;
+    a.tw2_lo = half->tw2_lo;
+    a.tw2_hi = half->tw2_hi;
+    a.tw_lo = pi.tw_lo;
+    a.tw_hi = pi.tw_hi;
+    a.tw_mode = pi.tw_mode;
+    a.ko_R = pi.ko_R;
+    a.inv_m = (float)(1.0 / (double)half->n);
+    const int grid = std::min(a.total_tiles, ctx->sm_count * per_sm);
+    StageTimer timer(ctx, "hilbert_mid");
+    kern<<<grid, K::T, K::SMEM, ctx->stream>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
 void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t xs, float2 *z, size_t zs, float *env,
                            size_t es, int batch) {
     const size_t M = (size_t)half->n;
+    const int P = half->npass;
     // x / env strides are in floats and must be even so that pair views stay aligned
+    const StoreEnvPairs store_env{(float2 *)env, (const float2 *)x, es / 2, xs / 2};
+    int R1 = 0, R2 = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (batch == 1 || (zs & 1) == 0);
+    if (ctx->use_fast && P >= 2 && aligned && (long long)batch * (long long)(M / half->Rs[P - 1]) < (1ll << 30) &&
+        fast::mid_pair(half->Rs[P - 1], &R1, &R2)) {
+        // passes 0 .. P-2 forward, the fused middle, passes P-2 .. 0 inverse
+        ensure_mid_tables(ctx, half);
+        launch_pass(ctx, half->fwd[0], load_c((const float2 *)x, xs / 2), StoreComplex{z, zs, 1.f, 0}, batch);
+        for (int i = 1; i < P - 1; ++i) launch_pass(ctx, half->fwd[i], load_c(z, zs), StoreComplex{z, zs, 1.f, 0}, batch);
+        launch_mid<14, 28>(ctx, half, z, zs, batch);
+        for (int i = P - 2; i >= 1; --i) launch_pass(ctx, half->inv[i], load_c(z, zs), StoreComplex{z, zs, 1.f, 0}, batch);
+        launch_pass(ctx, half->inv[0], load_c(z, zs), store_env, batch);
+        return;
+    }
     run_forward(ctx, half, load_c((const float2 *)x, xs / 2), StoreComplex{z, zs, 1.f, 0}, z, zs, batch);
     {
         StageTimer timer(ctx, "hilbert_pairs");
@@ -315,7 +413,7 @@ void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }
-    run_inverse(ctx, half, load_c(z, zs), StoreEnvPairs{(float2 *)env, (const float2 *)x, es / 2, xs / 2}, z, zs, batch);
+    run_inverse(ctx, half, load_c(z, zs), store_env, z, zs, batch);
 }
 
 void fft_c2c_natural(wefax_ctx *ctx, FftPlan *plan, const float2 *in, float2 *out, float2 *scratch, int batch,

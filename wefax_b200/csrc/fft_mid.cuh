@@ -1,0 +1,258 @@
+// Real-input Hilbert transform, middle of the sandwich in ONE kernel:
+//
+//     last forward pass (stride 1)  ->  pair untangling  ->  first inverse pass (stride 1)
+//
+// All three work on engine-order rows of R = R1*R2 contiguous elements (fft_exec.cu:
+// hilbert_pairs_kernel explains the pairing: the mirror M-k of frequency k = kb + ncols*j of
+// row o lives in row o2 at j2 = R-1-j).  A CTA takes four (row, mirrored row) pairs: eight
+// bulk TMA copies bring the rows into shared memory, both transforms and the untangling run
+// there, eight bulk TMA stores write them back.  Compared with three separate kernels this
+// removes two full read+write sweeps over the transform buffer.
+//
+// Row transform = two register stages (fft_fast.cuh codelets):
+//   stage 1  item (row, q):  R1 elements q + R2*t of the natural-order row -> DFT_R1 ->
+//            * w_R^(q*u) -> block u of the exchange buffer (block pitch R2|1: conflict-free)
+//   stage 2  item (row, u):  the R2 elements of block u -> DFT_R2 -> frequency u + R1*k2,
+//            natural order, (inverse only) times the inter-pass twiddle w^(ko*k).
+#pragma once
+
+#include "fft_fast.cuh"
+
+namespace wefax {
+namespace fast {
+
+template <> struct Dft<28> {
+    __device__ __forceinline__ static void run(float2 *v) { Pfa<4, 7>::run(v); }
+};
+template <> struct Dft<20> {
+    __device__ __forceinline__ static void run(float2 *v) { Pfa<4, 5>::run(v); }
+};
+template <> struct Dft<21> {
+    __device__ __forceinline__ static void run(float2 *v) { Pfa<3, 7>::run(v); }
+};
+template <> struct Dft<10> {
+    __device__ __forceinline__ static void run(float2 *v) { Pfa<2, 5>::run(v); }
+};
+
+struct MidRow {
+    int o, o2;      // engine-order row and its mirrored row (o2 >= o; o2 == o: self-mirrored)
+    int kb;         // base frequency of row o
+    int pad;
+};
+
+struct MidArgs {
+    float2 *z;
+    size_t zs;                     // batch stride (complex elements)
+    const MidRow *rows;            // npairs entries
+    int npairs, tiles_per_batch;   // tiles_per_batch = ceil(npairs / 4)
+    int total_tiles;
+    int ncols;                     // rows per sequence
+    const float2 *twR;             // w_R^e, e < R
+    const float2 *twB;             // w_{2R}^j, j < R   (= w_n^(ncols*j), n = 2*ncols*R)
+    const float2 *tw2_lo, *tw2_hi; // w_n^e two-level (row factor w_n^kb)
+    const float2 *tw_lo, *tw_hi;   // inter-pass twiddle tables of the pass that follows the first inverse pass
+    int tw_mode;                   // 2 when a pass follows (e = ko*k), 0 when R is the whole transform
+    int ko_R;
+    float inv_m;
+};
+
+__device__ __forceinline__ void tma_store_bulk(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int R1, int R2> struct MidCfg {
+    static constexpr int R = R1 * R2;
+    static constexpr int ROWS = 8;
+    static constexpr int T = 128;
+    static constexpr int BP = R2 | 1;          // block pitch of the exchange buffer
+    static constexpr int MIDP = R1 * BP;       // row pitch of the exchange buffer
+    static constexpr int SMEM = (ROWS * R + ROWS * MIDP + R + ROWS * R2) * (int)sizeof(float2) + 16;
+};
+
+template <int R1, int R2>
+__device__ __forceinline__ void mid_stage1(const float2 *nat, float2 *mid, const float2 *twQ, int tid) {
+    using K = MidCfg<R1, R2>;
+#pragma unroll 1
+    for (int item = tid; item < R2 * K::ROWS; item += K::T) {
+        const int row = item / R2, q = item - row * R2;
+        float2 v[R1];
+        const float2 *src = nat + row * K::R + q;
+#pragma unroll
+        for (int t = 0; t < R1; ++t) v[t] = src[R2 * t];
+        Dft<R1>::run(v);
+        float2 *dst = mid + row * K::MIDP + q;
+        const float2 *tq = twQ + q * R1;
+        dst[0] = v[0];
+#pragma unroll
+        for (int u = 1; u < R1; ++u) dst[u * K::BP] = cmul(v[u], tq[u]);
+    }
+}
+
+template <int R1, int R2, bool TW>
+__device__ __forceinline__ void mid_stage2(const float2 *mid, float2 *nat, const float2 *P, const MidArgs &a,
+                                           const int *s_ko, int tid) {
+    using K = MidCfg<R1, R2>;
+#pragma unroll 1
+    for (int item = tid; item < R1 * K::ROWS; item += K::T) {
+        const int row = item / R1, u = item - row * R1;
+        float2 Aval = make_float2(1.f, 0.f);
+        if (TW) {
+            const uint32_t e = (uint32_t)s_ko[row] * (uint32_t)u;
+            Aval = cmul(__ldg(a.tw_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw_hi + (e >> kTwLoBits)));
+        }
+        float2 y[R2];
+        const float2 *src = mid + row * K::MIDP + u * K::BP;
+#pragma unroll
+        for (int t = 0; t < R2; ++t) y[t] = src[t];
+        Dft<R2>::run(y);
+        float2 *dst = nat + row * K::R + u;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+            float2 val = y[k2];
+            if (TW) val = cmul(val, k2 == 0 ? Aval : cmul(Aval, P[row * R2 + k2]));
+            dst[R1 * k2] = val;
+        }
+    }
+}
+
+template <int R1, int R2>
+__global__ void __launch_bounds__(128, 4)
+hilbert_mid_kernel(const MidArgs a) {
+    using K = MidCfg<R1, R2>;
+    constexpr int R = K::R;
+    extern __shared__ __align__(128) unsigned char mid_smem[];
+    float2 *nat = reinterpret_cast<float2 *>(mid_smem);   // [8][R] natural-order rows (TMA source / destination)
+    float2 *mid = nat + K::ROWS * R;                      // [8][R1][BP] exchange buffer
+    float2 *twQ = mid + K::ROWS * K::MIDP;                // [q][u] stage twiddles
+    float2 *P = twQ + R;                                  // [8][R2] w^(ko*R1*k2)
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(P + K::ROWS * R2);
+    __shared__ int s_o[K::ROWS], s_kb[K::ROWS / 2], s_ko[K::ROWS];
+    __shared__ float2 s_wkb[K::ROWS / 2];
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < R; i += K::T) {
+        const int q = i / R1, u = i - q * R1;
+        twQ[i] = __ldg(a.twR + q * u);
+    }
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+
+    constexpr uint32_t kRowBytes = R * sizeof(float2);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        const int batch = tile / a.tiles_per_batch;
+        const int p0 = (tile - batch * a.tiles_per_batch) * (K::ROWS / 2);
+        float2 *zb = a.z + (size_t)batch * a.zs;
+        // rows of this tile: slot 2i = row o of pair i, slot 2i+1 = its mirror (-1: nothing to load)
+        if (tid < K::ROWS / 2) {
+            int o = -1, o2 = -1, kb = 0;
+            if (p0 + tid < a.npairs) {
+                const MidRow r = a.rows[p0 + tid];
+                o = r.o;
+                o2 = r.o2 == r.o ? -1 : r.o2;
+                kb = r.kb;
+                const uint32_t e = (uint32_t)kb;
+                s_wkb[tid] = cmul(__ldg(a.tw2_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw2_hi + (e >> kTwLoBits)));
+            }
+            s_o[2 * tid] = o;
+            s_o[2 * tid + 1] = o2;
+            s_kb[tid] = kb;
+            s_ko[2 * tid] = o >= 0 ? o % a.ko_R : 0;
+            s_ko[2 * tid + 1] = o2 >= 0 ? o2 % a.ko_R : 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t bytes = 0;
+            for (int s = 0; s < K::ROWS; ++s) bytes += s_o[s] >= 0 ? kRowBytes : 0u;
+            mbar_expect_tx(mbar, bytes);
+            for (int s = 0; s < K::ROWS; ++s)
+                if (s_o[s] >= 0) tma_load_bulk(nat + s * R, zb + (size_t)s_o[s] * R, kRowBytes, mbar);
+        }
+        // rows that are not loaded transform zeros
+        for (int s = 0; s < K::ROWS; ++s)
+            if (s_o[s] < 0)
+                for (int i = tid; i < R; i += K::T) nat[s * R + i] = make_float2(0.f, 0.f);
+        if (a.tw_mode != 0) {
+            for (int i = tid; i < K::ROWS * R2; i += K::T) {
+                const int row = i / R2, k2 = i - row * R2;
+                const uint32_t e = (uint32_t)s_ko[row] * (uint32_t)(R1 * k2);
+                P[i] = cmul(__ldg(a.tw_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw_hi + (e >> kTwLoBits)));
+            }
+        }
+        __syncthreads();
+        mbar_wait(mbar, it & 1);
+
+        // ---- last forward pass
+        mid_stage1<R1, R2>(nat, mid, twQ, tid);
+        __syncthreads();
+        mid_stage2<R1, R2, false>(mid, nat, P, a, s_ko, tid);
+        __syncthreads();
+
+        // ---- untangle the real-input spectrum, apply -i*sgn, re-tangle, conjugate, scale
+        for (int pr = 0; pr < K::ROWS / 2; ++pr) {
+            if (s_o[2 * pr] < 0) continue;
+            const bool self = s_o[2 * pr + 1] < 0;
+            const int kb = s_kb[pr];
+            float2 *row = nat + (2 * pr) * R;
+            float2 *row2 = self ? row : row + R;
+            const float2 wkb = s_wkb[pr];
+            for (int j = tid; j < R; j += K::T) {
+                const int j2 = kb ? R - 1 - j : (j ? R - j : 0);
+                if (self && j2 < j) continue;
+                if (kb == 0 && j == 0) {
+                    row[0] = make_float2(0.f, 0.f);
+                    continue;
+                }
+                const float2 zk = row[j], zm = row2[j2];
+                const float2 w = cmul(wkb, __ldg(a.twB + j));                                  // w_n^k, k = kb + ncols*j
+                const float2 s = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));   // (zk + conj zm)/2
+                const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));   // (zk - conj zm)/2
+                const float2 aa = cmul(make_float2(w.x, -w.y), s), bb = cmul(w, d);
+                row[j] = make_float2((aa.x - bb.x) * a.inv_m, -(aa.y - bb.y) * a.inv_m);
+                if (!(self && j2 == j)) {
+                    const float2 a2 = cmul(w, make_float2(s.x, -s.y)),
+                                 b2 = cmul(make_float2(w.x, -w.y), make_float2(d.x, -d.y));
+                    row2[j2] = make_float2(-(a2.x + b2.x) * a.inv_m, (a2.y + b2.y) * a.inv_m);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- first inverse pass (forward kernels on conjugated data)
+        mid_stage1<R1, R2>(nat, mid, twQ, tid);
+        __syncthreads();
+        if (a.tw_mode != 0)
+            mid_stage2<R1, R2, true>(mid, nat, P, a, s_ko, tid);
+        else
+            mid_stage2<R1, R2, false>(mid, nat, P, a, s_ko, tid);
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            for (int s = 0; s < K::ROWS; ++s)
+                if (s_o[s] >= 0) tma_store_bulk(zb + (size_t)s_o[s] * R, nat + s * R, kRowBytes);
+            tma_store_commit();
+            tma_store_wait_read();   // the rows may be overwritten by the next tile's loads
+        }
+        __syncthreads();
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+inline bool mid_pair(int R, int *R1, int *R2) {
+    static const int pairs[][2] = {{14, 28}};
+    for (auto &pr : pairs)
+        if (pr[0] * pr[1] == R) {
+            if (R1) *R1 = pr[0];
+            if (R2) *R2 = pr[1];
+            return true;
+        }
+    return false;
+}
+
+}  // namespace fast
+}  // namespace wefax
