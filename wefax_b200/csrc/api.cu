@@ -201,11 +201,22 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
         ctx->use_tma = !(tma && tma[0] == '0');
         const char *fastk = getenv("WEFAX_FFT_FAST");
         ctx->use_fast = !(fastk && fastk[0] == '0');
+        int prio_least = 0, prio_greatest = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         if (stream) {
             ctx->stream = (cudaStream_t)stream;
         } else {
-            CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            // the main stream outranks the auxiliary one: its small latency-bound kernels get SM slots first
+            CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
             ctx->own_stream = true;
+        }
+        // WEFAX_OVERLAP=1: grey-map tail on a side stream under the phasing search.  Measured on B200: the
+        // search's 1024-thread CTAs starve behind the bulk kernel (search 85 -> 131 us, step -0.5 %), so off by default.
+        const char *ovl = getenv("WEFAX_OVERLAP");
+        if (ovl && ovl[0] == '1') {
+            CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_least));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         }
     });
     if (rc != WEFAX_OK) {
@@ -220,6 +231,12 @@ void wefax_ctx_destroy(wefax_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_join);
+    }
     ctx->plans.clear();
     ctx->bluestein.clear();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -435,9 +452,9 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                 hilbert_envelope_bluestein(ctx, n, d_audio, (size_t)n, d_env, (size_t)n, g);
             // ---- median-5, percentiles, grey map (wefax.py:175,196-200) ---------------
             launch_percentiles(ctx, d_env, (size_t)n, n, g, d_sel, d_res);
-            launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res);
+            cudaEvent_t tail_done = launch_quantise_split(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res, splan);
             // ---- phasing search (wefax.py:218-294) and raster (wefax.py:296-327) -----
-            launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan);
+            launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, tail_done);
             if (d_raster)
                 launch_raster(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, d_raster, rs, max_width, (int)(n / min_width));
             float *d_demod = nullptr;
@@ -563,7 +580,7 @@ int wefax_digitalize(wefax_ctx *ctx, long long n, int batch, const float *envelo
         CUDA_CHECK(cudaMemcpyAsync(de, envelope, bytes, cudaMemcpyHostToDevice, st));
         CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * batch, st));
         launch_percentiles(ctx, de, (size_t)n, n, batch, d_sel, d_res);
-        launch_quantise(ctx, de, (size_t)n, dd, (size_t)n, n, batch, d_res);
+        launch_quantise(ctx, de, (size_t)n, dd, (size_t)n, n, batch, d_res, 0, n, ctx->stream, "quantise");
         if (demodulated) {
             launch_median5(ctx, de, (size_t)n, dm, (size_t)n, n, batch);
             CUDA_CHECK(cudaMemcpyAsync(demodulated, dm, bytes, cudaMemcpyDeviceToHost, st));

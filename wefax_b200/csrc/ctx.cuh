@@ -21,6 +21,9 @@ struct wefax_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // low-priority side stream for bulk work that may overlap latency-bound kernels of the main stream
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string last_error;
     long long launches = 0;
     long long workspace_limit = 24ll << 30;
@@ -55,7 +58,8 @@ FftPlan *get_plan(wefax_ctx *ctx, long long n);   // nullptr when n needs Bluest
 struct StageTimer {
     wefax_ctx *ctx;
     cudaEvent_t e1 = nullptr;
-    StageTimer(wefax_ctx *c, const char *name) : ctx(c) {
+    cudaStream_t stream;
+    StageTimer(wefax_ctx *c, const char *name, cudaStream_t on = nullptr) : ctx(c), stream(on ? on : c->stream) {
         if (!ctx->timing) return;
         cudaEvent_t ev[2];
         for (auto &e : ev) {
@@ -66,7 +70,7 @@ struct StageTimer {
                 CUDA_CHECK(cudaEventCreate(&e));
             }
         }
-        CUDA_CHECK(cudaEventRecord(ev[0], ctx->stream));
+        CUDA_CHECK(cudaEventRecord(ev[0], stream));
         e1 = ev[1];
         wefax_ctx::Span sp;
         strncpy(sp.name, name, sizeof(sp.name) - 1);
@@ -76,7 +80,7 @@ struct StageTimer {
         ctx->spans.push_back(sp);
     }
     ~StageTimer() {
-        if (e1) cudaEventRecord(e1, ctx->stream);
+        if (e1) cudaEventRecord(e1, stream);
     }
 };
 

@@ -77,9 +77,14 @@ template <int R1, int R2> struct MidCfg {
 template <int R1, int R2>
 __device__ __forceinline__ void mid_stage1(const float2 *nat, float2 *mid, const float2 *twQ, int tid) {
     using K = MidCfg<R1, R2>;
+    // G1 lanes per row (power of two >= R2): a half-warp never straddles two rows, so the 64-bit
+    // shared-memory accesses stay conflict-free
+    constexpr int G1 = R2 <= 16 ? 16 : 32;
+    static_assert(R2 <= 32, "stage-1 lane group");
 #pragma unroll 1
-    for (int item = tid; item < R2 * K::ROWS; item += K::T) {
-        const int row = item / R2, q = item - row * R2;
+    for (int item = tid; item < G1 * K::ROWS; item += K::T) {
+        const int row = item / G1, q = item % G1;
+        if (q >= R2) continue;
         float2 v[R1];
         const float2 *src = nat + row * K::R + q;
 #pragma unroll
@@ -97,9 +102,12 @@ template <int R1, int R2, bool TW>
 __device__ __forceinline__ void mid_stage2(const float2 *mid, float2 *nat, const float2 *P, const MidArgs &a,
                                            const int *s_ko, int tid) {
     using K = MidCfg<R1, R2>;
+    constexpr int G2 = R1 <= 16 ? 16 : 32;
+    static_assert(R1 <= 32, "stage-2 lane group");
 #pragma unroll 1
-    for (int item = tid; item < R1 * K::ROWS; item += K::T) {
-        const int row = item / R1, u = item - row * R1;
+    for (int item = tid; item < G2 * K::ROWS; item += K::T) {
+        const int row = item / G2, u = item % G2;
+        if (u >= R1) continue;
         float2 Aval = make_float2(1.f, 0.f);
         if (TW) {
             const uint32_t e = (uint32_t)s_ko[row] * (uint32_t)u;

@@ -424,6 +424,8 @@ struct PctState {                  // per recording, device
     unsigned long long below[2];   // elements with key < lo_a / < hi_a
     uint32_t len[2];               // candidates collected in each list (may exceed cap: overflow)
     int fallback;
+    uint32_t out_key[4];           // order statistics found by the two halves of the final selection
+    unsigned int done;             // halves that have delivered their keys
 };
 
 // Exact selection of NT order statistics among `count` keys produced by key_at(i),
@@ -553,7 +555,7 @@ pct_sample_kernel(const float *env, size_t es, PctGeom g, float *samp, size_t ss
 
 // scratch of the cooperative selections of one recording (zeroed before every use)
 struct PctCoop {
-    CoopSync sync[2];                // bracket kernel, final kernel
+    CoopSync sync[3];                // bracket kernel, final kernel (low list, high list)
     uint32_t hist[3][3 * 4 * 2048];  // [sample | low list | high list][level][target][bin]
 };
 
@@ -578,6 +580,7 @@ pct_bracket_kernel(const float *samp, size_t ss, PctGeom g, PctState *st_all, Pc
         st->below[0] = st->below[1] = 0;
         st->len[0] = st->len[1] = 0;
         st->fallback = 0;
+        st->done = 0;
     }
 }
 
@@ -676,12 +679,35 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
         return;
     }
     unsigned phase = 0;
+    if (ncta >= 2) {
+        // the CTAs of the recording split into two groups that select in the two lists at the same time
+        const int h = cta & 1, gcta = cta >> 1;
+        const unsigned gn = (unsigned)((ncta + 1 - h) >> 1);
+        const float *lst = h ? list_hi : list_lo;
+        if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)st->below[h];
+        __syncthreads();
+        coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], gcta, gn,
+                       &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
+        if (gcta == 0 && threadIdx.x == 0) {
+            st->out_key[2 * h] = s_prefix[0];
+            st->out_key[2 * h + 1] = s_prefix[1];
+            __threadfence();
+            if (atomicAdd(&st->done, 1u) == 1u) {   // the other half delivered first: finish
+                __threadfence();
+                uint32_t key[4];
+                for (int t = 0; t < 4; ++t) key[t] = *((volatile uint32_t *)&st->out_key[t]);
+                write_percentiles(res_all + rec, key, g.t_lo, g.t_hi);
+            }
+        }
+        return;
+    }
     for (int h = 0; h < 2; ++h) {
         const float *lst = h ? list_hi : list_lo;
         if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)st->below[h];
         __syncthreads();
         coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], cta,
-                       (unsigned)ncta, &coop->sync[1], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
+                       (unsigned)ncta, &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
+        phase = 0;   // each list has its own barrier counter
         if (threadIdx.x < 2) s_key[2 * h + threadIdx.x] = s_prefix[threadIdx.x];
         __syncthreads();
     }
@@ -819,14 +845,15 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
 // grey map  (wefax.py:197-200,216): round(255*(env-low)/(high-low)), clip, int
 // ===========================================================================
 __global__ void __launch_bounds__(256)
-quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long n, const RecResult *res_all) {
+quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long n, const RecResult *res_all,
+                long long i_begin, long long i_end) {
     const RecResult *res = res_all + blockIdx.y;
     const float *e = env + (size_t)blockIdx.y * es;
     uint8_t *d = dig + (size_t)blockIdx.y * ds;
     const double low = res->low;
     const double delta = __dsub_rn(res->high, low);
-    long long i0 = 8 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
-    if (i0 >= n) return;
+    long long i0 = i_begin + 8 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);   // i_begin % 8 == 0
+    if (i0 >= i_end) return;
     float m[8];
     load_med8(e, i0, n, m);
     // numpy: round(255 * (env - low) / delta) in float64 (rint = half to even = numpy.round).
@@ -858,11 +885,13 @@ quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long 
     }
 }
 
+// Grey levels of samples [i_begin, i_end) (i_begin a multiple of 8) on `stream`.
 void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
-                     const RecResult *res) {
-    StageTimer timer(ctx, "quantise");
-    dim3 grid((unsigned)((n + 2047) / 2048), batch);
-    quantise_kernel<<<grid, 256, 0, ctx->stream>>>(env, es, dig, ds, n, res);
+                     const RecResult *res, long long i_begin, long long i_end, cudaStream_t stream, const char *tag) {
+    if (i_end <= i_begin) return;
+    StageTimer timer(ctx, tag, stream);
+    dim3 grid((unsigned)((i_end - i_begin + 2047) / 2048), batch);
+    quantise_kernel<<<grid, 256, 0, stream>>>(env, es, dig, ds, n, res, i_begin, i_end);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -1307,7 +1336,7 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
 }
 
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
-                        RecResult *res, int min_mindistance, const SyncPlan &sp) {
+                        RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready) {
     StageTimer timer(ctx, "sync_search");
     cudaStream_t st = ctx->stream;
     if (sp.any_fast) {
@@ -1339,6 +1368,8 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
     } else {
         CUDA_CHECK(cudaMemsetAsync(sp.need_scan, 1, sizeof(int) * batch, st));
     }
+    // the parallel search above only reads the head of the recording; the sequential fallback may read all of it
+    if (all_data_ready) CUDA_CHECK(cudaStreamWaitEvent(st, all_data_ready, 0));
     if (min_mindistance >= 4096)
         sync_search_kernel<4><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
     else if (min_mindistance >= 2048)
@@ -1347,6 +1378,22 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         sync_search_kernel<1><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
+}
+
+cudaEvent_t launch_quantise_split(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n,
+                                  int batch, const RecResult *res, const SyncPlan &sp) {
+    // the parallel search reads positions < max_limc + template length
+    const long long head = sp.any_fast ? ((sp.max_limc + kSyncMaxL + 2047) / 2048) * 2048 : n;
+    if (!ctx->aux_stream || head >= n) {
+        launch_quantise(ctx, env, es, dig, ds, n, batch, res, 0, n, ctx->stream, "quantise");
+        return nullptr;
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    launch_quantise(ctx, env, es, dig, ds, n, batch, res, 0, head, ctx->stream, "quantise_head");
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    launch_quantise(ctx, env, es, dig, ds, n, batch, res, head, n, ctx->aux_stream, "quantise");
+    CUDA_CHECK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    return ctx->ev_join;
 }
 
 // ===========================================================================

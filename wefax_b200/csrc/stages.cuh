@@ -75,10 +75,16 @@ void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, siz
 void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
                         RecResult *res);
 void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
-                     const RecResult *res);
+                     const RecResult *res, long long i_begin, long long i_end, cudaStream_t stream, const char *tag);
+// Grey map of the whole recording with the tail (everything the parallel phasing search does not read)
+// on the context's low-priority auxiliary stream, so that it overlaps the latency-bound search kernels.
+// Returns the event the tail signals (nullptr when everything ran on the main stream).
+cudaEvent_t launch_quantise_split(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n,
+                                  int batch, const RecResult *res, const SyncPlan &sp);
 // min_mindistance: smallest LineDev.mindistance of the batch (sizes the scan chunk; must be >= 1024)
+// all_data_ready (may be null): event to wait for before the sequential fallback scan, which reads all of dig
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
-                        RecResult *res, int min_mindistance, const SyncPlan &sp);
+                        RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready = nullptr);
 // sizes the parallel search for recordings [first, first+count) and uploads its geometry
 SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long long n);
 void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
