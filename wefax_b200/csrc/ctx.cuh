@@ -130,6 +130,7 @@ bool try_launch_fast(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const S
         switch (p.fast_R1 * 100 + p.fast_R2) {
 #define WEFAX_FAST_CASE(a, b) \
     case (a) * 100 + (b): launch_fast_variant<a, b, StoreOp>(ctx, p, ld.src, ld.bstride, st, batch); break;
+            WEFAX_FAST_CASE(15, 7)
             WEFAX_FAST_CASE(12, 12)
             WEFAX_FAST_CASE(14, 12)
             WEFAX_FAST_CASE(15, 12)

@@ -394,7 +394,12 @@ void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t
         ensure_mid_tables(ctx, half);
         launch_pass(ctx, half->fwd[0], load_c((const float2 *)x, xs / 2), StoreComplex{z, zs, 1.f, 0}, batch);
         for (int i = 1; i < P - 1; ++i) launch_pass(ctx, half->fwd[i], load_c(z, zs), StoreComplex{z, zs, 1.f, 0}, batch);
-        launch_mid<14, 28>(ctx, half, z, zs, batch);
+        switch (R1 * 100 + R2) {
+            case 1428: launch_mid<14, 28>(ctx, half, z, zs, batch); break;
+            case 1014: launch_mid<10, 14>(ctx, half, z, zs, batch); break;
+            case 1520: launch_mid<15, 20>(ctx, half, z, zs, batch); break;
+            default: launch_mid<10, 15>(ctx, half, z, zs, batch); break;
+        }
         for (int i = P - 2; i >= 1; --i) launch_pass(ctx, half->inv[i], load_c(z, zs), StoreComplex{z, zs, 1.f, 0}, batch);
         launch_pass(ctx, half->inv[0], load_c(z, zs), store_env, batch);
         return;

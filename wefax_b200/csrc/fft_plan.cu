@@ -8,6 +8,7 @@
 
 #include "fft.cuh"
 #include "fft_fast.cuh"
+#include "fft_mid.cuh"
 
 namespace wefax {
 
@@ -98,6 +99,8 @@ double pass_cost(int R, long long n, bool strided) {
     if (sp.cost < 0) return -1.0;
     // specialised two-stage kernel (fft_fast.cuh): ~45 instructions per point
     if (strided && n >= (1 << 16) && env_int("WEFAX_FFT_FAST", 1) && fast::fast_pair(R, nullptr, nullptr)) return 50.0;
+    // stride-1 pass lengths the fused middle kernel of the real-input Hilbert transform handles (fft_mid.cuh)
+    if (!strided && n >= (1 << 16) && env_int("WEFAX_FFT_FAST", 1) && fast::mid_pair(R, nullptr, nullptr)) return 60.0;
     const int C = tile_cols(R, (int)std::min<long long>(n / R, 1 << 30), strided);
     double c = kPassCost;
     for (int r : sp.radices) {
