@@ -26,32 +26,127 @@
 
 #include "fft.cuh"
 
+#ifndef WEFAX_FAST_NBUF
+#define WEFAX_FAST_NBUF 2
+#endif
+#ifndef WEFAX_FAST_H
+#define WEFAX_FAST_H 1   // column halves per thread
+#endif
+
 namespace wefax {
 namespace fast {
 
+// ----------------------------- packed fp32 arithmetic ------------------------
+// Blackwell issues two fp32 operations per instruction on a 64-bit register pair (SASS FADD2 /
+// FMUL2 / FFMA2; PTX add/mul/fma.rn.f32x2) and can swap or negate the halves of an operand for
+// free.  A complex number is exactly such a pair, so complex add/sub cost one instruction, a
+// real-constant scale-and-accumulate one, and a complex multiply two (w given as (wx, wx) and
+// (-wy, wy)) or three (w given as (wx, wy)) instead of two, two and four.  Same IEEE roundings as
+// the scalar forms (no contraction beyond the explicit fma).
+#define WEFAX_P2(op)                                                                                          \
+    __device__ __forceinline__ float2 p##op(float2 a, float2 b) {                                             \
+        float2 r;                                                                                             \
+        asm("{.reg .b64 ta, tb, tr; mov.b64 ta, {%2,%3}; mov.b64 tb, {%4,%5}; " #op                           \
+            ".rn.f32x2 tr, ta, tb; mov.b64 {%0,%1}, tr;}"                                                      \
+            : "=f"(r.x), "=f"(r.y)                                                                            \
+            : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                        \
+        return r;                                                                                             \
+    }
+WEFAX_P2(add)
+WEFAX_P2(sub)
+WEFAX_P2(mul)
+#undef WEFAX_P2
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ta, tb, tc, tr; mov.b64 ta, {%2,%3}; mov.b64 tb, {%4,%5}; mov.b64 tc, {%6,%7}; "
+        "fma.rn.f32x2 tr, ta, tb, tc; mov.b64 {%0,%1}, tr;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 bc(float c) { return make_float2(c, c); }
+// v * w with w = (wx, wy) given as wa = (wx, wx), wb = (-wy, wy)
+__device__ __forceinline__ float2 pcmul2(float2 v, float2 wa, float2 wb) { return pfma(v, wa, pmul(swp(v), wb)); }
+// v * w with w = (wx, wy) as stored: wx*v + wy*(-v.y, v.x)
+__device__ __forceinline__ float2 pcmul3(float2 v, float2 w) {
+    return pfma(v, bc(w.x), pmul(bc(w.y), pmul(swp(v), make_float2(-1.f, 1.f))));
+}
+// v * (cx + i*cy) for literal cx, cy
+__device__ __forceinline__ float2 pcmulc(float2 v, float cx, float cy) {
+    return pfma(v, bc(cx), pmul(swp(v), make_float2(-cy, cy)));
+}
+
 // ----------------------------- codelets -------------------------------------
-template <int r> struct Cs {
-    __device__ __forceinline__ static void run(float2 *v) { Bfly<r>::run(v, nullptr); }   // 2, 4, 8
+// In-register butterflies, natural order in and out, X_u = sum_t x_t exp(-2*pi*i*t*u/r).
+template <int r> struct Cs;
+template <> struct Cs<2> {
+    __device__ __forceinline__ static void run(float2 *v) {
+        const float2 a = v[0], b = v[1];
+        v[0] = padd(a, b);
+        v[1] = psub(a, b);
+    }
+};
+template <> struct Cs<4> {
+    __device__ __forceinline__ static void run(float2 *v) {
+        const float2 t0 = padd(v[0], v[2]), t1 = psub(v[0], v[2]);
+        const float2 t2 = padd(v[1], v[3]), t3 = swp(psub(v[1], v[3]));
+        v[0] = padd(t0, t2);
+        v[2] = psub(t0, t2);
+        v[1] = pfma(make_float2(1.f, -1.f), t3, t1);    // t1 + (t3.y, -t3.x)
+        v[3] = pfma(make_float2(-1.f, 1.f), t3, t1);
+    }
+};
+// odd prime r: pair (t, r-t); CS[j-1] = (cos, sin)(2*pi*j/r)
+template <int r> struct OddCs {
+    static constexpr int h = (r - 1) / 2;
+    __device__ __forceinline__ static void run(float2 *v, const float (&co)[h], const float (&si)[h]) {
+        float2 a[h], b[h];
+#pragma unroll
+        for (int t = 1; t <= h; ++t) {
+            a[t - 1] = padd(v[t], v[r - t]);
+            b[t - 1] = swp(psub(v[t], v[r - t]));      // (d.y, d.x) of the difference d
+        }
+        const float2 v0 = v[0];
+        float2 s = v0;
+#pragma unroll
+        for (int t = 0; t < h; ++t) s = padd(s, a[t]);
+        v[0] = s;
+#pragma unroll
+        for (int u = 1; u <= h; ++u) {
+            float2 p = v0, q = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 1; t <= h; ++t) {
+                const int j = (t * u) % r;
+                const float c = j <= h ? co[j - 1] : co[r - j - 1];
+                const float sn = j <= h ? si[j - 1] : -si[r - j - 1];
+                p = pfma(bc(c), a[t - 1], p);
+                // q = sum sn * (d.y, -d.x) = -i * sum sn * d
+                q = t == 1 ? pmul(make_float2(sn, -sn), b[t - 1]) : pfma(make_float2(sn, -sn), b[t - 1], q);
+            }
+            v[u] = padd(p, q);
+            v[r - u] = psub(p, q);
+        }
+    }
 };
 template <> struct Cs<3> {
     __device__ __forceinline__ static void run(float2 *v) {
-        const float2 cs[1] = {make_float2(-0.5f, 0.86602540378443865f)};
-        Bfly<3>::run(v, cs);
+        const float co[1] = {-0.5f}, si[1] = {0.86602540378443865f};
+        OddCs<3>::run(v, co, si);
     }
 };
 template <> struct Cs<5> {
     __device__ __forceinline__ static void run(float2 *v) {
-        const float2 cs[2] = {make_float2(0.30901699437494742f, 0.95105651629515357f),
-                              make_float2(-0.80901699437494742f, 0.58778525229247313f)};
-        Bfly<5>::run(v, cs);
+        const float co[2] = {0.30901699437494742f, -0.80901699437494742f};
+        const float si[2] = {0.95105651629515357f, 0.58778525229247313f};
+        OddCs<5>::run(v, co, si);
     }
 };
 template <> struct Cs<7> {
     __device__ __forceinline__ static void run(float2 *v) {
-        const float2 cs[3] = {make_float2(0.62348980185873353f, 0.78183148246802981f),
-                              make_float2(-0.22252093395631440f, 0.97492791218182361f),
-                              make_float2(-0.90096886790241913f, 0.43388373911755812f)};
-        Bfly<7>::run(v, cs);
+        const float co[3] = {0.62348980185873353f, -0.22252093395631440f, -0.90096886790241913f};
+        const float si[3] = {0.78183148246802981f, 0.97492791218182361f, 0.43388373911755812f};
+        OddCs<7>::run(v, co, si);
     }
 };
 
@@ -92,6 +187,9 @@ template <int A, int B> struct Pfa {
 };
 
 template <int N> struct Dft;
+template <> struct Dft<7> {
+    __device__ __forceinline__ static void run(float2 *v) { Cs<7>::run(v); }
+};
 template <> struct Dft<12> {
     __device__ __forceinline__ static void run(float2 *v) { Pfa<3, 4>::run(v); }
 };
@@ -109,25 +207,23 @@ template <> struct Dft<16> {
 #pragma unroll
         for (int tb = 0; tb < 4; ++tb) {
             float2 x[4] = {v[tb], v[4 + tb], v[8 + tb], v[12 + tb]};
-            Bfly<4>::run(x, nullptr);
+            Cs<4>::run(x);
 #pragma unroll
             for (int ua = 0; ua < 4; ++ua) t[ua][tb] = x[ua];
         }
         // inner twiddles w16^(ua*tb)
-        const float2 w1 = make_float2(c1, -s1), w2 = make_float2(h, -h), w3 = make_float2(s1, -c1);
-        const float2 w6 = make_float2(-h, -h), w9 = make_float2(-c1, s1);
-        t[1][1] = cmul(t[1][1], w1);
-        t[1][2] = cmul(t[1][2], w2);
-        t[1][3] = cmul(t[1][3], w3);
-        t[2][1] = cmul(t[2][1], w2);
-        t[2][2] = make_float2(t[2][2].y, -t[2][2].x);   // w16^4 = -i
-        t[2][3] = cmul(t[2][3], w6);
-        t[3][1] = cmul(t[3][1], w3);
-        t[3][2] = cmul(t[3][2], w6);
-        t[3][3] = cmul(t[3][3], w9);
+        t[1][1] = pcmulc(t[1][1], c1, -s1);
+        t[1][2] = pcmulc(t[1][2], h, -h);
+        t[1][3] = pcmulc(t[1][3], s1, -c1);
+        t[2][1] = pcmulc(t[2][1], h, -h);
+        t[2][2] = pmul(swp(t[2][2]), make_float2(1.f, -1.f));   // w16^4 = -i
+        t[2][3] = pcmulc(t[2][3], -h, -h);
+        t[3][1] = pcmulc(t[3][1], s1, -c1);
+        t[3][2] = pcmulc(t[3][2], -h, -h);
+        t[3][3] = pcmulc(t[3][3], -c1, s1);
 #pragma unroll
         for (int ua = 0; ua < 4; ++ua) {
-            Bfly<4>::run(t[ua], nullptr);
+            Cs<4>::run(t[ua]);
 #pragma unroll
             for (int ub = 0; ub < 4; ++ub) v[ua + 4 * ub] = t[ua][ub];
         }
@@ -135,29 +231,42 @@ template <> struct Dft<16> {
 };
 
 // ----------------------------- the pass -------------------------------------
+// A tile is R rows x (C*H) adjacent columns.  Thread (row, cc) owns columns cc + h*C, h < H: with H = 2
+// the two 128-byte halves of a 256-byte row segment are requested back to back by the same warp, which is
+// what the HBM controller needs to keep a mixed read+write stream near the copy rate
+// (tools/strided_copy_bench.cu: 128-byte segments 3.5 TB/s, 256-byte segments 5.4 TB/s).
 template <int R1, int R2, int C> struct Cfg {
     static constexpr int R = R1 * R2;
+    static constexpr int H = WEFAX_FAST_H;
+    static constexpr int CW = C * H;                                // columns per tile
     static constexpr int ROWS = R1 > R2 ? R1 : R2;
     static constexpr int T = ((ROWS * C + 31) / 32) * 32;
-    static constexpr int BUF = R * C + R2 * C;                      // tile + P table, in float2
-    static constexpr int SMEM = (R + 2 * BUF) * (int)sizeof(float2);
-    static constexpr int MINB = (3 * SMEM + 3 * 1024 <= 227 * 1024 && 3 * T <= 768) ? 3 : 2;
+    static constexpr int BUF = R * CW + 2 * R2 * CW;                // tile (float2) + P table (float4), in float2
+    static constexpr int NBUF = WEFAX_FAST_NBUF;                    // 2: one barrier per tile; 1: two barriers, half the memory
+    static constexpr int SMEM = (2 * R + NBUF * BUF) * (int)sizeof(float2);   // twQ is a float4 table
+    // CTAs per SM: shared memory, and a register budget of 64 * H per thread
+    static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
+    static constexpr int BY_REGS = 1024 / (T * H);
+    static constexpr int MINB_ = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+    static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 3 ? 3 : MINB_);
 };
 
 template <int R1, int R2, int C, class StoreOp>
 __global__ void __launch_bounds__((Cfg<R1, R2, C>::T), (Cfg<R1, R2, C>::MINB))
 fft_fast_strided_kernel(const PassDev p, const float2 *src, size_t src_bstride, const StoreOp st, int total_tiles) {
     using K = Cfg<R1, R2, C>;
-    constexpr int R = K::R;
+    constexpr int R = K::R, H = K::H, CW = K::CW;
     extern __shared__ __align__(16) unsigned char fast_smem[];
-    float2 *twQ = reinterpret_cast<float2 *>(fast_smem);   // [q][u] stage twiddles w_R^(q*u)
-    float2 *buf0 = twQ + R;
+    // twiddles are kept as (wx, wx, -wy, wy): a complex multiply is then two packed instructions
+    float4 *twQ = reinterpret_cast<float4 *>(fast_smem);   // [q][u] stage twiddles w_R^(q*u)
+    float2 *buf0 = reinterpret_cast<float2 *>(twQ + R);
 
     const int tid = threadIdx.x;
     const int cc = tid % C, row = tid / C;                 // row = q in stage 1, = u in stage 2
     for (int i = tid; i < R; i += K::T) {
         const int q = i / R1, u = i - q * R1;
-        twQ[i] = __ldg(p.twR + q * u);
+        const float2 w = __ldg(p.twR + q * u);
+        twQ[i] = make_float4(w.x, w.x, -w.y, w.y);
     }
     __syncthreads();
     const bool act1 = row < R2, act2 = row < R1;
@@ -166,63 +275,101 @@ fft_fast_strided_kernel(const PassDev p, const float2 *src, size_t src_bstride, 
 
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        float2 *tb = buf0 + (it & 1) * K::BUF;
-        float2 *P = tb + R * C;
+        float2 *tb = buf0 + (K::NBUF == 2 ? (it & 1) * K::BUF : 0);
+        float4 *P = reinterpret_cast<float4 *>(tb + R * CW);
         const int batch = tile / p.fast_ntiles;
         const int t_in = tile - batch * p.fast_ntiles;
         const int o = p.fast_divTpo.div(t_in);
-        const uint32_t m = (uint32_t)((t_in - o * p.fast_tiles_per_o) * C + cc);
-        const bool colok = m < (uint32_t)p.S;
-        const size_t cbase = (size_t)o * (size_t)R * rstride + m;
-
-        // inter-pass twiddle factors of this thread (exact two-level look-ups, in flight with the data)
-        uint32_t e0 = 0, de = 0;
-        if (p.tw_mode == 1) {
-            de = m;
-        } else if (p.tw_mode == 2) {
-            const uint32_t ko = (uint32_t)o % (uint32_t)p.ko_R;
-            e0 = ko * m;
-            de = ko * (uint32_t)p.S;
+        const uint32_t m0 = (uint32_t)((t_in - o * p.fast_tiles_per_o) * CW + cc);
+        const size_t obase = (size_t)o * (size_t)R * rstride;
+        bool colok[H];
+        float2 Pval[H], Aval[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const uint32_t m = m0 + h * C;
+            colok[h] = m < (uint32_t)p.S;
+            // inter-pass twiddle factors of this thread (exact two-level look-ups, in flight with the data)
+            uint32_t e0 = 0, de = 0;
+            if (p.tw_mode == 1) {
+                de = m;
+            } else if (p.tw_mode == 2) {
+                const uint32_t ko = (uint32_t)o % (uint32_t)p.ko_R;
+                e0 = ko * m;
+                de = ko * (uint32_t)p.S;
+            }
+            if (!colok[h]) e0 = de = 0;
+            Pval[h] = Aval[h] = make_float2(1.f, 0.f);
+            if (p.tw_mode != 0) {
+                if (act1) Pval[h] = pass_twiddle(p, (uint32_t)(row * R1) * de);
+                if (act2) Aval[h] = pass_twiddle(p, e0 + (uint32_t)row * de);
+            }
         }
-        if (!colok) e0 = de = 0;
-        float2 Pval = make_float2(1.f, 0.f), Aval = make_float2(1.f, 0.f);
-        if (p.tw_mode != 0) {
-            if (act1) Pval = pass_twiddle(p, (uint32_t)(row * R1) * de);
-            if (act2) Aval = pass_twiddle(p, e0 + (uint32_t)row * de);
-        }
 
+        float2 v[H][R1];
         if (act1) {
-            float2 v[R1];
-            const float2 *g = src + (size_t)batch * src_bstride + cbase + (size_t)row * rstride;
+            const float2 *g = src + (size_t)batch * src_bstride + obase + m0 + (size_t)row * rstride;
 #pragma unroll
             for (int t = 0; t < R1; ++t)
-                v[t] = colok ? __ldg(g + (size_t)(R2 * t) * rstride) : make_float2(0.f, 0.f);
-            if (p.tw_mode != 0) P[row * C + cc] = Pval;
-            Dft<R1>::run(v);
-            const float2 *tq = twQ + row * R1;
-            tb[row * C + cc] = v[0];
 #pragma unroll
-            for (int u = 1; u < R1; ++u) tb[(row + R2 * u) * C + cc] = cmul(v[u], tq[u]);
+                for (int h = 0; h < H; ++h)
+                    v[h][t] = colok[h] ? __ldg(g + (size_t)(R2 * t) * rstride + h * C) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < H; ++h) Dft<R1>::run(v[h]);
+        }
+        if (K::NBUF == 1) __syncthreads();   // stage-2 readers of the previous tile are done with the buffer
+        if (act1) {
+            const float4 *tq = twQ + row * R1;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const int col = cc + h * C;
+                if (p.tw_mode != 0) P[row * CW + col] = make_float4(Pval[h].x, Pval[h].x, -Pval[h].y, Pval[h].y);
+                tb[row * CW + col] = v[h][0];
+#pragma unroll
+                for (int u = 1; u < R1; ++u) {
+                    const float4 w = tq[u];
+                    tb[(row + R2 * u) * CW + col] = pcmul2(v[h][u], make_float2(w.x, w.y), make_float2(w.z, w.w));
+                }
+            }
         }
         __syncthreads();
         if (act2) {
-            float2 y[R2];
-            typename StoreOp::Side side[R2];
+            float2 y[H][R2];
+            typename StoreOp::Side side[H][R2];
             if constexpr (kHasSide) {
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2)
-                    if (colok) side[k2] = st.side_load(cbase + (size_t)(row + R1 * k2) * rstride, batch);
+#pragma unroll
+                    for (int h = 0; h < H; ++h)
+                        if (colok[h])
+                            side[h][k2] = st.side_load(obase + m0 + h * C + (size_t)(row + R1 * k2) * rstride, batch);
             }
 #pragma unroll
-            for (int t = 0; t < R2; ++t) y[t] = tb[(row * R2 + t) * C + cc];
-            Dft<R2>::run(y);
-            if (colok) {
+            for (int h = 0; h < H; ++h) {
 #pragma unroll
-                for (int k2 = 0; k2 < R2; ++k2) {
-                    const int k = row + R1 * k2;
-                    float2 val = y[k2];
-                    if (p.tw_mode != 0) val = cmul(val, k2 == 0 ? Aval : cmul(Aval, P[k2 * C + cc]));
-                    st(cbase + (size_t)k * rstride, batch, val, k, 0, side[k2]);
+                for (int t = 0; t < R2; ++t) y[h][t] = tb[(row * R2 + t) * CW + cc + h * C];
+                Dft<R2>::run(y[h]);
+            }
+            float2 Aa[H], Ab[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                Aa[h] = bc(Aval[h].x);
+                Ab[h] = make_float2(-Aval[h].y, Aval[h].y);
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const int k = row + R1 * k2;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    if (!colok[h]) continue;
+                    float2 val = y[h][k2];
+                    if (p.tw_mode != 0) {
+                        val = pcmul2(val, Aa[h], Ab[h]);
+                        if (k2 > 0) {
+                            const float4 w = P[k2 * CW + cc + h * C];
+                            val = pcmul2(val, make_float2(w.x, w.y), make_float2(w.z, w.w));
+                        }
+                    }
+                    st(obase + m0 + h * C + (size_t)k * rstride, batch, val, k, 0, side[h][k2]);
                 }
             }
         }
@@ -231,7 +378,7 @@ fft_fast_strided_kernel(const PassDev p, const float2 *src, size_t src_bstride, 
 
 // (R1, R2) pairs with a compiled kernel; 0 when R has none
 inline bool fast_pair(int R, int *R1, int *R2) {
-    static const int pairs[][2] = {{12, 12}, {14, 12}, {15, 12}, {16, 12}, {14, 14},
+    static const int pairs[][2] = {{15, 7},  {12, 12}, {14, 12}, {15, 12}, {16, 12}, {14, 14},
                                    {15, 14}, {16, 14}, {15, 15}, {16, 15}, {16, 16}};
     for (auto &pr : pairs)
         if (pr[0] * pr[1] == R) {
@@ -242,7 +389,11 @@ inline bool fast_pair(int R, int *R1, int *R2) {
     return false;
 }
 
-constexpr int kFastC = 16;
+#ifndef WEFAX_FAST_C
+#define WEFAX_FAST_C 16
+#endif
+constexpr int kFastC = WEFAX_FAST_C;
+constexpr int kFastCW = WEFAX_FAST_C * WEFAX_FAST_H;   // columns per tile
 
 }  // namespace fast
 }  // namespace wefax

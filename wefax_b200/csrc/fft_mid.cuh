@@ -94,7 +94,7 @@ __device__ __forceinline__ void mid_stage1(const float2 *nat, float2 *mid, const
         const float2 *tq = twQ + q * R1;
         dst[0] = v[0];
 #pragma unroll
-        for (int u = 1; u < R1; ++u) dst[u * K::BP] = cmul(v[u], tq[u]);
+        for (int u = 1; u < R1; ++u) dst[u * K::BP] = pcmul3(v[u], tq[u]);
     }
 }
 
@@ -119,10 +119,14 @@ __device__ __forceinline__ void mid_stage2(const float2 *mid, float2 *nat, const
         for (int t = 0; t < R2; ++t) y[t] = src[t];
         Dft<R2>::run(y);
         float2 *dst = nat + row * K::R + u;
+        const float2 Aa = bc(Aval.x), Ab = make_float2(-Aval.y, Aval.y);
 #pragma unroll
         for (int k2 = 0; k2 < R2; ++k2) {
             float2 val = y[k2];
-            if (TW) val = cmul(val, k2 == 0 ? Aval : cmul(Aval, P[row * R2 + k2]));
+            if (TW) {
+                val = pcmul2(val, Aa, Ab);
+                if (k2 > 0) val = pcmul3(val, P[row * R2 + k2]);
+            }
             dst[R1 * k2] = val;
         }
     }

@@ -280,7 +280,7 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream) {
         d.fast_R1 = d.fast_R2 = 0;
         d.fast_tiles_per_o = d.fast_ntiles = 1;
         if (!d.contiguous && fast::fast_pair(R, &d.fast_R1, &d.fast_R2)) {
-            d.fast_tiles_per_o = (d.S + fast::kFastC - 1) / fast::kFastC;
+            d.fast_tiles_per_o = (d.S + fast::kFastCW - 1) / fast::kFastCW;
             d.fast_ntiles = (int)(nouter * d.fast_tiles_per_o);
         }
         d.fast_divTpo.init(d.fast_tiles_per_o);
