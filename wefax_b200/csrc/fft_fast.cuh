@@ -26,11 +26,17 @@
 
 #include "fft.cuh"
 
+// Tile-shape knobs of the strided pass.  Defaults are the measured best on B200 for the 60-min recording
+// (us per plain pass / last inverse pass):  C=16 NBUF=2: 78 / 105   C=32 NBUF=1: 72 / 101 (default)
+// C=32 NBUF=2 (one CTA per SM): 100 / 120   C=16 H=2 NBUF=1: 86 / 237 (spills)
 #ifndef WEFAX_FAST_NBUF
-#define WEFAX_FAST_NBUF 2
+#define WEFAX_FAST_NBUF 1   // exchange-tile buffers: 2 = one barrier per tile, 1 = two barriers, half the memory
 #endif
 #ifndef WEFAX_FAST_H
-#define WEFAX_FAST_H 1   // column halves per thread
+#define WEFAX_FAST_H 1      // column groups per thread
+#endif
+#ifndef WEFAX_FAST_C
+#define WEFAX_FAST_C 32     // adjacent columns per thread group: 32 = 256-byte row segments
 #endif
 
 namespace wefax {
@@ -43,6 +49,10 @@ namespace fast {
 // real-constant scale-and-accumulate one, and a complex multiply two (w given as (wx, wx) and
 // (-wy, wy)) or three (w given as (wx, wy)) instead of two, two and four.  Same IEEE roundings as
 // the scalar forms (no contraction beyond the explicit fma).
+#ifndef WEFAX_FAST_PACKED
+#define WEFAX_FAST_PACKED 1   // 0: the same formulas on scalar FADD / FMUL / FFMA (A/B measurements)
+#endif
+#if WEFAX_FAST_PACKED
 #define WEFAX_P2(op)                                                                                          \
     __device__ __forceinline__ float2 p##op(float2 a, float2 b) {                                             \
         float2 r;                                                                                             \
@@ -64,6 +74,14 @@ __device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return r;
 }
+#else
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) {
+    return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+}
+#endif
 __device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
 __device__ __forceinline__ float2 bc(float c) { return make_float2(c, c); }
 // v * w with w = (wx, wy) given as wa = (wx, wx), wb = (-wy, wy)
@@ -241,9 +259,9 @@ template <int R1, int R2, int C> struct Cfg {
     static constexpr int CW = C * H;                                // columns per tile
     static constexpr int ROWS = R1 > R2 ? R1 : R2;
     static constexpr int T = ((ROWS * C + 31) / 32) * 32;
-    static constexpr int BUF = R * CW + 2 * R2 * CW;                // tile (float2) + P table (float4), in float2
+    static constexpr int BUF = R * CW + R2 * CW;                    // tile + P table, in float2
     static constexpr int NBUF = WEFAX_FAST_NBUF;                    // 2: one barrier per tile; 1: two barriers, half the memory
-    static constexpr int SMEM = (2 * R + NBUF * BUF) * (int)sizeof(float2);   // twQ is a float4 table
+    static constexpr int SMEM = (R + NBUF * BUF) * (int)sizeof(float2);
     // CTAs per SM: shared memory, and a register budget of 64 * H per thread
     static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
     static constexpr int BY_REGS = 1024 / (T * H);
@@ -257,16 +275,16 @@ fft_fast_strided_kernel(const PassDev p, const float2 *src, size_t src_bstride, 
     using K = Cfg<R1, R2, C>;
     constexpr int R = K::R, H = K::H, CW = K::CW;
     extern __shared__ __align__(16) unsigned char fast_smem[];
-    // twiddles are kept as (wx, wx, -wy, wy): a complex multiply is then two packed instructions
-    float4 *twQ = reinterpret_cast<float4 *>(fast_smem);   // [q][u] stage twiddles w_R^(q*u)
-    float2 *buf0 = reinterpret_cast<float2 *>(twQ + R);
+    // tables stay plain (wx, wy): a 16-byte (wx, wx, -wy, wy) layout would make the multiply two instructions
+    // instead of three but doubles the shared-memory traffic of the twiddles, which costs more (measured)
+    float2 *twQ = reinterpret_cast<float2 *>(fast_smem);   // [q][u] stage twiddles w_R^(q*u)
+    float2 *buf0 = twQ + R;
 
     const int tid = threadIdx.x;
     const int cc = tid % C, row = tid / C;                 // row = q in stage 1, = u in stage 2
     for (int i = tid; i < R; i += K::T) {
         const int q = i / R1, u = i - q * R1;
-        const float2 w = __ldg(p.twR + q * u);
-        twQ[i] = make_float4(w.x, w.x, -w.y, w.y);
+        twQ[i] = __ldg(p.twR + q * u);
     }
     __syncthreads();
     const bool act1 = row < R2, act2 = row < R1;
@@ -276,7 +294,7 @@ fft_fast_strided_kernel(const PassDev p, const float2 *src, size_t src_bstride, 
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         float2 *tb = buf0 + (K::NBUF == 2 ? (it & 1) * K::BUF : 0);
-        float4 *P = reinterpret_cast<float4 *>(tb + R * CW);
+        float2 *P = tb + R * CW;
         const int batch = tile / p.fast_ntiles;
         const int t_in = tile - batch * p.fast_ntiles;
         const int o = p.fast_divTpo.div(t_in);
@@ -318,17 +336,14 @@ fft_fast_strided_kernel(const PassDev p, const float2 *src, size_t src_bstride, 
         }
         if (K::NBUF == 1) __syncthreads();   // stage-2 readers of the previous tile are done with the buffer
         if (act1) {
-            const float4 *tq = twQ + row * R1;
+            const float2 *tq = twQ + row * R1;
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 const int col = cc + h * C;
-                if (p.tw_mode != 0) P[row * CW + col] = make_float4(Pval[h].x, Pval[h].x, -Pval[h].y, Pval[h].y);
+                if (p.tw_mode != 0) P[row * CW + col] = Pval[h];
                 tb[row * CW + col] = v[h][0];
 #pragma unroll
-                for (int u = 1; u < R1; ++u) {
-                    const float4 w = tq[u];
-                    tb[(row + R2 * u) * CW + col] = pcmul2(v[h][u], make_float2(w.x, w.y), make_float2(w.z, w.w));
-                }
+                for (int u = 1; u < R1; ++u) tb[(row + R2 * u) * CW + col] = pcmul3(v[h][u], tq[u]);
             }
         }
         __syncthreads();
@@ -364,10 +379,7 @@ fft_fast_strided_kernel(const PassDev p, const float2 *src, size_t src_bstride, 
                     float2 val = y[h][k2];
                     if (p.tw_mode != 0) {
                         val = pcmul2(val, Aa[h], Ab[h]);
-                        if (k2 > 0) {
-                            const float4 w = P[k2 * CW + cc + h * C];
-                            val = pcmul2(val, make_float2(w.x, w.y), make_float2(w.z, w.w));
-                        }
+                        if (k2 > 0) val = pcmul3(val, P[k2 * CW + cc + h * C]);
                     }
                     st(obase + m0 + h * C + (size_t)k * rstride, batch, val, k, 0, side[h][k2]);
                 }
@@ -389,9 +401,9 @@ inline bool fast_pair(int R, int *R1, int *R2) {
     return false;
 }
 
-#ifndef WEFAX_FAST_C
-#define WEFAX_FAST_C 16
-#endif
+// 16 columns = 128-byte row segments.  Wider tiles were tried (32 columns with 512 threads, or two 16-column
+// halves per thread): the memory system likes them (tools/strided_copy_bench.cu) but the SM side loses more
+// to registers / occupancy than the 256-byte segments win (75-95 us against 80 us per pass on B200).
 constexpr int kFastC = WEFAX_FAST_C;
 constexpr int kFastCW = WEFAX_FAST_C * WEFAX_FAST_H;   // columns per tile
 
