@@ -184,3 +184,17 @@ def test_parallel_png_writer_roundtrip(tmp_path):
     a, b = rng.bytes(100003), rng.bytes(77)
     import zlib
     assert pngio._adler32_combine(zlib.adler32(a), zlib.adler32(b), len(b)) == zlib.adler32(a + b)
+
+
+def test_fft_plan_prefers_the_specialised_kernels():
+    """The half-length transforms of the BASELINE configs run on fft_fast_strided_kernel (strided pass
+    lengths = products of two radices from {12, 14, 15, 16} or 15*7) and hilbert_mid_kernel (last pass
+    392 / 300 / 210 / 150 / 140): csrc/fft_fast.cuh, csrc/fft_mid.cuh."""
+    fast = {a * b for a in (12, 14, 15, 16) for b in (12, 14, 15, 16)} | {105}
+    mid = {392, 300, 210, 150, 140}
+    for n_half in (39_690_000 // 2, 6_615_000 // 2, 13_230_000 // 2, 9_922_500):
+        lens, blu = N.fft_plan_describe(n_half)
+        assert not blu
+        assert all(r in fast for r in lens[:-1]), lens
+        assert lens[-1] in mid, lens
+    assert N.fft_plan_describe(39_690_000 // 2)[0] == [225, 225, 392]

@@ -398,6 +398,7 @@ void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t
             case 1428: launch_mid<14, 28>(ctx, half, z, zs, batch); break;
             case 1014: launch_mid<10, 14>(ctx, half, z, zs, batch); break;
             case 1520: launch_mid<15, 20>(ctx, half, z, zs, batch); break;
+            case 1415: launch_mid<14, 15>(ctx, half, z, zs, batch); break;
             default: launch_mid<10, 15>(ctx, half, z, zs, batch); break;
         }
         for (int i = P - 2; i >= 1; --i) launch_pass(ctx, half->inv[i], load_c(z, zs), StoreComplex{z, zs, 1.f, 0}, batch);

@@ -256,7 +256,7 @@ hilbert_mid_kernel(const MidArgs a) {
 }
 
 inline bool mid_pair(int R, int *R1, int *R2) {
-    static const int pairs[][2] = {{14, 28}, {10, 14}, {15, 20}, {10, 15}};   // keep in step with launch_mid_any
+    static const int pairs[][2] = {{14, 28}, {10, 14}, {15, 20}, {10, 15}, {14, 15}};   // keep in step with launch_mid_any
     for (auto &pr : pairs)
         if (pr[0] * pr[1] == R) {
             if (R1) *R1 = pr[0];
