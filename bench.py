@@ -199,6 +199,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
     def barrier():
