@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WEFAX_ABI_VERSION 2
+#define WEFAX_ABI_VERSION 3
 #define WEFAX_TARGET_RATE 11025   /* wefax.py:60 */
 #define WEFAX_MAX_PEAKS 100       /* wefax.py:251 */
 
@@ -190,6 +190,35 @@ typedef struct {
 int wefax_tone_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int channels, int sample_rate,
                     long long packet_frames, unsigned flags, const wefax_tone_settings *settings,
                     uint8_t *start_flags, uint8_t *stop_flags, int32_t *n_start_peaks, int32_t *n_stop_peaks);
+
+/* ---- EXTENSION: FM-discriminator demodulation, IOC pixel columns ---------
+ * Not in the reference's code (only described in its README.md:85-101): grey = instantaneous
+ * frequency mapped black_hz..white_hz -> 0..255, exact line length 60/lpm s, pi*ioc pixels per line.
+ * No reference parity exists for this entry point; it is checked against oracle/fm_oracle.py and the
+ * synthetic generator's ground truth. */
+typedef struct {
+    double lpm;               /* lines per minute                                         */
+    int ioc;                  /* index of cooperation: 576 or 288 -> round(pi*ioc) pixels  */
+    double black_hz, white_hz;        /* 1500 / 2300 (README.md:87-88)                     */
+    double band_lo_hz, band_hi_hz;    /* zero-phase FIR band-pass cut-offs, e.g. 1200 / 2600 */
+    int fir_taps;             /* odd, <= 63                                                */
+    long long search_from;    /* sample (at 11025 Hz) where the phasing search starts      */
+    int fold_lines;           /* lines folded by the phasing search                        */
+    long long image_end;      /* sample where the image ends (<= n_out; <= 0: n_out)       */
+} wefax_fm_params;
+
+typedef struct {
+    float *grey;              /* optional: per-sample grey in [0,1] before clipping, n_out floats */
+    uint8_t *image;           /* rows x width, row-major                                    */
+    long long image_capacity; /* bytes available at image                                   */
+    int32_t *rows, *width;    /* HOST pointers                                              */
+    int64_t *line_start;      /* HOST pointer: sample index of the first image line         */
+} wefax_fm_out;
+
+/* One recording (desc->n_recordings must be 1); desc->flags as for wefax_decode_batch (grey / image
+ * follow WEFAX_F_OUT_ON_DEVICE).  desc->notch_* are ignored. */
+int wefax_decode_fm(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm, const wefax_fm_params *params,
+                    const wefax_fm_out *out);
 
 #ifdef __cplusplus
 }

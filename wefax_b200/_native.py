@@ -26,9 +26,9 @@ EXPORTED_SYMBOLS = (
     "wefax_line_constants_for", "wefax_resampled_length", "wefax_notch_coefficients",
     "wefax_fft_plan_describe", "wefax_decode_batch", "wefax_fft_c2c", "wefax_hilbert_envelope",
     "wefax_resample", "wefax_filtfilt", "wefax_digitalize", "wefax_sync_raster",
-    "wefax_ctx_enable_timing", "wefax_ctx_timings", "wefax_tone_scan",
+    "wefax_ctx_enable_timing", "wefax_ctx_timings", "wefax_tone_scan", "wefax_decode_fm",
 )
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class LineConstants(C.Structure):
@@ -54,6 +54,17 @@ class ToneSettings(C.Structure):
     _fields_ = [("start_distance", C.c_double), ("stop_distance", C.c_double), ("height", C.c_double),
                 ("prominence", C.c_double), ("min_frequency", C.c_double), ("max_frequency", C.c_double),
                 ("min_amount", C.c_int), ("max_amount", C.c_int)]
+
+
+class FmParams(C.Structure):
+    _fields_ = [("lpm", C.c_double), ("ioc", C.c_int), ("black_hz", C.c_double), ("white_hz", C.c_double),
+                ("band_lo_hz", C.c_double), ("band_hi_hz", C.c_double), ("fir_taps", C.c_int),
+                ("search_from", C.c_longlong), ("fold_lines", C.c_int), ("image_end", C.c_longlong)]
+
+
+class FmOut(C.Structure):
+    _fields_ = [("grey", C.c_void_p), ("image", C.c_void_p), ("image_capacity", C.c_longlong),
+                ("rows", C.c_void_p), ("width", C.c_void_p), ("line_start", C.c_void_p)]
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -120,6 +131,8 @@ def load():
     lib.wefax_sync_raster.restype = i
     lib.wefax_tone_scan.argtypes = [vp, vp, ll, i, i, ll, C.c_uint, C.POINTER(ToneSettings), vp, vp, vp, vp]
     lib.wefax_tone_scan.restype = i
+    lib.wefax_decode_fm.argtypes = [vp, C.POINTER(BatchDesc), vp, C.POINTER(FmParams), C.POINTER(FmOut)]
+    lib.wefax_decode_fm.restype = i
     _lib = lib
     return lib
 

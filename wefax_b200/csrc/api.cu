@@ -680,4 +680,87 @@ int wefax_tone_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int 
     });
 }
 
+int wefax_decode_fm(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm, const wefax_fm_params *prm,
+                    const wefax_fm_out *out) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!desc || !pcm || !prm || !out || desc->n_recordings != 1 || desc->n_frames < 64 ||
+            (desc->channels != 1 && desc->channels != 2) || desc->sample_rate < 1)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        if (!(prm->lpm > 0.0) || prm->ioc < 1 || !(prm->white_hz > prm->black_hz) || prm->fold_lines < 1)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "bad FM parameters");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const long long n_in = desc->n_frames;
+        const int ch = desc->channels;
+        const bool resample = desc->sample_rate != WEFAX_TARGET_RATE;
+        const long long n = resample ? wefax_resampled_length(n_in, desc->sample_rate) : n_in;
+        if (n < 64) WEFAX_THROW(WEFAX_ERR_INVALID, "recording too short");
+        const bool pcm_dev = desc->flags & WEFAX_F_PCM_ON_DEVICE, out_dev = desc->flags & WEFAX_F_OUT_ON_DEVICE;
+        const double Ls = 60.0 / prm->lpm * (double)WEFAX_TARGET_RATE;   // exact (fractional) samples per line
+        const int W = (int)llround(M_PI * (double)prm->ioc);
+        const long long image_end = (prm->image_end > 0 && prm->image_end <= n) ? prm->image_end : n;
+        const long long from = std::max<long long>(0, std::min<long long>(prm->search_from, n - 1));
+        const int rows_max = (int)std::max<long long>(0, (long long)floor((double)(image_end - from) / Ls));
+        if (out->image && (long long)rows_max * W > out->image_capacity)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "image_capacity %lld too small (need %lld)", out->image_capacity,
+                        (long long)rows_max * W);
+        const FirParams fp = make_bandpass_fir(prm->band_lo_hz, prm->band_hi_hz, (double)WEFAX_TARGET_RATE, prm->fir_taps);
+
+        // the transform runs on the next even length whose half is smooth (zero padded)
+        long long half_len = next_smooth_length((n + 1) / 2);
+        FftPlan *half = half_len > 0 ? get_plan(ctx, half_len) : nullptr;
+        if (!half) WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "no transform length for n=%lld", n);
+        const long long npad = 2 * half_len;
+
+        const int16_t *d_pcm = pcm;
+        if (!pcm_dev) {
+            int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)n_in * ch * sizeof(int16_t));
+            CUDA_CHECK(cudaMemcpyAsync(buf, pcm, (size_t)n_in * ch * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+            d_pcm = buf;
+        }
+        float *x = (float *)ctx->work_a.reserve((size_t)npad * sizeof(float));
+        float *y = (float *)ctx->work_e.reserve((size_t)npad * sizeof(float));
+        if (npad > n) CUDA_CHECK(cudaMemsetAsync(x + n, 0, (size_t)(npad - n) * sizeof(float), st));
+        if (resample) {
+            float *xin = (float *)ctx->resample_in.reserve(((size_t)n_in + (size_t)n) * sizeof(float));
+            float *xrs = xin + n_in;
+            launch_ingest_float(ctx, d_pcm, (size_t)n_in, ch, xin, (size_t)n_in, n_in, 1);
+            resample_real(ctx, n_in, n, xin, (size_t)n_in, xrs, (size_t)n, 1);
+            launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, x, (size_t)npad, nullptr, 0, n, fp, 1);
+        } else {
+            launch_filtfilt(ctx, ch == 2 ? kInStereoI16 : kInMonoI16, d_pcm, (size_t)n_in, x, (size_t)npad, nullptr, 0, n,
+                            fp, 1);
+        }
+        float2 *z = (float2 *)ctx->work_z.reserve((size_t)half_len * sizeof(float2));
+        hilbert_envelope_real(ctx, half, x, (size_t)npad, z, (size_t)half_len, y, (size_t)npad, 1, /*want_y=*/true);
+
+        // grey stream (in the transform scratch, or straight into the caller's device buffer)
+        float *g = (out_dev && out->grey) ? out->grey : (float *)ctx->work_z.reserve((size_t)n * sizeof(float));
+        launch_fm_grey(ctx, x, y, g, n, prm->black_hz, prm->white_hz);
+        const int Lc = (int)ceil(Ls);
+        char *small = (char *)ctx->out_small.reserve((size_t)Lc * sizeof(float) + 64);
+        long long *d_ls = (long long *)small;
+        float *P = (float *)(small + 64);
+        launch_fm_phasing(ctx, g, n, from, Ls, prm->fold_lines, P, d_ls);
+        uint8_t *d_img = nullptr;
+        if (out->image && rows_max > 0) {
+            d_img = out_dev ? out->image : (uint8_t *)ctx->out_raster.reserve((size_t)rows_max * W);
+            launch_fm_image(ctx, g, n, d_ls, Ls, W, rows_max, image_end, d_img);
+        }
+        long long *h_ls = (long long *)pinned(ctx, 64);
+        CUDA_CHECK(cudaMemcpyAsync(h_ls, d_ls, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        if (!out_dev && out->grey)
+            CUDA_CHECK(cudaMemcpyAsync(out->grey, g, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        const long long line_start = *h_ls;
+        const int rows = (int)std::max<long long>(0, (long long)floor((double)(image_end - line_start) / Ls));
+        if (!out_dev && d_img && rows > 0)
+            CUDA_CHECK(cudaMemcpy(out->image, d_img, (size_t)rows * W, cudaMemcpyDeviceToHost));
+        if (out->rows) *out->rows = rows;
+        if (out->width) *out->width = W;
+        if (out->line_start) *out->line_start = line_start;
+    });
+}
+
 }  // extern "C"

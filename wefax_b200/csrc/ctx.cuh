@@ -180,8 +180,9 @@ void hilbert_envelope(wefax_ctx *ctx, FftPlan *plan, const float *x, size_t xs, 
 
 // Same result for even n through a half-length transform of the packed real input
 // (half = plan of n/2; x and env strides even).  x must stay intact until the end.
+// want_y: env receives the Hilbert transform y of x instead of the envelope sqrt(x^2 + y^2)
 void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t xs, float2 *z, size_t zs, float *env,
-                           size_t es, int batch);
+                           size_t es, int batch, bool want_y = false);
 
 // natural-order complex DFT (test entry / Bluestein building block)
 void fft_c2c_natural(wefax_ctx *ctx, FftPlan *plan, const float2 *in, float2 *out, float2 *scratch,

@@ -172,12 +172,14 @@ struct StoreEnvPairs {
     float2 *env;            // envelope viewed as pairs
     const float2 *x;        // the real input viewed as pairs
     size_t ebstride, xbstride;
+    int want_y = 0;         // 1: store the Hilbert transform y itself (FM discriminator, csrc/fm.cu) instead of |x + iy|
     using Side = float2;    // the x pair, fetched a few iterations ahead of its use
     __device__ __forceinline__ Side side_load(size_t i, int b) const { return __ldg(x + (size_t)b * xbstride + i); }
     __device__ __forceinline__ int column_aux(int) const { return 0; }
     __device__ __forceinline__ void operator()(size_t i, int b, float2 v, int, int, Side xs) const {
         env[(size_t)b * ebstride + i] =
-            make_float2(sqrtf(fmaf(xs.x, xs.x, v.x * v.x)), sqrtf(fmaf(xs.y, xs.y, v.y * v.y)));
+            want_y ? make_float2(v.x, -v.y)
+                   : make_float2(sqrtf(fmaf(xs.x, xs.x, v.x * v.x)), sqrtf(fmaf(xs.y, xs.y, v.y * v.y)));
     }
 };
 

@@ -381,11 +381,11 @@ static void launch_mid(wefax_ctx *ctx, FftPlan *half, float2 *z, size_t zs, int 
 }
 
 void hilbert_envelope_real(wefax_ctx *ctx, FftPlan *half, const float *x, size_t xs, float2 *z, size_t zs, float *env,
-                           size_t es, int batch) {
+                           size_t es, int batch, bool want_y) {
     const size_t M = (size_t)half->n;
     const int P = half->npass;
     // x / env strides are in floats and must be even so that pair views stay aligned
-    const StoreEnvPairs store_env{(float2 *)env, (const float2 *)x, es / 2, xs / 2};
+    const StoreEnvPairs store_env{(float2 *)env, (const float2 *)x, es / 2, xs / 2, want_y ? 1 : 0};
     int R1 = 0, R2 = 0;
     const bool aligned = (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (batch == 1 || (zs & 1) == 0);
     if (ctx->use_fast && P >= 2 && aligned && (long long)batch * (long long)(M / half->Rs[P - 1]) < (1ll << 30) &&

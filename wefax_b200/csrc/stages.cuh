@@ -95,4 +95,13 @@ void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, i
 void launch_tone_peaks(wefax_ctx *ctx, const float2 *X, size_t xs, long long packet_len, int sample_rate,
                        int n_packets, const wefax_tone_settings &s, uint8_t *flags, int32_t *counts);
 
+// ---- N4 extension: FM-discriminator demodulation and IOC pixel columns (fm.cu) ----
+FirParams make_bandpass_fir(double lo_hz, double hi_hz, double fs, int taps);
+void launch_fm_grey(wefax_ctx *ctx, const float *x, const float *y, float *g, long long n, double black_hz,
+                    double white_hz);
+void launch_fm_phasing(wefax_ctx *ctx, const float *g, long long n, long long from, double Ls, int lines, float *P,
+                       long long *d_line_start);
+void launch_fm_image(wefax_ctx *ctx, const float *g, long long n, const long long *d_line_start, double Ls, int W,
+                     int rows_max, long long image_end, uint8_t *img);
+
 }  // namespace wefax

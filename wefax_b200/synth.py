@@ -40,7 +40,8 @@ def synth_recording(duration_s: float,
                     carrier_offset_hz: float = 0.0,
                     drift_ppm: float = 0.0,
                     block: int = 8,
-                    amplitude: float = 0.25) -> np.ndarray:
+                    amplitude: float = 0.25,
+                    return_grey: bool = False):
     """One synthetic transmission, ``int(round(duration_s*sample_rate))`` int16 samples."""
     n = int(round(duration_s * sample_rate))
     rng = np.random.default_rng(seed)
@@ -95,6 +96,8 @@ def synth_recording(duration_s: float,
     if noise_sigma:
         x = x + rng.normal(0.0, noise_sigma, size=n)
     x = np.clip(np.round(x * 32767.0), -32768, 32767)
+    if return_grey:      # the per-sample grey level that was transmitted (ground truth of the FM extension)
+        return x.astype(np.int16), grey
     return x.astype(np.int16)
 
 
