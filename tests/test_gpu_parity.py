@@ -107,7 +107,9 @@ def test_hilbert_envelope_stage(dec, n):
 
 
 @pytest.mark.parametrize("n,num", [(48000, 11025), (48001, 11025), (44100, 11025), (8000, 11025), (8001, 11026),
-                                   (12000, 12000), (100003, 22973), (480000, 110250), (22050, 11025), (22051, 11025)])
+                                   (12000, 12000), (100003, 22973), (480000, 110250), (22050, 11025), (22051, 11025),
+                                   # even -> even with plannable halves: real-input fast path (rfft_gather / irfft_scatter)
+                                   (48000, 22050), (22050, 48000), (96000, 11026 * 2), (4_800_000, 1_102_500), (640, 146)])
 def test_resample_stage(dec, n, num):
     rng = np.random.default_rng(n + num)
     x = np.round(rng.normal(size=(2, n)) * 5000).astype(np.float32)

@@ -577,8 +577,88 @@ static void real_from_onesided(wefax_ctx *ctx, long long num, const float2 *Zc, 
                 batch);
 }
 
+// ---- real-input fast path of the resampler (n and num even, both halves plannable) ----------------
+// rfft through a half-length complex transform of the packed signal z[m] = x[2m] + i*x[2m+1]:
+// X[k] = E + w_n^k * O with E = (Z[k] + conj Z[M-k]) / 2, O = (Z[k] - conj Z[M-k]) / (2i), Z in engine order.
+__global__ void rfft_gather_kernel(const float2 *z, size_t zs, float2 *X, size_t xs, uint32_t keep, uint32_t M,
+                                   PosMap pm, const float2 *tw_lo, const float2 *tw_hi) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= keep) return;
+    const float2 *zb = z + (size_t)blockIdx.y * zs;
+    const uint32_t ka = k % M, kb = (M - ka) % M;
+    const float2 zk = zb[pm.pos(ka)], zm = zb[pm.pos(kb)];
+    const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm) / (2i)
+    const float2 w = cmul(__ldg(tw_lo + (k & ((1u << kTwLoBits) - 1))), __ldg(tw_hi + (k >> kTwLoBits)));   // w_n^k
+    X[(size_t)blockIdx.y * xs + k] = cadd(E, cmul(w, O));
+}
+
+// scipy's bin selection and scaling (see resample_spectrum_kernel) on the fly, then the packed spectrum of the
+// half-length inverse: Z'[k] = A + i*B, A = (Y[k] + conj Y[M'-k]) / 2, B = (Y[k] - conj Y[M'-k]) * w_num^(-k) / 2,
+// stored conjugated and scaled at its engine position (the inverse runs the forward kernels on conjugated data).
+__global__ void irfft_scatter_kernel(const float2 *X, size_t xs, uint32_t m2, uint32_t m, uint32_t n, uint32_t num,
+                                     float2 *z, size_t zs, uint32_t Mp, PosMap pm, const float2 *tw_lo,
+                                     const float2 *tw_hi, float scale) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Mp) return;
+    const float2 *Xb = X + (size_t)blockIdx.y * xs;
+    auto Y = [&](uint32_t k) {   // one-sided spectrum handed to irfft(., num): bins >= m2 are zero
+        float2 v = make_float2(0.f, 0.f);
+        if (k < m2) {
+            v = Xb[k];
+            if ((m & 1u) == 0 && num != n && k == m / 2) {
+                const float f = num < n ? 2.f : 0.5f;
+                v.x *= f;
+                v.y *= f;
+            }
+            if (k == 0 || k == Mp) v.y = 0.f;   // irfft ignores the imaginary part of DC and Nyquist
+        }
+        return v;
+    };
+    const uint32_t k = pm.freq(p);
+    const float2 yk = Y(k), ym = Y(Mp - k);                       // k = 0 pairs with the Nyquist bin
+    const float2 A = make_float2(0.5f * (yk.x + ym.x), 0.5f * (yk.y - ym.y));
+    const float2 D = make_float2(0.5f * (yk.x - ym.x), 0.5f * (yk.y + ym.y));
+    const float2 w = cmul(__ldg(tw_lo + (k & ((1u << kTwLoBits) - 1))), __ldg(tw_hi + (k >> kTwLoBits)));   // w_num^k
+    const float2 B = cmul(D, make_float2(w.x, -w.y));
+    // Z' = A + i*B;  store conj(Z') * scale
+    z[(size_t)blockIdx.y * zs + p] = make_float2((A.x - B.y) * scale, -(A.y + B.x) * scale);
+}
+
+static bool resample_real_fast(wefax_ctx *ctx, long long n, long long num, const float *x, size_t xs, float *y,
+                               size_t ys, int batch) {
+    if ((n & 1) || (num & 1) || (xs & 1) || (ys & 1) || !ctx->use_fast) return false;
+    if ((reinterpret_cast<uintptr_t>(x) & 7) || (reinterpret_cast<uintptr_t>(y) & 7)) return false;
+    FftPlan *hin = get_plan(ctx, n / 2), *hout = get_plan(ctx, num / 2);
+    if (!hin || !hout) return false;
+    const uint32_t M = (uint32_t)(n / 2), Mp = (uint32_t)(num / 2);
+    const uint32_t m = (uint32_t)std::min(n, num), m2 = m / 2 + 1;
+    float2 *z = (float2 *)ctx->work_z.reserve((size_t)std::max(M, Mp) * sizeof(float2) * batch);
+    float2 *X = (float2 *)ctx->work_misc.reserve((size_t)m2 * sizeof(float2) * batch);
+    run_forward(ctx, hin, load_c((const float2 *)x, xs / 2), StoreComplex{z, (size_t)M, 1.f, 0}, z, (size_t)M, batch);
+    {
+        StageTimer timer(ctx, "rfft_gather");
+        dim3 grid((m2 + 255) / 256, batch);
+        rfft_gather_kernel<<<grid, 256, 0, ctx->stream>>>(z, (size_t)M, X, (size_t)m2, m2, M, pos_map(hin), hin->tw2_lo,
+                                                         hin->tw2_hi);
+    }
+    {
+        StageTimer timer(ctx, "irfft_scatter");
+        dim3 grid((Mp + 255) / 256, batch);
+        // X * (num / n), the 1/2 of A and B is in the kernel, 1/M' of the inverse transform: together 2/n ... / 2 = 1/n * (num/Mp)/...
+        const float scale = (float)(((double)num / (double)n) / (double)Mp);
+        irfft_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(X, (size_t)m2, m2, m, (uint32_t)n, (uint32_t)num, z, (size_t)Mp,
+                                                           Mp, pos_map(hout), hout->tw2_lo, hout->tw2_hi, scale);
+    }
+    ctx->launches += 2;
+    CUDA_CHECK(cudaGetLastError());
+    run_inverse(ctx, hout, load_c(z, (size_t)Mp), StoreComplex{(float2 *)y, ys / 2, 1.f, 1}, z, (size_t)Mp, batch);
+    return true;
+}
+
 void resample_real(wefax_ctx *ctx, long long n, long long num, const float *x, size_t xs, float *y, size_t ys,
                    int batch) {
+    if (resample_real_fast(ctx, n, num, x, xs, y, ys, batch)) return;
     const uint32_t m = (uint32_t)std::min(n, num);
     const uint32_t m2 = m / 2 + 1;
     float2 *X = (float2 *)ctx->work_misc.reserve((size_t)m2 * sizeof(float2) * 2 * batch);

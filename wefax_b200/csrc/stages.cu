@@ -30,9 +30,40 @@ __global__ void ingest_kernel(const void *in, size_t in_stride, float *x, size_t
     if (i < n) x[(size_t)blockIdx.y * xs + i] = load_sample<MODE>(in, (size_t)blockIdx.y * in_stride, i);
 }
 
+// mono int16 -> float, 8 samples per thread (16-byte load, two 16-byte stores)
+__global__ void __launch_bounds__(256)
+ingest_mono8_kernel(const int16_t *in, size_t in_stride, float *x, size_t xs, long long n) {
+    const long long i = 8 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n) return;
+    const int16_t *src = in + (size_t)blockIdx.y * in_stride + i;
+    float *dst = x + (size_t)blockIdx.y * xs + i;
+    if (i + 8 <= n) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(src));
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = (float)(short)(w[k] & 0xffff);
+            f[2 * k + 1] = (float)(short)(w[k] >> 16);
+        }
+        reinterpret_cast<float4 *>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4 *>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+        for (long long k = i; k < n; ++k) dst[k - i] = (float)__ldg(src + (k - i));
+    }
+}
+
 void launch_ingest_float(wefax_ctx *ctx, const int16_t *pcm, size_t pcm_stride, int channels, float *x, size_t xs,
                          long long n, int batch) {
     StageTimer timer(ctx, "ingest");
+    if (channels == 1 && (reinterpret_cast<uintptr_t>(pcm) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (batch == 1 || (pcm_stride % 8 == 0 && xs % 4 == 0))) {
+        dim3 g8((unsigned)((n + 2047) / 2048), batch);
+        ingest_mono8_kernel<<<g8, 256, 0, ctx->stream>>>(pcm, pcm_stride, x, xs, n);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        return;
+    }
     dim3 grid((unsigned)((n + 255) / 256), batch);
     if (channels == 2)
         ingest_kernel<kInStereoI16><<<grid, 256, 0, ctx->stream>>>(pcm, pcm_stride, x, xs, n);
