@@ -557,3 +557,50 @@ def test_noisy_batch_at_scale(dec):
     # the fp32 envelope may flip single grey levels, which the greedy picker can amplify into a
     # different start line on noise; on this set every recording keeps the reference's start line
     assert n_same_start >= 30, n_same_start
+
+
+# --------------------------------------------------------------------------- every specialised kernel instantiation
+_FAST_R = sorted({a * b for a in (12, 14, 15, 16) for b in (12, 14, 15, 16)} | {105})
+_MID_L = (392, 300, 210, 150, 140)
+
+
+def _two_pass_cases():
+    from wefax_b200 import _native as N
+    cases = []
+    for R in _FAST_R:
+        for L in _MID_L:
+            if R * L >= (1 << 16) and N.fft_plan_describe(R * L) == ([R, L], 0):
+                cases.append((R, L))
+    return cases
+
+
+@pytest.mark.parametrize("R,L", _two_pass_cases())
+def test_hilbert_and_fft_on_every_specialised_kernel(dec, R, L):
+    """Half-length plans [R, L] with R on fft_fast_strided_kernel<R1, R2> (both store functors) and L on
+    hilbert_mid_kernel<R1, R2>: envelope against numpy's analytic signal, complex DFT against numpy's FFT."""
+    m = R * L
+    rng = np.random.default_rng(m)
+    x = (rng.normal(size=(2, 2 * m)) * 3000).astype(np.float32)
+    env = dec.hilbert_envelope(x)
+    ref = np.stack([np.abs(O.hilbert(r.astype(np.float64))) for r in x])
+    assert rel_err(env, ref) < 1e-5
+    c = (rng.normal(size=m) + 1j * rng.normal(size=m)).astype(np.complex64)
+    y = dec.fft(c)
+    refc = np.fft.fft(c.astype(np.complex128))
+    assert np.abs(y - refc).max() / np.abs(refc).max() < 2e-6
+    assert np.abs(dec.fft(y, inverse=True) - c).max() / np.abs(c).max() < 4e-6
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("m,plan", [(5_927_040, [105, 144, 392]), (2_315_250, [105, 105, 210]),
+                                    (1_653_750, [105, 105, 150]), (1_543_500, [105, 105, 140])])
+def test_hilbert_on_three_pass_plans_of_the_remaining_kernels(dec, m, plan):
+    """15x7 and 12x12 strided passes (plain store in the middle pass, envelope store in the last inverse pass)
+    and the 210 / 150 / 140-point fused middle kernels."""
+    from wefax_b200 import _native as N
+    assert N.fft_plan_describe(m)[0] == plan
+    rng = np.random.default_rng(m)
+    x = (rng.normal(size=2 * m) * 3000).astype(np.float32)
+    env = dec.hilbert_envelope(x[None, :])[0]
+    ref = np.abs(O.hilbert(x.astype(np.float64)))
+    assert rel_err(env, ref) < 1e-5
