@@ -1302,11 +1302,15 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
     }
     __syncthreads();
     if (threadIdx.x < 32) {
+        // every position of the precomputed region fits 31 bits (lim <= 1.5 M): 32-bit arithmetic keeps the
+        // dependent instruction chain of this single warp short (it is pure latency: ~5 cycles per instruction)
         const int lane = threadIdx.x;
-        const long long w = ln.mindistance;
+        const int w = ln.mindistance;
+        const int lim = (int)sd.lim;
+        const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
         // first settled position >= x inside [0, lim); -1 when the mask ends first
-        auto next_settled = [&](long long x) -> long long {
-            int wi = (int)(x >> 5);
+        auto next_settled = [&](int x) -> int {
+            int wi = x >> 5;
             uint32_t head = ~0u << (x & 31);
             while (wi < nwords) {
                 uint32_t v = (wi + lane < nwords) ? s_bits[wi + lane] : 0u;
@@ -1316,30 +1320,30 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
                 if (any) {
                     const int l = __ffs(any) - 1;
                     const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, l);
-                    return ((long long)(wi + l) << 5) + (__ffs(vv) - 1);
+                    return ((wi + l) << 5) + (__ffs(vv) - 1);
                 }
                 wi += 32;
             }
             return -1;
         };
         int np = 0, ok = 1;
-        long long P = 0;
+        int P = 0;
         const int j0 = first_pos[blockIdx.x];
         if (sd.m > 0 && j0 != 0x7F7F7F7F) {
             P = next_settled(j0);
             if (P < 0) ok = 0;
         }
-        if (lane == 0) s_peaks[0] = (int)P;
+        if (lane == 0) s_peaks[0] = P;
         np = 1;
         while (ok && sd.m > 0) {
-            const long long a = P + w + 1;
-            if (a > sd.m - 1) break;
+            const int a = P + w + 1;
+            if (a > last) break;
             np++;
             if (np == WEFAX_MAX_PEAKS) {
-                if (lane == 0) s_peaks[np - 1] = (int)a;   // the 100th peak is never refined (wefax.py:251)
+                if (lane == 0) s_peaks[np - 1] = a;   // the 100th peak is never refined (wefax.py:251)
                 break;
             }
-            if (a >= sd.lim) {
+            if (a >= lim) {
                 ok = 0;
                 break;
             }
@@ -1348,7 +1352,7 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
                 ok = 0;
                 break;
             }
-            if (lane == 0) s_peaks[np - 1] = (int)P;
+            if (lane == 0) s_peaks[np - 1] = P;
         }
         if (lane == 0) {
             s_np = np;
