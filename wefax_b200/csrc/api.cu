@@ -201,6 +201,8 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
         ctx->use_tma = !(tma && tma[0] == '0');
         const char *fastk = getenv("WEFAX_FFT_FAST");
         ctx->use_fast = !(fastk && fastk[0] == '0');
+        const char *tmaf = getenv("WEFAX_FFT_TMAFAST");
+        ctx->use_tma_fast = !(tmaf && tmaf[0] == '0');
         int prio_least = 0, prio_greatest = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         if (stream) {

@@ -30,6 +30,7 @@ struct wefax_ctx {
     int sm_count = 148;
     bool use_tma = true;   // WEFAX_FFT_TMA=0 forces the LDG tile loads
     bool use_fast = true;  // WEFAX_FFT_FAST=0 keeps every pass on the generic kernel
+    bool use_tma_fast = true;   // WEFAX_FFT_TMAFAST=0: register-direct loads/stores instead of TMA tiles in the strided pass
     std::map<long long, std::unique_ptr<wefax::FftPlan>> plans;
     std::map<long long, std::unique_ptr<wefax::Bluestein>> bluestein;
     std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
@@ -118,6 +119,33 @@ void launch_fast_variant(wefax_ctx *ctx, const PassDev &p, const float2 *src, si
     kern<<<grid, K::T, K::SMEM, ctx->stream>>>(p, src, bstride, st, (int)total);
 }
 
+template <int R1, int R2>
+bool launch_fast_tma(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t src_bs, float2 *dst, size_t dst_bs,
+                     int batch) {
+    using K = fast::TmaCfg<R1, R2>;
+    static_assert(fast::kFastCW == K::C, "tile geometry of the plan");
+    int rbox = 0;
+    for (int rb = std::min(K::R, 256); rb >= 1; --rb)
+        if (K::R % rb == 0) {
+            rbox = rb;
+            break;
+        }
+    if (K::R / rbox > 8) return false;
+    alignas(64) CUtensorMap in_map, out_map;
+    if (!encode_strided_map(p, src, src_bs, batch, K::C, rbox, &in_map)) return false;
+    if (!encode_strided_map(p, dst, dst_bs, batch, K::C, rbox, &out_map)) return false;
+    auto kern = fast::fft_fast_tma_kernel<R1, R2>;
+    const void *fn = (const void *)kern;
+    if (!ctx->smem_configured.count(fn)) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        ctx->smem_configured[fn] = 1;
+    }
+    const long long total = (long long)p.fast_ntiles * batch;
+    const int grid = (int)std::min<long long>(total, (long long)ctx->sm_count);
+    kern<<<grid, K::T, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total);
+    return true;
+}
+
 // Strided passes whose length has a compiled (R1, R2) pair go to the specialised kernel when the
 // tile comes from plain complex memory and the store functor is one of the hot-path ones.
 template <class LoadOp, class StoreOp>
@@ -127,6 +155,26 @@ bool try_launch_fast(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const S
         if (!ctx->use_fast || !p.fast_R1 || p.contiguous || ld.conj) return false;
         if ((long long)p.fast_ntiles * batch > 0x7fffffffll) return false;
         StageTimer timer(ctx, p.tag);
+        if constexpr (std::is_same<StoreOp, StoreComplex>::value) {
+            // plain complex in and out: the TMA-staged variant (tile loads and stores by the copy engine)
+            if (ctx->use_tma_fast && st.scale == 1.f && !st.conj) {
+                bool done = false;
+                switch (p.fast_R1 * 100 + p.fast_R2) {
+                    case 1515: done = launch_fast_tma<15, 15>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
+                    case 1615: done = launch_fast_tma<16, 15>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
+                    case 1616: done = launch_fast_tma<16, 16>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
+                    case 1514: done = launch_fast_tma<15, 14>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
+                    case 1414: done = launch_fast_tma<14, 14>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
+                    case 1507: done = launch_fast_tma<15, 7>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
+                    default: break;
+                }
+                if (done) {
+                    CUDA_CHECK(cudaGetLastError());
+                    ctx->launches++;
+                    return true;
+                }
+            }
+        }
         switch (p.fast_R1 * 100 + p.fast_R2) {
 #define WEFAX_FAST_CASE(a, b) \
     case (a) * 100 + (b): launch_fast_variant<a, b, StoreOp>(ctx, p, ld.src, ld.bstride, st, batch); break;

@@ -648,5 +648,7 @@ std::unique_ptr<FftPlan> make_plan(long long n, cudaStream_t stream);
 // Chooses how a pass reads its tile from `base` (see PassDev::load_mode) and, for
 // strided passes, encodes the 4-D tensor map {2S floats, R, outer, batch}.
 int choose_load_mode(const PassDev &p, const float2 *base, size_t bstride, int batch, CUtensorMap *map);
+bool encode_strided_map(const PassDev &p, const float2 *base, size_t bstride, int batch, int cols, int rbox,
+                        CUtensorMap *map);
 
 }  // namespace wefax

@@ -394,4 +394,23 @@ int choose_load_mode(const PassDev &p, const float2 *base, size_t bstride, int b
     return rc == CUDA_SUCCESS ? 1 : 0;
 }
 
+// 4-D tensor map {2S floats, R, outer, batch} with a box of `cols` complex columns x `rbox` rows for the
+// TMA-staged strided pass (fft_fast.cuh: fft_fast_tma_kernel); false when the geometry cannot be encoded.
+bool encode_strided_map(const PassDev &p, const float2 *base, size_t bstride, int batch, int cols, int rbox,
+                        CUtensorMap *map) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (p.S & 1) || rbox < 1 || rbox > 256) return false;
+    if (batch > 1 && (bstride & 1)) return false;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const unsigned long long nouter = (unsigned long long)p.ncols / (unsigned long long)p.S;
+    cuuint64_t dims[4] = {2ull * (unsigned long long)p.S, (cuuint64_t)p.R, nouter, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)p.S * 8ull, (cuuint64_t)p.R * (cuuint64_t)p.S * 8ull,
+                             (cuuint64_t)(batch > 1 ? bstride : (size_t)p.R * p.S * nouter) * 8ull};
+    cuuint32_t box[4] = {2u * (cuuint32_t)cols, (cuuint32_t)rbox, 1u, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace wefax
