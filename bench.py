@@ -335,7 +335,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     fast_passes = (os.environ.get("WEFAX_FFT_FAST", "1") != "0" and len(lens) >= 2 and n_rec // 2 >= (1 << 16)
                    and all(r in fast_lengths for r in lens[:-1]))
     if dominant_is_fft and fft_launches:
-        # strided passes of the long transforms run on the specialised two-stage kernel (csrc/fft_fast.cuh)
+        # strided passes of the long transforms run on the specialised two-stage kernels (csrc/fft_fast.cuh:
+        # fft_fast_tma_kernel for plain complex passes, fft_fast_strided_kernel for the envelope store)
         dom_name = "fft_fast_strided_kernel" if fast_passes else "fft_pass_kernel"
         dom_ms = fft_ms / fft_launches
         dom_bytes = fft_bytes / fft_launches
