@@ -325,25 +325,39 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                          "algo_bytes": b, "gbs": round(b / (avg * 1e-3) / 1e9, 1) if avg > 0 and b else None}
     sub = {k: kernels.pop(k) for k in list(kernels) if k.startswith("pct_")}   # parts of "percentiles"
     sub.update({k: kernels.pop(k) for k in list(kernels) if k.startswith("sync_") and k != "sync_search"})
-    fft = {k: v for k, v in kernels.items() if k.startswith("fft_")}
-    fft_ms = sum(v["ms"] * v["launches_per_step"] for v in fft.values())
-    fft_launches = sum(v["launches_per_step"] for v in fft.values())
-    fft_bytes = sum(v["algo_bytes"] * v["launches_per_step"] for v in fft.values())
-    other = {k: v["ms"] * v["launches_per_step"] for k, v in kernels.items() if not k.startswith("fft_")}
-    dominant_is_fft = fft_ms >= max(other.values(), default=0.0)
-    fast_lengths = {a * b for a in (12, 14, 15, 16) for b in (12, 14, 15, 16)}
-    fast_passes = (os.environ.get("WEFAX_FFT_FAST", "1") != "0" and len(lens) >= 2 and n_rec // 2 >= (1 << 16)
-                   and all(r in fast_lengths for r in lens[:-1]))
-    if dominant_is_fft and fft_launches:
-        # strided passes of the long transforms run on the specialised two-stage kernels (csrc/fft_fast.cuh:
-        # fft_fast_tma_kernel for plain complex passes, fft_fast_strided_kernel for the envelope store)
-        dom_name = "fft_fast_strided_kernel" if fast_passes else "fft_pass_kernel"
-        dom_ms = fft_ms / fft_launches
-        dom_bytes = fft_bytes / fft_launches
-    else:
-        dom_name = max(other, key=other.get)
-        dom_ms = kernels[dom_name]["ms"]
-        dom_bytes = kernels[dom_name]["algo_bytes"]
+    # kernel families: which CUDA kernel runs each timed stage
+    fast_lengths = {a * b for a in (12, 14, 15, 16) for b in (12, 14, 15, 16)} | {105}
+    tma_lengths = {225, 240, 256, 210, 196, 105}
+    fast_on = os.environ.get("WEFAX_FFT_FAST", "1") != "0" and len(lens) >= 2
+    tma_on = fast_on and os.environ.get("WEFAX_FFT_TMAFAST", "1") != "0"
+    npass = len(lens)
+
+    def family(stage: str) -> str:
+        if not stage.startswith("fft_"):
+            return {"hilbert_mid": "hilbert_mid_kernel", "filtfilt": "filtfilt_kernel", "raster": "raster_kernel",
+                    "quantise": "quantise_kernel", "percentiles": "pct_*_kernel (4 launches)",
+                    "sync_search": "sync_*_kernel (5 launches)"}.get(stage, stage)
+        i = int(stage.rsplit("_", 1)[1])
+        if i == npass - 1 or not fast_on or lens[i] not in fast_lengths:
+            return "fft_pass_kernel"                      # generic (stride-1 pass, or a length outside the menu)
+        if stage == "fft_inv_0" or not tma_on or lens[i] not in tma_lengths:
+            return "fft_fast_strided_kernel"              # register-direct (envelope store)
+        return "fft_fast_tma_kernel"                      # TMA-staged plain complex pass
+
+    # "percentiles" and "sync_search" bracket several small kernels plus their host-side launch work: they are
+    # reported as stages but are not candidates for the dominant KERNEL
+    fam = {}
+    for k, v in kernels.items():
+        if k in ("percentiles", "sync_search"):
+            continue
+        f = fam.setdefault(family(k), {"ms": 0.0, "launches": 0.0, "bytes": 0.0})
+        f["ms"] += v["ms"] * v["launches_per_step"]
+        f["launches"] += v["launches_per_step"]
+        f["bytes"] += v["algo_bytes"] * v["launches_per_step"]
+    dom_name = max(fam, key=lambda k: fam[k]["ms"])
+    dom_ms = fam[dom_name]["ms"] / max(fam[dom_name]["launches"], 1.0)
+    dom_bytes = fam[dom_name]["bytes"] / max(fam[dom_name]["launches"], 1.0)
+    dom_total_ms = fam[dom_name]["ms"]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     try:
@@ -352,6 +366,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     except Exception:
         pass
     stage_sum = sum(v["ms"] * v["launches_per_step"] for v in kernels.values())
+    roofline_valid = args.sample_rate == 11025   # with the resampler, its passes share the fft_* tags of the Hilbert transform
     path_gbs = ALGO_BYTES_PER_SAMPLE * (n / (ms_per_step * 1e-3)) / 1e9
 
     line = {
@@ -368,11 +383,12 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                 "ms_per_step": e2e_s / args.steps * 1e3, "pipeline_depth": depth,
                 "api": "Decoder.decode -> wefax_decode_batch (host pinned buffers), one host thread + context per pipeline slot"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+        "roofline": {"bound": "hbm", "kernel": dom_name if roofline_valid else None,
+                     "achieved": round(achieved, 1) if roofline_valid else None, "peak": peak,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4) if roofline_valid else None, "traffic": traffic,
                      "peak_source": peak_src, "algo_bytes_per_launch": dom_bytes, "avg_launch_ms": round(dom_ms, 5),
-                     "share_of_step": round((fft_ms if dominant_is_fft else other[dom_name]) / stage_sum, 3)
-                     if stage_sum else None,
+                     "share_of_step": round(dom_total_ms / stage_sum, 3) if stage_sum else None,
+                     "launches_per_step": fam[dom_name]["launches"],
                      "whole_path": {"algo_bytes_per_sample": ALGO_BYTES_PER_SAMPLE, "achieved": round(path_gbs, 1),
                                     "frac": round(path_gbs / peak, 4)}},
         "stages": kernels, "stage_parts": sub,

@@ -101,6 +101,7 @@ void line_constants(double lpm, int sr, wefax_line_constants *o) {
 void *pinned(wefax_ctx *ctx, size_t bytes) {
     if (bytes > ctx->pinned_cap) {
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_up) cudaFreeHost(ctx->pinned_up);
         ctx->pinned = nullptr;
         ctx->pinned_cap = 0;
         CUDA_CHECK(cudaMallocHost(&ctx->pinned, bytes + 4096));
@@ -242,6 +243,7 @@ void wefax_ctx_destroy(wefax_ctx *ctx) {
     ctx->plans.clear();
     ctx->bluestein.clear();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_up) cudaFreeHost(ctx->pinned_up);
     for (auto &sp : ctx->spans) {
         cudaEventDestroy(sp.e0);
         cudaEventDestroy(sp.e1);
@@ -405,7 +407,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             memcpy(h_lines, lines.data() + w0, sizeof(LineDev) * g);
             CUDA_CHECK(cudaMemcpyAsync(d_lines, h_lines, sizeof(LineDev) * g, cudaMemcpyHostToDevice, st));
             CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * g, st));
-            const SyncPlan splan = prepare_sync(ctx, lines.data() + w0, g, n);   // (synchronises: done while the stream is idle)
+            const SyncPlan splan = prepare_sync(ctx, lines.data() + w0, g, n);   // (asynchronous upload from pinned staging)
 
             float *d_env = (float *)ctx->work_e.reserve((size_t)g * n * sizeof(float));
             uint8_t *d_dig = (out_dev && out->digitalized) ? out->digitalized + (size_t)w0 * n

@@ -39,6 +39,8 @@ struct wefax_ctx {
     // pinned staging for small results
     void *pinned = nullptr;
     size_t pinned_cap = 0;
+    void *pinned_up = nullptr;   // pinned staging of small host->device uploads (no stream sync needed to reuse the source)
+    size_t pinned_up_cap = 0;
     // optional per-stage device timing (CUDA events on the context's stream)
     bool timing = false;
     struct Span {

@@ -1591,8 +1591,18 @@ SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long
     sp.first_pos = (int *)(sp.bits + sp.bs * count);
     sp.need_scan = sp.first_pos + count;
     sp.sd = (SyncDev *)(((uintptr_t)(sp.need_scan + count) + 15) & ~(uintptr_t)15);
-    CUDA_CHECK(cudaMemcpyAsync(sp.sd, sd.data(), sizeof(SyncDev) * count, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // sd is a stack temporary
+    // staged through pinned memory owned by the context: the copy is truly asynchronous and nothing has to wait
+    // for it on the host (every API call ends with a stream synchronisation before the staging area is reused)
+    const size_t up = sizeof(SyncDev) * (size_t)count;
+    if (up > ctx->pinned_up_cap) {
+        if (ctx->pinned_up) cudaFreeHost(ctx->pinned_up);
+        ctx->pinned_up = nullptr;
+        ctx->pinned_up_cap = 0;
+        CUDA_CHECK(cudaMallocHost(&ctx->pinned_up, up + 4096));
+        ctx->pinned_up_cap = up + 4096;
+    }
+    memcpy(ctx->pinned_up, sd.data(), up);
+    CUDA_CHECK(cudaMemcpyAsync(sp.sd, ctx->pinned_up, up, cudaMemcpyHostToDevice, ctx->stream));
     return sp;
 }
 
