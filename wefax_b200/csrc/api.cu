@@ -101,7 +101,6 @@ void line_constants(double lpm, int sr, wefax_line_constants *o) {
 void *pinned(wefax_ctx *ctx, size_t bytes) {
     if (bytes > ctx->pinned_cap) {
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->pinned_up) cudaFreeHost(ctx->pinned_up);
         ctx->pinned = nullptr;
         ctx->pinned_cap = 0;
         CUDA_CHECK(cudaMallocHost(&ctx->pinned, bytes + 4096));

@@ -182,22 +182,26 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[i + m], acc[i]);
         }
-        __syncthreads();   // everyone is done reading s_ext (stage 1) long ago; reuse it for the coalesced store
+        // each thread owns 8 consecutive outputs: two 16-byte stores per thread, 1 KiB contiguous per warp
+        const long long g = (long long)blockIdx.x * TS + i0;
+        if (out) {
+            float *o = out + (size_t)blockIdx.y * out_stride + g;
+            if (g + 7 < n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                reinterpret_cast<float4 *>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<float4 *>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_ext[i0 + i] = acc[i];
-    }
-    __syncthreads();
-    const long long n0 = (long long)blockIdx.x * TS;
-    // real output (audio_data) and / or the complex copy (x, 0) the transform reads through TMA
-    if (out) {
-        float *o = out + (size_t)blockIdx.y * out_stride;
-        for (int i = tid; i < TS; i += kFirThreads)
-            if (n0 + i < n) o[n0 + i] = s_ext[i];
-    }
-    if (zout) {
-        float2 *z = zout + (size_t)blockIdx.y * z_stride;
-        for (int i = tid; i < TS; i += kFirThreads)
-            if (n0 + i < n) z[n0 + i] = make_float2(s_ext[i], 0.f);
+                for (int i = 0; i < 8; ++i)
+                    if (g + i < n) o[i] = acc[i];
+            }
+        }
+        // the complex copy (x, 0) a full-length transform reads through TMA
+        if (zout) {
+            float2 *z = zout + (size_t)blockIdx.y * z_stride + g;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (g + i < n) z[i] = make_float2(acc[i], 0.f);
+        }
     }
 }
 
