@@ -55,6 +55,11 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=1,
                     help="recordings per GPU per step; > 1 selects the batch workload (BASELINE.json configs[3] shape: "
                          "--duration 600 --batch 64, LPM cycling 60/90/120/240)")
+    ap.add_argument("--segments", action="store_true",
+                    help="BASELINE configs[2]: ONE recording (default 20 min at 48 kHz) decoded in overlapping segments, "
+                         "one per GPU (strong scaling; wefax_b200/segments.py).  Not the headline workload.")
+    ap.add_argument("--local-segments", type=int, default=1, help="with --segments: contexts (segments) per GPU")
+    ap.add_argument("--halo", type=int, default=65536, help="with --segments: halo in 11025-Hz samples")
     return ap.parse_args()
 
 
@@ -412,6 +417,128 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         dist.destroy_process_group()
 
 
+def run_segments(args, rank: int, world: int, local_rank: int) -> None:
+    """ONE recording over world x local-segments contexts.  The timed region is the whole protocol with the
+    segments' PCM resident in HBM: per-segment kernels, the three histogram exchanges + start_frame broadcast
+    through the host, image rows left in each GPU's memory (`value`), or copied to pinned host memory and
+    gathered on rank 0 (`e2e`).  Host exchanges are part of the path, so the clock is the host's, bracketed by
+    barrier + synchronize, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from wefax_b200 import segments as S
+    from wefax_b200 import synth
+    from wefax_b200.decoder import Decoder
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rate = args.sample_rate
+    pcm = synth.synth_recording(args.duration, sample_rate=rate, lpm=args.lpm, seed=1)   # same on every rank
+    n_frames = int(pcm.shape[0])
+    L = args.local_segments
+    G = world * L
+    workers = [Decoder(local_rank) for _ in range(L)]
+    ex = S.HostExchange(device=local_rank)
+    segs = S.plan_decode(n_frames, rate, args.lpm, G, args.halo)
+    mine = {sg.index: torch.from_numpy(np.ascontiguousarray(S.segment_frames(pcm, sg))).cuda()
+            for sg in segs[rank * L:(rank + 1) * L]}
+    pinned = {sg.index: torch.from_numpy(np.ascontiguousarray(S.segment_frames(pcm, sg))).pin_memory()
+              for sg in segs[rank * L:(rank + 1) * L]}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def step(device_resident: bool):
+        src = mine if device_resident else pinned
+        return S.decode_segmented(None, rate, args.lpm, workers, halo=args.halo, exchange=ex, n_frames=n_frames,
+                                  segment_pcm=lambda sg: src[sg.index], want=("raster",), segments=segs,
+                                  rows_on_device=device_resident, gather=not device_resident)
+
+    res = step(True)
+    if res.error() is not None:
+        raise RuntimeError(f"decode failed: {res.error()!r}")
+    for _ in range(args.warmup):
+        step(True)
+    barrier()
+    l0 = sum(w.launch_count for w in workers)
+    sampler.region(True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)
+    barrier()
+    ms_per_step = max_over_ranks(time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.region(False)
+    launches = sum(w.launch_count for w in workers) - l0
+
+    for _ in range(max(1, args.warmup // 2)):
+        step(False)
+    barrier()
+    sampler.region(True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host = step(False)
+    barrier()
+    e2e_ms = max_over_ranks(time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.region(False)
+    clocks = sampler.stop()
+
+    # per-stage device times of this rank's first context (one more pass)
+    workers[0].enable_timing(True)
+    workers[0].timings(reset=True)
+    step(True)
+    stage_ms = workers[0].timings(reset=True)
+    workers[0].enable_timing(False)
+
+    if rank == 0:
+        n_total = res.n_out
+        algo = 2.0 * n_frames + 4.0 * res.width * ((n_total - res.start_frame) // res.width)   # int16 in, x4 raster out
+        peak, src_peak = hbm_peak()
+        line = {
+            "metric": "decoded audio Msamples/s", "value": n_frames / (ms_per_step * 1e-3) / 1e6, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.duration / 60:g}-min mono {rate} Hz WEFAX recording, {args.lpm} LPM, "
+                                   f"split into {G} overlapping segments over {world} GPU(s) (BASELINE.json configs[2])",
+                       "frames": n_frames, "samples_at_11025": n_total, "segments": G, "halo": args.halo,
+                       "segment_samples": [sg.n_out for sg in segs], "outputs": ["raster"],
+                       "exchange": "3 x 32 KiB histograms all-reduced + start_frame broadcast through the host; no "
+                                   "collective on the data path",
+                       "timing": "host clock around the whole protocol (it contains host exchanges), barrier + "
+                                 "synchronize both sides, max over ranks",
+                       "l2": "no explicit flush; note: an 8-way split leaves ~2 M-sample segments that fit in L2"},
+            "clocks": clocks,
+            "e2e": {"value": n_frames / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(sum(2 * (sg.in_end - sg.in_begin) for sg in segs)),
+                    "d2h_bytes_per_step": int(host.image.nbytes),
+                    "api": "segments.decode_segmented -> wefax_segment_* (pinned host PCM per segment, image rows "
+                           "gathered on rank 0)"},
+            "gpu_launches": int(launches) * world,
+            "roofline": {"bound": "hbm", "kernel": "whole segmented path (A = 2 B per input frame + 4 B per raster byte)",
+                         "achieved": algo / (ms_per_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": algo / (ms_per_step * 1e-3) / 1e9 / (peak * world), "traffic": None,
+                         "peak_source": src_peak},
+            "stages_rank0_ms": {k: v[0] for k, v in sorted(stage_ms.items())},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -427,6 +554,13 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.segments:
+        if "--duration" not in " ".join(sys.argv):
+            args.duration = 1200.0
+        if "--sample-rate" not in " ".join(sys.argv):
+            args.sample_rate = 48000
+        run_segments(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WEFAX_ABI_VERSION 3
+#define WEFAX_ABI_VERSION 4
 #define WEFAX_TARGET_RATE 11025   /* wefax.py:60 */
 #define WEFAX_MAX_PEAKS 100       /* wefax.py:251 */
 
@@ -166,6 +166,53 @@ int wefax_digitalize(wefax_ctx *ctx, long long n, int batch, const float *envelo
  * uses out->peaks .. out->status and out->raster / raster_stride; other fields ignored. */
 int wefax_sync_raster(wefax_ctx *ctx, long long n, int batch, const uint8_t *digitalized, const double *lpm,
                       const wefax_batch_out *out);
+
+/* ---- one long recording in overlapping segments, one per GPU (SURVEY.md 8(e), configs[2]) -----
+ * process() (wefax.py:46-93) couples a whole recording three times: resample / hilbert are length-N
+ * circular transforms (wefax.py:384,174), the two percentiles are global order statistics
+ * (wefax.py:196) and start_frame shifts every image row (wefax.py:80,300-304).  Segment mode keeps the
+ * last two EXACT across segments (histogram exchange below; start_frame from the first segment) and
+ * approximates the first with a halo that is discarded (tolerance stated in DESIGN.md section 6).
+ * All positions are 11025-Hz samples relative to the extended segment (core + halo) this context
+ * holds.  Call order per context: envelope -> histogram x3 -> quantise -> [sync] -> raster.  The host
+ * side (wefax_b200/segments.py) sums the histograms of all segments between the calls; no NCCL. */
+
+/* ingest (+ resample) + notch + |hilbert| of one extended segment; the envelope stays resident in the
+ * context.  desc: n_recordings == 1, n_frames = input frames of the extended segment; pcm as for
+ * wefax_decode_batch.  n_resampled = length of the extended segment at 11025 Hz (the planner cuts on
+ * whole 11025-Hz samples, so this is exact; 0 = wefax_resampled_length(n_frames), the reference's float
+ * formula for a whole recording).  [core_begin, core_end) = the samples this segment owns.
+ * seam (0 = none): the transforms of the reference are circular, so the halo in front of the FIRST segment
+ * is the END of the recording and the halo behind the LAST segment is its START; seam is the 11025-Hz
+ * position inside the extended segment where the recording's end meets its start.  The transforms run
+ * across the seam (as the whole-recording transforms do), the notch (filtfilt edge rules, wefax.py:72) and
+ * the median (zero padding, wefax.py:175) treat it as the two ends of the recording.  The core must lie on
+ * one side of it. */
+int wefax_segment_envelope(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm, long long n_resampled,
+                           long long seam, long long core_begin, long long core_end);
+
+/* Radix-digit histogram of the float bit patterns of medfilt(envelope, 5) over the core samples.
+ * level 0: bin = bits >> 21 of every core sample -> hist[0][..]; level 1: samples with
+ * bits >> 21 == prefix[t] -> hist[t][(bits >> 10) & 0x7FF]; level 2: samples with bits >> 10 == prefix[t]
+ * -> hist[t][bits & 0x3FF].  hist: HOST pointer, 4 x 2048 uint32. */
+int wefax_segment_histogram(wefax_ctx *ctx, int level, const uint32_t prefix[4], uint32_t *hist);
+
+/* Grey map of the whole extended segment with the GLOBAL percentiles (wefax.py:197-216); stays
+ * resident.  Optional outputs of the core samples only (host or device pointers, may be NULL):
+ * digitalized (uint8) and demodulated = medfilt(envelope, 5) (float32). */
+int wefax_segment_quantise(wefax_ctx *ctx, double low, double high, uint8_t *digitalized, float *demodulated);
+
+/* Phasing search (wefax.py:218-294) on the resident grey levels; meaningful on the segment that starts
+ * at sample 0 of the recording (the search reads at most the first 100 peaks).  Fills out->peaks,
+ * n_peaks, phasing, n_phasing, start_frame, status (host pointers, 1 recording). */
+int wefax_segment_sync(wefax_ctx *ctx, double lpm, const wefax_batch_out *out);
+
+/* Line raster + x4 vertical bicubic (wefax.py:296-327) of n_lines lines of width w = int(frame_len*11025)
+ * starting at first_sample; the lines [skip_lines, skip_lines + keep_lines) are this segment's own (the
+ * others are the bicubic margin: 2 lines each side unless the image ends there) and only their
+ * 4 * keep_lines rows are written to raster (host or device pointer, 4 * keep_lines * w bytes). */
+int wefax_segment_raster(wefax_ctx *ctx, double lpm, long long first_sample, int n_lines, int skip_lines,
+                         int keep_lines, uint8_t *raster);
 
 /* ---- start / stop tone test of packets ------------------- */
 

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (wefax_[a-z0-9_]+)", out))
     assert set(N.EXPORTED_SYMBOLS) <= exported
-    assert lib.wefax_abi_version() == N.ABI_VERSION == 3
+    assert lib.wefax_abi_version() == N.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():

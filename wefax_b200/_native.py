@@ -27,8 +27,10 @@ EXPORTED_SYMBOLS = (
     "wefax_fft_plan_describe", "wefax_decode_batch", "wefax_fft_c2c", "wefax_hilbert_envelope",
     "wefax_resample", "wefax_filtfilt", "wefax_digitalize", "wefax_sync_raster",
     "wefax_ctx_enable_timing", "wefax_ctx_timings", "wefax_tone_scan", "wefax_decode_fm",
+    "wefax_segment_envelope", "wefax_segment_histogram", "wefax_segment_quantise", "wefax_segment_sync",
+    "wefax_segment_raster",
 )
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class LineConstants(C.Structure):
@@ -133,6 +135,16 @@ def load():
     lib.wefax_tone_scan.restype = i
     lib.wefax_decode_fm.argtypes = [vp, C.POINTER(BatchDesc), vp, C.POINTER(FmParams), C.POINTER(FmOut)]
     lib.wefax_decode_fm.restype = i
+    lib.wefax_segment_envelope.argtypes = [vp, C.POINTER(BatchDesc), vp, ll, ll, ll, ll]
+    lib.wefax_segment_envelope.restype = i
+    lib.wefax_segment_histogram.argtypes = [vp, i, C.POINTER(C.c_uint32 * 4), vp]
+    lib.wefax_segment_histogram.restype = i
+    lib.wefax_segment_quantise.argtypes = [vp, d, d, vp, vp]
+    lib.wefax_segment_quantise.restype = i
+    lib.wefax_segment_sync.argtypes = [vp, d, C.POINTER(BatchOut)]
+    lib.wefax_segment_sync.restype = i
+    lib.wefax_segment_raster.argtypes = [vp, d, ll, i, i, i, vp]
+    lib.wefax_segment_raster.restype = i
     _lib = lib
     return lib
 

@@ -109,6 +109,8 @@ void *pinned(wefax_ctx *ctx, size_t bytes) {
     return ctx->pinned;
 }
 
+constexpr long long kSegMinPiece = 64;   // shortest piece either side of a segment's seam
+
 void use_device(wefax_ctx *ctx) { CUDA_CHECK(cudaSetDevice(ctx->device)); }
 
 struct LineSet {
@@ -627,6 +629,200 @@ int wefax_sync_raster(wefax_ctx *ctx, long long n, int batch, const uint8_t *dig
         CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult) * batch, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         deliver_results(ctx, h_res, batch, 0, ls, out, d_raster, rs, false);
+    });
+}
+
+// ---------------------------------------------------------------------------
+// segment mode: one long recording as overlapping segments, one per context / GPU
+// (host protocol in wefax_b200/segments.py)
+// ---------------------------------------------------------------------------
+int wefax_segment_envelope(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm, long long n_resampled,
+                           long long seam, long long core_begin, long long core_end) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!desc || !pcm) WEFAX_THROW(WEFAX_ERR_INVALID, "null argument");
+        const long long n_in = desc->n_frames;
+        const int ch = desc->channels;
+        if (desc->n_recordings != 1 || n_in < 1 || (ch != 1 && ch != 2) || desc->sample_rate <= 0)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "bad segment description");
+        const bool resample = desc->sample_rate != WEFAX_TARGET_RATE;
+        // the planner's exact length (cut points fall on whole 11025-Hz samples); 0: the reference's formula
+        const long long n = !resample ? n_in : (n_resampled > 0 ? n_resampled : wefax_resampled_length(n_in, desc->sample_rate));
+        if (!resample && n_resampled > 0 && n_resampled != n_in)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "n_resampled %lld != n_frames %lld at 11025 Hz", n_resampled, n_in);
+        if (n <= 9)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is 9.");
+        if (n_in >= (1ll << 31) - 4096 || n >= (1ll << 31) - 4096) WEFAX_THROW(WEFAX_ERR_INVALID, "segment too long");
+        if (core_begin < 0 || core_end < core_begin || core_end > n)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "core [%lld, %lld) outside the extended segment of %lld samples", core_begin,
+                        core_end, n);
+        // The recording's end meets its start at `seam` (circular halo of the first / last segment): the
+        // transforms see the junction exactly as the whole-recording circular transforms do, while the notch
+        // and the median treat the two sides as the two ends of the recording they are.
+        if (seam < 0 || seam >= n || (seam > 0 && (seam <= kSegMinPiece || n - seam <= kSegMinPiece)))
+            WEFAX_THROW(WEFAX_ERR_INVALID, "seam %lld outside the extended segment of %lld samples", seam, n);
+        if (seam > 0 && !(seam <= core_begin || core_end <= seam))
+            WEFAX_THROW(WEFAX_ERR_INVALID, "core [%lld, %lld) straddles the seam %lld", core_begin, core_end, seam);
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        ctx->seg.have_env = ctx->seg.have_dig = false;
+        const FirParams fp = make_fir((double)(long long)desc->notch_freq, desc->notch_q, (double)WEFAX_TARGET_RATE);
+
+        FftPlan *half = (n % 2 == 0) ? get_plan(ctx, n / 2) : nullptr;
+        FftPlan *plan = half ? nullptr : get_plan(ctx, n);
+        const int16_t *d_pcm = pcm;
+        if (!(desc->flags & WEFAX_F_PCM_ON_DEVICE)) {
+            int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)n_in * ch * sizeof(int16_t));
+            StageTimer timer(ctx, "h2d_pcm");
+            CUDA_CHECK(cudaMemcpyAsync(buf, pcm, (size_t)n_in * ch * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+            d_pcm = buf;
+        }
+        float *d_env = (float *)ctx->seg.env.reserve((size_t)n * sizeof(float));
+        float *d_audio = (float *)ctx->work_a.reserve((size_t)n * sizeof(float));
+        const size_t zbytes = half ? (size_t)(n / 2) * sizeof(float2) : (plan ? (size_t)n * sizeof(float2) : 0);
+        float2 *z = zbytes ? (float2 *)ctx->work_z.reserve(zbytes) : nullptr;
+        if (resample) {
+            float *xin = (float *)ctx->resample_in.reserve(((size_t)n_in + (size_t)n) * sizeof(float));
+            float *xrs = xin + n_in;
+            launch_ingest_float(ctx, d_pcm, (size_t)n_in, ch, xin, (size_t)n_in, n_in, 1);
+            resample_real(ctx, n_in, n, xin, (size_t)n_in, xrs, (size_t)n, 1);
+            z = zbytes ? (float2 *)ctx->work_z.reserve(zbytes) : nullptr;   // the resampler used work_z
+            float2 *zc = half ? nullptr : z;
+            if (seam > 0)
+                launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, d_audio, (size_t)n, zc, (size_t)n, seam, fp, 1);
+            launch_filtfilt(ctx, kInFloat, xrs + seam, (size_t)n, d_audio + seam, (size_t)n, zc ? zc + seam : nullptr,
+                            (size_t)n, n - seam, fp, 1);
+        } else {
+            const IngestMode mode = ch == 2 ? kInStereoI16 : kInMonoI16;
+            float2 *zc = half ? nullptr : z;
+            if (seam > 0)
+                launch_filtfilt(ctx, mode, d_pcm, (size_t)n_in, d_audio, (size_t)n, zc, (size_t)n, seam, fp, 1);
+            launch_filtfilt(ctx, mode, d_pcm + (size_t)seam * ch, (size_t)n_in, d_audio + seam, (size_t)n,
+                            zc ? zc + seam : nullptr, (size_t)n, n - seam, fp, 1);
+        }
+        if (half)
+            hilbert_envelope_real(ctx, half, d_audio, (size_t)n, z, (size_t)(n / 2), d_env, (size_t)n, 1);
+        else if (plan)
+            hilbert_envelope(ctx, plan, nullptr, 0, z, (size_t)n, d_env, (size_t)n, 1);
+        else
+            hilbert_envelope_bluestein(ctx, n, d_audio, (size_t)n, d_env, (size_t)n, 1);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        // only the side of the seam that holds the core is needed from here on
+        const bool tail_side = seam > 0 && seam <= core_begin;
+        ctx->seg.base = tail_side ? seam : 0;
+        ctx->seg.n = seam > 0 ? (tail_side ? n - seam : seam) : n;
+        ctx->seg.core_lo = core_begin - ctx->seg.base;
+        ctx->seg.core_hi = core_end - ctx->seg.base;
+        ctx->seg.have_env = true;
+    });
+}
+
+int wefax_segment_histogram(wefax_ctx *ctx, int level, const uint32_t prefix[4], uint32_t *hist) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (level < 0 || level > 2 || !hist || (level > 0 && !prefix)) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        if (!ctx->seg.have_env) WEFAX_THROW(WEFAX_ERR_INVALID, "wefax_segment_envelope has not run on this context");
+        use_device(ctx);
+        const uint32_t zero[4] = {0, 0, 0, 0};
+        uint32_t *d_hist = (uint32_t *)ctx->out_small.reserve(4 * 2048 * sizeof(uint32_t));
+        uint32_t *h_hist = (uint32_t *)pinned(ctx, 4 * 2048 * sizeof(uint32_t));
+        launch_segment_hist(ctx, ctx->seg.env.as<float>() + ctx->seg.base, ctx->seg.n, ctx->seg.core_lo, ctx->seg.core_hi, level,
+                            level > 0 ? prefix : zero, d_hist);
+        CUDA_CHECK(cudaMemcpyAsync(h_hist, d_hist, 4 * 2048 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        memcpy(hist, h_hist, 4 * 2048 * sizeof(uint32_t));
+    });
+}
+
+int wefax_segment_quantise(wefax_ctx *ctx, double low, double high, uint8_t *digitalized, float *demodulated) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!ctx->seg.have_env) WEFAX_THROW(WEFAX_ERR_INVALID, "wefax_segment_envelope has not run on this context");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const long long n = ctx->seg.n, lo = ctx->seg.core_lo, hi = ctx->seg.core_hi;
+        RecResult *d_res = (RecResult *)ctx->out_small.reserve(sizeof(RecResult));
+        RecResult *h_res = (RecResult *)pinned(ctx, sizeof(RecResult));
+        memset(h_res, 0, sizeof(RecResult));
+        h_res->low = low;
+        h_res->high = high;
+        CUDA_CHECK(cudaMemcpyAsync(d_res, h_res, sizeof(RecResult), cudaMemcpyHostToDevice, st));
+        uint8_t *d_dig = (uint8_t *)ctx->seg.dig.reserve((size_t)n);
+        const float *d_env = ctx->seg.env.as<float>() + ctx->seg.base;
+        launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, 1, d_res, 0, n, st, "quantise");
+        if (digitalized && hi > lo)
+            CUDA_CHECK(cudaMemcpyAsync(digitalized, d_dig + lo, (size_t)(hi - lo), cudaMemcpyDefault, st));
+        if (demodulated && hi > lo) {
+            float *d_med = (float *)ctx->work_a.reserve((size_t)(hi - lo) * sizeof(float));
+            launch_segment_median(ctx, d_env, n, lo, hi, d_med);
+            CUDA_CHECK(cudaMemcpyAsync(demodulated, d_med, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault, st));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        ctx->seg.have_dig = true;
+    });
+}
+
+int wefax_segment_sync(wefax_ctx *ctx, double lpm, const wefax_batch_out *out) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!out) WEFAX_THROW(WEFAX_ERR_INVALID, "null argument");
+        if (!ctx->seg.have_dig) WEFAX_THROW(WEFAX_ERR_INVALID, "wefax_segment_quantise has not run on this context");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const long long n = ctx->seg.n;
+        const LineSet ls = prepare_lines(&lpm, 1, n);
+        LineDev *d_lines = (LineDev *)ctx->out_small.reserve(sizeof(LineDev) + sizeof(RecResult));
+        RecResult *d_res = (RecResult *)(d_lines + 1);
+        RecResult *h_res = (RecResult *)pinned(ctx, sizeof(RecResult));
+        CUDA_CHECK(cudaMemcpyAsync(d_lines, ls.lines.data(), sizeof(LineDev), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult), st));
+        const SyncPlan splan = prepare_sync(ctx, ls.lines.data(), 1, n);
+        launch_sync_search(ctx, ctx->seg.dig.as<uint8_t>(), (size_t)n, n, 1, d_lines, d_res, ls.min_mind, splan);
+        CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        wefax_batch_out small = *out;
+        small.raster = nullptr;   // the raster of a segment comes from wefax_segment_raster
+        small.height = nullptr;   // (the height of the whole image is the host's to compute)
+        small.low_high = nullptr;
+        // a segment shorter than one line is not an error of the recording
+        h_res->status &= ~WEFAX_REC_NO_LINES;
+        deliver_results(ctx, h_res, 1, 0, ls, &small, nullptr, 0, false);
+    });
+}
+
+int wefax_segment_raster(wefax_ctx *ctx, double lpm, long long first_sample, int n_lines, int skip_lines,
+                         int keep_lines, uint8_t *raster) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&, first_sample]() mutable {
+        if (!raster || n_lines < 0 || skip_lines < 0 || keep_lines < 0 || skip_lines + keep_lines > n_lines)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        if (!ctx->seg.have_dig) WEFAX_THROW(WEFAX_ERR_INVALID, "wefax_segment_quantise has not run on this context");
+        if (keep_lines == 0) return;
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const long long n = ctx->seg.n;
+        const LineSet ls = prepare_lines(&lpm, 1, n);
+        const int w = ls.lines[0].width;
+        first_sample -= ctx->seg.base;   // positions of the API are relative to the extended segment
+        if (first_sample < 0 || first_sample + (long long)n_lines * w > n)
+            WEFAX_THROW(WEFAX_ERR_INVALID, "lines [%lld, +%d x %d) outside the extended segment of %lld samples",
+                        first_sample, n_lines, w, n);
+        LineDev *d_lines = (LineDev *)ctx->out_small.reserve(sizeof(LineDev) + sizeof(RecResult));
+        RecResult *d_res = (RecResult *)(d_lines + 1);
+        char *h_up = (char *)pinned(ctx, sizeof(LineDev) + sizeof(RecResult));
+        RecResult h_res;
+        memset(&h_res, 0, sizeof(h_res));
+        h_res.start_frame = first_sample;
+        h_res.height = 4 * n_lines;
+        memcpy(h_up, &ls.lines[0], sizeof(LineDev));
+        memcpy(h_up + sizeof(LineDev), &h_res, sizeof(RecResult));
+        CUDA_CHECK(cudaMemcpyAsync(d_lines, h_up, sizeof(LineDev) + sizeof(RecResult), cudaMemcpyHostToDevice, st));
+        const size_t rs = (size_t)4 * n_lines * w;
+        uint8_t *d_raster = (uint8_t *)ctx->out_raster.reserve(rs);
+        launch_raster(ctx, ctx->seg.dig.as<uint8_t>(), (size_t)n, n, 1, d_lines, d_res, d_raster, rs, w, n_lines);
+        CUDA_CHECK(cudaMemcpyAsync(raster, d_raster + (size_t)4 * skip_lines * w, (size_t)4 * keep_lines * w,
+                                   cudaMemcpyDefault, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
     });
 }
 

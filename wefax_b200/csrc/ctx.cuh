@@ -36,6 +36,13 @@ struct wefax_ctx {
     std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
     // scratch (grown on demand, reused between calls)
     wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in, sync_buf, pct_buf;
+    // segment mode: the extended segment's envelope and grey levels stay resident between the calls
+    struct Segment {
+        bool have_env = false, have_dig = false;
+        long long base = 0;                          // start, in env, of the side of the seam that holds the core
+        long long n = 0, core_lo = 0, core_hi = 0;   // length of that side and the core inside it (11025-Hz samples)
+        wefax::DevBuf env, dig;
+    } seg;
     // pinned staging for small results
     void *pinned = nullptr;
     size_t pinned_cap = 0;

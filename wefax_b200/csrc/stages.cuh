@@ -90,6 +90,13 @@ SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long
 void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                    const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines);
 
+// ---- segment mode (segment.cu): radix-digit histograms of the median-filtered envelope of the core
+// samples [core_lo, core_hi) of an extended segment of n samples; hist: 4 x 2048 counters (device)
+void launch_segment_hist(wefax_ctx *ctx, const float *env, long long n, long long core_lo, long long core_hi, int level,
+                         const uint32_t prefix[4], uint32_t *hist);
+void launch_segment_median(wefax_ctx *ctx, const float *env, long long n, long long core_lo, long long core_hi,
+                           float *out);
+
 // find_peaks-based start / stop tone decision on the spectra of n_packets packets (tones.cu);
 // flags / counts hold 2 entries per packet (start, stop), device pointers
 void launch_tone_peaks(wefax_ctx *ctx, const float2 *X, size_t xs, long long packet_len, int sample_rate,

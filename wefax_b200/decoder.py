@@ -318,3 +318,88 @@ class Decoder:
             peaks=[peaks[i, : n_peaks[i]].tolist() for i in range(B)],
             phasing_signals=[phasing[i, : n_phasing[i]].tolist() for i in range(B)],
             start_frame=start, height=height, low_high=np.zeros((B, 2)), digitalized=dig, raster_flat=raster)
+
+    # -- segment mode (one long recording over several contexts / GPUs; wefax_b200/segments.py) ----
+    def segment_envelope(self, pcm, sample_rate: int, core_begin: int, core_end: int,
+                         notch_freq=2600, notch_q=1, n_out: int | None = None, seam: int = 0) -> int:
+        """Ingest (+ resample) + notch + |hilbert| of one extended segment; the envelope stays on the
+        GPU.  ``[core_begin, core_end)``: the 11025-Hz samples this segment owns, relative to the
+        extended segment; ``n_out``: its planned length at 11025 Hz (None: the reference's formula);
+        ``seam``: where, inside the extended segment, the recording's end meets its start (0: nowhere).
+        Returns the extended segment's length at 11025 Hz."""
+        on_dev = _is_torch(pcm) and pcm.is_cuda
+        shape = tuple(pcm.shape)
+        ch = 2 if len(shape) == 2 else 1
+        if len(shape) not in (1, 2) or (len(shape) == 2 and shape[1] != 2):
+            raise ValueError(f"unsupported pcm shape {shape}")
+        if on_dev:
+            import torch
+            if pcm.dtype != torch.int16 or not pcm.is_contiguous():
+                raise ValueError("device pcm must be a contiguous int16 tensor")
+            ptr = pcm.data_ptr()
+        else:
+            if _is_torch(pcm):
+                pcm = pcm.numpy()
+            if pcm.dtype != np.int16:
+                raise TypeError(f"pcm must be int16 (got {pcm.dtype})")
+            pcm = np.ascontiguousarray(pcm)
+            ptr = pcm.ctypes.data
+        desc = N.BatchDesc(1, shape[0], ch, int(sample_rate), float(notch_freq), float(notch_q),
+                           N.F_PCM_ON_DEVICE if on_dev else 0)
+        sample_rate = int(sample_rate)
+        if n_out is None:
+            n_out = shape[0] if sample_rate == N.TARGET_RATE else N.resampled_length(shape[0], sample_rate)
+        self._check(self._lib.wefax_segment_envelope(self._h, C.byref(desc), C.c_void_p(ptr), int(n_out), int(seam),
+                                                     int(core_begin), int(core_end)))
+        self._seg_core = (int(core_begin), int(core_end))
+        return int(n_out)
+
+    def segment_histogram(self, level: int, prefix=(0, 0, 0, 0)) -> np.ndarray:
+        """``(4, 2048)`` uint32 radix-digit histogram of the core's median-filtered envelope."""
+        hist = np.zeros((4, 2048), dtype=np.uint32)
+        pre = (C.c_uint32 * 4)(*[int(v) for v in prefix])
+        self._check(self._lib.wefax_segment_histogram(self._h, int(level), pre, hist.ctypes.data))
+        return hist
+
+    def segment_quantise(self, low: float, high: float, want=("digitalized",)) -> dict:
+        """Grey map of the extended segment with the global percentiles; returns the core's share of
+        the outputs named in ``want`` (``digitalized`` uint8, ``demodulated`` float32)."""
+        lo, hi = self._seg_core
+        out = {}
+        dig = np.empty(hi - lo, dtype=np.uint8) if "digitalized" in want else None
+        dem = np.empty(hi - lo, dtype=np.float32) if "demodulated" in want else None
+        self._check(self._lib.wefax_segment_quantise(
+            self._h, float(low), float(high),
+            C.c_void_p(dig.ctypes.data if dig is not None and dig.size else None),
+            C.c_void_p(dem.ctypes.data if dem is not None and dem.size else None)))
+        if dig is not None:
+            out["digitalized"] = dig
+        if dem is not None:
+            out["demodulated"] = dem
+        return out
+
+    def segment_sync(self, lpm) -> dict:
+        """Phasing search on the resident grey levels (the segment that starts the recording)."""
+        peaks = np.zeros(N.MAX_PEAKS, dtype=np.int32)
+        phasing = np.zeros(N.MAX_PEAKS, dtype=np.int32)
+        n_peaks, n_phasing = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        start, status = np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int32)
+        o = N.BatchOut()
+        o.peaks, o.n_peaks = peaks.ctypes.data, n_peaks.ctypes.data
+        o.phasing, o.n_phasing = phasing.ctypes.data, n_phasing.ctypes.data
+        o.start_frame, o.status = start.ctypes.data, status.ctypes.data
+        self._check(self._lib.wefax_segment_sync(self._h, float(lpm), C.byref(o)))
+        return {"peaks": peaks[: n_peaks[0]].tolist(), "phasing_signals": phasing[: n_phasing[0]].tolist(),
+                "start_frame": int(start[0]), "status": int(status[0])}
+
+    def segment_raster(self, lpm, first_sample: int, n_lines: int, skip_lines: int, keep_lines: int,
+                       out=None) -> np.ndarray:
+        """``(4 * keep_lines, width)`` rows of the image lines this segment owns."""
+        w = N.line_constants(float(lpm))["width"]
+        if out is None:
+            out = np.empty((4 * keep_lines, w), dtype=np.uint8)
+        if keep_lines > 0:
+            ptr = out.data_ptr() if _is_torch(out) else out.ctypes.data
+            self._check(self._lib.wefax_segment_raster(self._h, float(lpm), int(first_sample), int(n_lines),
+                                                       int(skip_lines), int(keep_lines), C.c_void_p(ptr)))
+        return out
