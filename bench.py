@@ -60,6 +60,8 @@ def parse_args():
                          "one per GPU (strong scaling; wefax_b200/segments.py).  Not the headline workload.")
     ap.add_argument("--local-segments", type=int, default=1, help="with --segments: contexts (segments) per GPU")
     ap.add_argument("--halo", type=int, default=65536, help="with --segments: halo in 11025-Hz samples")
+    ap.add_argument("--repeat", type=int, default=1,
+                    help="with --segments: the synthetic recording tiled this many times (a very long recording)")
     return ap.parse_args()
 
 
@@ -72,6 +74,18 @@ def workload_name(args) -> str:
                 f"60/90/120/240 (BASELINE.json configs[3] shape)")
     return (f"synthetic {args.duration / 60:g}-min mono 11025 Hz WEFAX recording, IOC576/{args.lpm} LPM, "
             f"one per GPU (BASELINE.json configs[1])")
+
+
+JSON_OUT = sys.stdout
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so that
+    banners of native libraries (NCCL's version line) cannot land in front of the JSON."""
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 
 def hbm_peak():
@@ -175,7 +189,7 @@ def run_reference(args, rank: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------- our arm (GPU)
@@ -412,7 +426,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                           "start_frame_equal": bool(int(res.start_frame[0]) == int(o.get("start_frame", -1)))}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -449,6 +463,8 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
 
     rate = args.sample_rate
     pcm = synth.synth_recording(args.duration, sample_rate=rate, lpm=args.lpm, seed=1)   # same on every rank
+    if args.repeat > 1:
+        pcm = np.tile(pcm, args.repeat)
     n_frames = int(pcm.shape[0])
     L = args.local_segments
     G = world * L
@@ -466,7 +482,7 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
         src = mine if device_resident else pinned
         return S.decode_segmented(None, rate, args.lpm, workers, halo=args.halo, exchange=ex, n_frames=n_frames,
                                   segment_pcm=lambda sg: src[sg.index], want=("raster",), segments=segs,
-                                  rows_on_device=device_resident, gather=not device_resident)
+                                  rows_on_device=True, gather=not device_resident)
 
     res = step(True)
     if res.error() is not None:
@@ -511,7 +527,8 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
             "metric": "decoded audio Msamples/s", "value": n_frames / (ms_per_step * 1e-3) / 1e6, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.duration / 60:g}-min mono {rate} Hz WEFAX recording, {args.lpm} LPM, "
+            "config": {"workload": f"synthetic {args.duration * args.repeat / 60:g}-min mono {rate} Hz WEFAX recording"
+                                   f"{' (a ' + format(args.duration / 60, 'g') + '-min one tiled)' if args.repeat > 1 else ''}, {args.lpm} LPM, "
                                    f"split into {G} overlapping segments over {world} GPU(s) (BASELINE.json configs[2])",
                        "frames": n_frames, "samples_at_11025": n_total, "segments": G, "halo": args.halo,
                        "segment_samples": [sg.n_out for sg in segs], "outputs": ["raster"],
@@ -525,7 +542,7 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
                     "h2d_bytes_per_step": int(sum(2 * (sg.in_end - sg.in_begin) for sg in segs)),
                     "d2h_bytes_per_step": int(host.image.nbytes),
                     "api": "segments.decode_segmented -> wefax_segment_* (pinned host PCM per segment, image rows "
-                           "gathered on rank 0)"},
+                           "sent GPU to GPU to rank 0, one pinned device->host copy of the image)"},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "kernel": "whole segmented path (A = 2 B per input frame + 4 B per raster byte)",
                          "achieved": algo / (ms_per_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
@@ -534,7 +551,7 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
             "stages_rank0_ms": {k: v[0] for k, v in sorted(stage_ms.items())},
             "cpu_baseline": None,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -554,6 +571,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    claim_stdout()
     if args.segments:
         if "--duration" not in " ".join(sys.argv):
             args.duration = 1200.0

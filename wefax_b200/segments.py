@@ -233,6 +233,49 @@ class HostExchange:
         self.dist.broadcast_object_list(box, src=src, group=self.group)
         return box[0]
 
+    def broadcast_ints(self, values, count: int, src: int = 0) -> list:
+        """One fixed-size int64 tensor broadcast (cheaper than pickling an object through two collectives)."""
+        if self.world == 1:
+            return [int(v) for v in values]
+        import torch
+        t = torch.zeros(count, dtype=torch.int64)
+        if self.rank == src:
+            t[:len(values)] = torch.tensor([int(v) for v in values], dtype=torch.int64)
+        nccl = self.dist.get_backend(self.group) == "nccl"
+        if nccl:
+            t = t.cuda(self.device)
+        self.dist.broadcast(t, src=src, group=self.group)
+        return t.cpu().tolist()
+
+    def gather_rows_on_device(self, rows: dict, spans: Sequence, width: int, n_rows: int, local_workers: int):
+        """Image rows that live in each GPU's memory -> one image on rank 0's GPU (NCCL send / recv over NVLink),
+        then a single copy into pinned host memory.  spans: ``(first_row, end_row)`` of every segment, known to
+        every rank from the plan, so no metadata travels.  Returns the host image on rank 0, None elsewhere."""
+        import torch
+        img = None
+        if self.rank == 0:
+            key = (n_rows, width)
+            if getattr(self, "_img_key", None) != key:
+                self._img = torch.empty(key, dtype=torch.uint8, device=f"cuda:{self.device or 0}")
+                self._img_host = torch.empty(key, dtype=torch.uint8, pin_memory=True)
+                self._img_key = key
+            img = self._img
+        for index, (y0, y1) in enumerate(spans):
+            if y1 <= y0:
+                continue
+            owner = index // local_workers
+            if self.rank == 0 and owner == 0:
+                img[y0:y1].copy_(rows[y0], non_blocking=True)
+            elif self.rank == 0:
+                self.dist.recv(img[y0:y1], src=owner, group=self.group)
+            elif owner == self.rank:
+                self.dist.send(rows[y0], dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        self._img_host.copy_(img)
+        torch.cuda.current_stream().synchronize()
+        return self._img_host.numpy()
+
     def gather(self, obj, dst: int = 0):
         if self.world == 1:
             return [obj]
@@ -294,7 +337,8 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
     collected on rank 0 (``result.image``).  head: how far the first extended segment must reach for the
     phasing search (default: 101 line periods + 500 samples each, wefax.py:251,264-266).
     segments: a plan made by ``plan_decode`` with the same arguments (e.g. to stage the PCM beforehand).
-    rows_on_device: leave each worker's image rows in its GPU's memory (torch uint8 tensors; no gather)."""
+    rows_on_device: leave each worker's image rows in its GPU's memory (torch uint8 tensors); with ``gather``
+    they travel GPU to GPU (NCCL send / recv) to rank 0 and reach the host in one pinned copy."""
     ex = exchange or HostExchange()
     L = len(workers)
     G = n_segments or ex.world * L
@@ -349,7 +393,14 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
             # the search ran off the end of segment 0 before its 100th peak: more data would change it
             raise ValueError("first segment too short for the phasing search (it found fewer than 100 peaks "
                              "before its end); pass a larger head")
-    sync = ex.broadcast(sync, 0)
+    # one int64 tensor: [status, start_frame, n_peaks, n_phasing, peaks..., phasing...]
+    flat = []
+    if ex.rank == 0:
+        flat = [sync["status"], sync["start_frame"], len(sync["peaks"]), len(sync["phasing_signals"]),
+                *sync["peaks"], *sync["phasing_signals"]]
+    flat = ex.broadcast_ints(flat, 4 + 2 * N.MAX_PEAKS, 0)
+    sync = {"status": flat[0], "start_frame": flat[1], "peaks": flat[4:4 + flat[2]],
+            "phasing_signals": flat[4 + flat[2]:4 + flat[2] + flat[3]]}
     status |= sync["status"]
     start = sync["start_frame"]
 
@@ -373,7 +424,10 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
         status |= N.REC_NO_LINES
     res = SegmentedResult(n_total, w, low, high, sync["peaks"], sync["phasing_signals"], start, status, rows,
                           digitalized, demodulated)
-    if gather and "raster" in want and not rows_on_device:
+    if gather and "raster" in want and rows_on_device and status == N.REC_OK:
+        spans = [tuple(4 * r for r in owned_lines(sg, start, w, n_lines)) for sg in segs]
+        res.image = ex.gather_rows_on_device(rows, spans, w, 4 * n_lines, L)
+    elif gather and "raster" in want:
         parts = ex.gather(rows, 0)
         if ex.rank == 0 and status == N.REC_OK:
             img = np.empty((4 * n_lines, w), dtype=np.uint8)
