@@ -127,6 +127,10 @@ def test_stereo_and_device_resident_segments():
         dev = torch.from_numpy(mono).cuda()
         c = S.decode_segmented(None, 11025, 120, ds, n_frames=mono.shape[0],
                                segment_pcm=lambda sg: S.segment_frames(dev, sg).contiguous())
+        # image rows left on the GPU and assembled there (the multi-GPU path sends them to rank 0 the same way)
+        d = S.decode_segmented(mono, 11025, 120, ds, rows_on_device=True, exchange=S.HostExchange(device=0))
+        assert all(v.is_cuda for v in d.rows.values())
+        assert np.array_equal(a.image, d.image)
     finally:
         _close(ds)
     # (L + R) / 2 of identical channels wraps for |x| >= 16384 (wefax.py:372); this recording stays below
