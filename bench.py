@@ -339,7 +339,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     kernels = {}
     for name, (ms, cnt) in stage_ms.items():
         avg = ms / max(cnt, 1)
-        b = stage_bytes(name, n, half)
+        # a large batch runs in waves that fit the workspace: one launch then moves 1/waves of the step's bytes
+        b = stage_bytes(name, n, half) / max(1.0, cnt / args.steps)
         kernels[name] = {"ms": round(avg, 5), "launches_per_step": cnt / args.steps,
                          "algo_bytes": b, "gbs": round(b / (avg * 1e-3) / 1e9, 1) if avg > 0 and b else None}
     sub = {k: kernels.pop(k) for k in list(kernels) if k.startswith("pct_")}   # parts of "percentiles"
