@@ -1464,6 +1464,47 @@ raster_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lin
 #pragma unroll
     for (int j = 0; j < 4; ++j) load_line(r0 - 2 + j, win[j]);
     const bool full = x0 + 3 < w;
+    // Interior tiles (no line of the tile within 2 lines of the image's first / last line): Pillow's coefficients
+    // depend on the phase only (the filter argument t + xmin - center + 0.5 is exact in binary), phases 0,1 use
+    // lines r-2..r+1 and phases 2,3 lines r-1..r+2.  The 16 weights live in registers for the whole tile.
+    if (r0 >= 2 && r0 + kRasterRows + 2 <= h) {
+        int k[4][4];
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) k[ph][t] = s_k[ph][ph < 2 ? t : t + 1];
+#pragma unroll
+        for (int rr = 0; rr < kRasterRows; ++rr) {
+            const int r = r0 + rr;
+            load_line(r + 2, win[4]);
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {
+                const int b = ph < 2 ? 0 : 1;
+                int v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int acc = (1 << 21) + win[b][c] * k[ph][0] + win[b + 1][c] * k[ph][1] + win[b + 2][c] * k[ph][2] +
+                              win[b + 3][c] * k[ph][3];
+                    acc >>= 22;
+                    v[c] = __vimin_s32_relu(acc, 255);   // clamp to [0, 255] in one instruction
+                }
+                uint8_t *o = out + (size_t)(4 * r + ph) * w + x0;
+                if (full && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+                    *reinterpret_cast<uint32_t *>(o) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) |
+                                                       ((uint32_t)v[3] << 24);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (x0 + c < w) o[c] = (uint8_t)v[c];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) win[j][c] = win[j + 1][c];
+        }
+        return;
+    }
 #pragma unroll
     for (int rr = 0; rr < kRasterRows; ++rr) {
         const int r = r0 + rr;
@@ -1478,7 +1519,7 @@ raster_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lin
             for (int c = 0; c < 4; ++c) {
                 int acc = (1 << 21) + win[0][c] * k0 + win[1][c] * k1 + win[2][c] * k2 + win[3][c] * k3 + win[4][c] * k4;
                 acc >>= 22;
-                v[c] = min(max(acc, 0), 255);
+                v[c] = __vimin_s32_relu(acc, 255);   // clamp to [0, 255] in one instruction
             }
             uint8_t *o = out + (size_t)(4 * r + ph) * w + x0;
             if (full && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
