@@ -85,6 +85,18 @@ def workload_name(args) -> str:
 JSON_OUT = sys.stdout
 
 
+def bind_to_gpu_numa_node(index: int) -> None:
+    """Pin this rank (and the threads it starts) to the CPU cores NVML reports as local to its GPU, BEFORE any pinned
+    buffer is allocated: pinned staging then lives on the GPU's own NUMA node, and eight ranks do not push their
+    PCIe traffic through the inter-socket link.  Best effort (single-socket hosts / containers: no-op)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
+
+
 def claim_stdout() -> None:
     """stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so that
     banners of native libraries (NCCL's version line) cannot land in front of the JSON."""
@@ -222,6 +234,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     from wefax_b200 import _native as N
     from wefax_b200.decoder import Decoder
 
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
@@ -459,6 +473,8 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
     from wefax_b200 import synth
     from wefax_b200.decoder import Decoder
 
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):

@@ -82,6 +82,18 @@ FirParams make_fir(double f0, double q, double fs) {
     return fp;
 }
 
+// the notch of a context rarely changes between calls: the 4096-step impulse response is computed once per (f0, Q)
+const FirParams &cached_fir(wefax_ctx *ctx, double f0, double q) {
+    if (!(ctx->fir_valid && ctx->fir_f0 == f0 && ctx->fir_q == q)) {
+        ctx->fir_valid = false;
+        ctx->fir = make_fir(f0, q, (double)WEFAX_TARGET_RATE);
+        ctx->fir_f0 = f0;
+        ctx->fir_q = q;
+        ctx->fir_valid = true;
+    }
+    return ctx->fir;
+}
+
 void line_constants(double lpm, int sr, wefax_line_constants *o) {
     // Python: 1 / (lpm / 60); int(x * frame_len * sample_rate) evaluated left to right
     volatile double frame_len = 1.0 / (lpm / 60.0);
@@ -358,7 +370,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
         const bool out_dev = desc->flags & WEFAX_F_OUT_ON_DEVICE;
 
         // wefax.py:63: the frequency goes through int()
-        const FirParams fp = make_fir((double)(long long)desc->notch_freq, desc->notch_q, (double)WEFAX_TARGET_RATE);
+        const FirParams &fp = cached_fir(ctx, (double)(long long)desc->notch_freq, desc->notch_q);
 
         const LineSet ls = prepare_lines(lpm, nrec, n);
         const std::vector<LineDev> &lines = ls.lines;
@@ -666,7 +678,7 @@ int wefax_segment_envelope(wefax_ctx *ctx, const wefax_batch_desc *desc, const i
         use_device(ctx);
         cudaStream_t st = ctx->stream;
         ctx->seg.have_env = ctx->seg.have_dig = false;
-        const FirParams fp = make_fir((double)(long long)desc->notch_freq, desc->notch_q, (double)WEFAX_TARGET_RATE);
+        const FirParams &fp = cached_fir(ctx, (double)(long long)desc->notch_freq, desc->notch_q);
 
         FftPlan *half = (n % 2 == 0) ? get_plan(ctx, n / 2) : nullptr;
         FftPlan *plan = half ? nullptr : get_plan(ctx, n);

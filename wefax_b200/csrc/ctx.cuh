@@ -15,6 +15,18 @@ struct Bluestein {
     DevBuf chirp;              // c[i] = exp(-i*pi*i^2/n), i < n
     DevBuf vhat;               // FFT_m of the wrapped conj(chirp), engine order, scaled by 1/m
 };
+
+constexpr int kMaxFirTaps = 64;
+
+// Truncated impulse response of the notch section (wefax.py:68-72): filtfilt is
+// evaluated as a causal FIR h followed by an anti-causal FIR h with scipy's exact
+// edge treatment (odd extension by 9, steady-state initial conditions).
+struct FirParams {
+    int K;                    // taps actually used (<= kMaxFirTaps), padded to KP
+    int KP;                   // K rounded up to a multiple of 4
+    float h[kMaxFirTaps];     // h[m], zero padded
+    float hr[kMaxFirTaps];    // reversed: hr[j] = h[KP-1-j]
+};
 }  // namespace wefax
 
 struct wefax_ctx {
@@ -43,6 +55,10 @@ struct wefax_ctx {
         long long n = 0, core_lo = 0, core_hi = 0;   // length of that side and the core inside it (11025-Hz samples)
         wefax::DevBuf env, dig;
     } seg;
+    // FIR form of the notch for the last (f0, Q) seen (api.cu: cached_fir)
+    bool fir_valid = false;
+    double fir_f0 = 0.0, fir_q = 0.0;
+    wefax::FirParams fir;
     // pinned staging for small results
     void *pinned = nullptr;
     size_t pinned_cap = 0;

@@ -5,18 +5,6 @@
 
 namespace wefax {
 
-constexpr int kMaxFirTaps = 64;
-
-// Truncated impulse response of the notch section (wefax.py:68-72): filtfilt is
-// evaluated as a causal FIR h followed by an anti-causal FIR h with scipy's exact
-// edge treatment (odd extension by 9, steady-state initial conditions).
-struct FirParams {
-    int K;                    // taps actually used (<= kMaxFirTaps), padded to KP
-    int KP;                   // K rounded up to a multiple of 4
-    float h[kMaxFirTaps];     // h[m], zero padded
-    float hr[kMaxFirTaps];    // reversed: hr[j] = h[KP-1-j]
-};
-
 // per-recording line geometry (wefax_line_constants, device copy)
 struct LineDev {
     int n1, n0, L, mindistance, width;
