@@ -9,7 +9,8 @@ through ``oracle/ref_runner.py`` — so it only works in the build container whe
 * ``tests/golden/digests.json``      : for longer seeded synthetics, SHA-256 of
   the integer outputs and a strided float64 sample of the float stages.
 
-Usage (build container):  python tests/golden/make_golden.py
+Usage (build container):  python tests/golden/make_golden.py            # everything
+                          python tests/golden/make_golden.py NAME ...   # (re)make only these digest cases
 """
 from __future__ import annotations
 
@@ -59,6 +60,10 @@ DIGEST_CASES = {
                                  noise_sigma=0.02), 120),
     "upsamp_20s_8k_120": (dict(duration_s=20.0, sample_rate=8000, lpm=120, seed=8,
                                noise_sigma=0.02), 120),
+    # long enough for pattern_search to reach its 100-peak break (wefax.py:251); non-zero start_frame
+    "long_130s_120": (dict(duration_s=130.0, lpm=120, seed=21, noise_sigma=0.03), 120),
+    "long_100s_180": (dict(duration_s=100.0, lpm=180, seed=5, noise_sigma=0.04), 180),
+    "long_80s_240_offset": (dict(duration_s=80.0, lpm=240, seed=3, noise_sigma=0.02, carrier_offset_hz=30.0), 240),
 }
 
 FLOAT_SAMPLE = 4096
@@ -91,8 +96,9 @@ def main() -> None:
     from scipy.io import wavfile
     tmp = tempfile.mkdtemp()
     ver = versions()
+    only = sys.argv[1:]
 
-    for name, (kind, arg, lpm) in FULL_CASES.items():
+    for name, (kind, arg, lpm) in ({} if only else FULL_CASES).items():
         if kind == "wav":
             path = os.path.join(FIXTURE_DIR, arg)
             sr, pcm = wavfile.read(path)
@@ -114,7 +120,14 @@ def main() -> None:
         print(name, "error=", r["error"], "start_frame=", r.get("start_frame"))
 
     digests = {"versions": ver, "cases": {}}
+    if only:
+        with open(os.path.join(HERE, "digests.json")) as fh:
+            digests = json.load(fh)
+        if digests["versions"] != ver:
+            raise SystemExit(f"installed versions {ver} differ from the file's {digests['versions']}: regenerate all")
     for name, (kw, lpm) in DIGEST_CASES.items():
+        if only and name not in only:
+            continue
         pcm = synth.synth_recording(**kw)
         sr = kw.get("sample_rate", 11025)
         path = os.path.join(tmp, name + ".wav")
