@@ -62,6 +62,9 @@ def parse_args():
                     help="BASELINE configs[2]: ONE recording (default 20 min at 48 kHz) decoded in overlapping segments, "
                          "one per GPU (strong scaling; wefax_b200/segments.py).  Not the headline workload.")
     ap.add_argument("--local-segments", type=int, default=1, help="with --segments: contexts (segments) per GPU")
+    ap.add_argument("--devices", type=int, default=1,
+                    help="with --segments, without torchrun: ONE process drives this many GPUs, one segment and one "
+                         "host thread each; no process group, the histogram sums are plain host additions")
     ap.add_argument("--halo", type=int, default=65536, help="with --segments: halo in 11025-Hz samples")
     ap.add_argument("--repeat", type=int, default=1,
                     help="with --segments: the synthetic recording tiled this many times (a very long recording)")
@@ -498,13 +501,14 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
     if args.repeat > 1:
         pcm = np.tile(pcm, args.repeat)
     n_frames = int(pcm.shape[0])
-    L = args.local_segments
+    single = world == 1 and args.devices > 1
+    L = args.devices if single else args.local_segments
     G = world * L
-    workers = [Decoder(local_rank) for _ in range(L)]
+    workers = [Decoder(d) for d in range(L)] if single else [Decoder(local_rank) for _ in range(L)]
     ex = S.HostExchange(device=local_rank)
     segs = S.plan_decode(n_frames, rate, args.lpm, G, args.halo)
-    mine = {sg.index: torch.from_numpy(np.ascontiguousarray(S.segment_frames(pcm, sg))).cuda()
-            for sg in segs[rank * L:(rank + 1) * L]}
+    mine = {sg.index: torch.from_numpy(np.ascontiguousarray(S.segment_frames(pcm, sg))).cuda(workers[k].device)
+            for k, sg in enumerate(segs[rank * L:(rank + 1) * L])}
     pinned = {sg.index: torch.from_numpy(np.ascontiguousarray(S.segment_frames(pcm, sg))).pin_memory()
               for sg in segs[rank * L:(rank + 1) * L]}
     sampler = ClockSampler(local_rank)
@@ -557,11 +561,12 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
         peak, src_peak = hbm_peak()
         line = {
             "metric": "decoded audio Msamples/s", "value": n_frames / (ms_per_step * 1e-3) / 1e6, "unit": "Msamples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "n_gpus": L if single else world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"synthetic {args.duration * args.repeat / 60:g}-min mono {rate} Hz WEFAX recording"
                                    f"{' (a ' + format(args.duration / 60, 'g') + '-min one tiled)' if args.repeat > 1 else ''}, {args.lpm} LPM, "
-                                   f"split into {G} overlapping segments over {world} GPU(s) (BASELINE.json configs[2])",
+                                   f"split into {G} overlapping segments over {L if single else world} GPU(s)"
+                                   f"{' driven by one process' if single else ''} (BASELINE.json configs[2])",
                        "frames": n_frames, "samples_at_11025": n_total, "segments": G, "halo": args.halo,
                        "segment_samples": [sg.n_out for sg in segs], "outputs": ["raster"],
                        "exchange": "3 x 32 KiB histograms all-reduced + start_frame broadcast through the host; no "
@@ -575,10 +580,11 @@ def run_segments(args, rank: int, world: int, local_rank: int) -> None:
                     "d2h_bytes_per_step": int(host.image.nbytes),
                     "api": "segments.decode_segmented -> wefax_segment_* (pinned host PCM per segment, image rows "
                            "sent GPU to GPU to rank 0, one pinned device->host copy of the image)"},
-            "gpu_launches": int(launches) * world,
+            "gpu_launches": int(launches) * world,   # this rank's launches x ranks (every rank runs the same kernels)
             "roofline": {"bound": "hbm", "kernel": "whole segmented path (A = 2 B per input frame + 4 B per raster byte)",
-                         "achieved": algo / (ms_per_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
-                         "frac": algo / (ms_per_step * 1e-3) / 1e9 / (peak * world), "traffic": None,
+                         "achieved": algo / (ms_per_step * 1e-3) / 1e9, "peak": peak * (L if single else world),
+                         "unit": "GB/s",
+                         "frac": algo / (ms_per_step * 1e-3) / 1e9 / (peak * (L if single else world)), "traffic": None,
                          "peak_source": src_peak},
             "stages_rank0_ms": {k: v[0] for k, v in sorted(stage_ms.items())},
             "cpu_baseline": None,

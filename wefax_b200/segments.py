@@ -26,6 +26,7 @@ drives one worker per local GPU context.
 from __future__ import annotations
 
 import math
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Callable, Sequence
 
@@ -327,7 +328,8 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
                      plannable: Callable[[int], bool] | None = _plannable,
                      segment_pcm: Callable[[Segment], object] | None = None,
                      n_frames: int | None = None, head: int | None = None,
-                     rows_on_device: bool = False, segments: Sequence[Segment] | None = None) -> SegmentedResult:
+                     rows_on_device: bool = False, segments: Sequence[Segment] | None = None,
+                     parallel: bool = True) -> SegmentedResult:
     """Decode ONE recording in ``world * len(workers)`` segments; this process drives ``workers`` (one
     per local GPU context) on segments ``rank*len(workers) ...``.
 
@@ -338,7 +340,9 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
     phasing search (default: 101 line periods + 500 samples each, wefax.py:251,264-266).
     segments: a plan made by ``plan_decode`` with the same arguments (e.g. to stage the PCM beforehand).
     rows_on_device: leave each worker's image rows in its GPU's memory (torch uint8 tensors); with ``gather``
-    they travel GPU to GPU (NCCL send / recv) to rank 0 and reach the host in one pinned copy."""
+    they travel GPU to GPU (NCCL send / recv) to rank 0 and reach the host in one pinned copy.
+    parallel: drive several local workers from one host thread each (a single process over all GPUs of a host
+    needs no process group at all)."""
     ex = exchange or HostExchange()
     L = len(workers)
     G = n_segments or ex.world * L
@@ -357,21 +361,41 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
     if G > 1 and halo < (MARGIN_LINES + 1) * w:
         raise ValueError(f"halo {halo} shorter than {MARGIN_LINES + 1} lines of {w} samples")
 
+    # Several local workers (one per GPU of a single process, or several contexts on one GPU) run every phase
+    # concurrently, one host thread each: the native calls release the GIL and each context is only ever used by
+    # one thread at a time.
+    pool = ThreadPoolExecutor(L) if (parallel and L > 1) else None
+
+    def each(fn):
+        pairs = list(zip(workers, mine))
+        return list(pool.map(lambda p: fn(*p), pairs)) if pool else [fn(*p) for p in pairs]
+
+    try:
+        return _run_protocol(ex, each, workers, segs, L, pcm, sample_rate, lpm, w, n_total, n_frames, segment_pcm,
+                             notch_freq, notch_q, want, gather, rows_on_device)
+    finally:
+        if pool:
+            pool.shutdown(wait=True)
+
+
+def _run_protocol(ex, each, workers, segs, L, pcm, sample_rate, lpm, w, n_total, n_frames, segment_pcm, notch_freq,
+                  notch_q, want, gather, rows_on_device) -> SegmentedResult:
     # 1. envelopes of the extended segments (resident on each GPU)
-    for wk, sg in zip(workers, mine):
+    def envelope(wk, sg):
         part = segment_pcm(sg) if segment_pcm is not None else segment_frames(pcm, sg, n_frames)
         n_ext = wk.segment_envelope(part, sample_rate, sg.core_begin - sg.out_begin, sg.core_end - sg.out_begin,
                                     notch_freq, notch_q, n_out=sg.n_out, seam=sg.seam)
         if n_ext != sg.n_out:
             raise RuntimeError(f"segment {sg.index}: {n_ext} samples at 11025 Hz, planned {sg.n_out}")
+    each(envelope)
 
     # 2. exact global percentiles (three histogram exchanges)
     ranks, fracs = percentile_targets(n_total)
 
     def summed_histogram(level, prefix):
         local = np.zeros((4, 2048), dtype=np.int64)
-        for wk in workers:
-            local += wk.segment_histogram(level, prefix)
+        for h in each(lambda wk, sg: wk.segment_histogram(level, prefix)):
+            local += h
         return ex.sum(local)
 
     v = select_order_statistics(summed_histogram, ranks)
@@ -380,8 +404,8 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
 
     # 3. grey map everywhere; phasing search on the segment that starts the recording
     digitalized, demodulated = {}, {}
-    for wk, sg in zip(workers, mine):
-        got = wk.segment_quantise(low, high, tuple(x for x in want if x in ("digitalized", "demodulated")))
+    small = tuple(x for x in want if x in ("digitalized", "demodulated"))
+    for sg, got in each(lambda wk, sg: (sg, wk.segment_quantise(low, high, small))):
         if "digitalized" in got:
             digitalized[sg.core_begin] = got["digitalized"]
         if "demodulated" in got:
@@ -407,19 +431,22 @@ def decode_segmented(pcm, sample_rate: int, lpm, workers: Sequence, n_segments: 
     # 4. image lines by ownership of their first sample, with the bicubic margin taken from the halo
     n_lines = (n_total - start) // w                      # wefax.py:299
     rows = {}
+
+    def raster(wk, sg):
+        r0, r1 = owned_lines(sg, start, w, n_lines)
+        if r1 <= r0:
+            return None
+        top = min(MARGIN_LINES, r0)
+        bottom = min(MARGIN_LINES, n_lines - r1)
+        first = start + (r0 - top) * w - sg.out_begin
+        out = None
+        if rows_on_device:
+            import torch
+            out = torch.empty((4 * (r1 - r0), w), dtype=torch.uint8, device=f"cuda:{wk.device}")
+        return 4 * r0, wk.segment_raster(lpm, first, top + (r1 - r0) + bottom, top, r1 - r0, out=out)
+
     if "raster" in want and status == N.REC_OK:
-        for wk, sg in zip(workers, mine):
-            r0, r1 = owned_lines(sg, start, w, n_lines)
-            if r1 <= r0:
-                continue
-            top = min(MARGIN_LINES, r0)
-            bottom = min(MARGIN_LINES, n_lines - r1)
-            first = start + (r0 - top) * w - sg.out_begin
-            out = None
-            if rows_on_device:
-                import torch
-                out = torch.empty((4 * (r1 - r0), w), dtype=torch.uint8, device=f"cuda:{wk.device}")
-            rows[4 * r0] = wk.segment_raster(lpm, first, top + (r1 - r0) + bottom, top, r1 - r0, out=out)
+        rows = dict(r for r in each(raster) if r is not None)
     if n_lines == 0:
         status |= N.REC_NO_LINES
     res = SegmentedResult(n_total, w, low, high, sync["peaks"], sync["phasing_signals"], start, status, rows,
