@@ -227,3 +227,42 @@ def test_two_ranks_over_gloo_equal_two_local_segments():
                                plannable=None)
     assert (low, high, start) == (local.low, local.high, local.start_frame)
     assert np.array_equal(image, local.image)
+
+
+def test_plan_invariants_hold_for_arbitrary_recordings():
+    """Property test: any (length, rate, segment count, halo) either plans a valid tiling or is refused."""
+    import math
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(rate=st.sampled_from([8000, 11025, 16000, 22050, 44100, 48000]), units=st.integers(1, 400_000),
+           G=st.integers(1, 8), halo=st.integers(1, 70_000), head=st.integers(0, 2_000_000))
+    def check(rate, units, G, halo, head):
+        g = math.gcd(rate, 11025)
+        u_in, u_out = rate // g, 11025 // g
+        n_frames = units * u_in
+        n_total = n_frames if rate == 11025 else N.resampled_length(n_frames, rate)
+        try:
+            segs = S.plan_segments(n_frames, rate, G, halo=halo, plannable=None, head=head)
+        except ValueError:
+            assert G > 1            # one segment is always possible
+            return
+        assert len(segs) == G and segs[0].core_begin == 0 and segs[-1].core_end == n_total
+        for a, b in zip(segs, segs[1:]):
+            assert a.core_end == b.core_begin
+        for s in segs:
+            assert s.core_begin < s.core_end and s.out_begin <= s.core_begin and s.core_end <= s.out_end
+            assert s.n_out <= n_total                                  # never laps itself
+            if G > 1:
+                assert s.n_out * rate == (s.in_end - s.in_begin) * 11025
+                whole = s.n_out == n_total and s.seam == 0             # stretched to the whole recording
+                if not whole:
+                    assert s.core_begin - s.out_begin >= halo and s.out_end - s.core_end >= halo
+                if s.seam:
+                    assert s.seam <= s.core_begin - s.out_begin or s.core_end - s.out_begin <= s.seam
+            frames = S.segment_frames(np.empty(n_frames, dtype=np.int8), s)
+            assert frames.shape[0] == s.in_end - s.in_begin
+        if G > 1 and segs[0].n_out < n_total:
+            assert segs[0].out_end >= min(head, n_total - 1) or segs[0].out_end >= n_total - u_out
+
+    check()
