@@ -175,3 +175,24 @@ def test_configs2_full_size_in_segments(G):
     img = whole.image(0)
     assert res.image.shape == img.shape == (4 * ((13_230_000 - res.start_frame) // 5512), 5512)
     assert (np.abs(res.image.astype(int) - img.astype(int)) <= 1).mean() >= 0.995
+
+
+def test_one_process_drives_two_gpus():
+    """One host thread per GPU, no process group (skipped on single-GPU boxes)."""
+    from wefax_b200 import _native as N
+    if N.load().wefax_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    pcm = synth.synth_recording(130.0, lpm=120, seed=21, noise_sigma=0.03)
+    one = [Decoder(0), Decoder(0)]
+    two = [Decoder(0), Decoder(1)]
+    try:
+        a = S.decode_segmented(pcm, 11025, 120, one, want=("raster", "digitalized"))
+        b = S.decode_segmented(pcm, 11025, 120, two, want=("raster", "digitalized"))
+        c = S.decode_segmented(pcm, 11025, 120, two, rows_on_device=True, exchange=S.HostExchange(device=0))
+    finally:
+        _close(one + two)
+    assert (a.low, a.high, a.start_frame) == (b.low, b.high, b.start_frame) == (c.low, c.high, c.start_frame)
+    assert a.start_frame == 20541
+    assert np.array_equal(a.image, b.image) and np.array_equal(a.image, c.image)
+    assert all(np.array_equal(a.digitalized[k], b.digitalized[k]) for k in a.digitalized)
+    assert sorted(v.device.index for v in c.rows.values()) == [0, 1]
