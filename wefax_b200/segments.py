@@ -26,6 +26,7 @@ drives one worker per local GPU context.
 from __future__ import annotations
 
 import math
+import sys
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Callable, Sequence
@@ -209,11 +210,9 @@ class HostExchange:
 
     def __init__(self, group=None, device: int | None = None):
         self.group, self.device = group, device
-        try:
-            import torch.distributed as dist
-            self.dist = dist if dist.is_available() and dist.is_initialized() else None
-        except ImportError:
-            self.dist = None
+        # a process group can only exist if torch.distributed is already imported: never pay for the import here
+        dist = sys.modules.get("torch.distributed")
+        self.dist = dist if dist is not None and dist.is_available() and dist.is_initialized() else None
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0
 
