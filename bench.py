@@ -227,7 +227,9 @@ def stage_bytes(name: str, n: int, half: bool) -> float:
             return m * 16.0 + (n * 4.0 if i == 0 else 0.0)   # the last pass also re-reads x for sqrt(x^2 + y^2)
         return m * (8.0 + (4.0 if i == 0 else 8.0))           # the last pass (index 0) writes |z| fp32
     return {"filtfilt": n * (2 + 4.0), "hilbert_pairs": m * 16.0, "hilbert_mid": m * 16.0, "percentiles": n * 4.0 * 3,
-            "quantise": n * (4 + 1.0), "raster": n * (1 + 4.0), "median5": n * 8.0, "sync_search": 0.0}.get(name, 0.0)
+            "quantise": n * (4 + 1.0), "raster": n * (1 + 4.0), "median5": n * 8.0, "sync_search": 0.0,
+            # fused demod-to-pixel sweep: envelope in (4 B), digitalized (1 B) + x4 raster (4 B) out
+            "grey_raster": n * (4 + 1 + 4.0)}.get(name, 0.0)
 
 
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
@@ -385,7 +387,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     def family(stage: str) -> str:
         if not stage.startswith("fft_"):
-            return {"hilbert_mid": "hilbert_mid_kernel", "filtfilt": "filtfilt_kernel", "raster": "raster_kernel",
+            return {"hilbert_mid": "hilbert_mid_kernel", "filtfilt": "notch_sym_kernel", "raster": "raster_kernel",
+                    "grey_raster": "grey_raster_kernel",
                     "quantise": "quantise_kernel", "percentiles": "pct_*_kernel (4 launches)",
                     "sync_search": "sync_*_kernel (5 launches)"}.get(stage, stage)
         i = int(stage.rsplit("_", 1)[1])

@@ -1,0 +1,152 @@
+"""GPU tests of the fused median-5 + grey map + raster sweep (csrc/greyraster.cu).
+
+The fused kernel must reproduce, bit for bit, what the separate grey-map and raster
+kernels produce (those are pinned to the oracle / the reference's golden vectors in
+test_gpu_parity.py): same `digitalized_data`, same image, for every line width
+(aligned or not), any start_frame, any tiling of the lines, recordings that end in one
+of the reference's exceptions, and when the sequential phasing scan has to compute grey
+levels that do not exist yet.
+"""
+import numpy as np
+import pytest
+
+from oracle import wefax_oracle as O
+from wefax_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+WANT = ("digitalized", "raster")
+
+
+def _decoder(monkeypatch, **env):
+    from wefax_b200.decoder import Decoder
+    for k in ("WEFAX_FUSED", "WEFAX_GR_LINES", "WEFAX_SYNC_FORCE_SCAN"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    return Decoder(0)
+
+
+def _same(a, b, n_rec):
+    assert np.array_equal(a.status, b.status)
+    assert np.array_equal(a.start_frame, b.start_frame)
+    assert np.array_equal(a.height, b.height)
+    assert a.peaks == b.peaks and a.phasing_signals == b.phasing_signals
+    if a.digitalized is not None and b.digitalized is not None:
+        assert np.array_equal(a.digitalized, b.digitalized)
+    for i in range(n_rec):
+        assert np.array_equal(a.image(i), b.image(i)), i
+
+
+@pytest.mark.parametrize("lpm", [60, 90, 100, 120, 180, 240])
+def test_fused_equals_separate_kernels_every_width(monkeypatch, lpm):
+    """Widths 11025 / 7350 / 6615 / 5512 / 3675 / 2756: odd, even, multiples of 4 and of 8."""
+    pcm = np.stack([synth.synth_recording(40.0 + 0.013 * k, lpm=lpm, seed=300 + k, noise_sigma=0.02 * (k + 1))[: 440000]
+                    for k in range(3)])
+    plain = _decoder(monkeypatch, WEFAX_FUSED=0)
+    ref = plain.decode(pcm, 11025, lpm, want=WANT)
+    plain.close()
+    fused = _decoder(monkeypatch)
+    res = fused.decode(pcm, 11025, lpm, want=WANT)
+    fused.close()
+    _same(res, ref, 3)
+    assert any(int(h) > 0 for h in res.height)
+
+
+@pytest.mark.parametrize("lines", [1, 2, 3, 5, 7, 11, 64])
+def test_fused_is_independent_of_the_line_tiling(monkeypatch, lines):
+    pcm = np.stack([synth.synth_recording(33.0, lpm=l, seed=17 + l, noise_sigma=0.03) for l in (120, 240)])
+    lpms = [120, 240]
+    plain = _decoder(monkeypatch, WEFAX_FUSED=0)
+    ref = plain.decode(pcm, 11025, lpms, want=WANT)
+    plain.close()
+    fused = _decoder(monkeypatch, WEFAX_GR_LINES=lines)
+    res = fused.decode(pcm, 11025, lpms, want=WANT)
+    fused.close()
+    _same(res, ref, 2)
+
+
+def test_fused_with_odd_lengths_offsets_and_outputs(monkeypatch):
+    """Odd recording lengths (rows of a batch then start at every alignment), raster without digitalized,
+    all outputs at once, device-resident outputs."""
+    import torch
+    base = synth.synth_recording(37.0, lpm=120, seed=5, noise_sigma=0.04)
+    for n in (len(base), len(base) - 1, len(base) - 2, len(base) - 3, len(base) - 5):
+        pcm = np.stack([base[:n], np.roll(base, 1234)[:n], base[::-1][:n].copy()])
+        plain = _decoder(monkeypatch, WEFAX_FUSED=0)
+        ref = plain.decode(pcm, 11025, 120, want=("audio", "demodulated", "digitalized", "raster"))
+        plain.close()
+        fused = _decoder(monkeypatch)
+        res = fused.decode(pcm, 11025, 120, want=("audio", "demodulated", "digitalized", "raster"))
+        only_raster = fused.decode(pcm, 11025, 120, want=("raster",))
+        dev = fused.decode(torch.from_numpy(pcm).cuda(), 11025, 120, want=WANT, device_outputs=True)
+        torch.cuda.synchronize()
+        _same(res, ref, 3)
+        assert np.array_equal(res.demodulated, ref.demodulated)
+        assert only_raster.digitalized is None
+        for i in range(3):
+            assert np.array_equal(only_raster.image(i), ref.image(i))
+            h, w = int(ref.height[i]), ref.width[i]
+            assert np.array_equal(dev.raster_flat[i, : h * w].cpu().numpy(), ref.raster_flat[i][: h * w])
+        assert np.array_equal(dev.digitalized.cpu().numpy(), ref.digitalized)
+        fused.close()
+
+
+def test_fused_when_the_sequential_scan_needs_grey_levels_that_do_not_exist_yet(monkeypatch):
+    """WEFAX_SYNC_FORCE_SCAN=1 sends every recording through the sequential picker, which then reads far
+    beyond the head the grey-map pre-pass produced: those levels come from the envelope on the fly."""
+    pcm = np.stack([synth.synth_recording(130.0, lpm=120, seed=70 + k, noise_sigma=0.05) for k in range(2)])
+    plain = _decoder(monkeypatch, WEFAX_FUSED=0)
+    ref = plain.decode(pcm, 11025, 120, want=WANT)
+    plain.close()
+    forced = _decoder(monkeypatch, WEFAX_SYNC_FORCE_SCAN=1)
+    res = forced.decode(pcm, 11025, 120, want=WANT)
+    forced.close()
+    _same(res, ref, 2)
+    for i in range(2):
+        consts = O.line_constants(120)
+        assert res.peaks[i] == O.pattern_search(res.digitalized[i].astype(np.int64), consts)
+
+
+def test_fused_recordings_without_an_image_still_get_grey_levels(monkeypatch):
+    """A recording that ends in the reference's ValueError (wefax.py:294) or IndexError (wefax.py:304) has
+    digitalized_data but no image; a constant recording has neither a finite grey map (wefax.py:216)."""
+    rng = np.random.default_rng(3)
+    clean = synth.synth_recording(30.0, lpm=120, seed=1)                       # clean synthetic: groups == [[]]
+    noise = (rng.normal(0, 3000, size=clean.shape)).astype(np.int16)           # no regular peaks at all
+    short = synth.synth_recording(30.0, lpm=120, seed=2, noise_sigma=0.02)
+    pcm = np.stack([clean, noise, short])
+    plain = _decoder(monkeypatch, WEFAX_FUSED=0)
+    ref = plain.decode(pcm, 11025, 120, want=WANT)
+    plain.close()
+    fused = _decoder(monkeypatch)
+    res = fused.decode(pcm, 11025, 120, want=WANT)
+    _same(res, ref, 3)
+    const = np.full((1, 60000), 1000, dtype=np.int16)
+    plain = _decoder(monkeypatch, WEFAX_FUSED=0)
+    ref_c = plain.decode(const, 11025, 120, want=WANT)
+    plain.close()
+    res_c = fused.decode(const, 11025, 120, want=WANT)
+    fused.close()
+    assert np.array_equal(res_c.status, ref_c.status)
+    assert np.array_equal(res_c.digitalized, ref_c.digitalized)
+
+
+def test_fused_matches_the_oracle_end_to_end(monkeypatch):
+    """Same bar as test_decode_matches_oracle_and_digest, on a recording whose start_frame is deep inside it."""
+    pcm = synth.synth_recording(100.0, lpm=120, seed=11, noise_sigma=0.06)
+    o = O.decode(pcm, 11025, 120)
+    fused = _decoder(monkeypatch)
+    res = fused.decode(pcm, 11025, 120, want=("audio", "demodulated", "digitalized", "raster"))
+    fused.close()
+    d = np.abs(res.digitalized[0].astype(np.int64) - o["digitalized_data"])
+    assert (d <= 1).mean() >= 0.999
+    if o["error"] is None and res.phasing_signals[0] == list(o["phasing_signals"]):
+        img, ref_img = res.image(0), o["output_image"]
+        assert img.shape == ref_img.shape
+        assert (np.abs(img.astype(np.int64) - ref_img.astype(np.int64)) <= 1).mean() >= 0.999
+    # on the CUDA path's own grey levels the image is Pillow's, bit for bit
+    consts = O.line_constants(120)
+    if res.error(0) is None:
+        ref_img = O.convert_to_image(res.digitalized[0].astype(np.int64)[int(res.start_frame[0]):], consts["width"])
+        assert np.array_equal(res.image(0), ref_img)

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwefax_b200.so")
-SOURCES = ["api.cu", "stages.cu", "fft_exec.cu", "fft_plan.cu", "tones.cu", "fm.cu", "segment.cu"]
-HEADERS = ["common.cuh", "ctx.cuh", "fft.cuh", "fft_fast.cuh", "fft_mid.cuh", "stages.cuh", "median.cuh",
+SOURCES = ["api.cu", "stages.cu", "fft_exec.cu", "fft_plan.cu", "tones.cu", "fm.cu", "segment.cu", "greyraster.cu"]
+HEADERS = ["common.cuh", "ctx.cuh", "fft.cuh", "fft_fast.cuh", "fft_mid.cuh", "stages.cuh", "median.cuh", "grey.cuh",
            os.path.join("..", "..", "include", "wefax_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--use_fast_math=false"]

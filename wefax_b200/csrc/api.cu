@@ -79,6 +79,30 @@ FirParams make_fir(double f0, double q, double fs) {
         }
     for (int i = 0; i < K; ++i) fp.h[i] = (float)h[i];
     for (int j = 0; j < fp.KP; ++j) fp.hr[j] = fp.h[fp.KP - 1 - j];
+    // interior form: autocorrelation of the (untruncated) impulse response, cut where the rest is below fp32
+    // resolution of the sum (1e-7 of the total; 12 taps each side for Q = 1)
+    {
+        const int GM = 256;
+        std::vector<double> g(GM);
+        double gtot = 0.0;
+        for (int k = 0; k < GM; ++k) {
+            double acc = 0.0;
+            for (int m = 0; m + k < NMAX; ++m) acc += h[m] * h[m + k];
+            g[k] = acc;
+            gtot += (k ? 2.0 : 1.0) * fabs(acc);
+        }
+        double gtail = 0.0;
+        int KG = GM - 1;
+        while (KG > 1 && gtail + 2.0 * fabs(g[KG]) < 1e-7 * gtot) gtail += 2.0 * fabs(g[KG--]);
+        fp.KC = 0;
+        const int csizes[] = {8, 12, 16, 24, 32};
+        for (int s : csizes)
+            if (KG <= s) {
+                fp.KC = s;
+                break;
+            }
+        for (int k = 0; k <= fp.KC; ++k) fp.g[k] = (float)g[k];
+    }
     return fp;
 }
 
@@ -217,6 +241,10 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
         ctx->use_fast = !(fastk && fastk[0] == '0');
         const char *tmaf = getenv("WEFAX_FFT_TMAFAST");
         ctx->use_tma_fast = !(tmaf && tmaf[0] == '0');
+        const char *symn = getenv("WEFAX_NOTCH_SYM");
+        ctx->use_sym_notch = !(symn && symn[0] == '0');
+        const char *fused = getenv("WEFAX_FUSED");   // WEFAX_FUSED=0: separate grey-map and raster kernels
+        ctx->use_fused = !(fused && fused[0] == '0');
         int prio_least = 0, prio_greatest = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         if (stream) {
@@ -469,11 +497,28 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                 hilbert_envelope_bluestein(ctx, n, d_audio, (size_t)n, d_env, (size_t)n, g);
             // ---- median-5, percentiles, grey map (wefax.py:175,196-200) ---------------
             launch_percentiles(ctx, d_env, (size_t)n, n, g, d_sel, d_res);
-            cudaEvent_t tail_done = launch_quantise_split(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res, splan);
-            // ---- phasing search (wefax.py:218-294) and raster (wefax.py:296-327) -----
-            launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, tail_done);
-            if (d_raster)
-                launch_raster(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, d_raster, rs, max_width, (int)(n / min_width));
+            if (d_raster && ctx->use_fused) {
+                // fused demod-to-pixel path: grey levels of the head for the phasing search (wefax.py:218-294),
+                // then ONE sweep over the envelope writes digitalized_data and the raster (wefax.py:296-327)
+                GreyTable *d_tab = (GreyTable *)ctx->grey_tab.reserve(sizeof(GreyTable) * (size_t)g);
+                launch_grey_table(ctx, d_res, d_tab, g);
+                const long long head = sync_head(splan, n);
+                launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res, 0, head, st, "quantise_head");
+                LazyGrey lazy;
+                lazy.env = d_env;
+                lazy.es = (size_t)n;
+                lazy.tables = d_tab;
+                lazy.valid = head;
+                launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, nullptr, lazy);
+                launch_grey_raster(ctx, d_env, (size_t)n, out->digitalized ? d_dig : nullptr, (size_t)n, d_raster, rs, n, g,
+                                   d_lines, lines.data() + w0, d_res, d_tab);
+            } else {
+                cudaEvent_t tail_done = launch_quantise_split(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res, splan);
+                // ---- phasing search (wefax.py:218-294) and raster (wefax.py:296-327) -----
+                launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, tail_done);
+                if (d_raster)
+                    launch_raster(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, d_raster, rs, max_width, (int)(n / min_width));
+            }
             float *d_demod = nullptr;
             if (out->demodulated) {
                 d_demod = out_dev ? out->demodulated + (size_t)w0 * n

@@ -17,6 +17,7 @@ struct Bluestein {
 };
 
 constexpr int kMaxFirTaps = 64;
+constexpr int kMaxSymTaps = 32;
 
 // Truncated impulse response of the notch section (wefax.py:68-72): filtfilt is
 // evaluated as a causal FIR h followed by an anti-causal FIR h with scipy's exact
@@ -26,6 +27,10 @@ struct FirParams {
     int KP;                   // K rounded up to a multiple of 4
     float h[kMaxFirTaps];     // h[m], zero padded
     float hr[kMaxFirTaps];    // reversed: hr[j] = h[KP-1-j]
+    // Away from the ends of the signal the two sections collapse into ONE symmetric FIR g = h * reversed(h):
+    // out[i] = g[0] x[i] + sum_k g[k] (x[i-k] + x[i+k]), k <= KC (0: not available, use the two sections)
+    int KC;
+    float g[kMaxSymTaps + 1];
 };
 }  // namespace wefax
 
@@ -42,12 +47,14 @@ struct wefax_ctx {
     int sm_count = 148;
     bool use_tma = true;   // WEFAX_FFT_TMA=0 forces the LDG tile loads
     bool use_fast = true;  // WEFAX_FFT_FAST=0 keeps every pass on the generic kernel
+    bool use_sym_notch = true;   // WEFAX_NOTCH_SYM=0: every tile of the notch through the two-section kernel
+    bool use_fused = true;  // WEFAX_FUSED=0: grey map and raster as two kernels instead of the fused sweep
     bool use_tma_fast = true;   // WEFAX_FFT_TMAFAST=0: register-direct loads/stores instead of TMA tiles in the strided pass
     std::map<long long, std::unique_ptr<wefax::FftPlan>> plans;
     std::map<long long, std::unique_ptr<wefax::Bluestein>> bluestein;
     std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
     // scratch (grown on demand, reused between calls)
-    wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in, sync_buf, pct_buf;
+    wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in, sync_buf, pct_buf, grey_tab;
     // segment mode: the extended segment's envelope and grey levels stay resident between the calls
     struct Segment {
         bool have_env = false, have_dig = false;

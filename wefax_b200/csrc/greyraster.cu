@@ -1,0 +1,492 @@
+// Fused demod-to-pixel kernel: median-5 of the envelope, grey map, `digitalized` and the x4 bicubic
+// raster in ONE sweep (wefax.py:175, 197-200, 216, 296-327).  The envelope is read once (4 B / sample),
+// `digitalized` (1 B) and the raster (4 B) are written once; nothing else touches HBM.
+//
+//  * grey map without float64 in the hot loop: round(255 * (m - low) / delta) is a monotone step function of
+//    the fp32 median m, so a 256-entry table of the smallest float bit pattern of every level (found once per
+//    recording by bisection with the exact float64 formula) decides the level exactly: an fp32 estimate of the
+//    level, proven by the table builder to be within +-1 of the truth, is corrected by two compares against the
+//    neighbouring thresholds.
+//  * one thread owns 8 adjacent image columns and walks down `lines_per_item` lines with a 5-line window of grey
+//    levels in registers (compile-time rotation, no moves); every line yields 4 raster rows as 8-byte stores.
+//  * image lines start at start_frame + r * width: the envelope rows are misaligned with respect to the raster
+//    rows by an amount that is fixed per row.  The envelope comes in as four aligned 16-byte loads (one row
+//    prefetched ahead) and the median network is instantiated for the four possible offsets.
+#include <algorithm>
+#include <cmath>
+
+#include "grey.cuh"
+
+namespace wefax {
+
+constexpr int kGrThreads = 256;
+constexpr int kGrCols = 8;   // columns per thread
+
+// exact grey level of a median value (same operations, in the same order, as numpy: wefax.py:197-200, 216)
+__device__ __forceinline__ int grey_level_exact(float m, double low, double delta) {
+    float v = (float)rint(__ddiv_rn(__dmul_rn(255.0, __dsub_rn((double)m, low)), delta));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    return (int)v;
+}
+
+__device__ __forceinline__ int grey_estimate(float m, float scale, float off) {
+    const int k = __float2int_rn(fmaf(m, scale, off));
+    return min(max(k, 0), 255);
+}
+
+// One CTA of 256 threads per recording.
+__global__ void __launch_bounds__(256) grey_table_kernel(const RecResult *res_all, GreyTable *tables) {
+    const RecResult *res = res_all + blockIdx.x;
+    GreyTable *tab = tables + blockIdx.x;
+    const double low = res->low, delta = __dsub_rn(res->high, low);
+    const int k = threadIdx.x;
+    const uint32_t kInf = 0x7F800000u;
+    uint32_t t = 0u;
+    if (k >= 1) {
+        if (grey_level_exact(__uint_as_float(kInf), low, delta) < k) {
+            t = 0xFFFFFFFFu;   // no float reaches this level
+        } else {
+            uint32_t lo = 0u, hi = kInf;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (grey_level_exact(__uint_as_float(mid), low, delta) >= k) hi = mid;
+                else lo = mid + 1u;
+            }
+            t = lo;
+        }
+    }
+    tab->T[k] = t;
+    if (k == 0) {
+        tab->T[256] = 0xFFFFFFFFu;
+        tab->T[257] = tab->T[258] = tab->T[259] = 0xFFFFFFFFu;
+    }
+    // fp32 estimate of the level and the proof that it is never off by more than one: the estimate is monotone
+    // in m, the level is a step function, so it is enough to look at both sides of every step (and at +inf)
+    const float scale = (float)(255.0 / delta), off = (float)(-low * (255.0 / delta));
+    bool ok = scale >= 0.f && isfinite(scale) && isfinite(off);
+    auto near = [&](uint32_t bits) {
+        const float m = __uint_as_float(bits);
+        const int d = grey_estimate(m, scale, off) - grey_level_exact(m, low, delta);
+        return d >= -1 && d <= 1;
+    };
+    if (k >= 1) {
+        if (t == 0xFFFFFFFFu) ok = false;
+        else {
+            ok = ok && near(t);
+            if (t > 0u) ok = ok && near(t - 1u);
+        }
+    } else {
+        ok = ok && near(kInf) && near(0u);
+    }
+    const int all_ok = __syncthreads_and(ok ? 1 : 0);
+    if (k == 0) {
+        tab->scale = scale;
+        tab->off = off;
+        tab->est_ok = all_ok;
+        tab->pad = 0;
+    }
+}
+
+struct GreyRasterParams {
+    const float *env;
+    size_t es;
+    uint8_t *dig;      // may be null
+    size_t ds;
+    uint8_t *raster;   // may be null: grey map only
+    size_t rs;
+    long long n;
+    const LineDev *lines;
+    const RecResult *res;
+    const GreyTable *tables;
+    int lines_per_item;
+    int nk[4][4];      // negated interior Pillow coefficients of the 4 phases (taps in line order)
+    int ck[4];         // (1 << 21) + 255 * sum of the phase's coefficients
+};
+
+__device__ __forceinline__ double gr_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for output row yy of an image of h lines, as weights of
+// the input lines r-2 .. r+2 (r = yy / 4); lines outside the image get weight 0.
+__device__ void pillow_row_weights(int yy, int h, int kw5[5]) {
+    const int r = yy >> 2;
+    const double scale = 0.25, support = 2.0;
+    const double center = (yy + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > h) xmax = h;
+    xmax -= xmin;
+    double kw[5], ww = 0.0;
+    for (int t = 0; t < 5; ++t) {
+        kw[t] = t < xmax ? gr_bicubic((t + xmin - center + 0.5)) : 0.0;
+        ww += kw[t];
+    }
+    for (int t = 0; t < 5; ++t) kw5[t] = 0;
+    for (int t = 0; t < 5 && t < xmax; ++t) {
+        const double kv = (ww != 0.0) ? kw[t] / ww : kw[t];
+        const int ki = kv < 0 ? (int)(-0.5 + kv * 4194304.0) : (int)(0.5 + kv * 4194304.0);
+        const int sl = xmin + t - (r - 2);
+        if (sl >= 0 && sl < 5) kw5[sl] = ki;
+    }
+}
+
+// d = v0 | v1 << 8 | v2 << 16 | v3 << 24, every value clamped to [0, 255]
+__device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+    return d;
+}
+
+// 8 bytes (lo = bytes 0..3) to an address of any alignment, first `count` bytes only when count < 8
+__device__ __forceinline__ void store8(uint8_t *p, uint32_t lo, uint32_t hi, int count) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
+    if (count >= 8) {
+        if (a == 0u) {
+            *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
+        } else if ((a & 3u) == 0u) {
+            reinterpret_cast<uint32_t *>(p)[0] = lo;
+            reinterpret_cast<uint32_t *>(p)[1] = hi;
+        } else if ((a & 1u) == 0u) {
+            *reinterpret_cast<uint16_t *>(p) = (uint16_t)lo;
+            *reinterpret_cast<uint32_t *>(p + 2) = __funnelshift_r(lo, hi, 16);
+            *reinterpret_cast<uint16_t *>(p + 6) = (uint16_t)(hi >> 16);
+        } else if ((a & 3u) == 3u) {
+            p[0] = (uint8_t)lo;
+            *reinterpret_cast<uint32_t *>(p + 1) = __funnelshift_r(lo, hi, 8);
+            *reinterpret_cast<uint16_t *>(p + 5) = (uint16_t)(hi >> 8);
+            p[7] = (uint8_t)(hi >> 24);
+        } else {
+            p[0] = (uint8_t)lo;
+            *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(lo >> 8);
+            *reinterpret_cast<uint32_t *>(p + 3) = __funnelshift_r(lo, hi, 24);
+            p[7] = (uint8_t)(hi >> 24);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < count) p[c] = (uint8_t)((c < 4 ? lo >> (8 * c) : hi >> (8 * (c - 4))) & 0xFFu);
+    }
+}
+
+// medians of x[OFF + 2 .. OFF + 9] given x[OFF .. OFF + 11]: every adjacent pair is ordered once and shared
+// by the two windows it belongs to (same min / max expression tree as med5)
+template <int OFF>
+__device__ __forceinline__ void med8_from16(const float (&f)[16], float (&m)[8]) {
+    float lo[10], hi[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        lo[j] = fminf(f[OFF + j], f[OFF + j + 1]);
+        hi[j] = fmaxf(f[OFF + j], f[OFF + j + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float a = fmaxf(lo[k], lo[k + 2]);
+        const float b = fminf(hi[k], hi[k + 2]);
+        m[k] = med3(f[OFF + k + 4], a, b);
+    }
+}
+
+struct GreyQuant {
+    const uint2 *pairs;   // shared: (T[k], T[k + 1])
+    const uint32_t *T;    // shared: T[0 .. 256]
+    float scale, off;
+    int est_ok;
+    // estimate (within +-1, proven by the table builder) corrected by the two neighbouring thresholds
+    __device__ __forceinline__ int level_fast(float m) const {
+        const uint32_t bits = __float_as_uint(m);
+        const int k0 = grey_estimate(m, scale, off);
+        const uint2 t = pairs[k0];
+        return k0 + (bits >= t.y ? 1 : 0) - (bits < t.x ? 1 : 0);
+    }
+    __device__ __forceinline__ int level(float m) const {
+        return est_ok ? level_fast(m) : grey_from_table(T, __float_as_uint(m));
+    }
+};
+
+__global__ void __launch_bounds__(kGrThreads, 2) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
+    __shared__ uint32_t s_T[260];
+    __shared__ uint2 s_pairs[256];
+    const int rec = blockIdx.y;
+    const RecResult *res = P.res + rec;
+    const GreyTable *tab = P.tables + rec;
+    for (int i = threadIdx.x; i < 257; i += kGrThreads) s_T[i] = tab->T[i];
+    {
+        const int i = threadIdx.x;   // kGrThreads == 256
+        s_pairs[i] = make_uint2(tab->T[i], tab->T[i + 1]);
+    }
+    GreyQuant Q;
+    Q.pairs = s_pairs;
+    Q.T = s_T;
+    Q.scale = tab->scale;
+    Q.off = tab->off;
+    Q.est_ok = tab->est_ok;
+    const int w = P.lines[rec].width;
+    const long long s = res->start_frame;
+    const int h = (P.raster && res->status == WEFAX_REC_OK) ? res->height / 4 : 0;
+    const long long n = P.n;
+    __syncthreads();
+
+    // line space anchored at start_frame: line r holds samples s + r*w .. s + r*w + w - 1; the partial lines in
+    // front of start_frame and behind the image only produce grey levels
+    const long long r_lo = -((s + w - 1) / w);
+    const long long r_hi = (n - s + w - 1) / w;
+    const int ng = (w + kGrCols - 1) / kGrCols;
+    const int U = P.lines_per_item;
+    const long long ntiles = (r_hi - r_lo + U - 1) / U;
+    const long long item = (long long)blockIdx.x * kGrThreads + threadIdx.x;
+    if (item >= ntiles * ng) return;
+    const long long tile = item / ng;
+    const int grp = (int)(item - tile * ng);
+    const int c0 = grp * kGrCols;
+    const int ncols = min(kGrCols, w - c0);
+    const long long r_a = r_lo + tile * U, r_b = min(r_a + U, r_hi);
+
+    const float *e = P.env + (size_t)rec * P.es;
+    uint8_t *dg = P.dig ? P.dig + (size_t)rec * P.ds : nullptr;
+    uint8_t *out = P.raster ? P.raster + (size_t)rec * P.rs : nullptr;
+
+    const long long i_first = s + (r_a - 2) * w + c0;   // sample (line r_a - 2, column c0)
+    const bool interior = Q.est_ok && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 && s + (r_b + 1) * w + c0 + 14 <= n;
+    if (interior) {
+        const int nrows = (int)(r_b - r_a) + 4;
+        int win[5][kGrCols];
+        const float *prow = e + i_first - 2;   // x[0] of the row being fetched
+        float4 nx[4];
+        {
+            const float4 *pa = reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(prow) & ~(uintptr_t)15);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nx[q] = __ldg(pa + q);
+        }
+        uint8_t *drow = dg ? dg + i_first : nullptr;                     // digitalized of the row being computed
+        uint8_t *orow = out + (size_t)(4 * r_a) * w + c0;                // raster rows of the line being emitted
+        for (int jb = 0; jb < nrows; jb += 5) {
+#pragma unroll
+            for (int jj = 0; jj < 5; ++jj) {
+                const int j = jb + jj;
+                if (j < nrows) {
+                    float f[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        f[4 * q] = nx[q].x; f[4 * q + 1] = nx[q].y; f[4 * q + 2] = nx[q].z; f[4 * q + 3] = nx[q].w;
+                    }
+                    const int off = (int)((reinterpret_cast<uintptr_t>(prow) >> 2) & 3u);
+                    prow += w;
+                    if (j + 1 < nrows) {
+                        const float4 *pa =
+                            reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(prow) & ~(uintptr_t)15);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) nx[q] = __ldg(pa + q);
+                    }
+                    float m[8];
+                    switch (off) {
+                        case 0: med8_from16<0>(f, m); break;
+                        case 1: med8_from16<1>(f, m); break;
+                        case 2: med8_from16<2>(f, m); break;
+                        default: med8_from16<3>(f, m); break;
+                    }
+                    int(&g)[kGrCols] = win[jj];
+#pragma unroll
+                    for (int c = 0; c < kGrCols; ++c) g[c] = Q.level_fast(m[c]);
+                    if (drow) {
+                        if (j >= 2 && j < nrows - 2) {
+                            const uint32_t lo = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
+                            const uint32_t hi = (uint32_t)g[4] | ((uint32_t)g[5] << 8) | ((uint32_t)g[6] << 16) | ((uint32_t)g[7] << 24);
+                            store8(drow, lo, hi, ncols);
+                        }
+                        drow += w;
+                    }
+                    if (j >= 4) {
+                        // line q = r_a + j - 4 is complete: its window is lines q-2 .. q+2 = slots jj+1 .. jj+5 (mod 5)
+                        const int(&l0)[kGrCols] = win[(jj + 1) % 5];
+                        const int(&l1)[kGrCols] = win[(jj + 2) % 5];
+                        const int(&l2)[kGrCols] = win[(jj + 3) % 5];
+                        const int(&l3)[kGrCols] = win[(jj + 4) % 5];
+                        const int(&l4)[kGrCols] = win[jj];
+#pragma unroll
+                        for (int ph = 0; ph < 4; ++ph) {
+                            int v[kGrCols];
+#pragma unroll
+                            for (int c = 0; c < kGrCols; ++c) {
+                                int acc;
+                                if (ph < 2)
+                                    acc = P.ck[ph] + P.nk[ph][0] * l0[c] + P.nk[ph][1] * l1[c] + P.nk[ph][2] * l2[c] +
+                                          P.nk[ph][3] * l3[c];
+                                else
+                                    acc = P.ck[ph] + P.nk[ph][0] * l1[c] + P.nk[ph][1] * l2[c] + P.nk[ph][2] * l3[c] +
+                                          P.nk[ph][3] * l4[c];
+                                v[c] = acc >> 22;
+                            }
+                            store8(orow + (size_t)ph * w, pack4_sat(v[0], v[1], v[2], v[3]), pack4_sat(v[4], v[5], v[6], v[7]),
+                                   ncols);
+                        }
+                        orow += (size_t)4 * w;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- generic items: recording / image edges, recordings without an image -----------------------------
+    int win[5][kGrCols];
+#pragma unroll
+    for (int t = 0; t < 5; ++t)
+#pragma unroll
+        for (int c = 0; c < kGrCols; ++c) win[t][c] = 0;
+    // only lines that feed a raster row of this item or are its own need grey levels
+    const bool any_raster = out && r_a < h && r_b > 0;
+    const long long r_from = any_raster ? r_a - 2 : r_a, r_to = any_raster ? r_b + 2 : r_b;
+    for (long long r = r_from; r < r_to; ++r) {
+        const long long i0 = s + r * w + c0;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const long long i = i0 - 2 + j;
+            f[j] = (i >= 0 && i < n) ? __ldg(e + i) : 0.f;
+        }
+        f[12] = f[13] = f[14] = f[15] = 0.f;
+        float m[8];
+        med8_from16<0>(f, m);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int c = 0; c < kGrCols; ++c) win[t][c] = win[t + 1][c];
+#pragma unroll
+        for (int c = 0; c < kGrCols; ++c) win[4][c] = Q.level(m[c]);
+        if (dg && r >= r_a && r < r_b) {
+#pragma unroll
+            for (int c = 0; c < kGrCols; ++c) {
+                const long long i = i0 + c;
+                if (c < ncols && i >= 0 && i < n) dg[i] = (uint8_t)win[4][c];
+            }
+        }
+        const long long q = r - 2;
+        if (out && q >= r_a && q < r_b && q >= 0 && q < h) {
+            const bool inner = q >= 2 && q + 2 < h;
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {
+                int kw[5];
+                if (inner) {
+                    kw[0] = ph < 2 ? -P.nk[ph][0] : 0;
+                    kw[1] = ph < 2 ? -P.nk[ph][1] : -P.nk[ph][0];
+                    kw[2] = ph < 2 ? -P.nk[ph][2] : -P.nk[ph][1];
+                    kw[3] = ph < 2 ? -P.nk[ph][3] : -P.nk[ph][2];
+                    kw[4] = ph < 2 ? 0 : -P.nk[ph][3];
+                } else {
+                    pillow_row_weights((int)(4 * q + ph), h, kw);
+                }
+                int v[kGrCols];
+#pragma unroll
+                for (int c = 0; c < kGrCols; ++c) {
+                    int acc = 1 << 21;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) acc += kw[t] * (255 - win[t][c]);   // luminance 255 - value (wefax.py:303)
+                    v[c] = acc >> 22;
+                }
+                store8(out + (size_t)(4 * q + ph) * w + c0, pack4_sat(v[0], v[1], v[2], v[3]),
+                       pack4_sat(v[4], v[5], v[6], v[7]), ncols);
+            }
+        }
+    }
+}
+
+void launch_grey_table(wefax_ctx *ctx, const RecResult *res, GreyTable *tables, int batch) {
+    StageTimer timer(ctx, "grey_table");
+    grey_table_kernel<<<batch, 256, 0, ctx->stream>>>(res, tables);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+namespace {
+double host_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+}  // namespace
+
+void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, uint8_t *raster, size_t rs,
+                        long long n, int batch, const LineDev *d_lines, const LineDev *h_lines, const RecResult *res,
+                        const GreyTable *tables) {
+    StageTimer timer(ctx, "grey_raster");
+    GreyRasterParams P;
+    P.env = env; P.es = es; P.dig = dig; P.ds = ds; P.raster = raster; P.rs = rs; P.n = n;
+    P.lines = d_lines; P.res = res; P.tables = tables;
+    // interior rows: Pillow's coefficients depend on the phase only (filter arguments are exact binary fractions
+    // and sum to exactly 1), so they are computed here once, with Pillow's own arithmetic
+    for (int ph = 0; ph < 4; ++ph) {
+        const double center = (ph + 0.5) * 0.25 + 8.0;   // any line far from the edges
+        const int xmin = (int)(center - 2.0 + 0.5), xmax = (int)(center + 2.0 + 0.5) - xmin;
+        double kw[5], ww = 0.0;
+        for (int t = 0; t < 5; ++t) {
+            kw[t] = t < xmax ? host_bicubic(t + xmin - center + 0.5) : 0.0;
+            ww += kw[t];
+        }
+        long long sum = 0;
+        for (int t = 0; t < 4; ++t) {
+            const double kv = (ww != 0.0) ? kw[t] / ww : kw[t];
+            const int ki = kv < 0 ? (int)(-0.5 + kv * 4194304.0) : (int)(0.5 + kv * 4194304.0);
+            P.nk[ph][t] = -ki;
+            sum += ki;
+        }
+        P.ck[ph] = (int)((1ll << 21) + 255 * sum);
+    }
+    // lines per item: a long walk amortises the 4 extra lines of every item, but the grid should fill a whole
+    // number of waves of resident CTAs
+    int per_sm = 2;
+    {
+        const void *fn = (const void *)grey_raster_kernel;
+        auto it = ctx->smem_configured.find(fn);
+        if (it == ctx->smem_configured.end()) {
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel, kGrThreads, 0));
+            if (per_sm < 1) per_sm = 1;
+            ctx->smem_configured[fn] = per_sm;
+        } else {
+            per_sm = it->second;
+        }
+    }
+    const double resident = (double)ctx->sm_count * per_sm * kGrThreads;
+    auto items_for = [&](int U, long long *max_items) {
+        double total = 0;
+        long long mx = 0;
+        for (int r = 0; r < batch; ++r) {
+            const int w = h_lines[r].width;
+            const long long nl = n / w + 2;
+            const long long it = ((nl + U - 1) / U) * ((w + kGrCols - 1) / kGrCols);
+            total += (double)it;
+            mx = std::max(mx, it);
+        }
+        if (max_items) *max_items = mx;
+        return total;
+    };
+    int best_u = 16;
+    double best_eff = -1.0;
+    for (int U = 10; U <= 48; ++U) {
+        const double waves = items_for(U, nullptr) / resident;
+        const double eff = (double)U / (U + 4) * (waves / std::ceil(waves - 1e-9));
+        if (eff > best_eff) {
+            best_eff = eff;
+            best_u = U;
+        }
+    }
+    const char *force_u = getenv("WEFAX_GR_LINES");
+    if (force_u && atoi(force_u) >= 1) best_u = atoi(force_u);
+    P.lines_per_item = best_u;
+    long long max_items = 0;
+    items_for(best_u, &max_items);
+    dim3 grid((unsigned)((max_items + kGrThreads - 1) / kGrThreads), batch);
+    grey_raster_kernel<<<grid, kGrThreads, 0, ctx->stream>>>(P);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+}  // namespace wefax

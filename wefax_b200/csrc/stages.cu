@@ -5,8 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "median.cuh"
-#include "stages.cuh"
+#include "grey.cuh"
 
 namespace wefax {
 
@@ -84,7 +83,7 @@ constexpr int kPadLen = 9;   // 3 * max(len(a), len(b))
 template <int MODE, int KP>
 __global__ void __launch_bounds__(kFirThreads)
 filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout, size_t z_stride,
-                long long n, const FirParams fp) {
+                long long n, const FirParams fp, int tiles_first, int tiles_skip) {
     constexpr int TS = kFirTile;
     constexpr int NEXT = TS + 2 * (KP - 1);          // extended-signal samples a tile needs
     constexpr int NEXT_AL = (NEXT + 16 + 3) & ~3;
@@ -96,8 +95,10 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
 
     const int tid = threadIdx.x;
     const size_t base = (size_t)blockIdx.y * in_stride;
+    // the tiles between tiles_first and tiles_first + tiles_skip belong to notch_sym_kernel
+    const long long tile = (int)blockIdx.x < tiles_first ? blockIdx.x : blockIdx.x + tiles_skip;
     const long long E = n + 2 * kPadLen;                              // length of the odd-extended signal
-    const long long e0 = kPadLen + (long long)blockIdx.x * TS;        // first output of this tile, extended coords
+    const long long e0 = kPadLen + tile * TS;                         // first output of this tile, extended coords
 
     const long long e_first = e0 - (KP - 1);                          // extended index of s_ext[0]
     if (e_first >= kPadLen && e_first + NEXT <= n + kPadLen) {
@@ -184,7 +185,7 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
             for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[i + m], acc[i]);
         }
         // each thread owns 8 consecutive outputs: two 16-byte stores per thread, 1 KiB contiguous per warp
-        const long long g = (long long)blockIdx.x * TS + i0;
+        const long long g = tile * TS + i0;
         if (out) {
             float *o = out + (size_t)blockIdx.y * out_stride + g;
             if (g + 7 < n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -206,14 +207,132 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
     }
 }
 
+// Interior tiles (further than the filter's memory from both ends of the signal): the two sections are one
+// symmetric FIR, out[i] = g0 x[i] + sum_k g_k (x[i-k] + x[i+k]).  One shared-memory stage instead of two, half the
+// multiplies; mono int16 comes in as one 16-byte load per thread.
+template <int MODE, int KC>
+__global__ void __launch_bounds__(kFirThreads)
+notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout, size_t z_stride,
+                 long long n, const FirParams fp, int tile0) {
+    constexpr int TS = kFirTile;
+    constexpr int NX = TS + 2 * KC;
+    constexpr int W = 8 + 2 * KC;
+    __shared__ __align__(16) float s_x[NX];
+    const int tid = threadIdx.x;
+    const size_t base = (size_t)blockIdx.y * in_stride;
+    const long long t0 = (long long)(blockIdx.x + tile0) * TS;   // first output; [t0 - KC, t0 + TS + KC) is inside [0, n)
+    bool vec = false;
+    if (MODE == kInMonoI16) {
+        const int16_t *src = (const int16_t *)in + base + t0;
+        vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        if (vec) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(src) + tid);
+            int16_t hv = 0;
+            if (tid < 2 * KC) hv = __ldg(tid < KC ? src - KC + tid : src + TS + (tid - KC));
+            const int wv[4] = {v.x, v.y, v.z, v.w};
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                f[2 * k] = (float)(short)(wv[k] & 0xffff);
+                f[2 * k + 1] = (float)(short)(wv[k] >> 16);
+            }
+            float4 *dst = reinterpret_cast<float4 *>(&s_x[KC + 8 * tid]);
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+            if (tid < 2 * KC) s_x[tid < KC ? tid : TS + tid] = (float)hv;
+        }
+    }
+    if (!vec) {
+        constexpr int ITER = (NX + kFirThreads - 1) / kFirThreads;
+        float v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int j = tid + it * kFirThreads;
+            v[it] = j < NX ? load_sample<MODE>(in, base, t0 - KC + j) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int j = tid + it * kFirThreads;
+            if (j < NX) s_x[j] = v[it];
+        }
+    }
+    __syncthreads();
+
+    const int i0 = 8 * tid;
+    float w[W];
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4 *>(&s_x[i0 + 4 * q]);
+        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+    }
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fp.g[0] * w[KC + i];
+#pragma unroll
+    for (int k = 1; k <= KC; ++k) {
+        const float c = fp.g[k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[KC + i - k] + w[KC + i + k], acc[i]);
+    }
+    const long long g = t0 + i0;
+    if (out) {
+        float *o = out + (size_t)blockIdx.y * out_stride + g;
+        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            reinterpret_cast<float4 *>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            reinterpret_cast<float4 *>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = acc[i];
+        }
+    }
+    if (zout) {
+        float2 *z = zout + (size_t)blockIdx.y * z_stride + g;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = make_float2(acc[i], 0.f);
+    }
+}
+
+template <int MODE, int KC>
+static void launch_notch_sym(wefax_ctx *ctx, const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout,
+                             size_t z_stride, long long n, const FirParams &fp, int batch, int tile0, int ntiles) {
+    dim3 grid((unsigned)ntiles, batch);
+    notch_sym_kernel<MODE, KC><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp, tile0);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
 template <int MODE>
 static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_stride, float *out, size_t out_stride,
                                  float2 *zout, size_t z_stride, long long n, const FirParams &fp, int batch) {
     StageTimer timer(ctx, "filtfilt");
-    dim3 grid((unsigned)((n + kFirTile - 1) / kFirTile), batch);
+    const int ntiles = (int)((n + kFirTile - 1) / kFirTile);
+    // tiles [ti_lo, ti_hi) are further than the filter's memory from both ends: symmetric single-stage form
+    int ti_lo = 0, ti_hi = 0;
+    if (fp.KC > 0 && ctx->use_sym_notch) {
+        const long long margin = 2ll * fp.KP + 16;
+        ti_lo = (int)((margin + kFirTile - 1) / kFirTile);
+        ti_hi = (int)std::max<long long>(0, (n - margin) / kFirTile);
+        if (ti_hi <= ti_lo) ti_lo = ti_hi = 0;
+    }
+    if (ti_hi > ti_lo) {
+        switch (fp.KC) {
+#define WEFAX_SYM_CASE(KC_) \
+    case KC_: launch_notch_sym<MODE, KC_>(ctx, in, in_stride, out, out_stride, zout, z_stride, n, fp, batch, ti_lo, ti_hi - ti_lo); break;
+            WEFAX_SYM_CASE(8)
+            WEFAX_SYM_CASE(12)
+            WEFAX_SYM_CASE(16)
+            WEFAX_SYM_CASE(24)
+            WEFAX_SYM_CASE(32)
+#undef WEFAX_SYM_CASE
+            default: ti_lo = ti_hi = 0; break;
+        }
+    }
+    const int tiles_first = ti_lo, tiles_skip = ti_hi - ti_lo;
+    dim3 grid((unsigned)(ntiles - tiles_skip), batch);
 #define WEFAX_FIR_CASE(KP_)                                                                                   \
     if (fp.KP == KP_) {                                                                                       \
-        filtfilt_kernel<MODE, KP_><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp); \
+        filtfilt_kernel<MODE, KP_><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp, \
+                                                                         tiles_first, tiles_skip);          \
         CUDA_CHECK(cudaGetLastError());                                                                       \
         ctx->launches++;                                                                                      \
         return;                                                                                               \
@@ -958,7 +1077,7 @@ __device__ void finish_sync(const int *peaks, int np, const LineDev &ln, long lo
 template <int PER>
 __global__ void __launch_bounds__(kSyncThreads)
 sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, RecResult *res_all,
-                   const int *need_scan) {
+                   const int *need_scan, const LazyGrey lazy) {
     if (need_scan && !need_scan[blockIdx.x]) return;   // the windowed-maximum path already finished this recording
     constexpr int CH = kSyncThreads * PER;            // positions handled per iteration
     constexpr int TOTMAX = CH + kSyncMaxL;
@@ -971,6 +1090,12 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
     const LineDev ln = lines[blockIdx.x];
     RecResult *res = res_all + blockIdx.x;
     const uint8_t *dig = dig_all + (size_t)blockIdx.x * ds;
+    const float *lazy_env = lazy.env ? lazy.env + (size_t)blockIdx.x * lazy.es : nullptr;
+    const GreyTable *lazy_tab = lazy.env ? lazy.tables + blockIdx.x : nullptr;
+    auto grey_at = [&](long long i) -> int {
+        if (lazy_env && i >= lazy.valid) return grey_at_from_envelope(lazy_env, i, n, lazy_tab);
+        return (int)__ldg(dig + i);
+    };
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int L = ln.L, n1 = ln.n1, n0 = ln.n0, mind = ln.mindistance;
     const long long m = n - L;                        // range(len(data) - len(sync))
@@ -990,7 +1115,7 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             int idx = j0 + j;
-            int x = idx < tot ? (int)__ldg(dig + base + idx) - 128 : 0;
+            int x = idx < tot ? grey_at(base + idx) - 128 : 0;
             run += x;
             vals[j] = run;
         }
@@ -1237,13 +1362,13 @@ sync_settled_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr
 // the sequential part: <= 100 jumps over the settled-bit mask held in shared memory
 __global__ void __launch_bounds__(1024)
 sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, const uint32_t *bits_all, size_t bs,
-                  const int *first_pos, RecResult *res_all, int *need_scan) {
+                  const int *first_pos, RecResult *res_all, int *need_scan, int force_scan) {
     extern __shared__ uint32_t s_bits[];
     __shared__ int s_peaks[WEFAX_MAX_PEAKS];
     __shared__ int s_np, s_ok;
     const LineDev ln = lines[blockIdx.x];
     const SyncDev sd = sd_all[blockIdx.x];
-    if (!sd.fast) {
+    if (!sd.fast || force_scan) {   // force_scan: test hook (WEFAX_SYNC_FORCE_SCAN=1), the sequential scan decides
         if (threadIdx.x == 0) need_scan[blockIdx.x] = 1;
         return;
     }
@@ -1327,10 +1452,18 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
     }
 }
 
+long long sync_head(const SyncPlan &sp, long long n) {
+    // the parallel search reads positions < max_limc + template length
+    return sp.any_fast ? std::min(n, ((sp.max_limc + kSyncMaxL + 2047) / 2048) * 2048) : n;
+}
+
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
-                        RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready) {
+                        RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready,
+                        const LazyGrey &lazy) {
     StageTimer timer(ctx, "sync_search");
     cudaStream_t st = ctx->stream;
+    const char *fs = getenv("WEFAX_SYNC_FORCE_SCAN");
+    const int force_scan = fs && fs[0] == '1';
     if (sp.any_fast) {
         CUDA_CHECK(cudaMemsetAsync(sp.first_pos, 0x7F, sizeof(int) * batch, st));   // 0x7F7F7F7F = no positive correlation yet
         dim3 g1((unsigned)std::max<long long>(1, (sp.max_limc + kCorrTile - 1) / kCorrTile), batch);
@@ -1354,7 +1487,7 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         {
             StageTimer t1(ctx, "sync_chain");
             sync_chain_kernel<<<batch, 1024, (size_t)((sp.max_lim + 31) / 32 + 4) * sizeof(uint32_t), st>>>(
-                n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan);
+                n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan, force_scan);
         }
         ctx->launches += 3;
     } else {
@@ -1363,19 +1496,18 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
     // the parallel search above only reads the head of the recording; the sequential fallback may read all of it
     if (all_data_ready) CUDA_CHECK(cudaStreamWaitEvent(st, all_data_ready, 0));
     if (min_mindistance >= 4096)
-        sync_search_kernel<4><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
+        sync_search_kernel<4><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
     else if (min_mindistance >= 2048)
-        sync_search_kernel<2><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
+        sync_search_kernel<2><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
     else
-        sync_search_kernel<1><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan);
+        sync_search_kernel<1><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
 
 cudaEvent_t launch_quantise_split(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n,
                                   int batch, const RecResult *res, const SyncPlan &sp) {
-    // the parallel search reads positions < max_limc + template length
-    const long long head = sp.any_fast ? ((sp.max_limc + kSyncMaxL + 2047) / 2048) * 2048 : n;
+    const long long head = sync_head(sp, n);
     if (!ctx->aux_stream || head >= n) {
         launch_quantise(ctx, env, es, dig, ds, n, batch, res, 0, n, ctx->stream, "quantise");
         return nullptr;

@@ -51,6 +51,23 @@ struct SelState {
     uint32_t hist[3][4][2048];
 };
 
+// grey map of one recording as a table (greyraster.cu): level(m) = largest k with T[k] <= float bits of m
+struct GreyTable {
+    uint32_t T[260];     // T[0] = 0, T[k]: smallest non-negative float bit pattern whose level is >= k, T[256..] = ~0
+    float scale, off;    // fp32 estimate of the level: rint(m * scale + off)
+    int est_ok;          // the estimate is proven to be within +-1 of the exact level for every float
+    int pad;
+};
+
+// the sequential phasing scan may run past the grey levels that exist when it starts (fused grey map + raster):
+// levels at positions >= valid are then computed from the envelope on the fly
+struct LazyGrey {
+    const float *env = nullptr;
+    size_t es = 0;
+    const GreyTable *tables = nullptr;
+    long long valid = 0;
+};
+
 enum IngestMode { kInMonoI16 = 0, kInStereoI16 = 1, kInFloat = 2 };
 
 void launch_ingest_float(wefax_ctx *ctx, const int16_t *pcm, size_t pcm_stride, int channels, float *x, size_t xs,
@@ -72,11 +89,22 @@ cudaEvent_t launch_quantise_split(wefax_ctx *ctx, const float *env, size_t es, u
 // min_mindistance: smallest LineDev.mindistance of the batch (sizes the scan chunk; must be >= 1024)
 // all_data_ready (may be null): event to wait for before the sequential fallback scan, which reads all of dig
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
-                        RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready = nullptr);
+                        RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready = nullptr,
+                        const LazyGrey &lazy = LazyGrey());
+// samples the parallel phasing search reads: [0, sync_head(sp, n))
+long long sync_head(const SyncPlan &sp, long long n);
 // sizes the parallel search for recordings [first, first+count) and uploads its geometry
 SyncPlan prepare_sync(wefax_ctx *ctx, const LineDev *host_lines, int count, long long n);
 void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                    const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines);
+// ---- fused median-5 + grey map + raster (greyraster.cu) ----
+// threshold tables of the grey map from RecResult.low/high (one per recording)
+void launch_grey_table(wefax_ctx *ctx, const RecResult *res, GreyTable *tables, int batch);
+// envelope -> digitalized (all n samples; dig may be null) + raster (rows of recordings with status OK; raster may
+// be null).  Needs RecResult.start_frame / height / status, i.e. runs after the phasing search.
+void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, uint8_t *raster, size_t rs,
+                        long long n, int batch, const LineDev *d_lines, const LineDev *h_lines, const RecResult *res,
+                        const GreyTable *tables);
 
 // ---- segment mode (segment.cu): radix-digit histograms of the median-filtered envelope of the core
 // samples [core_lo, core_hi) of an extended segment of n samples; hist: 4 x 2048 counters (device)
