@@ -166,6 +166,9 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- reference arm (CPU)
+REFERENCE_SLEEP_S = 7.0   # wefax.py:59,73,75,77,193,202: fixed sleeps per process(), patched out and reported apart
+
+
 def _oracle_decode(job):
     pcm, lpm = job
     from oracle import wefax_oracle as O
@@ -173,44 +176,83 @@ def _oracle_decode(job):
     return int(out["digitalized_data"].shape[0])
 
 
+def _reference_decode(job):
+    """One process() of the UNMODIFIED reference (oracle/_ref or /root/reference) on a WAV file."""
+    wav, lpm = job
+    from oracle import ref_runner
+    _dt, n = ref_runner.time_reference_process(wav, lpm)
+    return int(n)
+
+
+def reference_kind() -> str:
+    try:
+        from oracle import ref_runner
+        return "reference" if ref_runner.reference_available() else "port"
+    except Exception:
+        return "port"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank: int) -> None:
-    """The reference's CPU implementation of the path on the host cores: the numpy
-    port in oracle/ (the reference itself is Python over scipy/numpy/Pillow and cannot
-    travel to the GPU box), one process per core, each decoding a bounded sample."""
+    """The reference's own CPU implementation of the path on the host cores: the unmodified
+    `wefax.Demodulator.process()` staged under oracle/_ref (oracle/make_ref.py), one process per host core
+    (the reference is single-threaded), each decoding one bounded recording of the same synthetic model per
+    step.  Falls back to the numpy port (oracle/wefax_oracle.py) only where the reference files are absent."""
     if rank != 0:
         return
     import multiprocessing as mp
+    import tempfile
     from wefax_b200 import synth
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
-    workers = max(1, min(cores, 32))
-    sample_s = min(args.duration, 600.0)
+    kind = reference_kind()
+    workers = max(1, min(host_cores(), 64))
+    # per-core cost of the reference: ~1.15 us per sample + up to 6.6 s of pattern_search per recording
+    # (BASELINE.md section 2); keep the whole run within a few minutes
+    budget_s = 240.0 / max(1, args.steps)
+    sample_s = 600.0 if kind == "port" else float(min(600.0, max(120.0, (budget_s - 6.6) / 1.27e-2)))
+    sample_s = min(sample_s, args.duration)
     pcm = synth.synth_recording(sample_s, lpm=args.lpm, seed=0)
-    jobs = [(pcm, args.lpm)] * workers
+    tiny = synth.synth_recording(20.0, lpm=args.lpm, seed=0)
+    tmp = tempfile.mkdtemp(prefix="wefax_ref_")
+    if kind == "reference":
+        wav, wav_tiny = os.path.join(tmp, "sample.wav"), os.path.join(tmp, "warm.wav")
+        synth.write_wav(wav, pcm, 11025)
+        synth.write_wav(wav_tiny, tiny, 11025)
+        fn, jobs, warm_jobs = _reference_decode, [(wav, args.lpm)] * workers, [(wav_tiny, args.lpm)] * workers
+    else:
+        fn, jobs, warm_jobs = _oracle_decode, [(pcm, args.lpm)] * workers, [(tiny, args.lpm)] * workers
     with mp.get_context("fork").Pool(workers) as pool:
-        for _ in range(args.warmup):
-            pool.map(_oracle_decode, jobs)
+        for _ in range(args.warmup):          # CPU code has nothing to warm but the page cache: a 20-s clip
+            pool.map(fn, warm_jobs)
         t0 = time.perf_counter()
         total = 0
         for _ in range(args.steps):
-            total += sum(pool.map(_oracle_decode, jobs))
+            total += sum(pool.map(fn, jobs))
         dt = time.perf_counter() - t0
     value = total / dt / 1e6
-    sample = (f"per step {workers} x one {sample_s:g} s recording ({pcm.shape[0]} samples) of the same synthetic "
-              f"model, one process per host core (oracle/wefax_oracle.py numpy port)")
+    what = ("the UNMODIFIED reference wefax.Demodulator.process() (oracle/_ref), matplotlib stubbed, its fixed "
+            f"{REFERENCE_SLEEP_S:g} s of time.sleep per call patched out") if kind == "reference" else \
+        "oracle/wefax_oracle.py numpy port (reference files not staged)"
+    sample = (f"per step {workers} x one {sample_s:g} s recording ({pcm.shape[0]} samples) of the same synthetic model, "
+              f"one process per host core; {what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample,
+                         "sleep_s_per_file_not_counted": REFERENCE_SLEEP_S if kind == "reference" else 0.0},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=JSON_OUT, flush=True)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
 
 
 # --------------------------------------------------------------------------- our arm (GPU)

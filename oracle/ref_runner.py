@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE — runs the UNMODIFIED reference decoder in-process.
+"""TEST / BENCH INFRASTRUCTURE — runs the UNMODIFIED reference decoder in-process.
 
-Only usable where ``/root/reference`` is mounted (the build container, not the
-GPU box).  It is used by ``tests/golden/make_golden.py`` to produce the golden
-vectors that pin ``oracle/wefax_oracle.py``, and by the container-only tests.
+Usable where ``/root/reference`` is mounted (the build container) or where
+``oracle/make_ref.py`` staged its byte-for-byte copy under ``oracle/_ref/`` (git-ignored;
+it travels to the GPU box).  It is used by ``tests/golden/make_golden.py`` to produce the
+golden vectors that pin ``oracle/wefax_oracle.py``, by the container-only tests, and by
+``bench.py`` to time the reference on the host cores (``--impl reference``, ``cpu_baseline``).
 Nothing on the product path may import this.
 
 Recipe: stub matplotlib (``wefax.py:6,9,10`` import it for debug
@@ -19,7 +21,20 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("WEFAX_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """The read-only mount in the build container, else the unmodified copy oracle/make_ref.py staged under
+    oracle/_ref/ (what travels to the GPU box; it holds the file decoder only, not data_packet.py)."""
+    env = os.environ.get("WEFAX_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for cand in ("/root/reference", staged):
+        if os.path.isfile(os.path.join(cand, "wefax.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -111,6 +126,32 @@ def run_reference(wav_path: str, lpm: int = 120) -> dict:
     out["progress_titles"] = [m.get("progress_title", m.get("message_content"))
                               for m in d.websocket_stack]
     return out
+
+
+def time_reference_process(wav_path: str, lpm: int = 120) -> tuple:
+    """Wall-clock seconds of the reference's own ``Demodulator(wav, lpm).process()`` (sleeps patched out; the
+    reference sleeps a fixed 7.0 s per call, wefax.py:59,73,75,77,193,202) and the number of samples it
+    decoded.  An exception the reference itself raises (wefax.py:294) still counts: the work up to it ran."""
+    import time
+    wefax = import_reference()
+    wav_path = os.path.abspath(wav_path)
+    with _in_reference_root():
+        d = wefax.Demodulator(wav_path, lines_per_minute=lpm, tcp_stream=False, quiet=True)
+        t0 = time.perf_counter()
+        try:
+            d.process()
+        except (ValueError, IndexError):
+            pass
+        finally:
+            dt = time.perf_counter() - t0
+            if sys.stdout is not sys.__stdout__:
+                try:
+                    sys.stdout.close()
+                except Exception:
+                    pass
+            sys.stdout = sys.__stdout__
+    n = len(d.digitalized_data) if hasattr(d, "digitalized_data") else 0
+    return dt, n
 
 
 def import_reference_data_packet():

@@ -164,7 +164,8 @@ LineSet prepare_lines(const double *lpm, int nrec, long long n) {
         line_constants(lpm[r], WEFAX_TARGET_RATE, &lc);
         if (lc.width < 1 || lc.template_len < 1 || lc.template_len > 2048 || lc.mindistance < 1024)
             WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "lines per minute %g outside the supported range (4..500)", lpm[r]);
-        ls.lines[r] = LineDev{lc.n1, lc.n0, lc.template_len, lc.mindistance, lc.width, lc.dev_min, lc.dev_max};
+        ls.lines[r] = LineDev{lc.n1, lc.n0, lc.template_len, lc.mindistance, lc.width, lc.dev_min, lc.dev_max,
+                              lc.width % 8 == 0 ? 2 : (lc.width % 4 == 0 ? 1 : 0), 0};
         ls.max_width = std::max(ls.max_width, lc.width);
         ls.min_width = std::min(ls.min_width, lc.width);
         ls.min_mind = std::min(ls.min_mind, lc.mindistance);

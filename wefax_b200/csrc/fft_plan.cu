@@ -1,6 +1,7 @@
 // Host-side FFT planning: factor n into pass lengths, size the shared-memory
 // tiles, build the twiddle / permutation tables on the device.
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -55,7 +56,9 @@ struct StagePlan {
     std::vector<int> radices;
 };
 const StagePlan &stage_plan(int R) {
-    static std::map<int, StagePlan> memo;
+    // per host thread: contexts are driven from several threads at once (one context per thread), and the memo
+    // is mutated while references into it are alive
+    thread_local std::map<int, StagePlan> memo;
     auto it = memo.find(R);
     if (it != memo.end()) return it->second;
     StagePlan best;
@@ -354,9 +357,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 static EncodeTiledFn encode_tiled() {
     static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void *ptr = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
@@ -364,7 +366,7 @@ static EncodeTiledFn encode_tiled() {
             fn = (EncodeTiledFn)ptr;
         else
             (void)cudaGetLastError();
-    }
+    });
     return fn;
 }
 

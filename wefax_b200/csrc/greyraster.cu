@@ -19,7 +19,7 @@
 
 namespace wefax {
 
-constexpr int kGrThreads = 256;
+constexpr int kGrThreads = 128;
 constexpr int kGrCols = 8;   // columns per thread
 
 // exact grey level of a median value (same operations, in the same order, as numpy: wefax.py:197-200, 216)
@@ -99,6 +99,7 @@ struct GreyRasterParams {
     const RecResult *res;
     const GreyTable *tables;
     int lines_per_item;
+    int only_class;    // >= 0: only recordings whose LineDev.gr_class equals it (mixed-width batches: one launch per class)
     int nk[4][4];      // negated interior Pillow coefficients of the 4 phases (taps in line order)
     int ck[4];         // (1 << 21) + 255 * sum of the phase's coefficients
 };
@@ -145,7 +146,8 @@ __device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
 }
 
 // 8 bytes (lo = bytes 0..3) to an address of any alignment, first `count` bytes only when count < 8
-__device__ __forceinline__ void store8(uint8_t *p, uint32_t lo, uint32_t hi, int count) {
+// (out of line: the hot loops only come here for the last, partial column group of a line)
+__device__ __noinline__ void store8(uint8_t *p, uint32_t lo, uint32_t hi, int count) {
     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
     if (count >= 8) {
         if (a == 0u) {
@@ -194,7 +196,7 @@ __device__ __forceinline__ void med8_from16(const float (&f)[16], float (&m)[8])
 }
 
 struct GreyQuant {
-    const uint2 *pairs;   // shared: (T[k], T[k + 1])
+    const uint2 *pairs;   // shared: (T[k], T[k + 1] - T[k])
     const uint32_t *T;    // shared: T[0 .. 256]
     float scale, off;
     int est_ok;
@@ -203,23 +205,157 @@ struct GreyQuant {
         const uint32_t bits = __float_as_uint(m);
         const int k0 = grey_estimate(m, scale, off);
         const uint2 t = pairs[k0];
-        return k0 + (bits >= t.y ? 1 : 0) - (bits < t.x ? 1 : 0);
+        return k0 + (bits - t.x >= t.y && bits >= t.x ? 1 : 0) - (bits < t.x ? 1 : 0);
     }
     __device__ __forceinline__ int level(float m) const {
         return est_ok ? level_fast(m) : grey_from_table(T, __float_as_uint(m));
     }
 };
 
-__global__ void __launch_bounds__(kGrThreads, 2) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
+// fp32 estimate of the level, clamped to 0..255 by the conversion itself
+__device__ __forceinline__ uint32_t grey_estimate_u8(float m, float scale, float off) {
+    uint32_t k;
+    asm("cvt.rni.u8.f32 %0, %1;" : "=r"(k) : "f"(fmaf(m, scale, off)));
+    return k;
+}
+
+template <int ALIGN>
+__device__ __forceinline__ void store_row8(uint8_t *p, uint32_t lo, uint32_t hi, int ncols) {
+    if (ALIGN == 8) {
+        if (ncols >= kGrCols) *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
+        else store8(p, lo, hi, ncols);
+    } else if (ALIGN == 4) {
+        if (ncols >= kGrCols) {
+            reinterpret_cast<uint32_t *>(p)[0] = lo;
+            reinterpret_cast<uint32_t *>(p)[1] = hi;
+        } else {
+            store8(p, lo, hi, ncols);
+        }
+    } else {
+        store8(p, lo, hi, ncols);
+    }
+}
+
+// One interior item: all its lines are image lines at least 2 lines from the image's first / last line, every
+// load stays inside the recording, the fp32 estimate is valid.  OFF: offset (in floats, mod 4) of the envelope
+// element two to the left of the item's first column from a 16-byte boundary, the same for every line when the
+// width is a multiple of 4; OFF < 0: evaluated per line.  ALIGN: guaranteed alignment of the raster stores.
+template <int OFF, int ALIGN>
+__device__ __forceinline__ void interior_item(const GreyRasterParams &P, const GreyQuant &Q, const float *e, uint8_t *dg,
+                                              uint8_t *out, long long i_first, long long r_a, int nrows, int w, int c0,
+                                              int ncols) {
+    int win[5][kGrCols];
+    const float *prow = e + i_first - 2;   // x[0] of the line being fetched
+    float4 nx[4];
+    auto fetch = [&]() {
+        const float4 *pa = reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(prow) & ~(uintptr_t)15);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nx[q] = __ldg(pa + q);
+    };
+    fetch();
+    uint8_t *drow = dg ? dg + i_first : nullptr;        // digitalized of the line being computed
+    uint8_t *orow = out + (size_t)(4 * r_a) * w + c0;   // raster rows of the line being emitted
+
+    // grey levels of the fetched line into window slot `slot`; starts the fetch of the next line
+    auto grey_line = [&](int (&g)[kGrCols], bool more) {
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            f[4 * q] = nx[q].x; f[4 * q + 1] = nx[q].y; f[4 * q + 2] = nx[q].z; f[4 * q + 3] = nx[q].w;
+        }
+        float m[8];
+        if (OFF >= 0) {
+            med8_from16<(OFF >= 0 ? OFF : 0)>(f, m);
+        } else {
+            switch ((int)((reinterpret_cast<uintptr_t>(prow) >> 2) & 3u)) {
+                case 0: med8_from16<0>(f, m); break;
+                case 1: med8_from16<1>(f, m); break;
+                case 2: med8_from16<2>(f, m); break;
+                default: med8_from16<3>(f, m); break;
+            }
+        }
+        prow += w;
+        if (more) fetch();   // the medians have consumed nx: the next line streams in under the rest of this one
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < kGrCols; ++c) {
+            const uint32_t k0 = grey_estimate_u8(m[c], Q.scale, Q.off);
+            const uint2 t = Q.pairs[k0];
+            bad = bad || (__float_as_uint(m[c]) - t.x >= t.y);
+            g[c] = (int)k0;
+        }
+        if (bad) {   // some estimate is one level off (rare): redo the line with the corrected form
+#pragma unroll
+            for (int c = 0; c < kGrCols; ++c) g[c] = Q.level_fast(m[c]);
+        }
+    };
+    auto store_dig = [&](const int (&g)[kGrCols]) {
+        const uint32_t lo = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
+        const uint32_t hi = (uint32_t)g[4] | ((uint32_t)g[5] << 8) | ((uint32_t)g[6] << 16) | ((uint32_t)g[7] << 24);
+        store8(drow, lo, hi, ncols);
+    };
+    auto emit = [&](const int (&l0)[kGrCols], const int (&l1)[kGrCols], const int (&l2)[kGrCols], const int (&l3)[kGrCols],
+                    const int (&l4)[kGrCols]) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            int v[kGrCols];
+#pragma unroll
+            for (int c = 0; c < kGrCols; ++c) {
+                int acc;
+                if (ph < 2)
+                    acc = P.ck[ph] + P.nk[ph][0] * l0[c] + P.nk[ph][1] * l1[c] + P.nk[ph][2] * l2[c] + P.nk[ph][3] * l3[c];
+                else
+                    acc = P.ck[ph] + P.nk[ph][0] * l1[c] + P.nk[ph][1] * l2[c] + P.nk[ph][2] * l3[c] + P.nk[ph][3] * l4[c];
+                v[c] = acc >> 22;
+            }
+            store_row8<ALIGN>(orow + (size_t)ph * w, pack4_sat(v[0], v[1], v[2], v[3]), pack4_sat(v[4], v[5], v[6], v[7]),
+                              ncols);
+        }
+        orow += (size_t)4 * w;
+    };
+
+    // lines r_a - 2 .. r_a + 1 fill the window (the last two of them are the item's own)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        grey_line(win[j], true);
+        if (drow) {
+            if (j >= 2) store_dig(win[j]);
+            drow += w;
+        }
+    }
+    // steady state: line j enters slot j % 5 and completes the window of line j - 2
+    for (int jb = 4; jb < nrows; jb += 5) {
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = jb + jj;
+            constexpr int kBase = 4;
+            const int slot = (kBase + jj) % 5;
+            if (j < nrows) {
+                grey_line(win[slot], j + 1 < nrows);
+                if (drow) {
+                    if (j < nrows - 2) store_dig(win[slot]);
+                    drow += w;
+                }
+                emit(win[(slot + 1) % 5], win[(slot + 2) % 5], win[(slot + 3) % 5], win[(slot + 4) % 5], win[slot]);
+            }
+        }
+    }
+}
+
+// ALIGN: alignment every raster row of the launch's recordings is known to have (8: width % 8 == 0, 4: width % 4 == 0,
+// 0: anything; for 8 and 4 the envelope rows of a recording also share one 16-byte phase)
+template <int ALIGN>
+__global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
     __shared__ uint32_t s_T[260];
     __shared__ uint2 s_pairs[256];
     const int rec = blockIdx.y;
+    if (P.only_class >= 0 && P.lines[rec].gr_class != P.only_class) return;
     const RecResult *res = P.res + rec;
     const GreyTable *tab = P.tables + rec;
     for (int i = threadIdx.x; i < 257; i += kGrThreads) s_T[i] = tab->T[i];
-    {
-        const int i = threadIdx.x;   // kGrThreads == 256
-        s_pairs[i] = make_uint2(tab->T[i], tab->T[i + 1]);
+    for (int i = threadIdx.x; i < 256; i += kGrThreads) {
+        const uint32_t t0 = tab->T[i], t1 = tab->T[i + 1];
+        s_pairs[i] = make_uint2(t0, t1 - t0);
     }
     GreyQuant Q;
     Q.pairs = s_pairs;
@@ -242,8 +378,10 @@ __global__ void __launch_bounds__(kGrThreads, 2) grey_raster_kernel(const __grid
     const long long ntiles = (r_hi - r_lo + U - 1) / U;
     const long long item = (long long)blockIdx.x * kGrThreads + threadIdx.x;
     if (item >= ntiles * ng) return;
-    const long long tile = item / ng;
+    // the first CTAs take the LAST tile (image / recording edge: the slow generic form), then tiles 0, 1, ...
+    long long tile = item / ng;
     const int grp = (int)(item - tile * ng);
+    tile = tile == 0 ? ntiles - 1 : tile - 1;
     const int c0 = grp * kGrCols;
     const int ncols = min(kGrCols, w - c0);
     const long long r_a = r_lo + tile * U, r_b = min(r_a + U, r_hi);
@@ -256,80 +394,15 @@ __global__ void __launch_bounds__(kGrThreads, 2) grey_raster_kernel(const __grid
     const bool interior = Q.est_ok && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 && s + (r_b + 1) * w + c0 + 14 <= n;
     if (interior) {
         const int nrows = (int)(r_b - r_a) + 4;
-        int win[5][kGrCols];
-        const float *prow = e + i_first - 2;   // x[0] of the row being fetched
-        float4 nx[4];
-        {
-            const float4 *pa = reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(prow) & ~(uintptr_t)15);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) nx[q] = __ldg(pa + q);
-        }
-        uint8_t *drow = dg ? dg + i_first : nullptr;                     // digitalized of the row being computed
-        uint8_t *orow = out + (size_t)(4 * r_a) * w + c0;                // raster rows of the line being emitted
-        for (int jb = 0; jb < nrows; jb += 5) {
-#pragma unroll
-            for (int jj = 0; jj < 5; ++jj) {
-                const int j = jb + jj;
-                if (j < nrows) {
-                    float f[16];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        f[4 * q] = nx[q].x; f[4 * q + 1] = nx[q].y; f[4 * q + 2] = nx[q].z; f[4 * q + 3] = nx[q].w;
-                    }
-                    const int off = (int)((reinterpret_cast<uintptr_t>(prow) >> 2) & 3u);
-                    prow += w;
-                    if (j + 1 < nrows) {
-                        const float4 *pa =
-                            reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(prow) & ~(uintptr_t)15);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) nx[q] = __ldg(pa + q);
-                    }
-                    float m[8];
-                    switch (off) {
-                        case 0: med8_from16<0>(f, m); break;
-                        case 1: med8_from16<1>(f, m); break;
-                        case 2: med8_from16<2>(f, m); break;
-                        default: med8_from16<3>(f, m); break;
-                    }
-                    int(&g)[kGrCols] = win[jj];
-#pragma unroll
-                    for (int c = 0; c < kGrCols; ++c) g[c] = Q.level_fast(m[c]);
-                    if (drow) {
-                        if (j >= 2 && j < nrows - 2) {
-                            const uint32_t lo = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
-                            const uint32_t hi = (uint32_t)g[4] | ((uint32_t)g[5] << 8) | ((uint32_t)g[6] << 16) | ((uint32_t)g[7] << 24);
-                            store8(drow, lo, hi, ncols);
-                        }
-                        drow += w;
-                    }
-                    if (j >= 4) {
-                        // line q = r_a + j - 4 is complete: its window is lines q-2 .. q+2 = slots jj+1 .. jj+5 (mod 5)
-                        const int(&l0)[kGrCols] = win[(jj + 1) % 5];
-                        const int(&l1)[kGrCols] = win[(jj + 2) % 5];
-                        const int(&l2)[kGrCols] = win[(jj + 3) % 5];
-                        const int(&l3)[kGrCols] = win[(jj + 4) % 5];
-                        const int(&l4)[kGrCols] = win[jj];
-#pragma unroll
-                        for (int ph = 0; ph < 4; ++ph) {
-                            int v[kGrCols];
-#pragma unroll
-                            for (int c = 0; c < kGrCols; ++c) {
-                                int acc;
-                                if (ph < 2)
-                                    acc = P.ck[ph] + P.nk[ph][0] * l0[c] + P.nk[ph][1] * l1[c] + P.nk[ph][2] * l2[c] +
-                                          P.nk[ph][3] * l3[c];
-                                else
-                                    acc = P.ck[ph] + P.nk[ph][0] * l1[c] + P.nk[ph][1] * l2[c] + P.nk[ph][2] * l3[c] +
-                                          P.nk[ph][3] * l4[c];
-                                v[c] = acc >> 22;
-                            }
-                            store8(orow + (size_t)ph * w, pack4_sat(v[0], v[1], v[2], v[3]), pack4_sat(v[4], v[5], v[6], v[7]),
-                                   ncols);
-                        }
-                        orow += (size_t)4 * w;
-                    }
-                }
+        if (ALIGN >= 4) {
+            switch ((int)((reinterpret_cast<uintptr_t>(e + i_first - 2) >> 2) & 3u)) {
+                case 0: interior_item<0, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                case 1: interior_item<1, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                case 2: interior_item<2, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                default: interior_item<3, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
             }
+        } else {
+            interior_item<-1, 0>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols);
         }
         return;
     }
@@ -370,7 +443,7 @@ __global__ void __launch_bounds__(kGrThreads, 2) grey_raster_kernel(const __grid
         const long long q = r - 2;
         if (out && q >= r_a && q < r_b && q >= 0 && q < h) {
             const bool inner = q >= 2 && q + 2 < h;
-#pragma unroll
+#pragma unroll 1
             for (int ph = 0; ph < 4; ++ph) {
                 int kw[5];
                 if (inner) {
@@ -440,14 +513,20 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         }
         P.ck[ph] = (int)((1ll << 21) + 255 * sum);
     }
+    // recordings by alignment class (LineDev.gr_class, set by api.cu from the width): raster rows of a recording are
+    // all 8- / 4-byte aligned when its width is a multiple of 8 / 4 and so are the raster base and stride
+    const bool base8 = (reinterpret_cast<uintptr_t>(raster) & 7) == 0 && rs % 8 == 0;
+    const bool base4 = (reinterpret_cast<uintptr_t>(raster) & 3) == 0 && rs % 4 == 0;
+    int count[3] = {0, 0, 0};   // class 0: generic, 1: ALIGN 4, 2: ALIGN 8
+    for (int r = 0; r < batch; ++r) count[h_lines[r].gr_class]++;
     // lines per item: a long walk amortises the 4 extra lines of every item, but the grid should fill a whole
     // number of waves of resident CTAs
-    int per_sm = 2;
+    int per_sm = 5;
     {
-        const void *fn = (const void *)grey_raster_kernel;
+        const void *fn = (const void *)grey_raster_kernel<8>;
         auto it = ctx->smem_configured.find(fn);
         if (it == ctx->smem_configured.end()) {
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel, kGrThreads, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<8>, kGrThreads, 0));
             if (per_sm < 1) per_sm = 1;
             ctx->smem_configured[fn] = per_sm;
         } else {
@@ -455,38 +534,48 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         }
     }
     const double resident = (double)ctx->sm_count * per_sm * kGrThreads;
-    auto items_for = [&](int U, long long *max_items) {
-        double total = 0;
-        long long mx = 0;
-        for (int r = 0; r < batch; ++r) {
-            const int w = h_lines[r].width;
-            const long long nl = n / w + 2;
-            const long long it = ((nl + U - 1) / U) * ((w + kGrCols - 1) / kGrCols);
-            total += (double)it;
-            mx = std::max(mx, it);
+    for (int cls = 2; cls >= 0; --cls) {
+        if (!count[cls]) continue;
+        auto items_for = [&](int U, long long *max_items) {
+            double total = 0;
+            long long mx = 0;
+            for (int r = 0; r < batch; ++r) {
+                if (h_lines[r].gr_class != cls) continue;
+                const int w = h_lines[r].width;
+                const long long nl = n / w + 2;
+                const long long it = ((nl + U - 1) / U) * ((w + kGrCols - 1) / kGrCols);
+                total += (double)it;
+                mx = std::max(mx, it);
+            }
+            if (max_items) *max_items = mx;
+            return total;
+        };
+        int best_u = 16;
+        double best_eff = -1.0;
+        for (int U = 10; U <= 48; ++U) {
+            const double waves = items_for(U, nullptr) / resident;
+            const double eff = (double)U / (U + 4) * (waves / std::ceil(waves - 1e-9));
+            if (eff > best_eff) {
+                best_eff = eff;
+                best_u = U;
+            }
         }
-        if (max_items) *max_items = mx;
-        return total;
-    };
-    int best_u = 16;
-    double best_eff = -1.0;
-    for (int U = 10; U <= 48; ++U) {
-        const double waves = items_for(U, nullptr) / resident;
-        const double eff = (double)U / (U + 4) * (waves / std::ceil(waves - 1e-9));
-        if (eff > best_eff) {
-            best_eff = eff;
-            best_u = U;
-        }
+        const char *force_u = getenv("WEFAX_GR_LINES");
+        if (force_u && atoi(force_u) >= 1) best_u = atoi(force_u);
+        P.lines_per_item = best_u;
+        P.only_class = count[cls] == batch ? -1 : cls;
+        long long max_items = 0;
+        items_for(best_u, &max_items);
+        dim3 grid((unsigned)((max_items + kGrThreads - 1) / kGrThreads), batch);
+        if (cls == 2 && base8)
+            grey_raster_kernel<8><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        else if (cls >= 1 && base4)
+            grey_raster_kernel<4><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        else
+            grey_raster_kernel<0><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
     }
-    const char *force_u = getenv("WEFAX_GR_LINES");
-    if (force_u && atoi(force_u) >= 1) best_u = atoi(force_u);
-    P.lines_per_item = best_u;
-    long long max_items = 0;
-    items_for(best_u, &max_items);
-    dim3 grid((unsigned)((max_items + kGrThreads - 1) / kGrThreads), batch);
-    grey_raster_kernel<<<grid, kGrThreads, 0, ctx->stream>>>(P);
-    CUDA_CHECK(cudaGetLastError());
-    ctx->launches++;
 }
 
 }  // namespace wefax

@@ -213,90 +213,112 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
 template <int MODE, int KC>
 __global__ void __launch_bounds__(kFirThreads)
 notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout, size_t z_stride,
-                 long long n, const FirParams fp, int tile0) {
+                 long long n, const FirParams fp, int tile0, int ntiles) {
     constexpr int TS = kFirTile;
     constexpr int NX = TS + 2 * KC;
     constexpr int W = 8 + 2 * KC;
-    __shared__ __align__(16) float s_x[NX];
+    __shared__ __align__(16) float s_x[2][NX];
     const int tid = threadIdx.x;
     const size_t base = (size_t)blockIdx.y * in_stride;
-    const long long t0 = (long long)(blockIdx.x + tile0) * TS;   // first output; [t0 - KC, t0 + TS + KC) is inside [0, n)
+    int t = blockIdx.x;                                   // persistent: tiles t, t + gridDim.x, ...
+    if (t >= ntiles) return;
+    // mono int16 whose tiles start on 16-byte boundaries: one 16-byte load per thread (+ the halo), issued a whole
+    // tile ahead of its use
     bool vec = false;
+    const int16_t *pcm16 = nullptr;
     if (MODE == kInMonoI16) {
-        const int16_t *src = (const int16_t *)in + base + t0;
-        vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        pcm16 = (const int16_t *)in + base + (long long)tile0 * TS;
+        vec = (reinterpret_cast<uintptr_t>(pcm16) & 15) == 0;
+    }
+    int4 pv = make_int4(0, 0, 0, 0);
+    int16_t ph = 0;
+    auto prefetch = [&](int tile) {
+        const int16_t *src = pcm16 + (long long)tile * TS;     // [src - KC, src + TS + KC) is inside the recording
+        pv = __ldg(reinterpret_cast<const int4 *>(src) + tid);
+        if (tid < 2 * KC) ph = __ldg(tid < KC ? src - KC + tid : src + TS + (tid - KC));
+    };
+    if (vec) prefetch(t);
+    int buf = 0;
+    while (true) {
+        float *sx = s_x[buf];
+        const long long t0 = (long long)(t + tile0) * TS;   // first output of the tile
         if (vec) {
-            const int4 v = __ldg(reinterpret_cast<const int4 *>(src) + tid);
-            int16_t hv = 0;
-            if (tid < 2 * KC) hv = __ldg(tid < KC ? src - KC + tid : src + TS + (tid - KC));
-            const int wv[4] = {v.x, v.y, v.z, v.w};
+            const int wv[4] = {pv.x, pv.y, pv.z, pv.w};
             float f[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 f[2 * k] = (float)(short)(wv[k] & 0xffff);
                 f[2 * k + 1] = (float)(short)(wv[k] >> 16);
             }
-            float4 *dst = reinterpret_cast<float4 *>(&s_x[KC + 8 * tid]);
+            float4 *dst = reinterpret_cast<float4 *>(&sx[KC + 8 * tid]);
             dst[0] = make_float4(f[0], f[1], f[2], f[3]);
             dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-            if (tid < 2 * KC) s_x[tid < KC ? tid : TS + tid] = (float)hv;
-        }
-    }
-    if (!vec) {
-        constexpr int ITER = (NX + kFirThreads - 1) / kFirThreads;
-        float v[ITER];
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int j = tid + it * kFirThreads;
-            v[it] = j < NX ? load_sample<MODE>(in, base, t0 - KC + j) : 0.f;
-        }
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int j = tid + it * kFirThreads;
-            if (j < NX) s_x[j] = v[it];
-        }
-    }
-    __syncthreads();
-
-    const int i0 = 8 * tid;
-    float w[W];
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-        const float4 t = *reinterpret_cast<const float4 *>(&s_x[i0 + 4 * q]);
-        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-    }
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fp.g[0] * w[KC + i];
-#pragma unroll
-    for (int k = 1; k <= KC; ++k) {
-        const float c = fp.g[k];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[KC + i - k] + w[KC + i + k], acc[i]);
-    }
-    const long long g = t0 + i0;
-    if (out) {
-        float *o = out + (size_t)blockIdx.y * out_stride + g;
-        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-            reinterpret_cast<float4 *>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            reinterpret_cast<float4 *>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            if (tid < 2 * KC) sx[tid < KC ? tid : TS + tid] = (float)ph;
         } else {
+            constexpr int ITER = (NX + kFirThreads - 1) / kFirThreads;
+            float v[ITER];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = acc[i];
+            for (int it = 0; it < ITER; ++it) {
+                const int j = tid + it * kFirThreads;
+                v[it] = j < NX ? load_sample<MODE>(in, base, t0 - KC + j) : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const int j = tid + it * kFirThreads;
+                if (j < NX) sx[j] = v[it];
+            }
         }
-    }
-    if (zout) {
-        float2 *z = zout + (size_t)blockIdx.y * z_stride + g;
+        // one barrier per tile: the other buffer was last read before the previous barrier
+        __syncthreads();
+        const int tn = t + gridDim.x;
+        if (vec && tn < ntiles) prefetch(tn);
+
+        const int i0 = 8 * tid;
+        float w[W];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = make_float2(acc[i], 0.f);
+        for (int q = 0; q < W / 4; ++q) {
+            const float4 x4 = *reinterpret_cast<const float4 *>(&sx[i0 + 4 * q]);
+            w[4 * q] = x4.x; w[4 * q + 1] = x4.y; w[4 * q + 2] = x4.z; w[4 * q + 3] = x4.w;
+        }
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fp.g[0] * w[KC + i];
+#pragma unroll
+        for (int k = 1; k <= KC; ++k) {
+            const float c = fp.g[k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[KC + i - k] + w[KC + i + k], acc[i]);
+        }
+        const long long g = t0 + i0;
+        if (out) {
+            float *o = out + (size_t)blockIdx.y * out_stride + g;
+            if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                reinterpret_cast<float4 *>(o)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<float4 *>(o)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = acc[i];
+            }
+        }
+        if (zout) {
+            float2 *z = zout + (size_t)blockIdx.y * z_stride + g;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = make_float2(acc[i], 0.f);
+        }
+        if (tn >= ntiles) break;
+        t = tn;
+        buf ^= 1;
     }
 }
 
 template <int MODE, int KC>
 static void launch_notch_sym(wefax_ctx *ctx, const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout,
                              size_t z_stride, long long n, const FirParams &fp, int batch, int tile0, int ntiles) {
-    dim3 grid((unsigned)ntiles, batch);
-    notch_sym_kernel<MODE, KC><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp, tile0);
+    // persistent CTAs: 5 of 256 threads fit an SM (47 registers, 16.6 KiB of shared memory each)
+    const int per_rec = std::max(1, (ctx->sm_count * 5 + batch - 1) / batch);
+    dim3 grid((unsigned)std::min(ntiles, per_rec), batch);
+    notch_sym_kernel<MODE, KC><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp,
+                                                                       tile0, ntiles);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

@@ -9,6 +9,8 @@ namespace wefax {
 struct LineDev {
     int n1, n0, L, mindistance, width;
     double dev_min, dev_max;
+    int gr_class;   // fused grey map + raster: 2 = width % 8 == 0, 1 = width % 4 == 0, else 0
+    int pad;
 };
 
 // per-recording results produced on the device

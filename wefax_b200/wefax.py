@@ -26,14 +26,19 @@ from . import wavio
 from .config import Config
 from .decoder import Decoder
 
-_decoders: dict = {}
-_decoder_lock = threading.Lock()
+# One native context per (host thread, device): main.py runs several conversions at once, each on its own
+# request thread (main.py:53,294-309), and a context serves one thread at a time.  No lock: concurrent
+# process() calls run concurrently, each on its own stream.  The context of a thread dies with the thread.
+_thread_state = threading.local()
 
 
-def _shared_decoder(device: int) -> Decoder:
-    if device not in _decoders:
-        _decoders[device] = Decoder(device)
-    return _decoders[device]
+def _thread_decoder(device: int) -> Decoder:
+    pool = getattr(_thread_state, "decoders", None)
+    if pool is None:
+        pool = _thread_state.decoders = {}
+    if device not in pool:
+        pool[device] = Decoder(device)
+    return pool[device]
 
 
 class Demodulator:
@@ -88,10 +93,9 @@ class Demodulator:
                       "resample audio\033[0m")
             self._progress("resampling audio", 0)
 
-        with _decoder_lock:
-            res = _shared_decoder(self.device).decode(
-                pcm, sample_rate, lpm=self.lines_per_minute, notch_freq=notch_freq, notch_q=notch_q,
-                want=("audio", "demodulated", "digitalized", "raster"))
+        res = _thread_decoder(self.device).decode(
+            pcm, sample_rate, lpm=self.lines_per_minute, notch_freq=notch_freq, notch_q=notch_q,
+            want=("audio", "demodulated", "digitalized", "raster"))
 
         if resample:
             self._progress("resampling audio", 100)
