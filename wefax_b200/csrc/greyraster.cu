@@ -20,7 +20,7 @@
 namespace wefax {
 
 constexpr int kGrThreads = 128;
-constexpr int kGrCols = 8;   // columns per thread
+constexpr int kGrCols = 4;   // columns per thread
 
 // exact grey level of a median value (same operations, in the same order, as numpy: wefax.py:197-200, 216)
 __device__ __forceinline__ int grey_level_exact(float m, double low, double delta) {
@@ -145,54 +145,35 @@ __device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
     return d;
 }
 
-// 8 bytes (lo = bytes 0..3) to an address of any alignment, first `count` bytes only when count < 8
-// (out of line: the hot loops only come here for the last, partial column group of a line)
-__device__ __noinline__ void store8(uint8_t *p, uint32_t lo, uint32_t hi, int count) {
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
-    if (count >= 8) {
+// 4 bytes to an address of any alignment, first `count` bytes only when count < 4
+// (out of line: the hot loop only comes here for unaligned rows and the last, partial column group of a line)
+__device__ __noinline__ void store4_any(uint8_t *p, uint32_t v, int count) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    if (count >= 4) {
         if (a == 0u) {
-            *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
-        } else if ((a & 3u) == 0u) {
-            reinterpret_cast<uint32_t *>(p)[0] = lo;
-            reinterpret_cast<uint32_t *>(p)[1] = hi;
-        } else if ((a & 1u) == 0u) {
-            *reinterpret_cast<uint16_t *>(p) = (uint16_t)lo;
-            *reinterpret_cast<uint32_t *>(p + 2) = __funnelshift_r(lo, hi, 16);
-            *reinterpret_cast<uint16_t *>(p + 6) = (uint16_t)(hi >> 16);
-        } else if ((a & 3u) == 3u) {
-            p[0] = (uint8_t)lo;
-            *reinterpret_cast<uint32_t *>(p + 1) = __funnelshift_r(lo, hi, 8);
-            *reinterpret_cast<uint16_t *>(p + 5) = (uint16_t)(hi >> 8);
-            p[7] = (uint8_t)(hi >> 24);
+            *reinterpret_cast<uint32_t *>(p) = v;
+        } else if (a == 2u) {
+            *reinterpret_cast<uint16_t *>(p) = (uint16_t)v;
+            *reinterpret_cast<uint16_t *>(p + 2) = (uint16_t)(v >> 16);
         } else {
-            p[0] = (uint8_t)lo;
-            *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(lo >> 8);
-            *reinterpret_cast<uint32_t *>(p + 3) = __funnelshift_r(lo, hi, 24);
-            p[7] = (uint8_t)(hi >> 24);
+            p[0] = (uint8_t)v;
+            if (a == 1u) {
+                *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(v >> 8);
+                p[3] = (uint8_t)(v >> 24);
+            } else {
+                p[1] = (uint8_t)(v >> 8);
+                *reinterpret_cast<uint16_t *>(p + 2) = (uint16_t)(v >> 16);
+            }
         }
     } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (c < count) p[c] = (uint8_t)((c < 4 ? lo >> (8 * c) : hi >> (8 * (c - 4))) & 0xFFu);
+        for (int c = 0; c < count; ++c) p[c] = (uint8_t)(v >> (8 * c));
     }
 }
 
-// medians of x[OFF + 2 .. OFF + 9] given x[OFF .. OFF + 11]: every adjacent pair is ordered once and shared
-// by the two windows it belongs to (same min / max expression tree as med5)
-template <int OFF>
-__device__ __forceinline__ void med8_from16(const float (&f)[16], float (&m)[8]) {
-    float lo[10], hi[10];
-#pragma unroll
-    for (int j = 0; j < 10; ++j) {
-        lo[j] = fminf(f[OFF + j], f[OFF + j + 1]);
-        hi[j] = fmaxf(f[OFF + j], f[OFF + j + 1]);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float a = fmaxf(lo[k], lo[k + 2]);
-        const float b = fminf(hi[k], hi[k + 2]);
-        m[k] = med3(f[OFF + k + 4], a, b);
-    }
+template <bool ALIGNED>
+__device__ __forceinline__ void store_row4(uint8_t *p, uint32_t v, int ncols) {
+    if (ALIGNED && ncols >= kGrCols) *reinterpret_cast<uint32_t *>(p) = v;
+    else store4_any(p, v, ncols);
 }
 
 struct GreyQuant {
@@ -219,137 +200,104 @@ __device__ __forceinline__ uint32_t grey_estimate_u8(float m, float scale, float
     return k;
 }
 
-template <int ALIGN>
-__device__ __forceinline__ void store_row8(uint8_t *p, uint32_t lo, uint32_t hi, int ncols) {
-    if (ALIGN == 8) {
-        if (ncols >= kGrCols) *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
-        else store8(p, lo, hi, ncols);
-    } else if (ALIGN == 4) {
-        if (ncols >= kGrCols) {
-            reinterpret_cast<uint32_t *>(p)[0] = lo;
-            reinterpret_cast<uint32_t *>(p)[1] = hi;
-        } else {
-            store8(p, lo, hi, ncols);
-        }
-    } else {
-        store8(p, lo, hi, ncols);
-    }
-}
-
 // One interior item: all its lines are image lines at least 2 lines from the image's first / last line, every
 // load stays inside the recording, the fp32 estimate is valid.  OFF: offset (in floats, mod 4) of the envelope
 // element two to the left of the item's first column from a 16-byte boundary, the same for every line when the
-// width is a multiple of 4; OFF < 0: evaluated per line.  ALIGN: guaranteed alignment of the raster stores.
-template <int OFF, int ALIGN>
+// width is a multiple of 4 (then the raster rows are 4-byte aligned too: ALIGNED); OFF < 0: evaluated per line.
+// The line loop is deliberately NOT unrolled: its body (~220 instructions) stays resident in the instruction
+// cache; the price is the 16 moves that shift the 5-line window.
+template <int OFF, bool ALIGNED>
 __device__ __forceinline__ void interior_item(const GreyRasterParams &P, const GreyQuant &Q, const float *e, uint8_t *dg,
                                               uint8_t *out, long long i_first, long long r_a, int nrows, int w, int c0,
                                               int ncols) {
     int win[5][kGrCols];
     const float *prow = e + i_first - 2;   // x[0] of the line being fetched
-    float4 nx[4];
+    float4 nx[3];
     auto fetch = [&]() {
         const float4 *pa = reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(prow) & ~(uintptr_t)15);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nx[q] = __ldg(pa + q);
+        for (int q = 0; q < 3; ++q) nx[q] = __ldg(pa + q);
     };
     fetch();
     uint8_t *drow = dg ? dg + i_first : nullptr;        // digitalized of the line being computed
     uint8_t *orow = out + (size_t)(4 * r_a) * w + c0;   // raster rows of the line being emitted
-
-    // grey levels of the fetched line into window slot `slot`; starts the fetch of the next line
-    auto grey_line = [&](int (&g)[kGrCols], bool more) {
-        float f[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+    for (int t = 0; t < 5; ++t)
+#pragma unroll
+        for (int c = 0; c < kGrCols; ++c) win[t][c] = 0;
+
+#pragma unroll 1
+    for (int j = 0; j < nrows; ++j) {
+        // ---- grey levels of line r_a - 2 + j into the newest window slot ---------------------------------
+        float f[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
             f[4 * q] = nx[q].x; f[4 * q + 1] = nx[q].y; f[4 * q + 2] = nx[q].z; f[4 * q + 3] = nx[q].w;
         }
-        float m[8];
+        float m[kGrCols];
         if (OFF >= 0) {
-            med8_from16<(OFF >= 0 ? OFF : 0)>(f, m);
+            med4_from12<(OFF >= 0 ? OFF : 0)>(f, m);
         } else {
             switch ((int)((reinterpret_cast<uintptr_t>(prow) >> 2) & 3u)) {
-                case 0: med8_from16<0>(f, m); break;
-                case 1: med8_from16<1>(f, m); break;
-                case 2: med8_from16<2>(f, m); break;
-                default: med8_from16<3>(f, m); break;
+                case 0: med4_from12<0>(f, m); break;
+                case 1: med4_from12<1>(f, m); break;
+                case 2: med4_from12<2>(f, m); break;
+                default: med4_from12<3>(f, m); break;
             }
         }
         prow += w;
-        if (more) fetch();   // the medians have consumed nx: the next line streams in under the rest of this one
+        if (j + 1 < nrows) fetch();   // the medians have consumed nx: the next line streams in under the rest of this one
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int c = 0; c < kGrCols; ++c) win[t][c] = win[t + 1][c];
         bool bad = false;
 #pragma unroll
         for (int c = 0; c < kGrCols; ++c) {
             const uint32_t k0 = grey_estimate_u8(m[c], Q.scale, Q.off);
             const uint2 t = Q.pairs[k0];
             bad = bad || (__float_as_uint(m[c]) - t.x >= t.y);
-            g[c] = (int)k0;
+            win[4][c] = (int)k0;
         }
         if (bad) {   // some estimate is one level off (rare): redo the line with the corrected form
 #pragma unroll
-            for (int c = 0; c < kGrCols; ++c) g[c] = Q.level_fast(m[c]);
+            for (int c = 0; c < kGrCols; ++c) win[4][c] = Q.level_fast(m[c]);
         }
-    };
-    auto store_dig = [&](const int (&g)[kGrCols]) {
-        const uint32_t lo = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
-        const uint32_t hi = (uint32_t)g[4] | ((uint32_t)g[5] << 8) | ((uint32_t)g[6] << 16) | ((uint32_t)g[7] << 24);
-        store8(drow, lo, hi, ncols);
-    };
-    auto emit = [&](const int (&l0)[kGrCols], const int (&l1)[kGrCols], const int (&l2)[kGrCols], const int (&l3)[kGrCols],
-                    const int (&l4)[kGrCols]) {
-#pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
-            int v[kGrCols];
-#pragma unroll
-            for (int c = 0; c < kGrCols; ++c) {
-                int acc;
-                if (ph < 2)
-                    acc = P.ck[ph] + P.nk[ph][0] * l0[c] + P.nk[ph][1] * l1[c] + P.nk[ph][2] * l2[c] + P.nk[ph][3] * l3[c];
-                else
-                    acc = P.ck[ph] + P.nk[ph][0] * l1[c] + P.nk[ph][1] * l2[c] + P.nk[ph][2] * l3[c] + P.nk[ph][3] * l4[c];
-                v[c] = acc >> 22;
-            }
-            store_row8<ALIGN>(orow + (size_t)ph * w, pack4_sat(v[0], v[1], v[2], v[3]), pack4_sat(v[4], v[5], v[6], v[7]),
-                              ncols);
-        }
-        orow += (size_t)4 * w;
-    };
-
-    // lines r_a - 2 .. r_a + 1 fill the window (the last two of them are the item's own)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        grey_line(win[j], true);
         if (drow) {
-            if (j >= 2) store_dig(win[j]);
+            if (j >= 2 && j < nrows - 2) {
+                const uint32_t v = (uint32_t)win[4][0] | ((uint32_t)win[4][1] << 8) | ((uint32_t)win[4][2] << 16) |
+                                   ((uint32_t)win[4][3] << 24);
+                store4_any(drow, v, ncols);
+            }
             drow += w;
         }
-    }
-    // steady state: line j enters slot j % 5 and completes the window of line j - 2
-    for (int jb = 4; jb < nrows; jb += 5) {
+        // ---- line r_a + j - 4 is complete: its 4 raster rows ---------------------------------------------------
+        if (j >= 4) {
 #pragma unroll
-        for (int jj = 0; jj < 5; ++jj) {
-            const int j = jb + jj;
-            constexpr int kBase = 4;
-            const int slot = (kBase + jj) % 5;
-            if (j < nrows) {
-                grey_line(win[slot], j + 1 < nrows);
-                if (drow) {
-                    if (j < nrows - 2) store_dig(win[slot]);
-                    drow += w;
+            for (int ph = 0; ph < 4; ++ph) {
+                const int b = ph < 2 ? 0 : 1;
+                int v[kGrCols];
+#pragma unroll
+                for (int c = 0; c < kGrCols; ++c) {
+                    const int acc = P.ck[ph] + P.nk[ph][0] * win[b][c] + P.nk[ph][1] * win[b + 1][c] +
+                                    P.nk[ph][2] * win[b + 2][c] + P.nk[ph][3] * win[b + 3][c];
+                    v[c] = acc >> 22;
                 }
-                emit(win[(slot + 1) % 5], win[(slot + 2) % 5], win[(slot + 3) % 5], win[(slot + 4) % 5], win[slot]);
+                store_row4<ALIGNED>(orow + (size_t)ph * w, pack4_sat(v[0], v[1], v[2], v[3]), ncols);
             }
+            orow += (size_t)4 * w;
         }
     }
 }
 
-// ALIGN: alignment every raster row of the launch's recordings is known to have (8: width % 8 == 0, 4: width % 4 == 0,
-// 0: anything; for 8 and 4 the envelope rows of a recording also share one 16-byte phase)
-template <int ALIGN>
-__global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
+// ALIGNED: the width of every recording of the launch is a multiple of 4 and the raster base / stride are 4-byte
+// aligned: all raster rows are, and the envelope rows of a recording share one 16-byte phase.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(kGrThreads, 6) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
     __shared__ uint32_t s_T[260];
     __shared__ uint2 s_pairs[256];
     const int rec = blockIdx.y;
-    if (P.only_class >= 0 && P.lines[rec].gr_class != P.only_class) return;
+    if (P.only_class >= 0 && (P.lines[rec].gr_class >= 1 ? 1 : 0) != P.only_class) return;
     const RecResult *res = P.res + rec;
     const GreyTable *tab = P.tables + rec;
     for (int i = threadIdx.x; i < 257; i += kGrThreads) s_T[i] = tab->T[i];
@@ -391,18 +339,18 @@ __global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid
     uint8_t *out = P.raster ? P.raster + (size_t)rec * P.rs : nullptr;
 
     const long long i_first = s + (r_a - 2) * w + c0;   // sample (line r_a - 2, column c0)
-    const bool interior = Q.est_ok && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 && s + (r_b + 1) * w + c0 + 14 <= n;
+    const bool interior = Q.est_ok && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 && s + (r_b + 1) * w + c0 + 10 <= n;
     if (interior) {
         const int nrows = (int)(r_b - r_a) + 4;
-        if (ALIGN >= 4) {
+        if (ALIGNED) {
             switch ((int)((reinterpret_cast<uintptr_t>(e + i_first - 2) >> 2) & 3u)) {
-                case 0: interior_item<0, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
-                case 1: interior_item<1, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
-                case 2: interior_item<2, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
-                default: interior_item<3, ALIGN>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                case 0: interior_item<0, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                case 1: interior_item<1, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                case 2: interior_item<2, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                default: interior_item<3, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
             }
         } else {
-            interior_item<-1, 0>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols);
+            interior_item<-1, false>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols);
         }
         return;
     }
@@ -418,15 +366,15 @@ __global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid
     const long long r_from = any_raster ? r_a - 2 : r_a, r_to = any_raster ? r_b + 2 : r_b;
     for (long long r = r_from; r < r_to; ++r) {
         const long long i0 = s + r * w + c0;
-        float f[16];
+        float f[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const long long i = i0 - 2 + j;
             f[j] = (i >= 0 && i < n) ? __ldg(e + i) : 0.f;
         }
-        f[12] = f[13] = f[14] = f[15] = 0.f;
-        float m[8];
-        med8_from16<0>(f, m);
+        f[8] = f[9] = f[10] = f[11] = 0.f;
+        float m[kGrCols];
+        med4_from12<0>(f, m);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -463,8 +411,7 @@ __global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid
                     for (int t = 0; t < 5; ++t) acc += kw[t] * (255 - win[t][c]);   // luminance 255 - value (wefax.py:303)
                     v[c] = acc >> 22;
                 }
-                store8(out + (size_t)(4 * q + ph) * w + c0, pack4_sat(v[0], v[1], v[2], v[3]),
-                       pack4_sat(v[4], v[5], v[6], v[7]), ncols);
+                store4_any(out + (size_t)(4 * q + ph) * w + c0, pack4_sat(v[0], v[1], v[2], v[3]), ncols);
             }
         }
     }
@@ -513,20 +460,17 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         }
         P.ck[ph] = (int)((1ll << 21) + 255 * sum);
     }
-    // recordings by alignment class (LineDev.gr_class, set by api.cu from the width): raster rows of a recording are
-    // all 8- / 4-byte aligned when its width is a multiple of 8 / 4 and so are the raster base and stride
-    const bool base8 = (reinterpret_cast<uintptr_t>(raster) & 7) == 0 && rs % 8 == 0;
+    // recordings by alignment class (LineDev.gr_class, set by api.cu from the width): the raster rows of a recording
+    // are all 4-byte aligned when its width is a multiple of 4 and so are the raster base and stride
     const bool base4 = (reinterpret_cast<uintptr_t>(raster) & 3) == 0 && rs % 4 == 0;
-    int count[3] = {0, 0, 0};   // class 0: generic, 1: ALIGN 4, 2: ALIGN 8
-    for (int r = 0; r < batch; ++r) count[h_lines[r].gr_class]++;
-    // lines per item: a long walk amortises the 4 extra lines of every item, but the grid should fill a whole
-    // number of waves of resident CTAs
-    int per_sm = 5;
+    int count[2] = {0, 0};   // 0: generic widths, 1: width % 4 == 0
+    for (int r = 0; r < batch; ++r) count[h_lines[r].gr_class >= 1 ? 1 : 0]++;
+    int per_sm = 6;
     {
-        const void *fn = (const void *)grey_raster_kernel<8>;
+        const void *fn = (const void *)grey_raster_kernel<true>;
         auto it = ctx->smem_configured.find(fn);
         if (it == ctx->smem_configured.end()) {
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<8>, kGrThreads, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<true>, kGrThreads, 0));
             if (per_sm < 1) per_sm = 1;
             ctx->smem_configured[fn] = per_sm;
         } else {
@@ -534,13 +478,13 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         }
     }
     const double resident = (double)ctx->sm_count * per_sm * kGrThreads;
-    for (int cls = 2; cls >= 0; --cls) {
+    for (int cls = 1; cls >= 0; --cls) {
         if (!count[cls]) continue;
         auto items_for = [&](int U, long long *max_items) {
             double total = 0;
             long long mx = 0;
             for (int r = 0; r < batch; ++r) {
-                if (h_lines[r].gr_class != cls) continue;
+                if ((h_lines[r].gr_class >= 1 ? 1 : 0) != cls) continue;
                 const int w = h_lines[r].width;
                 const long long nl = n / w + 2;
                 const long long it = ((nl + U - 1) / U) * ((w + kGrCols - 1) / kGrCols);
@@ -550,11 +494,13 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
             if (max_items) *max_items = mx;
             return total;
         };
+        // lines per item: a long walk amortises the 4 extra lines of every item (they cost the grey map only, ~40 % of
+        // a line), but the grid should be several waves of resident CTAs and end close to a whole one
         int best_u = 16;
         double best_eff = -1.0;
-        for (int U = 10; U <= 48; ++U) {
+        for (int U = 8; U <= 40; ++U) {
             const double waves = items_for(U, nullptr) / resident;
-            const double eff = (double)U / (U + 4) * (waves / std::ceil(waves - 1e-9));
+            const double eff = (double)U / (U + 1.6) * (waves / std::ceil(waves - 1e-9)) * (waves >= 3.0 ? 1.0 : 0.8);
             if (eff > best_eff) {
                 best_eff = eff;
                 best_u = U;
@@ -563,16 +509,14 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         const char *force_u = getenv("WEFAX_GR_LINES");
         if (force_u && atoi(force_u) >= 1) best_u = atoi(force_u);
         P.lines_per_item = best_u;
-        P.only_class = count[cls] == batch ? -1 : cls;
+        P.only_class = count[cls] == batch ? -1 : cls;   // LineDev.gr_class >= 1 <-> cls 1 (see the kernel's filter)
         long long max_items = 0;
         items_for(best_u, &max_items);
         dim3 grid((unsigned)((max_items + kGrThreads - 1) / kGrThreads), batch);
-        if (cls == 2 && base8)
-            grey_raster_kernel<8><<<grid, kGrThreads, 0, ctx->stream>>>(P);
-        else if (cls >= 1 && base4)
-            grey_raster_kernel<4><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        if (cls == 1 && base4)
+            grey_raster_kernel<true><<<grid, kGrThreads, 0, ctx->stream>>>(P);
         else
-            grey_raster_kernel<0><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+            grey_raster_kernel<false><<<grid, kGrThreads, 0, ctx->stream>>>(P);
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }

@@ -53,4 +53,39 @@ __device__ __forceinline__ void load_med8(const float *e, long long i0, long lon
     for (int j = 0; j < 8; ++j) out[j] = med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]);
 }
 
+// medians of x[OFF + 2 .. OFF + 9] given x[OFF .. OFF + 11]: every adjacent pair is ordered once and shared
+// by the two windows it belongs to (same min / max expression tree as med5)
+template <int OFF>
+__device__ __forceinline__ void med8_from16(const float (&f)[16], float (&m)[8]) {
+    float lo[10], hi[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        lo[j] = fminf(f[OFF + j], f[OFF + j + 1]);
+        hi[j] = fmaxf(f[OFF + j], f[OFF + j + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float a = fmaxf(lo[k], lo[k + 2]);
+        const float b = fminf(hi[k], hi[k + 2]);
+        m[k] = med3(f[OFF + k + 4], a, b);
+    }
+}
+
+// medians of x[OFF + 2 .. OFF + 5] given x[OFF .. OFF + 7] (OFF <= 4, 12 values loaded)
+template <int OFF>
+__device__ __forceinline__ void med4_from12(const float (&f)[12], float (&m)[4]) {
+    float lo[6], hi[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        lo[j] = fminf(f[OFF + j], f[OFF + j + 1]);
+        hi[j] = fmaxf(f[OFF + j], f[OFF + j + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = fmaxf(lo[k], lo[k + 2]);
+        const float b = fminf(hi[k], hi[k + 2]);
+        m[k] = med3(f[OFF + k + 4], a, b);
+    }
+}
+
 }  // namespace wefax

@@ -546,6 +546,7 @@ struct PctGeom {
     uint32_t r[4];                 // wanted ranks: i_lo, i_lo+1, i_hi, i_hi+1 (clipped)
     double t_lo, t_hi;             // numpy lerp weights
     uint32_t cap;                  // capacity of each candidate list
+    int over_mode;                 // PctState.below[1] counts the samples ABOVE the high bracket (pct_collect2_kernel)
 };
 
 struct PctState {                  // per recording, device
@@ -775,6 +776,101 @@ pct_collect_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, flo
             if (s_base[h] + i < g.cap) list[h][s_base[h] + i] = s_cand[h][i];
 }
 
+// Lean form of pct_collect_kernel: the samples outside the two brackets' span (99 % of them lie strictly
+// between the brackets) cost one subtract, one compare and one warp vote each; only warps that hold a sample
+// in a tail or a bracket enter the classification.  Counts: below[0] = samples under the low bracket,
+// below[1] = samples ABOVE the high bracket (the final selection derives its rank offset from it).
+__global__ void __launch_bounds__(256)
+pct_collect2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, float *lists, size_t ls) {
+    __shared__ unsigned long long s_cnt_out[2];
+    __shared__ float s_cand[2][kPctStage];
+    __shared__ uint32_t s_cnt[2], s_base[2];
+    PctState *st = st_all + blockIdx.y;
+    const float *e = env + (size_t)blockIdx.y * es;
+    float *list[2] = {lists + (size_t)blockIdx.y * ls, lists + (size_t)blockIdx.y * ls + g.cap};
+    const uint32_t k0 = st->key[0], k1 = st->key[1], k2 = st->key[2], k3 = st->key[3];
+    if (threadIdx.x < 2) {
+        s_cnt_out[threadIdx.x] = 0;
+        s_cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    auto append = [&](int h, float v) {
+        const uint32_t slot = atomicAdd(&s_cnt[h], 1u);
+        if (slot < kPctStage) {
+            s_cand[h][slot] = v;
+        } else {                                    // staging full (pathological data): append directly
+            const uint32_t gslot = atomicAdd(&st->len[h], 1u);
+            if (gslot < g.cap) list[h][gslot] = v;
+        }
+    };
+    // middle = k1 < key < k2  <=>  key - (k1 + 1) < k2 - k1 - 1 (unsigned); brackets that touch or overlap make
+    // the span empty: every sample is then classified
+    const uint32_t mid_lo = k1 + 1u, mid_span = k2 > k1 ? k2 - k1 - 1u : 0u;
+    uint32_t n_under = 0, n_over = 0;
+    const long long n = g.n;
+    const long long stride = 8ll * blockDim.x * gridDim.x;
+    const long long rounds = (n + stride - 1) / stride;   // every thread runs every round: the votes are warp-wide
+    long long i0 = 8 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    for (long long it = 0; it < rounds; ++it, i0 += stride) {
+        float m[8];
+        int nvalid = 0;
+        if (i0 < n) {
+            nvalid = (int)min(8ll, n - i0);
+            if (i0 >= 4 && i0 + 12 <= n && (reinterpret_cast<uintptr_t>(e + i0) & 15) == 0) {
+                float f[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(e + i0 - 4) + q);
+                    f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+                }
+                med8_from16<2>(f, m);
+            } else {
+                load_med8(e, i0, n, m);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t key = __float_as_uint(m[j]);
+            const bool out_mid = (key - mid_lo >= mid_span) && j < nvalid;
+            if (__any_sync(0xFFFFFFFFu, out_mid)) {
+                if (out_mid) {
+                    if (key <= k1) {
+                        if (key < k0) n_under++;
+                        else append(0, m[j]);
+                    }
+                    if (key >= k2) {
+                        if (key > k3) n_over++;
+                        else append(1, m[j]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        n_under += __shfl_xor_sync(0xFFFFFFFFu, n_under, d);
+        n_over += __shfl_xor_sync(0xFFFFFFFFu, n_over, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt_out[0], (unsigned long long)n_under);
+        atomicAdd(&s_cnt_out[1], (unsigned long long)n_over);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        atomicAdd(&st->below[threadIdx.x], s_cnt_out[threadIdx.x]);
+        const uint32_t c = min(s_cnt[threadIdx.x], (uint32_t)kPctStage);
+        s_cnt[threadIdx.x] = c;
+        s_base[threadIdx.x] = c ? atomicAdd(&st->len[threadIdx.x], c) : 0u;
+    }
+    __syncthreads();
+    for (int h = 0; h < 2; ++h)
+        for (uint32_t i = threadIdx.x; i < s_cnt[h]; i += blockDim.x)
+            if (s_base[h] + i < g.cap) list[h][s_base[h] + i] = s_cand[h][i];
+}
+
 __device__ void write_percentiles(RecResult *res, const uint32_t key[4], double t_lo, double t_hi) {
     // numpy _lerp: a + (b-a)*t for t < 0.5, b - (b-a)*(1-t) otherwise (no FMA contraction)
     double v[4];
@@ -799,8 +895,11 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
     const float *list_lo = lists + (size_t)rec * ls, *list_hi = list_lo + g.cap;
     // every CTA of the recording takes the same decision from the same data
     bool ok = st->len[0] <= g.cap && st->len[1] <= g.cap;
+    // samples under each bracket
+    const unsigned long long below_of[2] = {
+        st->below[0], g.over_mode ? (unsigned long long)g.n - st->below[1] - st->len[1] : st->below[1]};
     for (int h = 0; h < 2 && ok; ++h) {
-        const unsigned long long b = st->below[h];
+        const unsigned long long b = below_of[h];
         ok = b <= g.r[2 * h] && (unsigned long long)g.r[2 * h + 1] < b + st->len[h];
     }
     if (!ok) {
@@ -813,7 +912,7 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
         const int h = cta & 1, gcta = cta >> 1;
         const unsigned gn = (unsigned)((ncta + 1 - h) >> 1);
         const float *lst = h ? list_hi : list_lo;
-        if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)st->below[h];
+        if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)below_of[h];
         __syncthreads();
         coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], gcta, gn,
                        &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
@@ -832,7 +931,7 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
     }
     for (int h = 0; h < 2; ++h) {
         const float *lst = h ? list_hi : list_lo;
-        if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)st->below[h];
+        if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)below_of[h];
         __syncthreads();
         coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], cta,
                        (unsigned)ncta, &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
@@ -918,6 +1017,8 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     auto sclip = [&](long long r) { return (uint32_t)std::min<long long>(std::max<long long>(r, 0), g.ns - 1); };
     g.s_rank[0] = sclip(a_lo); g.s_rank[1] = sclip(b_lo); g.s_rank[2] = sclip(a_hi); g.s_rank[3] = sclip(b_hi);
     g.cap = (uint32_t)std::min<long long>(n, 4 * (2 * delta + 2) * kPctStride + 4096);
+    const char *pc = getenv("WEFAX_PCT_COLLECT");   // "old": the first collect kernel (A/B measurements)
+    g.over_mode = !(pc && pc[0] == 'o');
     const size_t ss = (size_t)((g.ns + 63) & ~63ll), ls = 2 * (size_t)g.cap;
     char *base = (char *)ctx->pct_buf.reserve((ss + ls) * sizeof(float) * batch +
                                               (sizeof(PctState) + sizeof(PctCoop)) * batch + 512);
@@ -951,7 +1052,10 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     blocks = std::max(1, blocks / std::max(1, std::min(batch, 8)));
     {
         StageTimer t1(ctx, "pct_collect");
-        pct_collect_kernel<<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
+        if (g.over_mode)
+            pct_collect2_kernel<<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
+        else
+            pct_collect_kernel<<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
     }
     {
         StageTimer t1(ctx, "pct_final");
@@ -1405,6 +1509,20 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    // second level: bit c of the summary = chunk c (32 words = 1024 positions) holds a settled position; warp k
+    // builds summary word k (<= 46 words for the 1.5 M positions the region is capped at)
+    __shared__ uint32_t s_sum[64];
+    const int nchunks = (nwords + 31) >> 5, nsum = (nchunks + 31) >> 5;
+    for (int sw = threadIdx.x >> 5; sw < nsum; sw += (int)(blockDim.x >> 5)) {
+        uint32_t word = 0u;
+        for (int j = 0; j < 32; ++j) {
+            const int wi = ((sw << 5) + j) * 32 + (int)(threadIdx.x & 31);
+            const uint32_t v = wi < nwords ? s_bits[wi] : 0u;
+            if (__ballot_sync(0xFFFFFFFFu, v != 0u)) word |= 1u << j;
+        }
+        if ((threadIdx.x & 31) == 0) s_sum[sw] = word;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
         // every position of the precomputed region fits 31 bits (lim <= 1.5 M): 32-bit arithmetic keeps the
         // dependent instruction chain of this single warp short (it is pure latency: ~5 cycles per instruction)
@@ -1412,21 +1530,37 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         const int w = ln.mindistance;
         const int lim = (int)sd.lim;
         const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
-        // first settled position >= x inside [0, lim); -1 when the mask ends first
+        // first settled position in chunk `c` at or after word `wfrom` (bits below `head_bit` of that word ignored)
+        auto scan_chunk = [&](int c, int wfrom, int head_bit) -> int {
+            const int wi = (c << 5) + lane;
+            uint32_t v = (wi < nwords && wi >= wfrom) ? s_bits[wi] : 0u;
+            if (wi == wfrom) v &= ~0u << head_bit;
+            const unsigned any = __ballot_sync(0xFFFFFFFFu, v != 0u);
+            if (!any) return -1;
+            const int l = __ffs(any) - 1;
+            const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, l);
+            return (((c << 5) + l) << 5) + (__ffs(vv) - 1);
+        };
+        // first settled position >= x inside [0, lim); -1 when the mask ends first: the rest of x's chunk, then
+        // the summary names the next chunk that holds one
         auto next_settled = [&](int x) -> int {
-            int wi = x >> 5;
-            uint32_t head = ~0u << (x & 31);
-            while (wi < nwords) {
-                uint32_t v = (wi + lane < nwords) ? s_bits[wi + lane] : 0u;
-                if (lane == 0) v &= head;
-                head = ~0u;
-                const unsigned any = __ballot_sync(0xFFFFFFFFu, v != 0u);
+            const int wi = x >> 5, c = wi >> 5;
+            if (wi >= nwords) return -1;
+            int p = scan_chunk(c, wi, x & 31);
+            if (p >= 0) return p;
+            int c1 = c + 1;
+            while (c1 < nchunks) {
+                const int sw = (c1 >> 5) + lane;
+                uint32_t sv = sw < nsum ? s_sum[sw] : 0u;
+                if (lane == 0) sv &= ~0u << (c1 & 31);
+                const unsigned any = __ballot_sync(0xFFFFFFFFu, sv != 0u);
                 if (any) {
                     const int l = __ffs(any) - 1;
-                    const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, l);
-                    return ((wi + l) << 5) + (__ffs(vv) - 1);
+                    const uint32_t vv = __shfl_sync(0xFFFFFFFFu, sv, l);
+                    const int c2 = ((((c1 >> 5) + l) << 5) + (__ffs(vv) - 1));
+                    return scan_chunk(c2, c2 << 5, 0);
                 }
-                wi += 32;
+                c1 = ((c1 >> 5) + 32) << 5;
             }
             return -1;
         };
