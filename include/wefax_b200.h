@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WEFAX_ABI_VERSION 4
+#define WEFAX_ABI_VERSION 5
 #define WEFAX_TARGET_RATE 11025   /* wefax.py:60 */
 #define WEFAX_MAX_PEAKS 100       /* wefax.py:251 */
 
@@ -54,6 +54,9 @@ typedef enum {
 /* wefax_batch_desc.flags */
 #define WEFAX_F_PCM_ON_DEVICE 1u   /* pcm points to device memory                 */
 #define WEFAX_F_OUT_ON_DEVICE 2u   /* every non-NULL output points to device mem  */
+#define WEFAX_F_PCM_FLOAT32 4u     /* wefax_decode_batch only: pcm points to float32 mono samples (WAV sample formats
+                                      other than 16-bit PCM, converted by the caller as scipy.io.wavfile.read would
+                                      deliver them, wefax.py:349); channels must be 1                              */
 
 /* ---- context -------------------------------------------------------------- */
 

@@ -427,10 +427,115 @@ def test_demodulator_stereo(dec, tmp_path):
     assert rel_err(d.audio_data, g["audio_data"]) < FLOAT_TOL
     frac, _ = frac_within_one(np.asarray(d.output_image), g["output_image"])
     assert frac >= PIXEL_FRACTION
+    # with the stream on: the same message sequence as the reference, "merging channels" included
+    # (wefax.py:364-370: one message per 1000 frames and one for the last frame)
+    import json
+    s = Demodulator(wav, lines_per_minute=240, tcp_stream=True, quiet=True)
+    s.process()
+    titles = [m.get("progress_title", m.get("message_content")) for m in s.websocket_stack]
+    assert titles == json.loads(str(g["progress_titles"]))
+    parts = g["pcm"].shape[0]
+    merging = [m["percentage"] for m in s.websocket_stack if m.get("progress_title") == "merging channels"]
+    expect = [(q + 1) / parts * 100 for q in range(parts) if q % 1000 == 0 or q == parts - 1]
+    assert merging == expect
 
 
 # --------------------------------------------------------------------------- full size (BASELINE.json configs[1])
 @pytest.mark.slow
+def _reference_ingest(data):
+    """What wefax.py:348-373 hands to filtfilt for scipy's ``data``: mono as stored, stereo merged frame by frame
+    with np.divide(np.add(L, R), 2) in the stored dtype (integer sums wrap)."""
+    if data.ndim == 1:
+        return np.asarray(data, dtype=np.float64)
+    with np.errstate(over="ignore"):
+        return np.asarray(np.divide(np.add(data[:, 0], data[:, 1]), 2), dtype=np.float64)
+
+
+@pytest.mark.parametrize("fmt", ["pcm24", "pcm32", "float32", "float64", "pcm32_stereo", "float32_stereo", "pcm24_stereo"])
+def test_demodulator_other_wav_sample_formats(dec, tmp_path, fmt):
+    """wefax.py:349 accepts whatever scipy.io.wavfile.read returns: 24 / 32-bit PCM (int32), IEEE float.  The
+    drop-in converts them on the host with the reference's arithmetic and feeds float32 to the same kernels."""
+    from scipy.io import wavfile
+    from test_host import write_wav_pcm24
+    from wefax_b200.wefax import Demodulator
+    base = synth.synth_recording(30.0, lpm=120, seed=77, noise_sigma=0.04).astype(np.int64)
+    other = np.roll(base, 5000) // 3
+    wav = str(tmp_path / f"{fmt}.wav")
+    stereo = fmt.endswith("_stereo")
+    kind = fmt.replace("_stereo", "")
+    cols = np.stack([base, other], axis=1) if stereo else base[:, None]
+    if kind == "pcm24":
+        write_wav_pcm24(wav, (cols * 200).astype(np.int32), 11025)
+    elif kind == "pcm32":
+        # the second channel is large enough for the stereo sum to wrap around int32
+        big = cols.astype(np.int64) * 60000
+        wavfile.write(wav, 11025, np.clip(big, -2 ** 31, 2 ** 31 - 1).astype(np.int32).squeeze())
+    elif kind == "float32":
+        wavfile.write(wav, 11025, (cols / 32768.0).astype(np.float32).squeeze())
+    else:
+        wavfile.write(wav, 11025, (cols / 32768.0).astype(np.float64).squeeze())
+    _, data = wavfile.read(wav)
+    x = _reference_ingest(data)
+    o = O.decode(x, 11025, 120)
+    d = Demodulator(wav, lines_per_minute=120, tcp_stream=False, quiet=True)
+    assert d.file_info()["channels"] == (2 if stereo else 1)
+    try:
+        d.process()
+        err = None
+    except (ValueError, IndexError) as exc:
+        err = [type(exc).__name__, str(exc)]
+    assert (err is None) == (o["error"] is None), (err, o["error"])
+    assert rel_err(d.audio_data, o["audio_data"]) < FLOAT_TOL
+    assert rel_err(d.demodulated_data, o["demodulated_data"]) < FLOAT_TOL
+    frac, worst = frac_within_one(d.digitalized_data, o["digitalized_data"])
+    assert frac >= PIXEL_FRACTION and worst <= 2, (frac, worst)
+    if err is None and list(d.phasing_signals) == list(o["phasing_signals"]):
+        frac, _ = frac_within_one(np.asarray(d.output_image), o["output_image"])
+        assert frac >= PIXEL_FRACTION
+
+
+def test_demodulator_concurrent_conversions(dec, tmp_path):
+    """main.py:53,294-309 keeps several conversions in flight, one request thread each.  Every thread gets its
+    own native context (no process-wide lock): results equal the sequential ones."""
+    import threading
+    from wefax_b200.wefax import Demodulator
+    wavs = []
+    for k, lpm in enumerate((120, 240, 120, 60)):
+        p = str(tmp_path / f"c{k}.wav")
+        synth.write_wav(p, synth.synth_recording(40.0 + k, lpm=lpm, seed=900 + k, noise_sigma=0.03), 11025)
+        wavs.append((p, lpm))
+    sequential = []
+    for p, lpm in wavs:
+        d = Demodulator(p, lines_per_minute=lpm, tcp_stream=False, quiet=True)
+        d.process()
+        sequential.append(d)
+    results, errors = [None] * len(wavs), []
+    barrier = threading.Barrier(len(wavs))
+
+    def work(i):
+        try:
+            p, lpm = wavs[i]
+            d = Demodulator(p, lines_per_minute=lpm, tcp_stream=True, quiet=True)
+            barrier.wait()
+            for _ in range(3):
+                d.process()
+            results[i] = d
+        except Exception as exc:   # surfaces in the main thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(wavs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for a, b in zip(results, sequential):
+        assert a.start_frame == b.start_frame and a.phasing_signals == b.phasing_signals
+        assert np.array_equal(a.digitalized_data, b.digitalized_data)
+        assert np.array_equal(np.asarray(a.output_image), np.asarray(b.output_image))
+        assert a.websocket_stack[-1] == {"data_type": "message", "message_content": "convert_end"}
+
+
 def test_full_size_60min_stage_properties(dec):
     """The 60-min / 39.69 M-sample recording the benchmark runs.  Every stage is checked
     against the oracle's stage applied to the CUDA path's own upstream output, which is

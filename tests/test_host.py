@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (wefax_[a-z0-9_]+)", out))
     assert set(N.EXPORTED_SYMBOLS) <= exported
-    assert lib.wefax_abi_version() == N.ABI_VERSION == 4
+    assert lib.wefax_abi_version() == N.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header():
@@ -138,11 +138,36 @@ def test_wav_reader_matches_scipy(tmp_path):
     wavfile.write(p, 8000, u8)
     sr2, d2 = wavio.read(p)
     assert sr2 == 8000 and d2.dtype == np.uint8 and np.array_equal(d2, u8)
-    f32 = rng.normal(size=100).astype(np.float32)
-    p = str(tmp_path / "f.wav")
-    wavfile.write(p, 8000, f32)
-    with pytest.raises(ValueError):
-        wavio.read(p)
+    # every sample format scipy.io.wavfile.read delivers (wefax.py:349 takes them all): same dtype, same values
+    for k, data in enumerate((rng.normal(size=100).astype(np.float32), rng.normal(size=(64, 2)).astype(np.float32),
+                              rng.normal(size=77), rng.integers(-2 ** 31, 2 ** 31 - 1, size=500, dtype=np.int32),
+                              rng.integers(-2 ** 31, 2 ** 31 - 1, size=(33, 2), dtype=np.int32))):
+        p = str(tmp_path / f"fmt{k}.wav")
+        wavfile.write(p, 8000, data)
+        sr2, d2 = wavio.read(p)
+        sr3, d3 = wavfile.read(p)
+        assert sr2 == sr3 == 8000 and d2.dtype == d3.dtype == data.dtype and np.array_equal(d2, d3)
+    for ch in (1, 2):
+        p = str(tmp_path / f"pcm24_{ch}.wav")
+        v = rng.integers(-2 ** 23, 2 ** 23 - 1, size=(321, ch), dtype=np.int32)
+        write_wav_pcm24(p, v, 22050)
+        sr2, d2 = wavio.read(p)
+        sr3, d3 = wavfile.read(p)
+        assert sr2 == sr3 == 22050 and d2.dtype == d3.dtype == np.int32 and np.array_equal(d2, d3)
+        assert np.array_equal(d2.reshape(321, ch), v * 256)   # left-justified, as scipy >= 1.6 stores 24-bit data
+
+
+def write_wav_pcm24(path, values, sample_rate):
+    """values: (n, channels) int32 in [-2^23, 2^23)."""
+    import struct
+    values = np.asarray(values, dtype=np.int32)
+    n, ch = values.shape
+    raw = (values.astype("<i4").view(np.uint8).reshape(n, ch, 4)[:, :, :3]).tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(raw)) + b"WAVE"
+    hdr += b"fmt " + struct.pack("<IHHIIHH", 16, 1, ch, sample_rate, sample_rate * ch * 3, ch * 3, 24)
+    hdr += b"data" + struct.pack("<I", len(raw))
+    with open(path, "wb") as fh:
+        fh.write(hdr + raw)
 
 
 def test_config_reads_reference_format(tmp_path, monkeypatch):

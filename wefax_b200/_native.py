@@ -17,7 +17,7 @@ TARGET_RATE = 11025
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 REC_OK, REC_NO_GROUPS, REC_NO_LINES, REC_NAN = 0, 1, 2, 4
-F_PCM_ON_DEVICE, F_OUT_ON_DEVICE = 1, 2
+F_PCM_ON_DEVICE, F_OUT_ON_DEVICE, F_PCM_FLOAT32 = 1, 2, 4
 
 #: every symbol include/wefax_b200.h declares
 EXPORTED_SYMBOLS = (
@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "wefax_segment_envelope", "wefax_segment_histogram", "wefax_segment_quantise", "wefax_segment_sync",
     "wefax_segment_raster",
 )
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class LineConstants(C.Structure):

@@ -397,6 +397,10 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
         cudaStream_t st = ctx->stream;
         const bool pcm_dev = desc->flags & WEFAX_F_PCM_ON_DEVICE;
         const bool out_dev = desc->flags & WEFAX_F_OUT_ON_DEVICE;
+        // float32 samples (the host side of WAV formats other than 16-bit PCM: int32 / 24-bit / float, wefax.py:349)
+        const bool pcm_f32 = desc->flags & WEFAX_F_PCM_FLOAT32;
+        if (pcm_f32 && ch != 1) WEFAX_THROW(WEFAX_ERR_INVALID, "float32 input must be mono (merge the channels on the host)");
+        const size_t esz = pcm_f32 ? sizeof(float) : sizeof(int16_t);
 
         // wefax.py:63: the frequency goes through int()
         const FirParams &fp = cached_fir(ctx, (double)(long long)desc->notch_freq, desc->notch_q);
@@ -424,7 +428,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             long long a = plan_factors(n_in, tmp) ? n_in : next_smooth_length(2 * n_in - 1);
             zlen_rs = std::max(a, zlen);
         }
-        const long long per_rec = (pcm_dev ? 0 : n_in * ch * 2) + (resample ? n_in * 4 + (n_in + n) * 8 : 0) +
+        const long long per_rec = (pcm_dev ? 0 : n_in * ch * (long long)esz) + (resample ? n_in * 4 + (n_in + n) * 8 : 0) +
                                   std::max(zlen, zlen_rs) * 8 + n * (4 + 4 + 4 + 1 + 4) + 4096;
         int wave = (int)std::max<long long>(1, std::min<long long>(nrec, ctx->workspace_limit / per_rec));
         wave = std::min(wave, 32768);
@@ -439,11 +443,11 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
         for (int w0 = 0; w0 < nrec; w0 += wave) {
             const int g = std::min(wave, nrec - w0);
             // ---- inputs ------------------------------------------------------------
-            const int16_t *d_pcm = pcm + (size_t)w0 * n_in * ch;
+            const int16_t *d_pcm = (const int16_t *)((const char *)pcm + (size_t)w0 * n_in * ch * esz);
             if (!pcm_dev) {
-                int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)g * n_in * ch * sizeof(int16_t));
+                int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)g * n_in * ch * esz);
                 StageTimer timer(ctx, "h2d_pcm");
-                CUDA_CHECK(cudaMemcpyAsync(buf, d_pcm, (size_t)g * n_in * ch * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+                CUDA_CHECK(cudaMemcpyAsync(buf, d_pcm, (size_t)g * n_in * ch * esz, cudaMemcpyHostToDevice, st));
                 d_pcm = buf;
             }
             memcpy(h_lines, lines.data() + w0, sizeof(LineDev) * g);
@@ -477,7 +481,10 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             if (resample) {
                 float *xin = (float *)ctx->resample_in.reserve(((size_t)g * n_in + (size_t)g * n) * sizeof(float));
                 float *xrs = xin + (size_t)g * n_in;
-                launch_ingest_float(ctx, d_pcm, (size_t)n_in, ch, xin, (size_t)n_in, n_in, g);
+                if (pcm_f32)
+                    xin = (float *)d_pcm;   // already float: the resampler reads it in place
+                else
+                    launch_ingest_float(ctx, d_pcm, (size_t)n_in, ch, xin, (size_t)n_in, n_in, g);
                 resample_real(ctx, n_in, n, xin, (size_t)n_in, xrs, (size_t)n, g);
                 // the resampler used work_z: take the (possibly re-allocated) buffer again
                 if (half)
@@ -486,8 +493,8 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                     z = zcopy = (float2 *)ctx->work_z.reserve((size_t)g * n * sizeof(float2));
                 launch_filtfilt(ctx, kInFloat, xrs, (size_t)n, d_audio, (size_t)n, zcopy, (size_t)n, n, fp, g);
             } else {
-                launch_filtfilt(ctx, ch == 2 ? kInStereoI16 : kInMonoI16, d_pcm, (size_t)n_in, d_audio, (size_t)n, zcopy,
-                                (size_t)n, n, fp, g);
+                launch_filtfilt(ctx, pcm_f32 ? kInFloat : (ch == 2 ? kInStereoI16 : kInMonoI16), d_pcm, (size_t)n_in, d_audio,
+                                (size_t)n, zcopy, (size_t)n, n, fp, g);
             }
             // ---- analytic-signal envelope (wefax.py:174) ------------------------------
             if (half)

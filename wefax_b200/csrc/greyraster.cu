@@ -155,25 +155,14 @@ __device__ __noinline__ void store4_any(uint8_t *p, uint32_t v, int count) {
         } else if (a == 2u) {
             *reinterpret_cast<uint16_t *>(p) = (uint16_t)v;
             *reinterpret_cast<uint16_t *>(p + 2) = (uint16_t)(v >> 16);
-        } else {
+        } else {   // odd address: p + 1 is even
             p[0] = (uint8_t)v;
-            if (a == 1u) {
-                *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(v >> 8);
-                p[3] = (uint8_t)(v >> 24);
-            } else {
-                p[1] = (uint8_t)(v >> 8);
-                *reinterpret_cast<uint16_t *>(p + 2) = (uint16_t)(v >> 16);
-            }
+            *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(v >> 8);
+            p[3] = (uint8_t)(v >> 24);
         }
     } else {
         for (int c = 0; c < count; ++c) p[c] = (uint8_t)(v >> (8 * c));
     }
-}
-
-template <bool ALIGNED>
-__device__ __forceinline__ void store_row4(uint8_t *p, uint32_t v, int ncols) {
-    if (ALIGNED && ncols >= kGrCols) *reinterpret_cast<uint32_t *>(p) = v;
-    else store4_any(p, v, ncols);
 }
 
 struct GreyQuant {
@@ -200,16 +189,33 @@ __device__ __forceinline__ uint32_t grey_estimate_u8(float m, float scale, float
     return k;
 }
 
+// Pillow's BICUBIC coefficients for the x4 up-scaling, rows whose 4 taps are all inside the image (precompute_coeffs
+// with a = -0.5, normalised, round(k * 2^22)): they depend on the phase yy % 4 only.  Phases 0 / 1 weigh lines
+// r-2 .. r+1, phases 2 / 3 (the mirror images) lines r-1 .. r+2.  launch_grey_raster() recomputes them with
+// Pillow's arithmetic and refuses to run if they differ.
+__host__ __device__ constexpr int bic_coeff(int ph, int t) {
+    // phases 2 / 3 mirror phases 1 / 0
+    return ph >= 2 ? bic_coeff(3 - ph, 3 - t)
+                   : (ph == 0 ? (t == 0 ? -184320 : t == 1 ? 1634304 : t == 2 ? 3051520 : -307200)
+                              : (t == 0 ? -28672 : t == 1 ? 380928 : t == 2 ? 4042752 : -200704));
+}
+constexpr int kBicBias = (1 << 21) + 255 * 4194304;   // (1 << 21) + 255 * sum: the raster works on 255 - level
+
+template <int PH>
+__device__ __forceinline__ int bic_phase(int a, int b, int c, int d) {
+    // acc = (1 << 21) + sum k_t * (255 - level_t) = bias - sum k_t * level_t
+    return (kBicBias - bic_coeff(PH, 0) * a - bic_coeff(PH, 1) * b - bic_coeff(PH, 2) * c - bic_coeff(PH, 3) * d) >> 22;
+}
+
 // One interior item: all its lines are image lines at least 2 lines from the image's first / last line, every
-// load stays inside the recording, the fp32 estimate is valid.  OFF: offset (in floats, mod 4) of the envelope
-// element two to the left of the item's first column from a 16-byte boundary, the same for every line when the
-// width is a multiple of 4 (then the raster rows are 4-byte aligned too: ALIGNED); OFF < 0: evaluated per line.
-// The line loop is deliberately NOT unrolled: its body (~220 instructions) stays resident in the instruction
-// cache; the price is the 16 moves that shift the 5-line window.
-template <int OFF, bool ALIGNED>
-__device__ __forceinline__ void interior_item(const GreyRasterParams &P, const GreyQuant &Q, const float *e, uint8_t *dg,
-                                              uint8_t *out, long long i_first, long long r_a, int nrows, int w, int c0,
-                                              int ncols) {
+// load stays inside the recording, the fp32 estimate is valid, the column group is complete.  OFF: offset (in
+// floats, mod 4) of the envelope element two to the left of the item's first column from a 16-byte boundary, the
+// same for every line when the width is a multiple of 4 (then the raster rows are 4-byte aligned too: ALIGNED);
+// OFF < 0: evaluated per line.  The line loop is deliberately NOT unrolled: its body (~200 instructions) stays
+// resident in the instruction cache; the price is the moves that shift the 5-line window.
+template <int OFF, bool ALIGNED, bool UNROLL5>
+__device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e, uint8_t *dg, uint8_t *out,
+                                              long long i_first, long long r_a, int nrows, int w, int c0) {
     int win[5][kGrCols];
     const float *prow = e + i_first - 2;   // x[0] of the line being fetched
     float4 nx[3];
@@ -221,14 +227,16 @@ __device__ __forceinline__ void interior_item(const GreyRasterParams &P, const G
     fetch();
     uint8_t *drow = dg ? dg + i_first : nullptr;        // digitalized of the line being computed
     uint8_t *orow = out + (size_t)(4 * r_a) * w + c0;   // raster rows of the line being emitted
+    const uint32_t dal = ALIGNED ? (uint32_t)(reinterpret_cast<uintptr_t>(drow) & 3u) : 0u;   // fixed per item when w % 4 == 0
 #pragma unroll
     for (int t = 0; t < 5; ++t)
 #pragma unroll
         for (int c = 0; c < kGrCols; ++c) win[t][c] = 0;
 
-#pragma unroll 1
-    for (int j = 0; j < nrows; ++j) {
-        // ---- grey levels of line r_a - 2 + j into the newest window slot ---------------------------------
+    // One line: grey levels of line r_a - 2 + j into l4 (the newest window line), its digitalized bytes, and the 4
+    // raster rows of line r_a + j - 4, whose window l0 .. l4 is now complete.
+    auto step = [&](int j, const int (&l0)[kGrCols], const int (&l1)[kGrCols], const int (&l2)[kGrCols],
+                    const int (&l3)[kGrCols], int (&l4)[kGrCols]) {
         float f[12];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -247,52 +255,83 @@ __device__ __forceinline__ void interior_item(const GreyRasterParams &P, const G
         }
         prow += w;
         if (j + 1 < nrows) fetch();   // the medians have consumed nx: the next line streams in under the rest of this one
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int c = 0; c < kGrCols; ++c) win[t][c] = win[t + 1][c];
-        bool bad = false;
+        uint32_t bad = 0u;
 #pragma unroll
         for (int c = 0; c < kGrCols; ++c) {
             const uint32_t k0 = grey_estimate_u8(m[c], Q.scale, Q.off);
             const uint2 t = Q.pairs[k0];
-            bad = bad || (__float_as_uint(m[c]) - t.x >= t.y);
-            win[4][c] = (int)k0;
+            bad |= (__float_as_uint(m[c]) - t.x >= t.y) ? 1u : 0u;
+            l4[c] = (int)k0;
         }
         if (bad) {   // some estimate is one level off (rare): redo the line with the corrected form
 #pragma unroll
-            for (int c = 0; c < kGrCols; ++c) win[4][c] = Q.level_fast(m[c]);
+            for (int c = 0; c < kGrCols; ++c) l4[c] = Q.level_fast(m[c]);
         }
         if (drow) {
             if (j >= 2 && j < nrows - 2) {
-                const uint32_t v = (uint32_t)win[4][0] | ((uint32_t)win[4][1] << 8) | ((uint32_t)win[4][2] << 16) |
-                                   ((uint32_t)win[4][3] << 24);
-                store4_any(drow, v, ncols);
+                const uint32_t v = (uint32_t)l4[0] | ((uint32_t)l4[1] << 8) | ((uint32_t)l4[2] << 16) | ((uint32_t)l4[3] << 24);
+                if (ALIGNED) {
+                    // start_frame fixes the alignment of every digitalized row of the item
+                    if (dal == 0u) {
+                        *reinterpret_cast<uint32_t *>(drow) = v;
+                    } else if (dal == 2u) {
+                        *reinterpret_cast<uint16_t *>(drow) = (uint16_t)v;
+                        *reinterpret_cast<uint16_t *>(drow + 2) = (uint16_t)(v >> 16);
+                    } else {
+                        drow[0] = (uint8_t)v;
+                        *reinterpret_cast<uint16_t *>(drow + 1) = (uint16_t)(v >> 8);
+                        drow[3] = (uint8_t)(v >> 24);
+                    }
+                } else {
+                    store4_any(drow, v, kGrCols);
+                }
             }
             drow += w;
         }
-        // ---- line r_a + j - 4 is complete: its 4 raster rows ---------------------------------------------------
         if (j >= 4) {
+            uint8_t *o = orow;
+            auto put = [&](int v0, int v1, int v2, int v3) {
+                const uint32_t px = pack4_sat(v0, v1, v2, v3);
+                if (ALIGNED) *reinterpret_cast<uint32_t *>(o) = px;
+                else store4_any(o, px, kGrCols);
+                o += w;
+            };
+            put(bic_phase<0>(l0[0], l1[0], l2[0], l3[0]), bic_phase<0>(l0[1], l1[1], l2[1], l3[1]),
+                bic_phase<0>(l0[2], l1[2], l2[2], l3[2]), bic_phase<0>(l0[3], l1[3], l2[3], l3[3]));
+            put(bic_phase<1>(l0[0], l1[0], l2[0], l3[0]), bic_phase<1>(l0[1], l1[1], l2[1], l3[1]),
+                bic_phase<1>(l0[2], l1[2], l2[2], l3[2]), bic_phase<1>(l0[3], l1[3], l2[3], l3[3]));
+            put(bic_phase<2>(l1[0], l2[0], l3[0], l4[0]), bic_phase<2>(l1[1], l2[1], l3[1], l4[1]),
+                bic_phase<2>(l1[2], l2[2], l3[2], l4[2]), bic_phase<2>(l1[3], l2[3], l3[3], l4[3]));
+            put(bic_phase<3>(l1[0], l2[0], l3[0], l4[0]), bic_phase<3>(l1[1], l2[1], l3[1], l4[1]),
+                bic_phase<3>(l1[2], l2[2], l3[2], l4[2]), bic_phase<3>(l1[3], l2[3], l3[3], l4[3]));
+            orow = o;
+        }
+    };
+
+    if (UNROLL5) {
+        // line j lives in window slot j % 5: no moves, five copies of the body
+        for (int jb = 0; jb < nrows; jb += 5) {
 #pragma unroll
-            for (int ph = 0; ph < 4; ++ph) {
-                const int b = ph < 2 ? 0 : 1;
-                int v[kGrCols];
+            for (int jj = 0; jj < 5; ++jj)
+                if (jb + jj < nrows)
+                    step(jb + jj, win[(jj + 1) % 5], win[(jj + 2) % 5], win[(jj + 3) % 5], win[(jj + 4) % 5], win[jj]);
+        }
+    } else {
+        // one copy of the body (~200 instructions, resident in the instruction cache); the window shifts by moves
+#pragma unroll 1
+        for (int j = 0; j < nrows; ++j) {
 #pragma unroll
-                for (int c = 0; c < kGrCols; ++c) {
-                    const int acc = P.ck[ph] + P.nk[ph][0] * win[b][c] + P.nk[ph][1] * win[b + 1][c] +
-                                    P.nk[ph][2] * win[b + 2][c] + P.nk[ph][3] * win[b + 3][c];
-                    v[c] = acc >> 22;
-                }
-                store_row4<ALIGNED>(orow + (size_t)ph * w, pack4_sat(v[0], v[1], v[2], v[3]), ncols);
-            }
-            orow += (size_t)4 * w;
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int c = 0; c < kGrCols; ++c) win[t][c] = win[t + 1][c];
+            step(j, win[0], win[1], win[2], win[3], win[4]);
         }
     }
 }
 
 // ALIGNED: the width of every recording of the launch is a multiple of 4 and the raster base / stride are 4-byte
 // aligned: all raster rows are, and the envelope rows of a recording share one 16-byte phase.
-template <bool ALIGNED>
+template <bool ALIGNED, bool UNROLL5>
 __global__ void __launch_bounds__(kGrThreads, 6) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
     __shared__ uint32_t s_T[260];
     __shared__ uint2 s_pairs[256];
@@ -339,18 +378,19 @@ __global__ void __launch_bounds__(kGrThreads, 6) grey_raster_kernel(const __grid
     uint8_t *out = P.raster ? P.raster + (size_t)rec * P.rs : nullptr;
 
     const long long i_first = s + (r_a - 2) * w + c0;   // sample (line r_a - 2, column c0)
-    const bool interior = Q.est_ok && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 && s + (r_b + 1) * w + c0 + 10 <= n;
+    const bool interior = Q.est_ok && ncols == kGrCols && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 &&
+                          s + (r_b + 1) * w + c0 + 10 <= n;
     if (interior) {
         const int nrows = (int)(r_b - r_a) + 4;
         if (ALIGNED) {
             switch ((int)((reinterpret_cast<uintptr_t>(e + i_first - 2) >> 2) & 3u)) {
-                case 0: interior_item<0, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
-                case 1: interior_item<1, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
-                case 2: interior_item<2, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
-                default: interior_item<3, true>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols); break;
+                case 0: interior_item<0, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
+                case 1: interior_item<1, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
+                case 2: interior_item<2, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
+                default: interior_item<3, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
             }
         } else {
-            interior_item<-1, false>(P, Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols);
+            interior_item<-1, false, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0);
         }
         return;
     }
@@ -459,6 +499,11 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
             sum += ki;
         }
         P.ck[ph] = (int)((1ll << 21) + 255 * sum);
+        for (int t = 0; t < 4; ++t) {
+            const int expect = bic_coeff(ph, t);
+            if (P.nk[ph][t] != -expect || P.ck[ph] != kBicBias)
+                WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "bicubic coefficient table does not match Pillow's arithmetic on this host");
+        }
     }
     // recordings by alignment class (LineDev.gr_class, set by api.cu from the width): the raster rows of a recording
     // are all 4-byte aligned when its width is a multiple of 4 and so are the raster base and stride
@@ -467,10 +512,10 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
     for (int r = 0; r < batch; ++r) count[h_lines[r].gr_class >= 1 ? 1 : 0]++;
     int per_sm = 6;
     {
-        const void *fn = (const void *)grey_raster_kernel<true>;
+        const void *fn = (const void *)grey_raster_kernel<true, false>;
         auto it = ctx->smem_configured.find(fn);
         if (it == ctx->smem_configured.end()) {
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<true>, kGrThreads, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<true, false>, kGrThreads, 0));
             if (per_sm < 1) per_sm = 1;
             ctx->smem_configured[fn] = per_sm;
         } else {
@@ -513,10 +558,15 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         long long max_items = 0;
         items_for(best_u, &max_items);
         dim3 grid((unsigned)((max_items + kGrThreads - 1) / kGrThreads), batch);
-        if (cls == 1 && base4)
-            grey_raster_kernel<true><<<grid, kGrThreads, 0, ctx->stream>>>(P);
-        else
-            grey_raster_kernel<false><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        const char *un = getenv("WEFAX_GR_UNROLL");   // "1": five unrolled copies of the line body instead of window moves
+        const bool unroll5 = un && un[0] == '1';
+        if (cls == 1 && base4) {
+            if (unroll5) grey_raster_kernel<true, true><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+            else grey_raster_kernel<true, false><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        } else {
+            if (unroll5) grey_raster_kernel<false, true><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+            else grey_raster_kernel<false, false><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        }
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }

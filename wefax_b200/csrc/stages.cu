@@ -217,7 +217,13 @@ notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride
     constexpr int TS = kFirTile;
     constexpr int NX = TS + 2 * KC;
     constexpr int W = 8 + 2 * KC;
-    __shared__ __align__(16) float s_x[2][NX];
+    // Shared-memory layout: chunks of 8 samples, 12 floats apart.  A thread's window is W / 8 whole chunks; with a
+    // 48-byte chunk pitch the 16-byte reads of the 8 lanes of a quarter-warp fall into 8 different bank groups (with
+    // the natural 32-byte pitch lanes t and t + 4 collide on every read).
+    constexpr int NXP = (NX / 8) * 12;
+    static_assert(KC % 4 == 0 && NX % 8 == 0, "chunked layout needs whole chunks");
+    auto sidx = [](int i) { return (i >> 3) * 12 + (i & 7); };
+    __shared__ __align__(16) float s_x[2][NXP];
     const int tid = threadIdx.x;
     const size_t base = (size_t)blockIdx.y * in_stride;
     int t = blockIdx.x;                                   // persistent: tiles t, t + gridDim.x, ...
@@ -250,10 +256,9 @@ notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride
                 f[2 * k] = (float)(short)(wv[k] & 0xffff);
                 f[2 * k + 1] = (float)(short)(wv[k] >> 16);
             }
-            float4 *dst = reinterpret_cast<float4 *>(&sx[KC + 8 * tid]);
-            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-            if (tid < 2 * KC) sx[tid < KC ? tid : TS + tid] = (float)ph;
+            *reinterpret_cast<float4 *>(&sx[sidx(KC + 8 * tid)]) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4 *>(&sx[sidx(KC + 8 * tid + 4)]) = make_float4(f[4], f[5], f[6], f[7]);
+            if (tid < 2 * KC) sx[sidx(tid < KC ? tid : TS + tid)] = (float)ph;
         } else {
             constexpr int ITER = (NX + kFirThreads - 1) / kFirThreads;
             float v[ITER];
@@ -265,7 +270,7 @@ notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride
 #pragma unroll
             for (int it = 0; it < ITER; ++it) {
                 const int j = tid + it * kFirThreads;
-                if (j < NX) sx[j] = v[it];
+                if (j < NX) sx[sidx(j)] = v[it];
             }
         }
         // one barrier per tile: the other buffer was last read before the previous barrier
@@ -277,7 +282,7 @@ notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride
         float w[W];
 #pragma unroll
         for (int q = 0; q < W / 4; ++q) {
-            const float4 x4 = *reinterpret_cast<const float4 *>(&sx[i0 + 4 * q]);
+            const float4 x4 = *reinterpret_cast<const float4 *>(&sx[sidx(i0 + 4 * q)]);
             w[4 * q] = x4.x; w[4 * q + 1] = x4.y; w[4 * q + 2] = x4.z; w[4 * q + 3] = x4.w;
         }
         float acc[8];

@@ -161,18 +161,25 @@ class Decoder:
             B, n, ch = shape[0], shape[1], 2
         else:
             raise ValueError(f"unsupported pcm shape {shape}")
+        as_float = False
         if on_dev_in:
             import torch
-            if pcm.dtype != torch.int16 or not pcm.is_contiguous():
-                raise ValueError("device pcm must be a contiguous int16 tensor")
+            if pcm.dtype not in (torch.int16, torch.float32) or not pcm.is_contiguous():
+                raise ValueError("device pcm must be a contiguous int16 (or mono float32) tensor")
+            as_float = pcm.dtype == torch.float32
             pcm_ptr = pcm.data_ptr()
         else:
             if _is_torch(pcm):
                 pcm = pcm.numpy()
-            if pcm.dtype != np.int16:
-                raise TypeError(f"pcm must be int16 (got {pcm.dtype}); other WAV sample formats are not supported")
+            if pcm.dtype == np.float32:
+                as_float = True   # WAV sample formats other than 16-bit PCM, converted by the caller (wefax.py:349)
+            elif pcm.dtype != np.int16:
+                raise TypeError(f"pcm must be int16 or float32 (got {pcm.dtype}); convert other WAV sample formats "
+                                "first (wefax_b200.wefax.Demodulator does)")
             pcm = np.ascontiguousarray(pcm)
             pcm_ptr = pcm.ctypes.data
+        if as_float and ch != 1:
+            raise ValueError("float32 input must be mono: merge the channels first (wefax.py:360-373)")
         lpms = [float(lpm)] * B if np.isscalar(lpm) else [float(v) for v in lpm]
         if len(lpms) != B:
             raise ValueError("need one lpm per recording")
@@ -185,11 +192,27 @@ class Decoder:
                 raise ValueError(f"unknown output {name!r}")
 
         keep = [pcm]
+        if out is not None:
+            keep.extend(out._keepalive)   # pinned tensors behind reused host buffers
         bufs = {}
 
         def alloc(name, shape_, dtype):
-            if out is not None and getattr(out, name if name != "raster" else "raster_flat") is not None:
-                return getattr(out, name if name != "raster" else "raster_flat")
+            prev = getattr(out, name if name != "raster" else "raster_flat") if out is not None else None
+            if prev is not None:
+                # a reused buffer must be exactly what this call would allocate: the native side writes
+                # B * n_out (or raster_stride) elements through the raw pointer
+                prev_dev = _is_torch(prev) and prev.is_cuda
+                prev_dtype = str(prev.dtype).replace("torch.", "")
+                if (tuple(prev.shape) != tuple(shape_) or prev_dtype != np.dtype(dtype).name
+                        or prev_dev != bool(device_outputs)
+                        or (prev_dev and prev.device.index != self.device)
+                        or (_is_torch(prev) and not prev.is_contiguous())
+                        or (not _is_torch(prev) and not prev.flags["C_CONTIGUOUS"])):
+                    raise ValueError(f"out.{name} has shape {tuple(prev.shape)} / dtype {prev_dtype} / "
+                                     f"{'device' if prev_dev else 'host'} memory; this call needs shape "
+                                     f"{tuple(shape_)}, {np.dtype(dtype).name}, "
+                                     f"{'device' if device_outputs else 'host'} memory")
+                return prev
             if device_outputs:
                 import torch
                 tdt = {np.float32: torch.float32, np.uint8: torch.uint8}[dtype]
@@ -228,7 +251,8 @@ class Decoder:
         o.status, o.low_high = status.ctypes.data, low_high.ctypes.data
 
         desc = N.BatchDesc(B, n, ch, sample_rate, float(notch_freq), float(notch_q),
-                           (N.F_PCM_ON_DEVICE if on_dev_in else 0) | (N.F_OUT_ON_DEVICE if device_outputs else 0))
+                           (N.F_PCM_ON_DEVICE if on_dev_in else 0) | (N.F_OUT_ON_DEVICE if device_outputs else 0) |
+                           (N.F_PCM_FLOAT32 if as_float else 0))
         lpm_arr = (C.c_double * B)(*lpms)
         self._check(self._lib.wefax_decode_batch(self._h, C.byref(desc), C.c_void_p(pcm_ptr),
                                                  C.cast(lpm_arr, C.c_void_p), C.byref(o)))

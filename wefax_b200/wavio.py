@@ -2,10 +2,10 @@
 ``scipy.io.wavfile.read``, wefax.py:343,349).
 
 Returns ``(sample_rate, data)`` with scipy's conventions: ``data`` is ``(n,)``
-for mono and ``(n, channels)`` otherwise, in the stored integer type (uint8 for
-8-bit, int16 for 16-bit PCM).  Only the formats the GPU ingest kernel consumes
-are accepted; anything else raises ``ValueError`` instead of being converted
-silently.
+for mono and ``(n, channels)`` otherwise, in the dtype scipy delivers (uint8,
+int16, int32 — 24-bit PCM left-justified —, float32, float64).  16-bit PCM is
+what the GPU ingest kernel eats directly; the drop-in class converts the other
+formats to float32 with the reference's arithmetic (wefax.py:360-373) first.
 """
 from __future__ import annotations
 
@@ -14,6 +14,7 @@ import struct
 import numpy as np
 
 WAVE_FORMAT_PCM = 0x0001
+WAVE_FORMAT_IEEE_FLOAT = 0x0003
 WAVE_FORMAT_EXTENSIBLE = 0xFFFE
 
 
@@ -48,15 +49,26 @@ def read_header(path: str) -> dict:
 
 
 def read(path: str):
-    """``scipy.io.wavfile.read`` for 8/16-bit PCM."""
+    """``scipy.io.wavfile.read``: ``(sample_rate, data)`` with scipy's dtypes — uint8 (8-bit PCM), int16, int32
+    (32-bit PCM, and 24-bit PCM left-justified in int32 as scipy >= 1.6 does), float32 / float64 (IEEE float)."""
     h = read_header(path)
-    if h["format_tag"] != WAVE_FORMAT_PCM or h["bits"] not in (8, 16):
-        raise ValueError(f"unsupported WAV sample format (tag {h['format_tag']}, {h['bits']} bit): "
-                         "the GPU ingest path takes 8/16-bit PCM")
-    dtype = np.uint8 if h["bits"] == 8 else np.dtype("<i2")
-    frame = h["channels"] * (h["bits"] // 8)
+    tag, bits = h["format_tag"], h["bits"]
+    frame = h["block_align"] or h["channels"] * ((bits + 7) // 8)
     n = h["data_bytes"] // frame
-    data = np.fromfile(path, dtype=dtype, count=n * h["channels"], offset=h["data_offset"])
+    count = n * h["channels"]
+    if tag == WAVE_FORMAT_PCM and bits in (8, 16, 32):
+        dtype = {8: np.uint8, 16: np.dtype("<i2"), 32: np.dtype("<i4")}[bits]
+        data = np.fromfile(path, dtype=dtype, count=count, offset=h["data_offset"])
+    elif tag == WAVE_FORMAT_PCM and bits == 24:
+        raw = np.fromfile(path, dtype=np.uint8, count=count * 3, offset=h["data_offset"]).reshape(-1, 3)
+        data = np.zeros((raw.shape[0], 4), dtype=np.uint8)
+        data[:, 1:] = raw                                   # little endian: the 24 bits become the top of an int32
+        data = data.view("<i4").reshape(-1)
+    elif tag == WAVE_FORMAT_IEEE_FLOAT and bits in (32, 64):
+        data = np.fromfile(path, dtype=np.dtype("<f4") if bits == 32 else np.dtype("<f8"), count=count,
+                           offset=h["data_offset"])
+    else:
+        raise ValueError(f"Unsupported bit depth: the WAV file has {bits}-bit data of format tag {tag}.")
     if h["channels"] > 1:
         data = data.reshape(n, h["channels"])
     return h["sample_rate"], data

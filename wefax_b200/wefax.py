@@ -80,11 +80,16 @@ class Demodulator:
         if stereo:
             self._log("\033[0;33mWARNING: two channels audio detected. Program will try to merge audio to one "
                       "channel\033[0m")
-            self._progress("merging channels", 0)
-            pcm = self._stereo_as_int16(pcm)
-            self._progress("merging channels", 100)
+            parts = pcm.shape[0]
+            for q in range(0, parts, 1000):                             # wefax.py:364-370: every 1000th frame ...
+                self._progress("merging channels", (q + 1) / parts * 100)
+            if parts and (parts - 1) % 1000 != 0:                       # ... and the last one
+                self._progress("merging channels", parts / parts * 100)
+            pcm = self._stereo_merge(pcm)
         elif pcm.dtype == np.uint8:
             pcm = pcm.astype(np.int16)                                  # same numeric values as the stored uint8
+        elif pcm.dtype != np.int16:
+            pcm = pcm.astype(np.float32)                                # int32 / 24-bit / float WAVs (wefax.py:349)
         self.sample_rate = sample_rate
         self.length = pcm.shape[0] / sample_rate                        # wefax.py:357
         resample = sample_rate != N.TARGET_RATE
@@ -144,15 +149,21 @@ class Demodulator:
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
-    def _stereo_as_int16(pcm: np.ndarray) -> np.ndarray:
-        """First two channels as int16 L/R whose wrapped sum / 2 equals the reference's
-        ``np.divide(np.add(L, R), 2)`` in the stored dtype (wefax.py:372)."""
+    def _stereo_merge(pcm: np.ndarray) -> np.ndarray:
+        """First two channels merged as the reference does, ``np.divide(np.add(L, R), 2)`` in the stored dtype
+        (wefax.py:372: the sum of two integer scalars WRAPS).  int16 goes to the GPU as interleaved L/R and is
+        merged by the ingest kernel; uint8 as a wrapped sum the kernel halves; every other sample format is merged
+        here with numpy's own arithmetic and handed over as mono float32."""
         if pcm.dtype == np.int16:
             return np.ascontiguousarray(pcm[:, :2])
-        s = np.add(pcm[:, 0], pcm[:, 1])                               # uint8: wraps at 256
-        out = np.zeros((pcm.shape[0], 2), dtype=np.int16)
-        out[:, 0] = s
-        return out
+        if pcm.dtype == np.uint8:
+            s = np.add(pcm[:, 0], pcm[:, 1])                            # wraps at 256
+            out = np.zeros((pcm.shape[0], 2), dtype=np.int16)
+            out[:, 0] = s
+            return out
+        with np.errstate(over="ignore"):
+            s = np.add(pcm[:, 0], pcm[:, 1])                            # int32 wraps; floats add in their own type
+        return np.divide(s, 2).astype(np.float32)
 
     def _log(self, text: str) -> None:
         if not self.quiet:
