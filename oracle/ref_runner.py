@@ -181,3 +181,17 @@ def run_reference_tones(samples: np.ndarray, sample_rate: int, lpm: int = 120) -
     with _in_reference_root():
         packet = dp.DataPacket(sample_rate, np.asarray(samples), lpm, "/tmp/", len(samples) / sample_rate, 0)
         return bool(packet.contain_start_tone()), bool(packet.contain_stop_tone())
+
+
+def run_reference_sync_pulse(samples: np.ndarray, sample_rate: int, lpm: int = 120) -> dict:
+    """``DataPacket.find_sync_pulse()`` of the unmodified reference for one packet (data_packet.py:301-343) and
+    the packet's processed samples (data_packet.py:408-419)."""
+    dp = import_reference_data_packet()
+    with _in_reference_root():
+        packet = dp.DataPacket(sample_rate, np.asarray(samples), lpm, "/tmp/", len(samples) / sample_rate, 0)
+        info = packet.find_sync_pulse()
+    return dict(pulse_found=bool(info["pulse_found"]), frequency_peak_found=bool(info["frequency_peak_found"]),
+                samples_peak_found=bool(info["samples_peak_found"]),
+                peaks_samples=[int(p) for p in info["peaks_samples"]],
+                n_fft_peaks=int(len(info["peaks_fft"][0])),
+                samples=np.asarray(packet.samples, dtype=np.int64))

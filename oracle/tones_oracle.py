@@ -130,6 +130,109 @@ def contain_stop_tone(raw_samples, sample_rate, settings=None) -> bool:
     return contain_tone(raw_samples, sample_rate, s["stop_distance"], s)
 
 
+# --------------------------------------------------------------------------- #
+# per-packet sync pulse (phasing gate of the live decoder)                      #
+# --------------------------------------------------------------------------- #
+#: config/config.json "sync_pulse_settings" of the reference (peaks_minimum_distance is read but never used)
+DEFAULT_SYNC_SETTINGS = dict(height=0.5, prominence=0.2, min_frequency=1400, max_frequency=1600)
+
+
+def process_samples(raw_samples: np.ndarray, sample_rate: int, notch_freq=2600, notch_q=1) -> np.ndarray:
+    """data_packet.py:408-465 ``__process_samples``: the packet's own notch (``iirnotch`` at the PACKET's sample
+    rate + ``filtfilt``), ``abs(hilbert)``, ``medfilt(., 3)`` (zero padded), then the 0.5 / 99.5 percentile
+    stretch ``rint(255 * (am - low) / (delta + 0.000001))`` clipped to 0..255, as int."""
+    from oracle import wefax_oracle as O
+    x = np.asarray(raw_samples, dtype=np.float64)
+    b, a = O.notch_coefficients(notch_freq, notch_q, sample_rate)
+    am = np.abs(O.hilbert(O.filtfilt(b, a, x)))
+    padded = np.concatenate([[0.0], am, [0.0]])
+    am = np.median(np.stack([padded[:-2], padded[1:-1], padded[2:]]), axis=0)
+    low, high = O.percentile_linear(am, 0.5), O.percentile_linear(am, 99.5)
+    d = np.rint(255 * (am - low) / ((high - low) + 0.000001))
+    return np.clip(d, 0, 255).astype(np.int64)
+
+
+def packet_pattern_search(samples: np.ndarray, sample_rate: int) -> list:
+    """data_packet.py:313-331: template ``[255] + [0]*samples(0.025) + [255]`` and signal both shifted by -128,
+    greedy picker seeded with the sentinel ``(-mindistance, 0)`` (which the first positive correlation within
+    ``mindistance`` REPLACES), no peak limit; the first entry of the list is dropped on return."""
+    n = len(samples)
+    length = n / sample_rate
+
+    def nsamp(x):
+        return int((x / length) * n)
+
+    k = nsamp(0.025)
+    mindistance = nsamp(0.4)
+    L = k + 2
+    d = np.asarray(samples, dtype=np.int64) - 128
+    csum = np.concatenate([[0], np.cumsum(d)])
+    m = n - L
+    if m <= 0:
+        return []
+    i = np.arange(m)
+    corr = 127 * d[i] + 127 * d[i + k + 1] - 128 * (csum[i + k + 1] - csum[i + 1])
+    peaks = [(-mindistance, 0)]
+    for pos in range(m):
+        c = int(corr[pos])
+        if pos - peaks[-1][0] > mindistance:
+            peaks.append((pos, c))
+        elif c > peaks[-1][1]:
+            peaks[-1] = (pos, c)
+    return [p[0] for p in peaks][1:]
+
+
+def find_sync_pulse(raw_samples: np.ndarray, sample_rate: int, settings=None, notch_freq=2600, notch_q=1) -> dict:
+    """data_packet.py:301-343: exactly one spectral peak (height 0.5, prominence 0.2, NO distance filter), inside
+    1400..1600 Hz, and at least one pulse position from the template search on the packet's own grey levels."""
+    s = dict(DEFAULT_SYNC_SETTINGS, **(settings or {}))
+    freq, amp = fourier_transform(raw_samples, sample_rate)
+    peaks = find_peaks(amp, 1, s["height"], s["prominence"])
+    in_range = all(s["min_frequency"] <= f <= s["max_frequency"] for f in freq[peaks])
+    pulses = packet_pattern_search(process_samples(raw_samples, sample_rate, notch_freq, notch_q), sample_rate)
+    freq_found = bool(in_range and len(peaks) == 1)
+    return dict(frequency_peak_found=freq_found, samples_peak_found=bool(pulses),
+                pulse_found=bool(freq_found and pulses), n_fft_peaks=int(len(peaks)),
+                peaks_samples=[int(p) for p in pulses])
+
+
+def state_machine(pcm: np.ndarray, sample_rate: int, packet_seconds: float = 1.0, settings=None, sync_settings=None):
+    """wefax_live.py:175-200 run over the consecutive packets of a recording: start tone for >= 4 s of consecutive
+    packets, THEN the first packet whose sync pulse is found starts the picture at its last pulse
+    (``data_points = packet.samples[peaks_samples[-1]:]``), THEN the stop tone for >= 4 s ends it.  Returns the
+    list of ``(start_packet, image_start_sample, stop_packet)`` (entries are None where the recording ends first)."""
+    plen = int(sample_rate * packet_seconds)
+    npk = pcm.shape[0] // plen
+    out = []
+    start_found = phasing_found = False
+    n_start = n_stop = 0
+    cur = None
+    for k in range(npk):
+        seg = pcm[k * plen:(k + 1) * plen]
+        if not start_found:
+            n_start = n_start + 1 if contain_start_tone(seg, sample_rate, settings) else 0
+            if n_start * packet_seconds >= 4:
+                start_found = True
+                cur = [k, None, None]
+        if start_found and not phasing_found:
+            info = find_sync_pulse(seg, sample_rate, sync_settings)
+            if info["pulse_found"]:
+                phasing_found = True
+                cur[1] = k * plen + info["peaks_samples"][-1]
+        if start_found and phasing_found:
+            n_stop = n_stop + 1 if contain_stop_tone(seg, sample_rate, settings) else 0
+            if n_stop * packet_seconds >= 4:
+                cur[2] = k
+                out.append(tuple(cur))
+                # the live decoder ends its session here; a file scan looks for the next transmission
+                start_found = phasing_found = False
+                n_start = n_stop = 0
+                cur = None
+    if cur is not None:
+        out.append(tuple(cur))
+    return out
+
+
 def scan(pcm: np.ndarray, sample_rate: int, packet_seconds: float = 1.0, settings=None):
     """Start / stop flags of consecutive packets of a recording (what the live state machine,
     wefax_live.py:175-200, evaluates packet by packet)."""

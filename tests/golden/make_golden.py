@@ -160,6 +160,13 @@ TONE_CASES = {
 }
 
 
+def sync_entry(sp: dict) -> dict:
+    """DataPacket.find_sync_pulse() of the reference for one packet + a digest of its processed samples."""
+    return dict(pulse_found=sp["pulse_found"], frequency_peak_found=sp["frequency_peak_found"],
+                samples_peak_found=sp["samples_peak_found"], n_fft_peaks=sp["n_fft_peaks"],
+                peaks_samples=sp["peaks_samples"], samples_sha256=sha(sp["samples"].astype(np.uint8)))
+
+
 def make_tones() -> None:
     """tests/golden/tones.json: contain_start_tone / contain_stop_tone of the reference's DataPacket."""
     from scipy.io import wavfile
@@ -167,14 +174,17 @@ def make_tones() -> None:
     for name in ("image.wav", "stop_tone.wav", "start_tone.wav", "start_tone_noisy.wav", "start_tone_start.wav"):
         sr, pcm = wavfile.read(os.path.join(FIXTURE_DIR, name))
         start, stop = ref_runner.run_reference_tones(pcm, sr)
-        out["fixtures"][name] = dict(sample_rate=int(sr), start=start, stop=stop)
-        print(name, sr, start, stop)
+        sp = ref_runner.run_reference_sync_pulse(pcm, sr)
+        out["fixtures"][name] = dict(sample_rate=int(sr), start=start, stop=stop, sync_pulse=sync_entry(sp))
+        print(name, sr, start, stop, sp["pulse_found"], sp["peaks_samples"])
     for name, kw in TONE_CASES.items():
         pcm = synth.synth_recording(**kw)
         flags = [ref_runner.run_reference_tones(pcm[k * 11025:(k + 1) * 11025], 11025, kw["lpm"])
                  for k in range(pcm.shape[0] // 11025)]
+        pulses = [ref_runner.run_reference_sync_pulse(pcm[k * 11025:(k + 1) * 11025], 11025, kw["lpm"])
+                  for k in range(pcm.shape[0] // 11025)]
         out["synthetic"][name] = dict(synth=kw, pcm_sha256=sha(pcm), start=[f[0] for f in flags],
-                                      stop=[f[1] for f in flags])
+                                      stop=[f[1] for f in flags], sync_pulse=[sync_entry(p) for p in pulses])
         print(name, "start:", "".join("1" if f[0] else "." for f in flags), "stop:",
               "".join("1" if f[1] else "." for f in flags))
     with open(os.path.join(HERE, "tones.json"), "w") as fh:

@@ -638,7 +638,7 @@ def test_decode_rejects_what_the_reference_rejects(dec):
     with pytest.raises(ValueError, match="greater than padlen"):
         dec.decode(np.zeros(9, dtype=np.int16), 11025, 120)
     with pytest.raises(TypeError):
-        dec.decode(np.zeros(100, dtype=np.float32), 11025, 120)
+        dec.decode(np.zeros(100, dtype=np.float64), 11025, 120)
     with pytest.raises(Exception):
         dec.decode(np.zeros(5000, dtype=np.int16), 11025, 0)
 

@@ -20,7 +20,7 @@
 namespace wefax {
 
 constexpr int kGrThreads = 128;
-constexpr int kGrCols = 4;   // columns per thread
+constexpr int kGrCols = 8;   // columns per thread
 
 // exact grey level of a median value (same operations, in the same order, as numpy: wefax.py:197-200, 216)
 __device__ __forceinline__ int grey_level_exact(float m, double low, double delta) {
@@ -145,23 +145,33 @@ __device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
     return d;
 }
 
-// 4 bytes to an address of any alignment, first `count` bytes only when count < 4
-// (out of line: the hot loop only comes here for unaligned rows and the last, partial column group of a line)
-__device__ __noinline__ void store4_any(uint8_t *p, uint32_t v, int count) {
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
-    if (count >= 4) {
+// kGrCols bytes (lo = bytes 0..3) to an address of any alignment, first `count` bytes only when count < kGrCols
+// (out of line: the hot loop only comes here for rows of unaligned widths; the generic items use it throughout)
+__device__ __noinline__ void store_any(uint8_t *p, uint32_t lo, uint32_t hi, int count) {
+    if (count >= kGrCols) {
+        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
         if (a == 0u) {
-            *reinterpret_cast<uint32_t *>(p) = v;
-        } else if (a == 2u) {
-            *reinterpret_cast<uint16_t *>(p) = (uint16_t)v;
-            *reinterpret_cast<uint16_t *>(p + 2) = (uint16_t)(v >> 16);
-        } else {   // odd address: p + 1 is even
-            p[0] = (uint8_t)v;
-            *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(v >> 8);
-            p[3] = (uint8_t)(v >> 24);
+            *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
+        } else if (a == 4u) {
+            reinterpret_cast<uint32_t *>(p)[0] = lo;
+            reinterpret_cast<uint32_t *>(p)[1] = hi;
+        } else if ((a & 1u) == 0u) {   // 2 or 6
+            *reinterpret_cast<uint16_t *>(p) = (uint16_t)lo;
+            *reinterpret_cast<uint32_t *>(p + 2) = __funnelshift_r(lo, hi, 16);
+            *reinterpret_cast<uint16_t *>(p + 6) = (uint16_t)(hi >> 16);
+        } else if ((a & 3u) == 3u) {   // 3 or 7: p + 1 is 4-byte aligned
+            p[0] = (uint8_t)lo;
+            *reinterpret_cast<uint32_t *>(p + 1) = __funnelshift_r(lo, hi, 8);
+            *reinterpret_cast<uint16_t *>(p + 5) = (uint16_t)(hi >> 8);
+            p[7] = (uint8_t)(hi >> 24);
+        } else {                       // 1 or 5: p + 3 is 4-byte aligned
+            p[0] = (uint8_t)lo;
+            *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(lo >> 8);
+            *reinterpret_cast<uint32_t *>(p + 3) = __funnelshift_r(lo, hi, 24);
+            p[7] = (uint8_t)(hi >> 24);
         }
     } else {
-        for (int c = 0; c < count; ++c) p[c] = (uint8_t)(v >> (8 * c));
+        for (int c = 0; c < count; ++c) p[c] = (uint8_t)((c < 4 ? lo >> (8 * c) : hi >> (8 * (c - 4))) & 0xFFu);
     }
 }
 
@@ -201,142 +211,182 @@ __host__ __device__ constexpr int bic_coeff(int ph, int t) {
 }
 constexpr int kBicBias = (1 << 21) + 255 * 4194304;   // (1 << 21) + 255 * sum: the raster works on 255 - level
 
+// The same row in fp32, two columns per instruction (FFMA2).  Every coefficient is a multiple of 4096 and the four
+// of a phase sum to 2^22, so   ((1 << 21) + sum k_t (255 - g_t)) >> 22  =  floor(255.5 - sum (k_t / 2^22) g_t)
+// and every partial sum is a multiple of 2^-10 below 2^11 in magnitude: exact in fp32.
+static_assert(bic_coeff(0, 0) % 4096 == 0 && bic_coeff(0, 1) % 4096 == 0 && bic_coeff(0, 2) % 4096 == 0 &&
+              bic_coeff(0, 3) % 4096 == 0 && bic_coeff(1, 0) % 4096 == 0 && bic_coeff(1, 1) % 4096 == 0 &&
+              bic_coeff(1, 2) % 4096 == 0 && bic_coeff(1, 3) % 4096 == 0, "coefficients are multiples of 2^12");
+static_assert(bic_coeff(0, 0) + bic_coeff(0, 1) + bic_coeff(0, 2) + bic_coeff(0, 3) == 4194304 &&
+              bic_coeff(1, 0) + bic_coeff(1, 1) + bic_coeff(1, 2) + bic_coeff(1, 3) == 4194304, "coefficients sum to 2^22");
+
+__device__ __forceinline__ float2 gr_fma2(float w, float2 x, float2 acc) {
+    float2 r;
+    asm("{.reg .b64 ta, tb, tc, tr; mov.b64 ta, {%2,%3}; mov.b64 tb, {%4,%4}; mov.b64 tc, {%5,%6}; "
+        "fma.rn.f32x2 tr, ta, tb, tc; mov.b64 {%0,%1}, tr;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(x.x), "f"(x.y), "f"(w), "f"(acc.x), "f"(acc.y));
+    return r;
+}
+__device__ __forceinline__ int gr_floor(float x) {
+    int k;
+    asm("cvt.rmi.s32.f32 %0, %1;" : "=r"(k) : "f"(x));
+    return k;
+}
+
 template <int PH>
-__device__ __forceinline__ int bic_phase(int a, int b, int c, int d) {
-    // acc = (1 << 21) + sum k_t * (255 - level_t) = bias - sum k_t * level_t
-    return (kBicBias - bic_coeff(PH, 0) * a - bic_coeff(PH, 1) * b - bic_coeff(PH, 2) * c - bic_coeff(PH, 3) * d) >> 22;
+__device__ __forceinline__ float2 bic_phase2(float2 a, float2 b, float2 c, float2 d) {
+    constexpr float w0 = -(float)bic_coeff(PH, 0) / 4194304.f, w1 = -(float)bic_coeff(PH, 1) / 4194304.f;
+    constexpr float w2 = -(float)bic_coeff(PH, 2) / 4194304.f, w3 = -(float)bic_coeff(PH, 3) / 4194304.f;
+    float2 acc = make_float2(255.5f, 255.5f);
+    acc = gr_fma2(w0, a, acc);
+    acc = gr_fma2(w1, b, acc);
+    acc = gr_fma2(w2, c, acc);
+    acc = gr_fma2(w3, d, acc);
+    return acc;
 }
 
 // One interior item: all its lines are image lines at least 2 lines from the image's first / last line, every
 // load stays inside the recording, the fp32 estimate is valid, the column group is complete.  OFF: offset (in
 // floats, mod 4) of the envelope element two to the left of the item's first column from a 16-byte boundary, the
-// same for every line when the width is a multiple of 4 (then the raster rows are 4-byte aligned too: ALIGNED);
-// OFF < 0: evaluated per line.  The line loop is deliberately NOT unrolled: its body (~200 instructions) stays
-// resident in the instruction cache; the price is the moves that shift the 5-line window.
-template <int OFF, bool ALIGNED, bool UNROLL5>
+// same for every line when the width is a multiple of 4; OFF < 0: evaluated per line.  ALIGN: alignment every
+// raster row of the item is known to have (8, 4, or 0 = anything).  HAS_DIG: digitalized is written.
+// The line loop is deliberately NOT unrolled: its body stays resident in the instruction cache; the price is the
+// moves that shift the 5-line window (grey levels as floats, two columns per register pair).
+template <int OFF, int ALIGN, bool HAS_DIG>
 __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e, uint8_t *dg, uint8_t *out,
                                               long long i_first, long long r_a, int nrows, int w, int c0) {
-    int win[5][kGrCols];
+    constexpr int NP = kGrCols / 2;
+    float2 win[5][NP];
     const float *prow = e + i_first - 2;   // x[0] of the line being fetched
-    float4 nx[3];
+    float4 nx[4];
     auto fetch = [&]() {
         const float4 *pa = reinterpret_cast<const float4 *>(reinterpret_cast<uintptr_t>(prow) & ~(uintptr_t)15);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) nx[q] = __ldg(pa + q);
+        for (int q = 0; q < 4; ++q) nx[q] = __ldg(pa + q);
     };
     fetch();
-    uint8_t *drow = dg ? dg + i_first : nullptr;        // digitalized of the line being computed
+    uint8_t *drow = dg + i_first;                       // digitalized of the line being computed
     uint8_t *orow = out + (size_t)(4 * r_a) * w + c0;   // raster rows of the line being emitted
-    const uint32_t dal = ALIGNED ? (uint32_t)(reinterpret_cast<uintptr_t>(drow) & 3u) : 0u;   // fixed per item when w % 4 == 0
+    const uint32_t dal = (uint32_t)(reinterpret_cast<uintptr_t>(drow) & 7u);   // fixed per item when ALIGN == 8
 #pragma unroll
     for (int t = 0; t < 5; ++t)
 #pragma unroll
-        for (int c = 0; c < kGrCols; ++c) win[t][c] = 0;
+        for (int c = 0; c < NP; ++c) win[t][c] = make_float2(0.f, 0.f);
 
-    // One line: grey levels of line r_a - 2 + j into l4 (the newest window line), its digitalized bytes, and the 4
-    // raster rows of line r_a + j - 4, whose window l0 .. l4 is now complete.
-    auto step = [&](int j, const int (&l0)[kGrCols], const int (&l1)[kGrCols], const int (&l2)[kGrCols],
-                    const int (&l3)[kGrCols], int (&l4)[kGrCols]) {
-        float f[12];
+#pragma unroll 1
+    for (int j = 0; j < nrows; ++j) {
+        // ---- grey levels of line r_a - 2 + j ----------------------------------------------------------------
+        float f[16];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < 4; ++q) {
             f[4 * q] = nx[q].x; f[4 * q + 1] = nx[q].y; f[4 * q + 2] = nx[q].z; f[4 * q + 3] = nx[q].w;
         }
         float m[kGrCols];
         if (OFF >= 0) {
-            med4_from12<(OFF >= 0 ? OFF : 0)>(f, m);
+            med8_from16<(OFF >= 0 ? OFF : 0)>(f, m);
         } else {
             switch ((int)((reinterpret_cast<uintptr_t>(prow) >> 2) & 3u)) {
-                case 0: med4_from12<0>(f, m); break;
-                case 1: med4_from12<1>(f, m); break;
-                case 2: med4_from12<2>(f, m); break;
-                default: med4_from12<3>(f, m); break;
+                case 0: med8_from16<0>(f, m); break;
+                case 1: med8_from16<1>(f, m); break;
+                case 2: med8_from16<2>(f, m); break;
+                default: med8_from16<3>(f, m); break;
             }
         }
         prow += w;
         if (j + 1 < nrows) fetch();   // the medians have consumed nx: the next line streams in under the rest of this one
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int c = 0; c < NP; ++c) win[t][c] = win[t + 1][c];
+        uint32_t g[kGrCols];
         uint32_t bad = 0u;
 #pragma unroll
         for (int c = 0; c < kGrCols; ++c) {
-            const uint32_t k0 = grey_estimate_u8(m[c], Q.scale, Q.off);
-            const uint2 t = Q.pairs[k0];
+            g[c] = grey_estimate_u8(m[c], Q.scale, Q.off);
+            const uint2 t = Q.pairs[g[c]];
             bad |= (__float_as_uint(m[c]) - t.x >= t.y) ? 1u : 0u;
-            l4[c] = (int)k0;
         }
         if (bad) {   // some estimate is one level off (rare): redo the line with the corrected form
 #pragma unroll
-            for (int c = 0; c < kGrCols; ++c) l4[c] = Q.level_fast(m[c]);
+            for (int c = 0; c < kGrCols; ++c) g[c] = (uint32_t)Q.level_fast(m[c]);
         }
-        if (drow) {
+#pragma unroll
+        for (int c = 0; c < NP; ++c) win[4][c] = make_float2((float)g[2 * c], (float)g[2 * c + 1]);
+        if (HAS_DIG) {
             if (j >= 2 && j < nrows - 2) {
-                const uint32_t v = (uint32_t)l4[0] | ((uint32_t)l4[1] << 8) | ((uint32_t)l4[2] << 16) | ((uint32_t)l4[3] << 24);
-                if (ALIGNED) {
+                const uint32_t lo = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24);
+                const uint32_t hi = g[4] | (g[5] << 8) | (g[6] << 16) | (g[7] << 24);
+                if (ALIGN == 8) {
                     // start_frame fixes the alignment of every digitalized row of the item
                     if (dal == 0u) {
-                        *reinterpret_cast<uint32_t *>(drow) = v;
-                    } else if (dal == 2u) {
-                        *reinterpret_cast<uint16_t *>(drow) = (uint16_t)v;
-                        *reinterpret_cast<uint16_t *>(drow + 2) = (uint16_t)(v >> 16);
+                        *reinterpret_cast<uint2 *>(drow) = make_uint2(lo, hi);
+                    } else if (dal == 4u) {
+                        reinterpret_cast<uint32_t *>(drow)[0] = lo;
+                        reinterpret_cast<uint32_t *>(drow)[1] = hi;
+                    } else if ((dal & 1u) == 0u) {
+                        *reinterpret_cast<uint16_t *>(drow) = (uint16_t)lo;
+                        *reinterpret_cast<uint32_t *>(drow + 2) = __funnelshift_r(lo, hi, 16);
+                        *reinterpret_cast<uint16_t *>(drow + 6) = (uint16_t)(hi >> 16);
+                    } else if ((dal & 3u) == 3u) {
+                        drow[0] = (uint8_t)lo;
+                        *reinterpret_cast<uint32_t *>(drow + 1) = __funnelshift_r(lo, hi, 8);
+                        *reinterpret_cast<uint16_t *>(drow + 5) = (uint16_t)(hi >> 8);
+                        drow[7] = (uint8_t)(hi >> 24);
                     } else {
-                        drow[0] = (uint8_t)v;
-                        *reinterpret_cast<uint16_t *>(drow + 1) = (uint16_t)(v >> 8);
-                        drow[3] = (uint8_t)(v >> 24);
+                        drow[0] = (uint8_t)lo;
+                        *reinterpret_cast<uint16_t *>(drow + 1) = (uint16_t)(lo >> 8);
+                        *reinterpret_cast<uint32_t *>(drow + 3) = __funnelshift_r(lo, hi, 24);
+                        drow[7] = (uint8_t)(hi >> 24);
                     }
                 } else {
-                    store4_any(drow, v, kGrCols);
+                    store_any(drow, lo, hi, kGrCols);
                 }
             }
             drow += w;
         }
+        // ---- line r_a + j - 4 is complete: its 4 raster rows ---------------------------------------------------
         if (j >= 4) {
             uint8_t *o = orow;
-            auto put = [&](int v0, int v1, int v2, int v3) {
-                const uint32_t px = pack4_sat(v0, v1, v2, v3);
-                if (ALIGNED) *reinterpret_cast<uint32_t *>(o) = px;
-                else store4_any(o, px, kGrCols);
+            auto put = [&](const float2 (&v)[NP]) {
+                const uint32_t lo = pack4_sat(gr_floor(v[0].x), gr_floor(v[0].y), gr_floor(v[1].x), gr_floor(v[1].y));
+                const uint32_t hi = pack4_sat(gr_floor(v[2].x), gr_floor(v[2].y), gr_floor(v[3].x), gr_floor(v[3].y));
+                if (ALIGN == 8) {
+                    *reinterpret_cast<uint2 *>(o) = make_uint2(lo, hi);
+                } else if (ALIGN == 4) {
+                    reinterpret_cast<uint32_t *>(o)[0] = lo;
+                    reinterpret_cast<uint32_t *>(o)[1] = hi;
+                } else {
+                    store_any(o, lo, hi, kGrCols);
+                }
                 o += w;
             };
-            put(bic_phase<0>(l0[0], l1[0], l2[0], l3[0]), bic_phase<0>(l0[1], l1[1], l2[1], l3[1]),
-                bic_phase<0>(l0[2], l1[2], l2[2], l3[2]), bic_phase<0>(l0[3], l1[3], l2[3], l3[3]));
-            put(bic_phase<1>(l0[0], l1[0], l2[0], l3[0]), bic_phase<1>(l0[1], l1[1], l2[1], l3[1]),
-                bic_phase<1>(l0[2], l1[2], l2[2], l3[2]), bic_phase<1>(l0[3], l1[3], l2[3], l3[3]));
-            put(bic_phase<2>(l1[0], l2[0], l3[0], l4[0]), bic_phase<2>(l1[1], l2[1], l3[1], l4[1]),
-                bic_phase<2>(l1[2], l2[2], l3[2], l4[2]), bic_phase<2>(l1[3], l2[3], l3[3], l4[3]));
-            put(bic_phase<3>(l1[0], l2[0], l3[0], l4[0]), bic_phase<3>(l1[1], l2[1], l3[1], l4[1]),
-                bic_phase<3>(l1[2], l2[2], l3[2], l4[2]), bic_phase<3>(l1[3], l2[3], l3[3], l4[3]));
+            float2 v[NP];
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<0>(win[0][c], win[1][c], win[2][c], win[3][c]);
+            put(v);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<1>(win[0][c], win[1][c], win[2][c], win[3][c]);
+            put(v);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<2>(win[1][c], win[2][c], win[3][c], win[4][c]);
+            put(v);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<3>(win[1][c], win[2][c], win[3][c], win[4][c]);
+            put(v);
             orow = o;
-        }
-    };
-
-    if (UNROLL5) {
-        // line j lives in window slot j % 5: no moves, five copies of the body
-        for (int jb = 0; jb < nrows; jb += 5) {
-#pragma unroll
-            for (int jj = 0; jj < 5; ++jj)
-                if (jb + jj < nrows)
-                    step(jb + jj, win[(jj + 1) % 5], win[(jj + 2) % 5], win[(jj + 3) % 5], win[(jj + 4) % 5], win[jj]);
-        }
-    } else {
-        // one copy of the body (~200 instructions, resident in the instruction cache); the window shifts by moves
-#pragma unroll 1
-        for (int j = 0; j < nrows; ++j) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-#pragma unroll
-                for (int c = 0; c < kGrCols; ++c) win[t][c] = win[t + 1][c];
-            step(j, win[0], win[1], win[2], win[3], win[4]);
         }
     }
 }
 
-// ALIGNED: the width of every recording of the launch is a multiple of 4 and the raster base / stride are 4-byte
-// aligned: all raster rows are, and the envelope rows of a recording share one 16-byte phase.
-template <bool ALIGNED, bool UNROLL5>
-__global__ void __launch_bounds__(kGrThreads, 6) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
+// ALIGN: alignment every raster row of the launch's recordings is known to have: 8 (width % 8 == 0), 4 (width % 4 == 0)
+// or 0 (anything); for 8 and 4 the envelope rows of a recording also share one 16-byte phase.
+template <int ALIGN>
+__global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
     __shared__ uint32_t s_T[260];
     __shared__ uint2 s_pairs[256];
     const int rec = blockIdx.y;
-    if (P.only_class >= 0 && (P.lines[rec].gr_class >= 1 ? 1 : 0) != P.only_class) return;
+    if (P.only_class >= 0 && P.lines[rec].gr_class != P.only_class) return;
     const RecResult *res = P.res + rec;
     const GreyTable *tab = P.tables + rec;
     for (int i = threadIdx.x; i < 257; i += kGrThreads) s_T[i] = tab->T[i];
@@ -379,23 +429,27 @@ __global__ void __launch_bounds__(kGrThreads, 6) grey_raster_kernel(const __grid
 
     const long long i_first = s + (r_a - 2) * w + c0;   // sample (line r_a - 2, column c0)
     const bool interior = Q.est_ok && ncols == kGrCols && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 &&
-                          s + (r_b + 1) * w + c0 + 10 <= n;
+                          s + (r_b + 1) * w + c0 + 14 <= n;
     if (interior) {
         const int nrows = (int)(r_b - r_a) + 4;
-        if (ALIGNED) {
+#define WEFAX_GR_RUN(OFF_)                                                                        \
+    if (dg) interior_item<OFF_, ALIGN, true>(Q, e, dg, out, i_first, r_a, nrows, w, c0);          \
+    else interior_item<OFF_, ALIGN, false>(Q, e, dg, out, i_first, r_a, nrows, w, c0);
+        if (ALIGN >= 4) {
             switch ((int)((reinterpret_cast<uintptr_t>(e + i_first - 2) >> 2) & 3u)) {
-                case 0: interior_item<0, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
-                case 1: interior_item<1, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
-                case 2: interior_item<2, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
-                default: interior_item<3, true, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0); break;
+                case 0: WEFAX_GR_RUN(0) break;
+                case 1: WEFAX_GR_RUN(1) break;
+                case 2: WEFAX_GR_RUN(2) break;
+                default: WEFAX_GR_RUN(3) break;
             }
         } else {
-            interior_item<-1, false, UNROLL5>(Q, e, dg, out, i_first, r_a, nrows, w, c0);
+            WEFAX_GR_RUN(-1)
         }
+#undef WEFAX_GR_RUN
         return;
     }
 
-    // ---- generic items: recording / image edges, recordings without an image -----------------------------
+    // ---- generic items: recording / image edges, partial column groups, recordings without an image ------
     int win[5][kGrCols];
 #pragma unroll
     for (int t = 0; t < 5; ++t)
@@ -404,17 +458,18 @@ __global__ void __launch_bounds__(kGrThreads, 6) grey_raster_kernel(const __grid
     // only lines that feed a raster row of this item or are its own need grey levels
     const bool any_raster = out && r_a < h && r_b > 0;
     const long long r_from = any_raster ? r_a - 2 : r_a, r_to = any_raster ? r_b + 2 : r_b;
+#pragma unroll 1
     for (long long r = r_from; r < r_to; ++r) {
         const long long i0 = s + r * w + c0;
-        float f[12];
+        float f[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 12; ++j) {
             const long long i = i0 - 2 + j;
             f[j] = (i >= 0 && i < n) ? __ldg(e + i) : 0.f;
         }
-        f[8] = f[9] = f[10] = f[11] = 0.f;
+        f[12] = f[13] = f[14] = f[15] = 0.f;
         float m[kGrCols];
-        med4_from12<0>(f, m);
+        med8_from16<0>(f, m);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -451,7 +506,8 @@ __global__ void __launch_bounds__(kGrThreads, 6) grey_raster_kernel(const __grid
                     for (int t = 0; t < 5; ++t) acc += kw[t] * (255 - win[t][c]);   // luminance 255 - value (wefax.py:303)
                     v[c] = acc >> 22;
                 }
-                store4_any(out + (size_t)(4 * q + ph) * w + c0, pack4_sat(v[0], v[1], v[2], v[3]), ncols);
+                store_any(out + (size_t)(4 * q + ph) * w + c0, pack4_sat(v[0], v[1], v[2], v[3]),
+                          pack4_sat(v[4], v[5], v[6], v[7]), ncols);
             }
         }
     }
@@ -506,16 +562,17 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         }
     }
     // recordings by alignment class (LineDev.gr_class, set by api.cu from the width): the raster rows of a recording
-    // are all 4-byte aligned when its width is a multiple of 4 and so are the raster base and stride
+    // are all 8- / 4-byte aligned when its width is a multiple of 8 / 4 and so are the raster base and stride
+    const bool base8 = (reinterpret_cast<uintptr_t>(raster) & 7) == 0 && rs % 8 == 0;
     const bool base4 = (reinterpret_cast<uintptr_t>(raster) & 3) == 0 && rs % 4 == 0;
-    int count[2] = {0, 0};   // 0: generic widths, 1: width % 4 == 0
-    for (int r = 0; r < batch; ++r) count[h_lines[r].gr_class >= 1 ? 1 : 0]++;
-    int per_sm = 6;
+    int count[3] = {0, 0, 0};   // 0: generic widths, 1: width % 4 == 0, 2: width % 8 == 0
+    for (int r = 0; r < batch; ++r) count[h_lines[r].gr_class]++;
+    int per_sm = 5;
     {
-        const void *fn = (const void *)grey_raster_kernel<true, false>;
+        const void *fn = (const void *)grey_raster_kernel<8>;
         auto it = ctx->smem_configured.find(fn);
         if (it == ctx->smem_configured.end()) {
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<true, false>, kGrThreads, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<8>, kGrThreads, 0));
             if (per_sm < 1) per_sm = 1;
             ctx->smem_configured[fn] = per_sm;
         } else {
@@ -523,13 +580,13 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         }
     }
     const double resident = (double)ctx->sm_count * per_sm * kGrThreads;
-    for (int cls = 1; cls >= 0; --cls) {
+    for (int cls = 2; cls >= 0; --cls) {
         if (!count[cls]) continue;
         auto items_for = [&](int U, long long *max_items) {
             double total = 0;
             long long mx = 0;
             for (int r = 0; r < batch; ++r) {
-                if ((h_lines[r].gr_class >= 1 ? 1 : 0) != cls) continue;
+                if (h_lines[r].gr_class != cls) continue;
                 const int w = h_lines[r].width;
                 const long long nl = n / w + 2;
                 const long long it = ((nl + U - 1) / U) * ((w + kGrCols - 1) / kGrCols);
@@ -554,19 +611,16 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         const char *force_u = getenv("WEFAX_GR_LINES");
         if (force_u && atoi(force_u) >= 1) best_u = atoi(force_u);
         P.lines_per_item = best_u;
-        P.only_class = count[cls] == batch ? -1 : cls;   // LineDev.gr_class >= 1 <-> cls 1 (see the kernel's filter)
+        P.only_class = count[cls] == batch ? -1 : cls;
         long long max_items = 0;
         items_for(best_u, &max_items);
         dim3 grid((unsigned)((max_items + kGrThreads - 1) / kGrThreads), batch);
-        const char *un = getenv("WEFAX_GR_UNROLL");   // "1": five unrolled copies of the line body instead of window moves
-        const bool unroll5 = un && un[0] == '1';
-        if (cls == 1 && base4) {
-            if (unroll5) grey_raster_kernel<true, true><<<grid, kGrThreads, 0, ctx->stream>>>(P);
-            else grey_raster_kernel<true, false><<<grid, kGrThreads, 0, ctx->stream>>>(P);
-        } else {
-            if (unroll5) grey_raster_kernel<false, true><<<grid, kGrThreads, 0, ctx->stream>>>(P);
-            else grey_raster_kernel<false, false><<<grid, kGrThreads, 0, ctx->stream>>>(P);
-        }
+        if (cls == 2 && base8)
+            grey_raster_kernel<8><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        else if (cls >= 1 && base4)
+            grey_raster_kernel<4><<<grid, kGrThreads, 0, ctx->stream>>>(P);
+        else
+            grey_raster_kernel<0><<<grid, kGrThreads, 0, ctx->stream>>>(P);
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }

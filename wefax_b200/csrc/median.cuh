@@ -17,7 +17,9 @@ __device__ __forceinline__ float med5(float a, float b, float c, float d, float 
     return med3(e, f, g);
 }
 
-// medians of elements i0..i0+3 of one recording (zero outside [0, n))
+// medians (window MED = 5, or 3 for the live path's packets: data_packet.py:440) of elements i0..i0+3 of one
+// recording (zero outside [0, n))
+template <int MED = 5>
 __device__ __forceinline__ void load_med4(const float *e, long long i0, long long n, float out[4]) {
     float w[8];
 #pragma unroll
@@ -26,11 +28,13 @@ __device__ __forceinline__ void load_med4(const float *e, long long i0, long lon
         w[j] = (i >= 0 && i < n) ? __ldg(e + i) : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]);
+    for (int j = 0; j < 4; ++j)
+        out[j] = MED == 5 ? med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]) : med3(w[j + 1], w[j + 2], w[j + 3]);
 }
 
 // medians of elements i0..i0+7 (i0 a multiple of 8); interior 16-byte aligned runs
 // come in as four 128-bit loads
+template <int MED = 5>
 __device__ __forceinline__ void load_med8(const float *e, long long i0, long long n, float out[8]) {
     float w[12];   // elements i0-2 .. i0+9
     if (i0 >= 4 && i0 + 12 <= n && (reinterpret_cast<uintptr_t>(e + i0) & 15) == 0) {
@@ -50,7 +54,8 @@ __device__ __forceinline__ void load_med8(const float *e, long long i0, long lon
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]);
+    for (int j = 0; j < 8; ++j)
+        out[j] = MED == 5 ? med5(w[j], w[j + 1], w[j + 2], w[j + 3], w[j + 4]) : med3(w[j + 1], w[j + 2], w[j + 3]);
 }
 
 // medians of x[OFF + 2 .. OFF + 9] given x[OFF .. OFF + 11]: every adjacent pair is ordered once and shared

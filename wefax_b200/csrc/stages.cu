@@ -417,7 +417,7 @@ void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, siz
 __device__ __forceinline__ int level_shift(int level) { return level == 0 ? 21 : (level == 1 ? 10 : 0); }
 __device__ __forceinline__ uint32_t level_mask(int level) { return level == 2 ? 0x3FFu : 0x7FFu; }
 
-template <int LEVEL>
+template <int LEVEL, int MED>
 __global__ void __launch_bounds__(256) hist_kernel(const float *env, size_t es, long long n, SelState *sel_all) {
     constexpr int NH = LEVEL == 0 ? 1 : 4;
     __shared__ uint32_t s_hist[NH][2048];
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(256) hist_kernel(const float *env, size_t es, 
     for (long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i0 < ((n + stride - 1) / stride) * stride;
          i0 += stride) {
         float m[4] = {0.f, 0.f, 0.f, 0.f};
-        if (i0 < n) load_med4(e, i0, n, m);
+        if (i0 < n) load_med4<MED>(e, i0, n, m);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool valid = i0 + j < n;
@@ -978,7 +978,7 @@ pct_fallback_kernel(const float *env, size_t es, PctGeom g, const PctState *st_a
 }
 
 void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
-                        RecResult *res) {
+                        RecResult *res, int med) {
     StageTimer timer(ctx, "percentiles");
     cudaStream_t st = ctx->stream;
     // numpy 'linear' method: virtual index (n-1)*q, q = 0.5/100 and 99.5/100
@@ -987,7 +987,9 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     const double t_lo = v_lo - (double)i_lo, t_hi = v_hi - (double)i_hi;
     auto clip = [&](long long r) { return (uint32_t)std::min(r, n - 1); };
     const char *force = getenv("WEFAX_PCT_MODE");   // "radix" | "bracket" (tests); default by length
-    const bool bracket = force ? (force[0] == 'b') : (n >= (1ll << 20));
+    if (med != 5 && med != 3) WEFAX_THROW(WEFAX_ERR_INVALID, "median window %d", med);
+    // (the bracketed selection is written for the file path's median-5; packets are short anyway)
+    const bool bracket = med == 5 && (force ? (force[0] == 'b') : (n >= (1ll << 20)));
     if (!bracket) {
         CUDA_CHECK(cudaMemsetAsync(sel, 0, sizeof(SelState) * batch, st));
         select_init_kernel<<<batch, 32, 0, st>>>(sel, clip(i_lo), clip(i_lo + 1), clip(i_hi), clip(i_hi + 1));
@@ -995,12 +997,21 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
         int blocks = (int)std::min<long long>((n + per_block - 1) / per_block, (long long)ctx->sm_count * 8);
         blocks = std::max(1, blocks / std::max(1, std::min(batch, 8)));
         dim3 grid(blocks, batch);
-        hist_kernel<0><<<grid, 256, 0, st>>>(env, es, n, sel);
-        select_kernel<<<batch, 256, 0, st>>>(sel, 0, res, t_lo, t_hi);
-        hist_kernel<1><<<grid, 256, 0, st>>>(env, es, n, sel);
-        select_kernel<<<batch, 256, 0, st>>>(sel, 1, res, t_lo, t_hi);
-        hist_kernel<2><<<grid, 256, 0, st>>>(env, es, n, sel);
-        select_kernel<<<batch, 256, 0, st>>>(sel, 2, res, t_lo, t_hi);
+        if (med == 3) {
+            hist_kernel<0, 3><<<grid, 256, 0, st>>>(env, es, n, sel);
+            select_kernel<<<batch, 256, 0, st>>>(sel, 0, res, t_lo, t_hi);
+            hist_kernel<1, 3><<<grid, 256, 0, st>>>(env, es, n, sel);
+            select_kernel<<<batch, 256, 0, st>>>(sel, 1, res, t_lo, t_hi);
+            hist_kernel<2, 3><<<grid, 256, 0, st>>>(env, es, n, sel);
+            select_kernel<<<batch, 256, 0, st>>>(sel, 2, res, t_lo, t_hi);
+        } else {
+            hist_kernel<0, 5><<<grid, 256, 0, st>>>(env, es, n, sel);
+            select_kernel<<<batch, 256, 0, st>>>(sel, 0, res, t_lo, t_hi);
+            hist_kernel<1, 5><<<grid, 256, 0, st>>>(env, es, n, sel);
+            select_kernel<<<batch, 256, 0, st>>>(sel, 1, res, t_lo, t_hi);
+            hist_kernel<2, 5><<<grid, 256, 0, st>>>(env, es, n, sel);
+            select_kernel<<<batch, 256, 0, st>>>(sel, 2, res, t_lo, t_hi);
+        }
         CUDA_CHECK(cudaGetLastError());
         ctx->launches += 7;
         return;
@@ -1082,18 +1093,21 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
 // ===========================================================================
 // grey map  (wefax.py:197-200,216): round(255*(env-low)/(high-low)), clip, int
 // ===========================================================================
+template <int MED>
 __global__ void __launch_bounds__(256)
 quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long n, const RecResult *res_all,
-                long long i_begin, long long i_end) {
+                long long i_begin, long long i_end, double eps) {
     const RecResult *res = res_all + blockIdx.y;
     const float *e = env + (size_t)blockIdx.y * es;
     uint8_t *d = dig + (size_t)blockIdx.y * ds;
     const double low = res->low;
-    const double delta = __dsub_rn(res->high, low);
+    // the file path divides by high - low (wefax.py:198), the live path's packets by high - low + 0.000001
+    // (data_packet.py:461)
+    const double delta = __dadd_rn(__dsub_rn(res->high, low), eps);
     long long i0 = i_begin + 8 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);   // i_begin % 8 == 0
     if (i0 >= i_end) return;
     float m[8];
-    load_med8(e, i0, n, m);
+    load_med8<MED>(e, i0, n, m);
     // numpy: round(255 * (env - low) / delta) in float64 (rint = half to even = numpy.round).
     // The float64 divide is only needed when the value is close to a rounding boundary: an
     // fp32 estimate (error << 1e-3 grey levels) decides every other element.
@@ -1125,11 +1139,15 @@ quantise_kernel(const float *env, size_t es, uint8_t *dig, size_t ds, long long 
 
 // Grey levels of samples [i_begin, i_end) (i_begin a multiple of 8) on `stream`.
 void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
-                     const RecResult *res, long long i_begin, long long i_end, cudaStream_t stream, const char *tag) {
+                     const RecResult *res, long long i_begin, long long i_end, cudaStream_t stream, const char *tag,
+                     int med, double eps) {
     if (i_end <= i_begin) return;
     StageTimer timer(ctx, tag, stream);
     dim3 grid((unsigned)((i_end - i_begin + 2047) / 2048), batch);
-    quantise_kernel<<<grid, 256, 0, stream>>>(env, es, dig, ds, n, res, i_begin, i_end);
+    if (med == 3)
+        quantise_kernel<3><<<grid, 256, 0, stream>>>(env, es, dig, ds, n, res, i_begin, i_end, eps);
+    else
+        quantise_kernel<5><<<grid, 256, 0, stream>>>(env, es, dig, ds, n, res, i_begin, i_end, eps);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

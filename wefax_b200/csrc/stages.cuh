@@ -79,10 +79,13 @@ void launch_filtfilt(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_
                      float2 *zout, size_t z_stride, long long n, const FirParams &fp, int batch);
 void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, size_t os, long long n, int batch);
 // 0.5 / 99.5 percentiles of median5(env) -> RecResult.low/high (+ WEFAX_REC_NAN)
+// med: median window in front of the percentiles (5: file path, wefax.py:175; 3: packets, data_packet.py:440)
 void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
-                        RecResult *res);
+                        RecResult *res, int med = 5);
+// eps: added to high - low (0 on the file path, 0.000001 for packets: data_packet.py:461)
 void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
-                     const RecResult *res, long long i_begin, long long i_end, cudaStream_t stream, const char *tag);
+                     const RecResult *res, long long i_begin, long long i_end, cudaStream_t stream, const char *tag,
+                     int med = 5, double eps = 0.0);
 // Grey map of the whole recording with the tail (everything the parallel phasing search does not read)
 // on the context's low-priority auxiliary stream, so that it overlaps the latency-bound search kernels.
 // Returns the event the tail signals (nullptr when everything ran on the main stream).
