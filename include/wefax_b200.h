@@ -241,6 +241,32 @@ int wefax_tone_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int 
                     long long packet_frames, unsigned flags, const wefax_tone_settings *settings,
                     uint8_t *start_flags, uint8_t *stop_flags, int32_t *n_start_peaks, int32_t *n_stop_peaks);
 
+/* config/config.json "sync_pulse_settings" + "notch_filter_settings" as data_packet.py:20-46 reads them
+ * (peaks_minimum_distance is read there but never used). */
+typedef struct {
+    double height;           /* peaks_minimum_height      data_packet.py:304 */
+    double prominence;       /* peaks_minimum_prominence  data_packet.py:305 */
+    double min_frequency;    /* peaks_minimum_frequency (Hz)  data_packet.py:309-311 */
+    double max_frequency;    /* peaks_maximum_frequency (Hz)                          */
+    double notch_freq;       /* notch_filter_frequency    data_packet.py:428 (designed at the PACKET's sample rate) */
+    double notch_q;          /* notch_filter_quality_factor                           */
+} wefax_sync_pulse_settings;
+
+#define WEFAX_MAX_PULSES 16   /* pulse positions reported per packet (a 1-s packet holds at most 3) */
+
+/* DataPacket.find_sync_pulse() (data_packet.py:301-343) for every consecutive packet of packet_frames frames of
+ * ONE recording - the phasing gate of the live decoder's state machine (wefax_live.py:187-192): exactly one
+ * spectral peak, inside [min_frequency, max_frequency], and at least one pulse from the template search over
+ * the packet's own grey levels (data_packet.py:408-465: notch at the packet's rate, |hilbert|, median-3,
+ * percentile stretch).  pcm / flags as for wefax_tone_scan.  Outputs are HOST pointers of n_packets entries
+ * (pulses: n_packets x WEFAX_MAX_PULSES, -1 padded; samples: n_packets x packet_frames grey levels, host or
+ * device per cudaMemcpyDefault); any may be NULL.  last_pulse = peaks_samples[-1] (-1: none): where the live
+ * decoder starts the picture inside the packet (wefax_live.py:191). */
+int wefax_sync_pulse_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int channels, int sample_rate,
+                          long long packet_frames, unsigned flags, const wefax_sync_pulse_settings *settings,
+                          uint8_t *pulse_found, uint8_t *frequency_peak_found, int32_t *n_fft_peaks, int32_t *n_pulses,
+                          int32_t *last_pulse, int32_t *pulses, uint8_t *samples);
+
 /* ---- EXTENSION: FM-discriminator demodulation, IOC pixel columns ---------
  * Not in the reference's code (only described in its README.md:85-101): grey = instantaneous
  * frequency mapped black_hz..white_hz -> 0..255, exact line length 60/lpm s, pi*ioc pixels per line.

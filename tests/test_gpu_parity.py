@@ -114,6 +114,35 @@ def test_filtfilt_other_notch_settings(dec):
         assert rel_err(dec.filtfilt(x, f0, q), O.filtfilt(b, a, x.astype(np.float64))) < 5e-6
 
 
+def test_filtfilt_high_quality_factors_take_the_recursive_form(dec, tmp_path, monkeypatch):
+    """config.json may hold any notch_filter_quality_factor (wefax.py:64): responses too long for the FIR kernels
+    (Q = 3 needs 76 taps, Q = 30 needs 773) run scipy's recursion itself, in float64, block-parallel."""
+    rng = np.random.default_rng(6)
+    for n in (5000, 123457):
+        x = np.round(rng.normal(size=n) * 6000).astype(np.float32)
+        for f0, q in ((2600, 3), (2600, 30), (1900, 8), (2600, 100)):
+            b, a = O.notch_coefficients(f0, q, 11025)
+            assert rel_err(dec.filtfilt(x, f0, q), O.filtfilt(b, a, x.astype(np.float64))) < 5e-6, (n, f0, q)
+    # the whole decode with the reference's config format carrying Q = 30
+    import json
+    from wefax_b200.wefax import Demodulator
+    pcm = synth.synth_recording(30.0, lpm=120, seed=41, noise_sigma=0.03)
+    (tmp_path / "config").mkdir()
+    (tmp_path / "config" / "config.json").write_text(json.dumps(
+        {"notch_filter_settings": {"notch_filter_frequency": 2600, "notch_filter_quality_factor": 30}}))
+    wav = str(tmp_path / "q30.wav")
+    synth.write_wav(wav, pcm, 11025)
+    monkeypatch.chdir(tmp_path)
+    d = Demodulator(wav, lines_per_minute=120, tcp_stream=False, quiet=True)
+    try:
+        d.process()
+    except (ValueError, IndexError):
+        pass
+    o = O.decode(pcm, 11025, 120, notch_freq=2600, notch_q=30)
+    assert rel_err(d.audio_data, o["audio_data"]) < FLOAT_TOL
+    assert rel_err(d.demodulated_data, o["demodulated_data"]) < FLOAT_TOL
+
+
 def test_filtfilt_rejects_short_input(dec):
     with pytest.raises(ValueError, match="greater than padlen"):
         dec.filtfilt(np.zeros(9, dtype=np.float32))

@@ -140,3 +140,77 @@ def test_tone_scan_rejects_bad_arguments(dec):
     assert all(len(a) == 0 for a in out)
     start, stop, ns, nt = scan_tones(dec, np.zeros(11025, dtype=np.int16), 11025)   # silence: no peaks
     assert not start[0] and not stop[0] and ns[0] == 0 and nt[0] == 0
+
+
+# --------------------------------------------------------------------------- per-packet sync pulse + state machine
+def _check_sync_packet(sp, k, want, samples=None):
+    """CUDA result of packet k against a golden / oracle entry.  The FFT-peak test and the grey levels are
+    thresholded fp32 quantities: flags and pulse positions must be identical on every committed case, the grey
+    levels within +-1 (the picker runs on the CUDA path's own levels)."""
+    assert bool(sp["frequency_peak_found"][k]) == want["frequency_peak_found"], k
+    assert int(sp["n_fft_peaks"][k]) == want["n_fft_peaks"], k
+    assert sp["peaks_samples"][k] == want["peaks_samples"], (k, sp["peaks_samples"][k], want["peaks_samples"])
+    assert bool(sp["pulse_found"][k]) == want["pulse_found"], k
+
+
+@pytest.mark.parametrize("name", sorted(_golden()["fixtures"]))
+def test_sync_pulse_scan_matches_reference_fixtures(dec, name):
+    """DataPacket.find_sync_pulse() of the unmodified reference on the five shipped packets (11025 Hz and 48 kHz:
+    at 48 kHz the packet's notch has a long impulse response and takes the recursive form)."""
+    from wefax_b200.tones import scan_sync_pulses
+    c = _golden()["fixtures"][name]
+    g = load_golden_full("fixture_" + name[:-len(".wav")])
+    sr = c["sample_rate"]
+    pcm = g["pcm"][: sr]
+    sp = scan_sync_pulses(dec, pcm, sr, want_samples=True)
+    ref = T.process_samples(pcm, sr)
+    d = np.abs(sp["samples"][0].astype(np.int64) - ref)
+    assert (d <= 1).mean() >= 0.999 and d.max() <= 2
+    # the picker on the CUDA path's own grey levels: bit-exact
+    assert sp["peaks_samples"][0] == T.packet_pattern_search(sp["samples"][0].astype(np.int64), sr)
+    _check_sync_packet(sp, 0, c["sync_pulse"])
+
+
+@pytest.mark.parametrize("name", sorted(_golden()["synthetic"]))
+def test_sync_pulse_scan_matches_reference_synthetic(dec, name):
+    from wefax_b200.tones import scan_sync_pulses
+    c = _golden()["synthetic"][name]
+    pcm = synth.synth_recording(**c["synth"])
+    sp = scan_sync_pulses(dec, pcm, 11025, want_samples=True)
+    assert len(sp["pulse_found"]) == len(c["sync_pulse"])
+    for k, want in enumerate(c["sync_pulse"]):
+        seg = sp["samples"][k].astype(np.int64)
+        assert sp["peaks_samples"][k] == T.packet_pattern_search(seg, 11025), k
+        _check_sync_packet(sp, k, want)
+
+
+def test_state_machine_matches_the_oracle_and_crops_the_picture(dec):
+    """Tone scan + sync pulse scan + wefax_live.py:175-200: the same transmissions as the oracle's state machine
+    (which runs the float64 restatements packet by packet), on clean and noisy recordings, device input included."""
+    import torch
+    from wefax_b200.tones import scan_recording
+    for kw in (dict(duration_s=30.0, lpm=120, ioc=576, seed=3), dict(duration_s=30.0, lpm=120, seed=5, noise_sigma=0.05),
+               dict(duration_s=60.0, lpm=120, seed=8, noise_sigma=0.03), dict(duration_s=30.0, lpm=60, seed=6, noise_sigma=0.02,
+                                                                             carrier_offset_hz=40.0)):
+        pcm = synth.synth_recording(**kw)
+        want = T.state_machine(pcm, 11025)
+        assert scan_recording(dec, pcm, 11025) == want, kw
+        assert scan_recording(dec, torch.from_numpy(pcm).cuda(), 11025) == want, kw
+
+
+def test_sync_pulse_scan_full_hour(dec):
+    """Every packet of the 60-min recording in one call; a sample of packets against the oracle."""
+    from wefax_b200.tones import scan_sync_pulses
+    pcm = synth.synth_recording(3600.0, seed=0)
+    sp = scan_sync_pulses(dec, pcm, 11025, want_samples=True)
+    assert sp["pulse_found"].shape == (3600,)
+    rng = np.random.default_rng(1)
+    for k in sorted(set(range(12)) | set(rng.integers(12, 3600, size=40).tolist())):
+        seg = pcm[k * 11025:(k + 1) * 11025]
+        want = T.find_sync_pulse(seg, 11025)
+        d = np.abs(sp["samples"][k].astype(np.int64) - T.process_samples(seg, 11025))
+        assert (d <= 1).mean() >= 0.999, k
+        assert sp["peaks_samples"][k] == T.packet_pattern_search(sp["samples"][k].astype(np.int64), 11025), k
+        assert bool(sp["frequency_peak_found"][k]) == want["frequency_peak_found"], k
+        if sp["peaks_samples"][k] == want["peaks_samples"]:
+            assert bool(sp["pulse_found"][k]) == want["pulse_found"], k

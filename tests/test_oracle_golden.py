@@ -152,3 +152,47 @@ def test_tone_oracle_matches_reference_fixtures(name):
     assert g["sample_rate_in"] == c["sample_rate"]
     assert T.contain_start_tone(g["pcm"], c["sample_rate"]) == c["start"]
     assert T.contain_stop_tone(g["pcm"], c["sample_rate"]) == c["stop"]
+
+
+# ---- N2, second half: the per-packet sync pulse (oracle/tones_oracle.py vs DataPacket.find_sync_pulse) ----------
+
+def _check_sync(info, samples, want):
+    import hashlib
+    assert info["pulse_found"] == want["pulse_found"]
+    assert info["frequency_peak_found"] == want["frequency_peak_found"]
+    assert info["samples_peak_found"] == want["samples_peak_found"]
+    assert info["n_fft_peaks"] == want["n_fft_peaks"]
+    assert info["peaks_samples"] == want["peaks_samples"]
+    assert hashlib.sha256(np.asarray(samples).astype(np.uint8).tobytes()).hexdigest() == want["samples_sha256"]
+
+
+@pytest.mark.parametrize("name", sorted(_load_tones()["fixtures"]))
+def test_sync_pulse_oracle_matches_reference_fixtures(name):
+    """find_sync_pulse() and the packet's processed samples (data_packet.py:301-343, 408-465) on the five shipped
+    packets, 11025 Hz and 48 kHz."""
+    from oracle import tones_oracle as T
+    c = _load_tones()["fixtures"][name]
+    g = load_golden_full("fixture_" + name[:-len(".wav")])
+    sr = c["sample_rate"]
+    _check_sync(T.find_sync_pulse(g["pcm"], sr), T.process_samples(g["pcm"], sr), c["sync_pulse"])
+
+
+@pytest.mark.parametrize("name", sorted(_load_tones()["synthetic"]))
+def test_sync_pulse_oracle_matches_reference_synthetic(name):
+    from oracle import tones_oracle as T
+    c = _load_tones()["synthetic"][name]
+    pcm = synth.synth_recording(**c["synth"])
+    for k, want in enumerate(c["sync_pulse"]):
+        seg = pcm[k * 11025:(k + 1) * 11025]
+        _check_sync(T.find_sync_pulse(seg, 11025), T.process_samples(seg, 11025), want)
+
+
+def test_state_machine_gates_the_picture_on_the_sync_pulse():
+    """wefax_live.py:175-200 on a synthetic transmission: the start tone is found after 4 s, the picture starts at
+    the last pulse of the first packet whose pulse is found, the stop tone ends it."""
+    from oracle import tones_oracle as T
+    pcm = synth.synth_recording(30.0, lpm=120, ioc=576, seed=3)
+    (start_packet, image_start, stop_packet), = T.state_machine(pcm, 11025)
+    assert start_packet == 3 and stop_packet == 21
+    first = next(k for k in range(start_packet, 30) if T.find_sync_pulse(pcm[k * 11025:(k + 1) * 11025], 11025)["pulse_found"])
+    assert image_start == first * 11025 + T.find_sync_pulse(pcm[first * 11025:(first + 1) * 11025], 11025)["peaks_samples"][-1]

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "wefax_resample", "wefax_filtfilt", "wefax_digitalize", "wefax_sync_raster",
     "wefax_ctx_enable_timing", "wefax_ctx_timings", "wefax_tone_scan", "wefax_decode_fm",
     "wefax_segment_envelope", "wefax_segment_histogram", "wefax_segment_quantise", "wefax_segment_sync",
-    "wefax_segment_raster",
+    "wefax_segment_raster", "wefax_sync_pulse_scan",
 )
 ABI_VERSION = 5
 
@@ -56,6 +56,14 @@ class ToneSettings(C.Structure):
     _fields_ = [("start_distance", C.c_double), ("stop_distance", C.c_double), ("height", C.c_double),
                 ("prominence", C.c_double), ("min_frequency", C.c_double), ("max_frequency", C.c_double),
                 ("min_amount", C.c_int), ("max_amount", C.c_int)]
+
+
+class SyncPulseSettings(C.Structure):
+    _fields_ = [("height", C.c_double), ("prominence", C.c_double), ("min_frequency", C.c_double),
+                ("max_frequency", C.c_double), ("notch_freq", C.c_double), ("notch_q", C.c_double)]
+
+
+MAX_PULSES = 16
 
 
 class FmParams(C.Structure):
@@ -133,6 +141,9 @@ def load():
     lib.wefax_sync_raster.restype = i
     lib.wefax_tone_scan.argtypes = [vp, vp, ll, i, i, ll, C.c_uint, C.POINTER(ToneSettings), vp, vp, vp, vp]
     lib.wefax_tone_scan.restype = i
+    lib.wefax_sync_pulse_scan.argtypes = [vp, vp, ll, i, i, ll, C.c_uint, C.POINTER(SyncPulseSettings), vp, vp, vp, vp, vp,
+                                          vp, vp]
+    lib.wefax_sync_pulse_scan.restype = i
     lib.wefax_decode_fm.argtypes = [vp, C.POINTER(BatchDesc), vp, C.POINTER(FmParams), C.POINTER(FmOut)]
     lib.wefax_decode_fm.restype = i
     lib.wefax_segment_envelope.argtypes = [vp, C.POINTER(BatchDesc), vp, ll, ll, ll, ll]

@@ -49,7 +49,7 @@ void notch_coefficients(double f0, double q, double fs, double b[3], double a[3]
 FirParams make_fir(double f0, double q, double fs) {
     double b[3], a[3];
     notch_coefficients(f0, q, fs, b, a);
-    const int NMAX = 4096;
+    const int NMAX = 1 << 16;
     std::vector<double> h(NMAX);
     double z0 = 0.0, z1 = 0.0, x = 1.0;
     for (int i = 0; i < NMAX; ++i) {
@@ -64,10 +64,25 @@ FirParams make_fir(double f0, double q, double fs) {
     double tail = 0.0;
     int K = NMAX;
     while (K > 1 && tail + fabs(h[K - 1]) < 3e-9 * total) tail += fabs(h[--K]);
-    if (K > kMaxFirTaps)
-        WEFAX_THROW(WEFAX_ERR_UNSUPPORTED,
-                    "notch impulse response needs %d taps (max %d): quality factor too high for the FIR path", K,
-                    kMaxFirTaps);
+    if (K > kMaxFirTaps) {
+        // too long for the FIR form: the recursion itself (float64, blocks with a warm-up of K samples)
+        if (K >= NMAX)
+            WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "notch impulse response longer than %d samples: quality factor too high", NMAX);
+        FirParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.K = K;
+        fp.iir = 1;
+        fp.warm = K;
+        for (int i = 0; i < 3; ++i) {
+            fp.b[i] = b[i];
+            fp.a[i] = a[i];
+        }
+        // lfilter_zi: steady state for a unit step, y = H(1)
+        const double g1 = (b[0] + b[1] + b[2]) / (1.0 + a[1] + a[2]);
+        fp.zi[1] = b[2] - a[2] * g1;
+        fp.zi[0] = b[1] - a[1] * g1 + fp.zi[1];
+        return fp;
+    }
     FirParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.K = K;
@@ -940,6 +955,134 @@ int wefax_tone_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int 
             if (stop_flags) stop_flags[k] = h_flags[2 * k + 1];
             if (n_start_peaks) n_start_peaks[k] = h_counts[2 * k];
             if (n_stop_peaks) n_stop_peaks[k] = h_counts[2 * k + 1];
+        }
+    });
+}
+
+// DataPacket.find_sync_pulse() (data_packet.py:301-343) for every consecutive packet of a recording: the packet's
+// spectrum must hold exactly one peak (height / prominence, no distance rule) inside [min, max] Hz, and the template
+// search over the packet's OWN grey levels (its own notch at the packet's sample rate, |hilbert|, median-3, 0.5 / 99.5
+// percentile stretch with delta + 1e-6: data_packet.py:408-465) must return at least one pulse.
+int wefax_sync_pulse_scan(wefax_ctx *ctx, const int16_t *pcm, long long n_frames, int channels, int sample_rate,
+                          long long packet_frames, unsigned flags, const wefax_sync_pulse_settings *settings,
+                          uint8_t *pulse_found, uint8_t *frequency_peak_found, int32_t *n_fft_peaks, int32_t *n_pulses,
+                          int32_t *last_pulse, int32_t *pulses, uint8_t *samples) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!pcm || !settings || n_frames < 0 || packet_frames < 16 || sample_rate < 1 || (channels != 1 && channels != 2))
+            WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        const long long n_packets = n_frames / packet_frames;
+        if (n_packets == 0) return;
+        if (n_packets > 0x7fffffff) WEFAX_THROW(WEFAX_ERR_INVALID, "too many packets");
+        if (packet_frames >= (1ll << 31) - 4096) WEFAX_THROW(WEFAX_ERR_INVALID, "packet too long");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const long long P = packet_frames;
+        const uint32_t half_bins = (uint32_t)(P / 2);
+        // samples(x) = int((x / (len / rate)) * len)  (data_packet.py:315), Python float arithmetic
+        volatile double length = (double)P / (double)sample_rate;
+        auto nsamp = [&](double x) { volatile double q = x / length; return (int)(q * (double)P); };
+        const int k0 = nsamp(0.025), mind = nsamp(0.4);
+        if (k0 + 2 > 2048 || mind < 1024 || P <= k0 + 2)
+            WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "packet geometry outside the supported range (template %d, distance %d)",
+                        k0 + 2, mind);
+        const FirParams fp = make_fir(settings->notch_freq, settings->notch_q, (double)sample_rate);
+        wefax_tone_settings ts;
+        ts.start_distance = ts.stop_distance = 1.0;   // find_peaks without a distance rule
+        ts.height = settings->height;
+        ts.prominence = settings->prominence;
+        ts.min_frequency = settings->min_frequency;
+        ts.max_frequency = settings->max_frequency;
+        ts.min_amount = ts.max_amount = 1;
+
+        FftPlan *halfp = (P % 2 == 0) ? get_plan(ctx, P / 2) : nullptr;
+        FftPlan *plan = halfp ? nullptr : get_plan(ctx, P);
+        long long zlen = halfp ? P / 2 : P;
+        if (!plan && !halfp) {
+            zlen = next_smooth_length(2 * P - 1);
+            if (zlen <= 0) WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "no transform length for packets of %lld frames", P);
+        }
+        const size_t per_packet = (size_t)P * (sizeof(float) * 3 + sizeof(float2) * 4 + 1) + (size_t)half_bins * sizeof(float2) +
+                                  (size_t)zlen * sizeof(float2) + sizeof(RecResult) + sizeof(SelState);
+        long long wave = (long long)((size_t)ctx->workspace_limit / per_packet);
+        wave = std::max<long long>(1, std::min<long long>(std::min<long long>(wave, n_packets), 32768));
+        const bool on_dev = (flags & WEFAX_F_PCM_ON_DEVICE) != 0;
+
+        LineDev line;
+        memset(&line, 0, sizeof(line));
+        line.n1 = k0;
+        line.L = k0 + 2;
+        line.mindistance = mind;
+        line.width = (int)P;
+        char *small = (char *)ctx->out_small.reserve(sizeof(LineDev) + 256 + (sizeof(RecResult) + sizeof(SelState)) * (size_t)wave +
+                                                     (size_t)wave * (2 + 2 * sizeof(int32_t)) + 64);
+        LineDev *d_line = (LineDev *)small;
+        RecResult *d_res = (RecResult *)(small + 256);
+        SelState *d_sel = (SelState *)(((uintptr_t)(d_res + wave) + 255) & ~(uintptr_t)255);
+        uint8_t *d_flags = (uint8_t *)(d_sel + wave);
+        int32_t *d_counts = (int32_t *)(d_flags + (((size_t)wave * 2 + 15) & ~(size_t)15));
+        char *hbuf = (char *)pinned(ctx, sizeof(LineDev) + (sizeof(RecResult)) * (size_t)wave +
+                                             (size_t)wave * (2 + 2 * sizeof(int32_t)) + 64);
+        LineDev *h_line = (LineDev *)hbuf;
+        RecResult *h_res = (RecResult *)(h_line + 1);
+        uint8_t *h_flags = (uint8_t *)(h_res + wave);
+        int32_t *h_counts = (int32_t *)(h_flags + (((size_t)wave * 2 + 15) & ~(size_t)15));
+        *h_line = line;
+        CUDA_CHECK(cudaMemcpyAsync(d_line, h_line, sizeof(LineDev), cudaMemcpyHostToDevice, st));
+
+        for (long long p0 = 0; p0 < n_packets; p0 += wave) {
+            const int np = (int)std::min(wave, n_packets - p0);
+            const int16_t *src = pcm + (size_t)p0 * P * channels;
+            const int16_t *d_pcm = src;
+            if (!on_dev) {
+                int16_t *buf = (int16_t *)ctx->pcm.reserve((size_t)np * P * channels * sizeof(int16_t));
+                CUDA_CHECK(cudaMemcpyAsync(buf, src, (size_t)np * P * channels * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+                d_pcm = buf;
+            }
+            // ---- the spectral test on the raw samples (data_packet.py:302-311) -----------------------------
+            float *x = (float *)ctx->resample_in.reserve((size_t)np * P * sizeof(float));
+            float2 *X = (float2 *)ctx->work_misc.reserve((size_t)np * half_bins * sizeof(float2));
+            launch_ingest_float(ctx, d_pcm, (size_t)P, channels, x, (size_t)P, P, np);
+            spectrum_natural(ctx, P, x, (size_t)P, X, half_bins, half_bins, np);
+            launch_tone_peaks(ctx, X, half_bins, P, sample_rate, np, ts, d_flags, d_counts);
+            // ---- the packet's grey levels (data_packet.py:408-465) ----------------------------------------
+            float *d_audio = (float *)ctx->work_a.reserve((size_t)np * P * sizeof(float));
+            float *d_env = (float *)ctx->work_e.reserve((size_t)np * P * sizeof(float));
+            uint8_t *d_dig = (uint8_t *)ctx->out_dig.reserve((size_t)np * P);
+            float2 *z = nullptr;
+            if (halfp)
+                z = (float2 *)ctx->work_z.reserve((size_t)np * (P / 2) * sizeof(float2));
+            else if (plan)
+                z = (float2 *)ctx->work_z.reserve((size_t)np * P * sizeof(float2));
+            launch_filtfilt(ctx, kInFloat, x, (size_t)P, d_audio, (size_t)P, halfp ? nullptr : z, (size_t)P, P, fp, np);
+            if (halfp)
+                hilbert_envelope_real(ctx, halfp, d_audio, (size_t)P, z, (size_t)(P / 2), d_env, (size_t)P, np);
+            else if (plan)
+                hilbert_envelope(ctx, plan, nullptr, 0, z, (size_t)P, d_env, (size_t)P, np);
+            else
+                hilbert_envelope_bluestein(ctx, P, d_audio, (size_t)P, d_env, (size_t)P, np);
+            CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * np, st));
+            launch_percentiles(ctx, d_env, (size_t)P, P, np, d_sel, d_res, 3);
+            launch_quantise(ctx, d_env, (size_t)P, d_dig, (size_t)P, P, np, d_res, 0, P, st, "packet_quantise", 3, 0.000001);
+            // ---- the template search (data_packet.py:313-331) -----------------------------------------------
+            launch_packet_pulse_search(ctx, d_dig, (size_t)P, P, np, d_line, d_res, mind);
+            CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, sizeof(RecResult) * np, cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(h_flags, d_flags, (size_t)np * 2, cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(h_counts, d_counts, (size_t)np * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            if (samples) CUDA_CHECK(cudaMemcpyAsync(samples + (size_t)p0 * P, d_dig, (size_t)np * P, cudaMemcpyDefault, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            for (int k = 0; k < np; ++k) {
+                const long long K = p0 + k;
+                const bool freq_ok = h_flags[2 * k] != 0;
+                const int npl = h_res[k].n_peaks;
+                if (frequency_peak_found) frequency_peak_found[K] = freq_ok ? 1 : 0;
+                if (n_fft_peaks) n_fft_peaks[K] = h_counts[2 * k];
+                if (n_pulses) n_pulses[K] = npl;
+                if (last_pulse) last_pulse[K] = npl > 0 ? h_res[k].peaks[npl - 1] : -1;
+                if (pulse_found) pulse_found[K] = (freq_ok && npl > 0) ? 1 : 0;
+                if (pulses)
+                    for (int t = 0; t < WEFAX_MAX_PULSES; ++t) pulses[(size_t)K * WEFAX_MAX_PULSES + t] = t < npl ? h_res[k].peaks[t] : -1;
+            }
         }
     });
 }

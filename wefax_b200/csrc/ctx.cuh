@@ -31,6 +31,13 @@ struct FirParams {
     // out[i] = g[0] x[i] + sum_k g[k] (x[i-k] + x[i+k]), k <= KC (0: not available, use the two sections)
     int KC;
     float g[kMaxSymTaps + 1];
+    // Impulse response longer than kMaxFirTaps (high quality factor, or a high sample rate in front of the notch
+    // as in the live path's packets): the recursive form itself, in float64, in blocks that warm up over `warm`
+    // samples (the response has decayed below 3e-9 of its sum by then); K then only reports the length.
+    int iir;
+    int warm;
+    double b[3], a[3];
+    double zi[2];             // scipy.signal.lfilter_zi(b, a): steady state of the transposed direct form II for a unit step
 };
 }  // namespace wefax
 
@@ -54,7 +61,7 @@ struct wefax_ctx {
     std::map<long long, std::unique_ptr<wefax::Bluestein>> bluestein;
     std::map<const void *, int> smem_configured;   // kernels whose dynamic-smem limit was raised
     // scratch (grown on demand, reused between calls)
-    wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in, sync_buf, pct_buf, grey_tab;
+    wefax::DevBuf pcm, work_a, work_z, work_e, work_misc, out_dig, out_raster, out_small, resample_in, sync_buf, pct_buf, grey_tab, iir_tmp;
     // segment mode: the extended segment's envelope and grey levels stay resident between the calls
     struct Segment {
         bool have_env = false, have_dig = false;

@@ -374,8 +374,109 @@ static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_strid
     WEFAX_THROW(WEFAX_ERR_UNSUPPORTED, "notch impulse response needs %d taps (max %d)", fp.K, kMaxFirTaps);
 }
 
+// ---------------------------------------------------------------------------
+// Recursive form for notches whose impulse response is too long for the FIR kernels (high quality factor, or a
+// high sample rate in front of the filter as in the live path's packets, data_packet.py:421-431): scipy's
+// filtfilt itself - odd extension by 9, lfilter with zi * ext[0], the same backwards - in float64, one thread per
+// block of kIirBlock samples.  A block that does not start at the signal's edge warms up from zero state over
+// `warm` samples, by which the response has decayed below 3e-9 of its sum (the FIR form's truncation rule).
+// ---------------------------------------------------------------------------
+constexpr int kIirBlock = 2048;
+
+template <int MODE>
+__device__ __forceinline__ double iir_ext(const void *in, size_t base, long long e, long long n) {
+    // odd extension (scipy signaltools.odd_ext, padlen 9) of the ingested signal, extended index e in [0, n + 18)
+    if (e < kPadLen) return 2.0 * (double)load_sample<MODE>(in, base, 0) - (double)load_sample<MODE>(in, base, kPadLen - e);
+    if (e >= n + kPadLen)
+        return 2.0 * (double)load_sample<MODE>(in, base, n - 1) - (double)load_sample<MODE>(in, base, 2 * n + 7 - e);
+    return (double)load_sample<MODE>(in, base, e - kPadLen);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+iir_forward_kernel(const void *in, size_t in_stride, double *yf, size_t yf_stride, long long n, const FirParams fp) {
+    const long long E = n + 2 * kPadLen;
+    const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long start = blk * kIirBlock;
+    if (start >= E) return;
+    const long long end = min(start + kIirBlock, E);
+    const size_t base = (size_t)blockIdx.y * in_stride;
+    double *y_out = yf + (size_t)blockIdx.y * yf_stride;
+    const double b0 = fp.b[0], b1 = fp.b[1], b2 = fp.b[2], a1 = fp.a[1], a2 = fp.a[2];
+    long long i = start - fp.warm;
+    double z0 = 0.0, z1 = 0.0;
+    if (i <= 0) {
+        i = 0;
+        const double x0 = iir_ext<MODE>(in, base, 0, n);
+        z0 = fp.zi[0] * x0;
+        z1 = fp.zi[1] * x0;
+    }
+    for (; i < end; ++i) {
+        const double x = iir_ext<MODE>(in, base, i, n);
+        const double y = b0 * x + z0;
+        z0 = b1 * x - a1 * y + z1;
+        z1 = b2 * x - a2 * y;
+        if (i >= start) y_out[i] = y;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+iir_backward_kernel(const double *yf, size_t yf_stride, float *out, size_t out_stride, float2 *zout, size_t z_stride,
+                    long long n, const FirParams fp) {
+    // reversed coordinate j = E - 1 - i: lfilter over yf reversed, zi * yf[E - 1]; sample j is output E - 1 - j - 9
+    const long long E = n + 2 * kPadLen;
+    const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long start = blk * kIirBlock;
+    if (start >= E) return;
+    const long long end = min(start + kIirBlock, E);
+    const double *y_in = yf + (size_t)blockIdx.y * yf_stride;
+    const double b0 = fp.b[0], b1 = fp.b[1], b2 = fp.b[2], a1 = fp.a[1], a2 = fp.a[2];
+    long long j = start - fp.warm;
+    double z0 = 0.0, z1 = 0.0;
+    if (j <= 0) {
+        j = 0;
+        const double x0 = y_in[E - 1];
+        z0 = fp.zi[0] * x0;
+        z1 = fp.zi[1] * x0;
+    }
+    for (; j < end; ++j) {
+        const double x = y_in[E - 1 - j];
+        const double y = b0 * x + z0;
+        z0 = b1 * x - a1 * y + z1;
+        z1 = b2 * x - a2 * y;
+        const long long o = E - 1 - j - kPadLen;
+        if (j >= start && o >= 0 && o < n) {
+            if (out) out[(size_t)blockIdx.y * out_stride + o] = (float)y;
+            if (zout) zout[(size_t)blockIdx.y * z_stride + o] = make_float2((float)y, 0.f);
+        }
+    }
+}
+
+static void launch_filtfilt_iir(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_stride, float *out,
+                                size_t out_stride, float2 *zout, size_t z_stride, long long n, const FirParams &fp,
+                                int batch) {
+    StageTimer timer(ctx, "filtfilt");
+    const long long E = n + 2 * kPadLen;
+    const size_t ys = (size_t)((E + 1) & ~1ll);
+    double *yf = (double *)ctx->iir_tmp.reserve(ys * (size_t)batch * sizeof(double));
+    const long long nblk = (E + kIirBlock - 1) / kIirBlock;
+    dim3 grid((unsigned)((nblk + 127) / 128), batch);
+    switch (mode) {
+        case kInMonoI16: iir_forward_kernel<kInMonoI16><<<grid, 128, 0, ctx->stream>>>(in, in_stride, yf, ys, n, fp); break;
+        case kInStereoI16: iir_forward_kernel<kInStereoI16><<<grid, 128, 0, ctx->stream>>>(in, in_stride, yf, ys, n, fp); break;
+        default: iir_forward_kernel<kInFloat><<<grid, 128, 0, ctx->stream>>>(in, in_stride, yf, ys, n, fp); break;
+    }
+    iir_backward_kernel<<<grid, 128, 0, ctx->stream>>>(yf, ys, out, out_stride, zout, z_stride, n, fp);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches += 2;
+}
+
 void launch_filtfilt(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_stride, float *out, size_t out_stride,
                      float2 *zout, size_t z_stride, long long n, const FirParams &fp, int batch) {
+    if (fp.iir) {
+        launch_filtfilt_iir(ctx, mode, in, in_stride, out, out_stride, zout, z_stride, n, fp, batch);
+        return;
+    }
     switch (mode) {
         case kInMonoI16:
             launch_filtfilt_mode<kInMonoI16>(ctx, in, in_stride, out, out_stride, zout, z_stride, n, fp, batch);
@@ -1223,7 +1324,10 @@ __device__ void finish_sync(const int *peaks, int np, const LineDev &ln, long lo
     res->status = status;
 }
 
-template <int PER>
+// PACKET: the live path's per-packet picker (data_packet.py:313-331) instead of the file path's: template
+// [255] + [0] * n1 + [255] shifted by -128 (LineDev.n1 zeros, L = n1 + 2), sentinel (-mindistance, 0) instead of
+// (0, 0), no 100-peak stop, and the first entry of the list is dropped on return (one CTA per packet).
+template <int PER, bool PACKET>
 __global__ void __launch_bounds__(kSyncThreads)
 sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *lines, RecResult *res_all,
                    const int *need_scan, const LazyGrey lazy) {
@@ -1236,7 +1340,7 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
     __shared__ unsigned long long s_red[32];
     __shared__ int s_peaks[WEFAX_MAX_PEAKS];
 
-    const LineDev ln = lines[blockIdx.x];
+    const LineDev ln = lines[PACKET ? 0 : blockIdx.x];   // packets of one scan share their geometry
     RecResult *res = res_all + blockIdx.x;
     const uint8_t *dig = dig_all + (size_t)blockIdx.x * ds;
     const float *lazy_env = lazy.env ? lazy.env + (size_t)blockIdx.x * lazy.es : nullptr;
@@ -1249,11 +1353,20 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
     const int L = ln.L, n1 = ln.n1, n0 = ln.n0, mind = ln.mindistance;
     const long long m = n - L;                        // range(len(data) - len(sync))
 
-    long long p = 0;       // position of the newest peak
+    long long p = PACKET ? -(long long)mind : 0;   // position of the newest peak
     int v = 0;             // its correlation
-    int npeaks = 1;        // peaks = [(0, 0)]
+    int npeaks = 1;        // peaks = [(0, 0)]  /  [(-mindistance, 0)]
     bool done = false;
-    if (tid == 0) s_peaks[0] = 0;
+    if (tid == 0) s_peaks[0] = (int)p;
+    // correlation at position i of the chunk from the exclusive prefix sums of (d - 128)
+    auto corr_at = [&](int i) -> int {
+        if (PACKET) {
+            const int a = s_p[i], b = s_p[i + 1], cc = s_p[i + L - 1], d = s_p[i + L];
+            return 127 * (b - a) - 128 * (cc - b) + 127 * (d - cc);
+        }
+        const int a = s_p[i], b = s_p[i + n1], cc = s_p[i + n1 + n0], d = s_p[i + L];
+        return -127 * (b - a) - 128 * (cc - b) - 127 * (d - cc);
+    };
 
     for (long long base = 0; base < m && !done; base += CH) {
         const int valid = (int)min((long long)CH, m - base);
@@ -1299,10 +1412,7 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
         for (int u = 0; u < PER; ++u) {
             int i = tid + u * kSyncThreads;
             int c = 0;
-            if (i < valid) {
-                int a = s_p[i], b = s_p[i + n1], cc = s_p[i + n1 + n0], d = s_p[i + L];
-                c = -127 * (b - a) - 128 * (cc - b) - 127 * (d - cc);
-            }
+            if (i < valid) c = corr_at(i);
             corr[u] = c;
         }
         auto range_max = [&](int lo, int hi) -> unsigned long long {   // max over positions [lo, hi)
@@ -1329,11 +1439,10 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
                 v = key_corr(k);
             } else {
                 // open a new peak at i_exp
-                int a = s_p[a_exp], b = s_p[a_exp + n1], cc = s_p[a_exp + n1 + n0], d = s_p[a_exp + L];
                 p = i_exp;
-                v = -127 * (b - a) - 128 * (cc - b) - 127 * (d - cc);
+                v = corr_at(a_exp);
                 npeaks++;
-                if (npeaks == WEFAX_MAX_PEAKS) {
+                if (npeaks == WEFAX_MAX_PEAKS) {   // wefax.py:251 (a packet never gets there: <= n / mindistance peaks)
                     done = true;
                 } else if (a_exp + 1 < valid) {
                     unsigned long long k2 = range_max(a_exp + 1, valid);
@@ -1354,6 +1463,14 @@ sync_search_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev
     }
     __syncthreads();
 
+    if (PACKET) {
+        if (tid == 0) {
+            res->n_peaks = npeaks - 1;
+            for (int i = 1; i < npeaks; ++i) res->peaks[i - 1] = s_peaks[i];
+            res->start_frame = npeaks > 1 ? s_peaks[npeaks - 1] : -1;   // the last pulse: where the live decoder starts
+        }
+        return;
+    }
     if (tid == 0) finish_sync(s_peaks, npeaks, ln, n, res);
 }
 
@@ -1532,60 +1649,70 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    // second level: bit c of the summary = chunk c (32 words = 1024 positions) holds a settled position; warp k
-    // builds summary word k (<= 46 words for the 1.5 M positions the region is capped at)
-    __shared__ uint32_t s_sum[64];
-    const int nchunks = (nwords + 31) >> 5, nsum = (nchunks + 31) >> 5;
-    for (int sw = threadIdx.x >> 5; sw < nsum; sw += (int)(blockDim.x >> 5)) {
-        uint32_t word = 0u;
-        for (int j = 0; j < 32; ++j) {
-            const int wi = ((sw << 5) + j) * 32 + (int)(threadIdx.x & 31);
-            const uint32_t v = wi < nwords ? s_bits[wi] : 0u;
-            if (__ballot_sync(0xFFFFFFFFu, v != 0u)) word |= 1u << j;
+    // "next non-empty word" table, one entry per group of 4 words (uint16: <= 46 875 words for the 1.5 M positions
+    // the region is capped at; 0xFFFF = none): with it one step of the chain is a handful of dependent
+    // instructions of ONE thread instead of warp-wide ballots over many words.  Built in parallel: every thread
+    // walks its run of groups backwards, a suffix minimum over the threads supplies what lies beyond the run.
+    uint16_t *s_nw = reinterpret_cast<uint16_t *>(s_bits + (((size_t)nwords + 3) & ~(size_t)3));
+    __shared__ int s_first[1024 / 32];
+    const int ngroups = (nwords + 3) >> 2;
+    {
+        const int per = (ngroups + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int g0 = (int)threadIdx.x * per, g1 = min(g0 + per, ngroups);
+        int cur = 0x7FFFFFFF;   // first non-empty word at or after the group being visited, inside this run
+        for (int g = g1 - 1; g >= g0; --g) {
+#pragma unroll
+            for (int k = 3; k >= 0; --k) {
+                const int wi = 4 * g + k;
+                if (wi < nwords && s_bits[wi] != 0u) cur = wi;
+            }
+            s_nw[g] = cur == 0x7FFFFFFF ? (uint16_t)0xFFFF : (uint16_t)cur;
         }
-        if ((threadIdx.x & 31) == 0) s_sum[sw] = word;
+        // exclusive suffix minimum of `cur` over the threads (word indices grow with the thread index)
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int incl = cur;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_down_sync(0xFFFFFFFFu, incl, d);
+            if (lane + d < 32) incl = min(incl, o);
+        }
+        if (lane == 0) s_first[wid] = incl;
+        __syncthreads();
+        int beyond = 0x7FFFFFFF;
+        for (int k = wid + 1; k < (int)(blockDim.x >> 5); ++k) beyond = min(beyond, s_first[k]);
+        const int next_lane = __shfl_down_sync(0xFFFFFFFFu, incl, 1);
+        if (lane < 31) beyond = min(beyond, next_lane);
+        if (beyond != 0x7FFFFFFF)
+            for (int g = g1 - 1; g >= g0 && s_nw[g] == (uint16_t)0xFFFF; --g) s_nw[g] = (uint16_t)beyond;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
         // every position of the precomputed region fits 31 bits (lim <= 1.5 M): 32-bit arithmetic keeps the
-        // dependent instruction chain of this single warp short (it is pure latency: ~5 cycles per instruction)
-        const int lane = threadIdx.x;
+        // dependent instruction chain of this single thread short (it is pure latency)
+        const int lane = 0;
         const int w = ln.mindistance;
         const int lim = (int)sd.lim;
         const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
-        // first settled position in chunk `c` at or after word `wfrom` (bits below `head_bit` of that word ignored)
-        auto scan_chunk = [&](int c, int wfrom, int head_bit) -> int {
-            const int wi = (c << 5) + lane;
-            uint32_t v = (wi < nwords && wi >= wfrom) ? s_bits[wi] : 0u;
-            if (wi == wfrom) v &= ~0u << head_bit;
-            const unsigned any = __ballot_sync(0xFFFFFFFFu, v != 0u);
-            if (!any) return -1;
-            const int l = __ffs(any) - 1;
-            const uint32_t vv = __shfl_sync(0xFFFFFFFFu, v, l);
-            return (((c << 5) + l) << 5) + (__ffs(vv) - 1);
-        };
-        // first settled position >= x inside [0, lim); -1 when the mask ends first: the rest of x's chunk, then
-        // the summary names the next chunk that holds one
+        // first settled position >= x inside [0, lim); -1 when the mask ends first
         auto next_settled = [&](int x) -> int {
-            const int wi = x >> 5, c = wi >> 5;
+            int wi = x >> 5;
             if (wi >= nwords) return -1;
-            int p = scan_chunk(c, wi, x & 31);
-            if (p >= 0) return p;
-            int c1 = c + 1;
-            while (c1 < nchunks) {
-                const int sw = (c1 >> 5) + lane;
-                uint32_t sv = sw < nsum ? s_sum[sw] : 0u;
-                if (lane == 0) sv &= ~0u << (c1 & 31);
-                const unsigned any = __ballot_sync(0xFFFFFFFFu, sv != 0u);
-                if (any) {
-                    const int l = __ffs(any) - 1;
-                    const uint32_t vv = __shfl_sync(0xFFFFFFFFu, sv, l);
-                    const int c2 = ((((c1 >> 5) + l) << 5) + (__ffs(vv) - 1));
-                    return scan_chunk(c2, c2 << 5, 0);
+            uint32_t v = s_bits[wi] & (~0u << (x & 31));
+            if (v == 0u) {
+                const int g = (wi >> 2) + 1;              // the rest of this group, then the table
+                for (++wi; wi < 4 * g && wi < nwords; ++wi) {
+                    v = s_bits[wi];
+                    if (v != 0u) break;
                 }
-                c1 = ((c1 >> 5) + 32) << 5;
+                if (v == 0u) {
+                    if (g >= ngroups) return -1;
+                    const uint32_t nxt = s_nw[g];
+                    if (nxt == 0xFFFFu) return -1;
+                    wi = (int)nxt;
+                    v = s_bits[wi];
+                }
             }
-            return -1;
+            return (wi << 5) + (__ffs(v) - 1);
         };
         int np = 0, ok = 1;
         int P = 0;
@@ -1654,7 +1781,7 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         const void *fn = (const void *)sync_settled_kernel;
         if (!ctx->smem_configured.count(fn)) {
             CUDA_CHECK(cudaFuncSetAttribute(sync_settled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute(sync_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(sync_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             ctx->smem_configured[fn] = 1;
         }
         {
@@ -1665,7 +1792,9 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         }
         {
             StageTimer t1(ctx, "sync_chain");
-            sync_chain_kernel<<<batch, 1024, (size_t)((sp.max_lim + 31) / 32 + 4) * sizeof(uint32_t), st>>>(
+            // the settled bits + one uint16 per 4 words (the "next non-empty word" table)
+            const size_t chain_words = (size_t)(((sp.max_lim + 31) / 32 + 4 + 3) & ~3ll);
+            sync_chain_kernel<<<batch, 1024, chain_words * sizeof(uint32_t) + (chain_words / 4 + 4) * sizeof(uint16_t), st>>>(
                 n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan, force_scan);
         }
         ctx->launches += 3;
@@ -1675,11 +1804,27 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
     // the parallel search above only reads the head of the recording; the sequential fallback may read all of it
     if (all_data_ready) CUDA_CHECK(cudaStreamWaitEvent(st, all_data_ready, 0));
     if (min_mindistance >= 4096)
-        sync_search_kernel<4><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
+        sync_search_kernel<4, false><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
     else if (min_mindistance >= 2048)
-        sync_search_kernel<2><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
+        sync_search_kernel<2, false><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
     else
-        sync_search_kernel<1><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
+        sync_search_kernel<1, false><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// data_packet.py:313-331 for n_packets packets of n grey levels each (stride ds); line: one LineDev on the device
+// with n1 = samples(0.025), L = n1 + 2, mindistance = samples(0.4).  RecResult.peaks / n_peaks / start_frame (= last
+// pulse or -1) per packet.
+void launch_packet_pulse_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int n_packets,
+                                const LineDev *line, RecResult *res, int mindistance) {
+    StageTimer timer(ctx, "packet_pulses");
+    if (mindistance >= 4096)
+        sync_search_kernel<4, true><<<n_packets, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, line, res, nullptr, LazyGrey());
+    else if (mindistance >= 2048)
+        sync_search_kernel<2, true><<<n_packets, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, line, res, nullptr, LazyGrey());
+    else
+        sync_search_kernel<1, true><<<n_packets, kSyncThreads, 0, ctx->stream>>>(dig, ds, n, line, res, nullptr, LazyGrey());
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

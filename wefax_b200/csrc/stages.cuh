@@ -96,6 +96,8 @@ cudaEvent_t launch_quantise_split(wefax_ctx *ctx, const float *env, size_t es, u
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                         RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready = nullptr,
                         const LazyGrey &lazy = LazyGrey());
+void launch_packet_pulse_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int n_packets,
+                                const LineDev *line, RecResult *res, int mindistance);
 // samples the parallel phasing search reads: [0, sync_head(sp, n))
 long long sync_head(const SyncPlan &sp, long long n);
 // sizes the parallel search for recordings [first, first+count) and uploads its geometry
