@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "stages.cuh"
 
@@ -217,6 +218,84 @@ void deliver_results(wefax_ctx *ctx, const RecResult *h_res, int g, int w0, cons
     if (copied) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
+
+// Depth-first form of a batch (see wefax_ctx::max_wave).  Returns false when the batch should run breadth-first on
+// the context itself: single recordings, working sets larger than the L2 cache, stage timing on (the per-stage
+// event pairs belong to one stream), or WEFAX_DEPTH_FIRST=0.
+bool decode_depth_first(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm, const double *lpm,
+                        const wefax_batch_out *out, long long n) {
+    const int nrec = desc->n_recordings;
+    if (ctx->is_lane || ctx->timing || ctx->depth_first == 0 || ctx->lanes < 1) return false;
+    // live buffers of one recording between two stages: transform buffer + audio + envelope (+ raster at the end)
+    const long long working_set = n * (8 + 4 + 4);
+    const bool fits = working_set * ctx->lane_wave <= (96ll << 20);
+    if (ctx->depth_first < 0 && (!fits || nrec < 2 * ctx->lanes)) return false;
+    if (nrec < 2) return false;
+    const int L = std::min(ctx->lanes, nrec);
+    while ((int)ctx->lane_ctx.size() < L) {
+        wefax_ctx *lane = nullptr;
+        const int rc = wefax_ctx_create(ctx->device, nullptr, &lane);
+        if (rc != WEFAX_OK) WEFAX_THROW(rc, "cannot create a decode lane on device %d", ctx->device);
+        lane->is_lane = true;
+        lane->workspace_limit = ctx->workspace_limit;
+        ctx->lane_ctx.push_back(lane);
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_lane_join.push_back(e);
+    }
+    if (!ctx->ev_lane_fork) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lane_fork, cudaEventDisableTiming));
+    // the lanes start after whatever the caller queued on the context's stream (e.g. the producer of a device PCM)
+    CUDA_CHECK(cudaEventRecord(ctx->ev_lane_fork, ctx->stream));
+    const size_t esz = (desc->flags & WEFAX_F_PCM_FLOAT32) ? sizeof(float) : sizeof(int16_t);
+    const long long n_in = desc->n_frames;
+    std::vector<int> rc(L, WEFAX_OK);
+    std::vector<std::thread> threads;
+    for (int l = 0; l < L; ++l) {
+        const int r0 = (int)((long long)nrec * l / L), r1 = (int)((long long)nrec * (l + 1) / L);
+        wefax_ctx *lane = ctx->lane_ctx[l];
+        lane->max_wave = ctx->lane_wave;
+        lane->use_fused = ctx->use_fused;
+        lane->use_sym_notch = ctx->use_sym_notch;
+        threads.emplace_back([=, &rc] {
+            cudaSetDevice(lane->device);
+            if (cudaStreamWaitEvent(lane->stream, ctx->ev_lane_fork, 0) != cudaSuccess) {
+                rc[l] = WEFAX_ERR_CUDA;
+                return;
+            }
+            wefax_batch_desc d = *desc;
+            d.n_recordings = r1 - r0;
+            wefax_batch_out o = *out;
+            const size_t R = (size_t)r0;
+            if (o.audio) o.audio += R * (size_t)n;
+            if (o.demodulated) o.demodulated += R * (size_t)n;
+            if (o.digitalized) o.digitalized += R * (size_t)n;
+            if (o.peaks) o.peaks += R * WEFAX_MAX_PEAKS;
+            if (o.n_peaks) o.n_peaks += R;
+            if (o.phasing) o.phasing += R * WEFAX_MAX_PEAKS;
+            if (o.n_phasing) o.n_phasing += R;
+            if (o.start_frame) o.start_frame += R;
+            if (o.height) o.height += R;
+            if (o.status) o.status += R;
+            if (o.low_high) o.low_high += 2 * R;
+            if (o.raster) o.raster += R * (size_t)o.raster_stride;
+            const int16_t *p = (const int16_t *)((const char *)pcm + R * (size_t)n_in * (size_t)desc->channels * esz);
+            rc[l] = wefax_decode_batch(lane, &d, p, lpm + r0, &o);
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (int l = 0; l < L; ++l) {
+        wefax_ctx *lane = ctx->lane_ctx[l];
+        ctx->launches += lane->launches;
+        lane->launches = 0;
+        // (every lane call ends with a synchronisation of its stream; the event keeps the stream semantics explicit)
+        CUDA_CHECK(cudaEventRecord(ctx->ev_lane_join[l], lane->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_join[l], 0));
+    }
+    for (int l = 0; l < L; ++l)
+        if (rc[l] != WEFAX_OK) WEFAX_THROW(rc[l], "%s", ctx->lane_ctx[l]->last_error.c_str());
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -257,6 +336,9 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
         ctx->use_fast = !(fastk && fastk[0] == '0');
         const char *tmaf = getenv("WEFAX_FFT_TMAFAST");
         ctx->use_tma_fast = !(tmaf && tmaf[0] == '0');
+        if (const char *df = getenv("WEFAX_DEPTH_FIRST")) ctx->depth_first = atoi(df) != 0 ? 1 : 0;
+        if (const char *ln = getenv("WEFAX_LANES")) ctx->lanes = std::max(1, std::min(8, atoi(ln)));
+        if (const char *lw = getenv("WEFAX_LANE_WAVE")) ctx->lane_wave = std::max(1, atoi(lw));
         const char *symn = getenv("WEFAX_NOTCH_SYM");
         ctx->use_sym_notch = !(symn && symn[0] == '0');
         const char *fused = getenv("WEFAX_FUSED");   // WEFAX_FUSED=0: separate grey-map and raster kernels
@@ -291,6 +373,10 @@ void wefax_ctx_destroy(wefax_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (wefax_ctx *lane : ctx->lane_ctx) wefax_ctx_destroy(lane);
+    ctx->lane_ctx.clear();
+    if (ctx->ev_lane_fork) cudaEventDestroy(ctx->ev_lane_fork);
+    for (cudaEvent_t e : ctx->ev_lane_join) cudaEventDestroy(e);
     if (ctx->aux_stream) {
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamDestroy(ctx->aux_stream);
@@ -410,6 +496,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
         if (n_in >= (1ll << 31) - 4096 || n >= (1ll << 31) - 4096) WEFAX_THROW(WEFAX_ERR_INVALID, "recording too long");
         use_device(ctx);
         cudaStream_t st = ctx->stream;
+        if (decode_depth_first(ctx, desc, pcm, lpm, out, n)) return;
         const bool pcm_dev = desc->flags & WEFAX_F_PCM_ON_DEVICE;
         const bool out_dev = desc->flags & WEFAX_F_OUT_ON_DEVICE;
         // float32 samples (the host side of WAV formats other than 16-bit PCM: int32 / 24-bit / float, wefax.py:349)
@@ -447,6 +534,7 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                                   std::max(zlen, zlen_rs) * 8 + n * (4 + 4 + 4 + 1 + 4) + 4096;
         int wave = (int)std::max<long long>(1, std::min<long long>(nrec, ctx->workspace_limit / per_rec));
         wave = std::min(wave, 32768);
+        if (ctx->max_wave > 0) wave = std::min(wave, ctx->max_wave);
 
         LineDev *d_lines = (LineDev *)ctx->out_small.reserve((sizeof(LineDev) + sizeof(RecResult)) * (size_t)wave +
                                                              sizeof(SelState) * (size_t)wave + 256);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "fft.cuh"
@@ -51,6 +52,17 @@ struct wefax_ctx {
     std::string last_error;
     long long launches = 0;
     long long workspace_limit = 24ll << 30;
+    // Depth-first batches: recordings whose working set fits the L2 cache go through ALL stages one (or a few) at a
+    // time instead of stage by stage over the whole batch, so the transform buffer never leaves L2; two lanes (child
+    // contexts with their own stream and scratch, one host thread each) keep the GPU busy across launch gaps.
+    int max_wave = 0;                         // > 0: cap on the recordings of one wave (set on the lanes)
+    int depth_first = -1;                     // WEFAX_DEPTH_FIRST: -1 auto, 0 off, 1 on
+    int lanes = 2;                            // WEFAX_LANES
+    int lane_wave = 1;                        // WEFAX_LANE_WAVE: recordings per wave on a lane
+    bool is_lane = false;
+    std::vector<wefax_ctx *> lane_ctx;        // owned
+    cudaEvent_t ev_lane_fork = nullptr;
+    std::vector<cudaEvent_t> ev_lane_join;
     int sm_count = 148;
     bool use_tma = true;   // WEFAX_FFT_TMA=0 forces the LDG tile loads
     bool use_fast = true;  // WEFAX_FFT_FAST=0 keeps every pass on the generic kernel
