@@ -401,6 +401,39 @@ def test_decode_waves_equal_single_wave(dec):
         assert np.array_equal(res.image(i), ref.image(i))
 
 
+@pytest.mark.parametrize("lanes,lane_wave", [(1, 1), (2, 1), (3, 2), (4, 3)])
+def test_decode_lanes_equal_one_wave(dec, monkeypatch, lanes, lane_wave):
+    """Depth-first lanes (child contexts on their own streams and host threads, a few recordings at a time)
+    produce bit for bit what the whole batch produces in one wave: host and device buffers, mixed LPM."""
+    import torch
+    from wefax_b200.decoder import Decoder
+    specs = [synth.batch_spec(k, noisy=(k % 3 == 0)) for k in range(11)]
+    pcm = np.stack([synth.synth_recording(24.0, **s) for s in specs])
+    lpms = [s["lpm"] for s in specs]
+    want = ("audio", "demodulated", "digitalized", "raster")
+    ref = dec.decode(pcm, 11025, lpms, want=want)
+    monkeypatch.setenv("WEFAX_DEPTH_FIRST", "1")
+    monkeypatch.setenv("WEFAX_LANES", str(lanes))
+    monkeypatch.setenv("WEFAX_LANE_WAVE", str(lane_wave))
+    laned = Decoder(0)
+    try:
+        res = laned.decode(pcm, 11025, lpms, want=want)
+        dev = laned.decode(torch.from_numpy(pcm).cuda(), 11025, lpms, want=want, device_outputs=True)
+        torch.cuda.synchronize()
+    finally:
+        laned.close()
+    assert np.array_equal(res.status, ref.status) and np.array_equal(res.start_frame, ref.start_frame)
+    assert res.peaks == ref.peaks and res.phasing_signals == ref.phasing_signals
+    assert np.array_equal(res.low_high, ref.low_high)
+    for name in ("audio", "demodulated", "digitalized"):
+        assert np.array_equal(getattr(res, name), getattr(ref, name)), name
+        assert np.array_equal(getattr(dev, name).cpu().numpy(), getattr(ref, name)), name
+    for i in range(len(specs)):
+        assert np.array_equal(res.image(i), ref.image(i)), i
+        h, w = int(ref.height[i]), ref.width[i]
+        assert np.array_equal(dev.raster_flat[i, : h * w].cpu().numpy(), ref.raster_flat[i][: h * w]), i
+
+
 # --------------------------------------------------------------------------- the drop-in class
 def test_demodulator_drop_in(dec, tmp_path):
     import json

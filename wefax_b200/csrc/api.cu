@@ -225,12 +225,18 @@ void deliver_results(wefax_ctx *ctx, const RecResult *h_res, int g, int w0, cons
 bool decode_depth_first(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16_t *pcm, const double *lpm,
                         const wefax_batch_out *out, long long n) {
     const int nrec = desc->n_recordings;
-    if (ctx->is_lane || ctx->timing || ctx->depth_first == 0 || ctx->lanes < 1) return false;
-    // live buffers of one recording between two stages: transform buffer + audio + envelope (+ raster at the end)
-    const long long working_set = n * (8 + 4 + 4);
-    const bool fits = working_set * ctx->lane_wave <= (96ll << 20);
-    if (ctx->depth_first < 0 && (!fits || nrec < 2 * ctx->lanes)) return false;
-    if (nrec < 2) return false;
+    if (ctx->is_lane || ctx->timing || ctx->depth_first == 0 || ctx->lanes < 1 || nrec < 2) return false;
+    // Measured on B200 (profiles/bench_r02_lanes.md): with everything resident in HBM a lane is bound by its ~25
+    // kernel launches per recording (the host, not the GPU), so device-resident batches stay breadth-first unless
+    // WEFAX_DEPTH_FIRST=1 asks otherwise.  With HOST buffers the lanes are a copy / compute pipeline: the PCM of one
+    // chunk goes up and the results of another come down while a third is in the kernels (1.7x end to end).
+    const bool host_io = !(desc->flags & WEFAX_F_PCM_ON_DEVICE) || !(desc->flags & WEFAX_F_OUT_ON_DEVICE);
+    int lane_wave = ctx->lane_wave;
+    if (ctx->depth_first < 0) {
+        if (!host_io || nrec < 2 * ctx->lanes) return false;
+        if (!getenv("WEFAX_LANE_WAVE")) lane_wave = (int)std::max(1ll, std::min(16ll, (long long)nrec / (4 * ctx->lanes)));
+    }
+    (void)n;
     const int L = std::min(ctx->lanes, nrec);
     while ((int)ctx->lane_ctx.size() < L) {
         wefax_ctx *lane = nullptr;
@@ -253,7 +259,7 @@ bool decode_depth_first(wefax_ctx *ctx, const wefax_batch_desc *desc, const int1
     for (int l = 0; l < L; ++l) {
         const int r0 = (int)((long long)nrec * l / L), r1 = (int)((long long)nrec * (l + 1) / L);
         wefax_ctx *lane = ctx->lane_ctx[l];
-        lane->max_wave = ctx->lane_wave;
+        lane->max_wave = lane_wave;
         lane->use_fused = ctx->use_fused;
         lane->use_sym_notch = ctx->use_sym_notch;
         threads.emplace_back([=, &rc] {

@@ -52,12 +52,12 @@ struct wefax_ctx {
     std::string last_error;
     long long launches = 0;
     long long workspace_limit = 24ll << 30;
-    // Depth-first batches: recordings whose working set fits the L2 cache go through ALL stages one (or a few) at a
-    // time instead of stage by stage over the whole batch, so the transform buffer never leaves L2; two lanes (child
-    // contexts with their own stream and scratch, one host thread each) keep the GPU busy across launch gaps.
+    // Lanes: a batch is split over child contexts (own stream and scratch, one host thread each) that take their
+    // recordings through ALL stages a few at a time.  With host buffers that is a copy / compute pipeline; with
+    // device-resident data it keeps a recording's working set in L2 (depth first), at the price of more launches.
     int max_wave = 0;                         // > 0: cap on the recordings of one wave (set on the lanes)
     int depth_first = -1;                     // WEFAX_DEPTH_FIRST: -1 auto, 0 off, 1 on
-    int lanes = 2;                            // WEFAX_LANES
+    int lanes = 3;                            // WEFAX_LANES
     int lane_wave = 1;                        // WEFAX_LANE_WAVE: recordings per wave on a lane
     bool is_lane = false;
     std::vector<wefax_ctx *> lane_ctx;        // owned

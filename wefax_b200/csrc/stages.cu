@@ -689,10 +689,13 @@ __device__ __forceinline__ void coop_barrier(CoopSync *cs, unsigned ncta, unsign
     __syncthreads();
 }
 
+// nbar: CTAs that meet at the barrier (0: ncta).  With ncta = 1, cta = 0 and nbar = the real number of CTAs every CTA
+// histograms its OWN keys (e.g. a slice it holds in shared memory) and the CTAs still select together.
 template <int NT, class KeyAt>
 __device__ void coop_select(KeyAt key_at, long long count, int cta, unsigned ncta, CoopSync *cs, unsigned &phase,
                             uint32_t *ghist, uint32_t *s_hist /* NT*2048 */, uint32_t *s_rank, uint32_t *s_prefix,
-                            uint32_t *s_scan /* 32 */) {
+                            uint32_t *s_scan /* 32 */, unsigned nbar = 0) {
+    if (nbar == 0) nbar = ncta;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < NT) s_prefix[tid] = 0;
     for (int level = 0; level < 3; ++level) {
@@ -739,7 +742,7 @@ __device__ void coop_select(KeyAt key_at, long long count, int cta, unsigned nct
             const uint32_t c = s_hist[i];
             if (c) atomicAdd(&gh[i], c);
         }
-        coop_barrier(cs, ncta, phase);
+        coop_barrier(cs, nbar, phase);
         // locate each target in the recording-wide histogram: thread tid owns bins 2*tid, 2*tid+1
         for (int t = 0; t < NT; ++t) {
             const int hsel = level == 0 ? 0 : t;
@@ -807,6 +810,47 @@ pct_bracket_kernel(const float *samp, size_t ss, PctGeom g, PctState *st_all, Pc
     unsigned phase = 0;
     coop_select<4>([&](long long i) { return __float_as_uint(__ldg(sp + i)); }, g.ns, cta, (unsigned)ncta, &coop->sync[0],
                    phase, coop->hist[0], s_hist, s_rank, s_prefix, s_scan);
+    if (cta == 0 && threadIdx.x == 0) {
+        PctState *st = st_all + rec;
+        st->key[0] = g.open_lo ? 0u : s_prefix[0];
+        st->key[1] = s_prefix[1];
+        st->key[2] = s_prefix[2];
+        st->key[3] = g.open_hi ? 0xFFFFFFFFu : s_prefix[3];
+        st->below[0] = st->below[1] = 0;
+        st->len[0] = st->len[1] = 0;
+        st->fallback = 0;
+        st->done = 0;
+    }
+}
+
+// pct_sample_kernel + pct_bracket_kernel in one: every CTA takes its slice of the sample positions, keeps the
+// medians' keys in shared memory, and the three radix levels of the cooperative selection read them from there.
+__global__ void __launch_bounds__(kSelThreads)
+pct_bracket2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, PctCoop *coop_all, int ncta, int per) {
+    extern __shared__ uint32_t s_brk[];
+    uint32_t *s_hist = s_brk;                 // 4 * 2048
+    uint32_t *s_keys = s_brk + 4 * 2048;      // per
+    __shared__ uint32_t s_rank[4], s_prefix[4], s_scan[32];
+    const int rec = blockIdx.x / ncta, cta = blockIdx.x % ncta;
+    const float *e = env + (size_t)rec * es;
+    PctCoop *coop = coop_all + rec;
+    const long long s0 = (long long)cta * per;
+    const int cnt = (int)max(0ll, min((long long)per, g.ns - s0));
+    for (int j = threadIdx.x; j < cnt; j += kSelThreads) {
+        const long long i = (s0 + j) * kPctStride;
+        float w[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const long long k = i - 2 + t;
+            w[t] = (k >= 0 && k < g.n) ? __ldg(e + k) : 0.f;
+        }
+        s_keys[j] = __float_as_uint(med5(w[0], w[1], w[2], w[3], w[4]));
+    }
+    if (threadIdx.x < 4) s_rank[threadIdx.x] = g.s_rank[threadIdx.x];
+    __syncthreads();
+    unsigned phase = 0;
+    coop_select<4>([&](long long i) { return s_keys[i]; }, (long long)cnt, 0, 1u, &coop->sync[0], phase, coop->hist[0], s_hist,
+                   s_rank, s_prefix, s_scan, (unsigned)ncta);
     if (cta == 0 && threadIdx.x == 0) {
         PctState *st = st_all + rec;
         st->key[0] = g.open_lo ? 0u : s_prefix[0];
@@ -920,19 +964,33 @@ pct_collect2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, fl
     for (long long it = 0; it < rounds; ++it, i0 += stride) {
         float m[8];
         int nvalid = 0;
+        bool need = false;   // this thread may hold a median outside the middle
+        float f[16];
+        bool fast = false;
         if (i0 < n) {
             nvalid = (int)min(8ll, n - i0);
-            if (i0 >= 4 && i0 + 12 <= n && (reinterpret_cast<uintptr_t>(e + i0) & 15) == 0) {
-                float f[16];
+            fast = i0 >= 4 && i0 + 12 <= n && (reinterpret_cast<uintptr_t>(e + i0) & 15) == 0;
+            if (fast) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 v = __ldg(reinterpret_cast<const float4 *>(e + i0 - 4) + q);
                     f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
                 }
-                med8_from16<2>(f, m);
+                // A median of 5 lies outside the middle only if at least 3 of its 5 values do: fewer than 3 such
+                // values among the 12 this thread's 8 windows cover settles all 8 at once (the usual case: 99 % of
+                // the samples are in the middle), without a single median.
+                int outside = 0;
+#pragma unroll
+                for (int j = 2; j < 14; ++j) outside += (__float_as_uint(f[j]) - mid_lo >= mid_span) ? 1 : 0;
+                need = outside >= 3;
             } else {
-                load_med8(e, i0, n, m);
+                need = true;
             }
+        }
+        if (!__any_sync(0xFFFFFFFFu, need)) continue;
+        if (i0 < n) {
+            if (fast) med8_from16<2>(f, m);
+            else load_med8(e, i0, n, m);
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) m[j] = 0.f;
@@ -992,7 +1050,7 @@ __device__ void write_percentiles(RecResult *res, const uint32_t key[4], double 
 
 __global__ void __launch_bounds__(kSelThreads)
 pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, RecResult *res_all, PctCoop *coop_all,
-                 int ncta) {
+                 int ncta, int local_per) {
     __shared__ uint32_t s_hist[2 * 2048];
     __shared__ uint32_t s_rank[2], s_prefix[2], s_scan[32], s_key[4];
     const int rec = blockIdx.x / ncta, cta = blockIdx.x % ncta;
@@ -1019,9 +1077,21 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
         const unsigned gn = (unsigned)((ncta + 1 - h) >> 1);
         const float *lst = h ? list_hi : list_lo;
         if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)below_of[h];
-        __syncthreads();
-        coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], gcta, gn,
-                       &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
+        if (local_per > 0) {
+            // this CTA's slice of the list goes to shared memory once; the three radix levels read it from there
+            extern __shared__ uint32_t s_fin[];
+            const long long len = (long long)st->len[h];
+            const long long per = (len + gn - 1) / gn, s0 = (long long)gcta * per;
+            const int cnt = (int)max(0ll, min(per, len - s0));   // per <= local_per (the launcher sized it from cap)
+            for (int j = threadIdx.x; j < cnt; j += kSelThreads) s_fin[j] = __float_as_uint(__ldg(lst + s0 + j));
+            __syncthreads();
+            coop_select<2>([&](long long i) { return s_fin[i]; }, (long long)cnt, 0, 1u, &coop->sync[1 + h], phase,
+                           coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan, gn);
+        } else {
+            __syncthreads();
+            coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], gcta, gn,
+                           &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
+        }
         if (gcta == 0 && threadIdx.x == 0) {
             st->out_key[2 * h] = s_prefix[0];
             st->out_key[2 * h + 1] = s_prefix[1];
@@ -1148,6 +1218,26 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     // 1024-thread CTAs, two per SM
     const int ncta = std::max(1, std::min(32, ctx->sm_count / batch));
 
+    const int per = (int)((g.ns + ncta - 1) / ncta);
+    const size_t fused_smem = ((size_t)4 * 2048 + (size_t)per) * sizeof(uint32_t);
+    const char *pb = getenv("WEFAX_PCT_BRACKET");   // "old": separate sample + bracket kernels (A/B measurements)
+    if (fused_smem <= 200 * 1024 && !(pb && pb[0] == 'o')) {
+        StageTimer t1(ctx, "pct_bracket");
+        const void *fn = (const void *)pct_bracket2_kernel;
+        if (!ctx->smem_configured.count(fn)) {
+            CUDA_CHECK(cudaFuncSetAttribute(pct_bracket2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ctx->smem_configured[fn] = 1;
+        }
+        int ncta_arg = ncta, per_arg = per;
+        size_t es_arg = es;
+        void *args[] = {(void *)&env, (void *)&es_arg, (void *)&g, (void *)&pst, (void *)&coop, (void *)&ncta_arg, (void *)&per_arg};
+        if (ncta > 1)
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pct_bracket2_kernel, dim3(batch * ncta), dim3(kSelThreads), args,
+                                                   fused_smem, st));
+        else
+            pct_bracket2_kernel<<<batch, kSelThreads, fused_smem, st>>>(env, es, g, pst, coop, 1, per);
+        ctx->launches -= 1;   // (one kernel instead of two; the total below counts five)
+    } else {
     dim3 g1((unsigned)((g.ns + 255) / 256), batch);
     {
         StageTimer t1(ctx, "pct_sample");
@@ -1165,6 +1255,7 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
         else   // one CTA per recording: no cross-CTA barrier, any grid size
             pct_bracket_kernel<<<batch, kSelThreads, 0, st>>>(samp, ss, g, pst, coop, 1);
     }
+    }
     int blocks = (int)std::min<long long>((n + 2047) / 2048, (long long)ctx->sm_count * 8);
     blocks = std::max(1, blocks / std::max(1, std::min(batch, 8)));
     {
@@ -1178,13 +1269,28 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
         StageTimer t1(ctx, "pct_final");
         int ncta_arg = ncta;
         size_t ls_arg = ls;
+        // keys of a CTA's slice of a candidate list in shared memory (two groups of ncta / 2 CTAs, one per list)
+        int local_per = 0;
+        size_t fin_smem = 0;
+        if (ncta >= 2) {
+            const long long per_max = ((long long)g.cap + (ncta / 2) - 1) / (ncta / 2);
+            if (per_max * 4 <= 160 * 1024) {
+                local_per = (int)per_max;
+                fin_smem = (size_t)per_max * sizeof(uint32_t);
+                const void *fn = (const void *)pct_final_kernel;
+                if (!ctx->smem_configured.count(fn)) {
+                    CUDA_CHECK(cudaFuncSetAttribute(pct_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                    ctx->smem_configured[fn] = 1;
+                }
+            }
+        }
         void *args[] = {(void *)&g, (void *)&pst, (void *)&lists, (void *)&ls_arg, (void *)&res, (void *)&coop,
-                        (void *)&ncta_arg};
+                        (void *)&ncta_arg, (void *)&local_per};
         if (ncta > 1)
             CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)pct_final_kernel, dim3(batch * ncta), dim3(kSelThreads),
-                                                   args, 0, st));
+                                                   args, fin_smem, st));
         else
-            pct_final_kernel<<<batch, kSelThreads, 0, st>>>(g, pst, lists, ls, res, coop, 1);
+            pct_final_kernel<<<batch, kSelThreads, 0, st>>>(g, pst, lists, ls, res, coop, 1, 0);
         pct_fallback_kernel<<<batch, kSelThreads, 0, st>>>(env, es, g, pst, res, coop);
     }
     CUDA_CHECK(cudaGetLastError());
@@ -1649,11 +1755,128 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    // ---- usual case: few settled positions.  Compact them into a sorted list S, let every entry look up its
+    // successor succ[i] = first entry >= S[i] + w + 1 in parallel; the sequential chain is then 100 dependent
+    // shared-memory loads of one thread.  (Degenerate data - e.g. a constant signal settles EVERY position - does
+    // not fit the list and takes the table walk below.)
+    uint32_t *s_aux = s_bits + (((size_t)nwords + 3) & ~(size_t)3);   // list / table area behind the bits
+    __shared__ int s_warp_tot[32];
+    __shared__ int s_total;
+    constexpr int kListCap = 4096;
+    int *s_list = reinterpret_cast<int *>(s_aux), *s_succ = s_list + kListCap;
+    {
+        const int per = (nwords + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int w0 = (int)threadIdx.x * per, w1 = min(w0 + per, nwords);
+        int cnt = 0;
+        for (int wi = w0; wi < w1; ++wi) cnt += __popc(s_bits[wi]);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp_tot[wid] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int k = 0; k < wid; ++k) woff += s_warp_tot[k];
+        if (threadIdx.x == blockDim.x - 1) s_total = woff + incl;
+        __syncthreads();
+        const int M = s_total;
+        if (M <= kListCap) {
+            int off = woff + incl - cnt;
+            for (int wi = w0; wi < w1; ++wi) {
+                uint32_t v = s_bits[wi];
+                while (v) {
+                    s_list[off++] = (wi << 5) + (__ffs(v) - 1);
+                    v &= v - 1;
+                }
+            }
+            __syncthreads();
+            const int wdist = ln.mindistance;
+            for (int i = threadIdx.x; i < M; i += blockDim.x) {
+                const int target = s_list[i] + wdist + 1;
+                int lo = i + 1, hi = M;             // first index with S[idx] >= target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_list[mid] >= target) hi = mid;
+                    else lo = mid + 1;
+                }
+                s_succ[i] = lo;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int w = ln.mindistance;
+                const int lim = (int)sd.lim;
+                const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
+                int np = 1, ok = 1, P = 0, idx = -1;
+                const int j0 = first_pos[blockIdx.x];
+                if (sd.m > 0 && j0 != 0x7F7F7F7F) {
+                    int lo = 0, hi = M;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_list[mid] >= j0) hi = mid;
+                        else lo = mid + 1;
+                    }
+                    if (lo < M) {
+                        idx = lo;
+                        P = s_list[lo];
+                    } else {
+                        ok = 0;
+                    }
+                }
+                s_peaks[0] = P;
+                while (ok && sd.m > 0) {
+                    const int a = P + w + 1;
+                    if (a > last) break;
+                    np++;
+                    if (np == WEFAX_MAX_PEAKS) {
+                        s_peaks[np - 1] = a;   // the 100th peak is never refined (wefax.py:251)
+                        break;
+                    }
+                    if (a >= lim) {
+                        ok = 0;
+                        break;
+                    }
+                    if (idx >= 0) {
+                        idx = s_succ[idx];
+                    } else {                     // the chain started at the unrefined (0, 0): first entry >= a
+                        int lo = 0, hi = M;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_list[mid] >= a) hi = mid;
+                            else lo = mid + 1;
+                        }
+                        idx = lo;
+                    }
+                    if (idx >= M) {
+                        ok = 0;
+                        break;
+                    }
+                    P = s_list[idx];
+                    s_peaks[np - 1] = P;
+                }
+                s_np = np;
+                s_ok = ok;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (s_ok) {
+                    need_scan[blockIdx.x] = 0;
+                    finish_sync(s_peaks, s_np, ln, n, res_all + blockIdx.x);
+                } else {
+                    need_scan[blockIdx.x] = 1;   // ran out of precomputed region: let the sequential scan do it
+                }
+            }
+            return;
+        }
+        __syncthreads();
+    }
     // "next non-empty word" table, one entry per group of 4 words (uint16: <= 46 875 words for the 1.5 M positions
     // the region is capped at; 0xFFFF = none): with it one step of the chain is a handful of dependent
     // instructions of ONE thread instead of warp-wide ballots over many words.  Built in parallel: every thread
     // walks its run of groups backwards, a suffix minimum over the threads supplies what lies beyond the run.
-    uint16_t *s_nw = reinterpret_cast<uint16_t *>(s_bits + (((size_t)nwords + 3) & ~(size_t)3));
+    uint16_t *s_nw = reinterpret_cast<uint16_t *>(s_aux);
     __shared__ int s_first[1024 / 32];
     const int ngroups = (nwords + 3) >> 2;
     {
@@ -1781,7 +2004,7 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         const void *fn = (const void *)sync_settled_kernel;
         if (!ctx->smem_configured.count(fn)) {
             CUDA_CHECK(cudaFuncSetAttribute(sync_settled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CUDA_CHECK(cudaFuncSetAttribute(sync_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            CUDA_CHECK(cudaFuncSetAttribute(sync_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
             ctx->smem_configured[fn] = 1;
         }
         {
@@ -1794,7 +2017,9 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
             StageTimer t1(ctx, "sync_chain");
             // the settled bits + one uint16 per 4 words (the "next non-empty word" table)
             const size_t chain_words = (size_t)(((sp.max_lim + 31) / 32 + 4 + 3) & ~3ll);
-            sync_chain_kernel<<<batch, 1024, chain_words * sizeof(uint32_t) + (chain_words / 4 + 4) * sizeof(uint16_t), st>>>(
+            // ... or, in the same area, the compacted list of settled positions and its successor table (2 x 4096 ints)
+            const size_t chain_aux = std::max<size_t>((chain_words / 4 + 4) * sizeof(uint16_t), 2 * 4096 * sizeof(int));
+            sync_chain_kernel<<<batch, 1024, chain_words * sizeof(uint32_t) + chain_aux, st>>>(
                 n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan, force_scan);
         }
         ctx->launches += 3;
