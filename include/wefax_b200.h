@@ -205,6 +205,22 @@ int wefax_segment_histogram(wefax_ctx *ctx, int level, const uint32_t prefix[4],
  * digitalized (uint8) and demodulated = medfilt(envelope, 5) (float32). */
 int wefax_segment_quantise(wefax_ctx *ctx, double low, double high, uint8_t *digitalized, float *demodulated);
 
+/* ---- the same percentile exchange with everything resident on the devices (no host round trip per level) ----
+ * `state` is a DEVICE buffer of WEFAX_SEG_STATE_WORDS uint32 owned by the caller (one per context):
+ *   [0..3] remaining ranks, [4..7] prefixes, [8..9] t_lo, [10..11] t_hi, [12..13] low, [14..15] high (doubles),
+ *   [16] WEFAX_REC_* status bits, [WEFAX_SEG_STATE_HIST ..) the 4 x 2048 histogram of the current level.
+ * wefax_segment_select_init once, then per level 0, 1, 2:  wefax_segment_histogram_dev  ->  the caller sums
+ * state[WEFAX_SEG_STATE_HIST ..] over all segments ON THE CONTEXT'S STREAM (e.g. ncclAllReduce, 32 KiB of control
+ * data, not the compute path)  ->  wefax_segment_select_dev (every rank narrows the same targets redundantly).
+ * After level 2 low / high / status are in the state and wefax_segment_quantise_dev maps the grey levels.  None of
+ * these calls synchronises; with one segment the result is bit-identical to the host protocol's. */
+#define WEFAX_SEG_STATE_HIST 32
+#define WEFAX_SEG_STATE_WORDS (32 + 4 * 2048)
+int wefax_segment_select_init(wefax_ctx *ctx, uint32_t *state, const uint32_t ranks[4], double t_lo, double t_hi);
+int wefax_segment_histogram_dev(wefax_ctx *ctx, int level, uint32_t *state);
+int wefax_segment_select_dev(wefax_ctx *ctx, int level, uint32_t *state);
+int wefax_segment_quantise_dev(wefax_ctx *ctx, const uint32_t *state, uint8_t *digitalized, float *demodulated);
+
 /* Phasing search (wefax.py:218-294) on the resident grey levels; meaningful on the segment that starts
  * at sample 0 of the recording (the search reads at most the first 100 peaks).  Fills out->peaks,
  * n_peaks, phasing, n_phasing, start_frame, status (host pointers, 1 recording). */

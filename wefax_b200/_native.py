@@ -28,7 +28,8 @@ EXPORTED_SYMBOLS = (
     "wefax_resample", "wefax_filtfilt", "wefax_digitalize", "wefax_sync_raster",
     "wefax_ctx_enable_timing", "wefax_ctx_timings", "wefax_tone_scan", "wefax_decode_fm",
     "wefax_segment_envelope", "wefax_segment_histogram", "wefax_segment_quantise", "wefax_segment_sync",
-    "wefax_segment_raster", "wefax_sync_pulse_scan",
+    "wefax_segment_raster", "wefax_sync_pulse_scan", "wefax_segment_select_init", "wefax_segment_histogram_dev",
+    "wefax_segment_select_dev", "wefax_segment_quantise_dev",
 )
 ABI_VERSION = 5
 
@@ -64,6 +65,7 @@ class SyncPulseSettings(C.Structure):
 
 
 MAX_PULSES = 16
+SEG_STATE_HIST, SEG_STATE_WORDS = 32, 32 + 4 * 2048
 
 
 class FmParams(C.Structure):
@@ -152,6 +154,14 @@ def load():
     lib.wefax_segment_histogram.restype = i
     lib.wefax_segment_quantise.argtypes = [vp, d, d, vp, vp]
     lib.wefax_segment_quantise.restype = i
+    lib.wefax_segment_select_init.argtypes = [vp, vp, C.POINTER(C.c_uint32 * 4), d, d]
+    lib.wefax_segment_select_init.restype = i
+    lib.wefax_segment_histogram_dev.argtypes = [vp, i, vp]
+    lib.wefax_segment_histogram_dev.restype = i
+    lib.wefax_segment_select_dev.argtypes = [vp, i, vp]
+    lib.wefax_segment_select_dev.restype = i
+    lib.wefax_segment_quantise_dev.argtypes = [vp, vp, vp, vp]
+    lib.wefax_segment_quantise_dev.restype = i
     lib.wefax_segment_sync.argtypes = [vp, d, C.POINTER(BatchOut)]
     lib.wefax_segment_sync.restype = i
     lib.wefax_segment_raster.argtypes = [vp, d, ll, i, i, i, vp]

@@ -936,6 +936,60 @@ int wefax_segment_quantise(wefax_ctx *ctx, double low, double high, uint8_t *dig
     });
 }
 
+int wefax_segment_select_init(wefax_ctx *ctx, uint32_t *state, const uint32_t ranks[4], double t_lo, double t_hi) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!state || !ranks) WEFAX_THROW(WEFAX_ERR_INVALID, "null argument");
+        use_device(ctx);
+        launch_segment_state_init(ctx, state, ranks, t_lo, t_hi);
+    });
+}
+
+int wefax_segment_histogram_dev(wefax_ctx *ctx, int level, uint32_t *state) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (level < 0 || level > 2 || !state) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        if (!ctx->seg.have_env) WEFAX_THROW(WEFAX_ERR_INVALID, "wefax_segment_envelope has not run on this context");
+        use_device(ctx);
+        launch_segment_hist(ctx, ctx->seg.env.as<float>() + ctx->seg.base, ctx->seg.n, ctx->seg.core_lo, ctx->seg.core_hi, level,
+                            nullptr, state + WEFAX_SEG_STATE_HIST, level > 0 ? state + 4 : nullptr);
+    });
+}
+
+int wefax_segment_select_dev(wefax_ctx *ctx, int level, uint32_t *state) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (level < 0 || level > 2 || !state) WEFAX_THROW(WEFAX_ERR_INVALID, "bad argument");
+        use_device(ctx);
+        launch_segment_select_dev(ctx, state, level);
+    });
+}
+
+int wefax_segment_quantise_dev(wefax_ctx *ctx, const uint32_t *state, uint8_t *digitalized, float *demodulated) {
+    if (!ctx) return WEFAX_ERR_INVALID;
+    return guarded(ctx, [&] {
+        if (!state) WEFAX_THROW(WEFAX_ERR_INVALID, "null argument");
+        if (!ctx->seg.have_env) WEFAX_THROW(WEFAX_ERR_INVALID, "wefax_segment_envelope has not run on this context");
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const long long n = ctx->seg.n, lo = ctx->seg.core_lo, hi = ctx->seg.core_hi;
+        RecResult *d_res = (RecResult *)ctx->out_small.reserve(sizeof(RecResult));
+        CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult), st));
+        launch_segment_state_to_result(ctx, state, d_res);
+        uint8_t *d_dig = (uint8_t *)ctx->seg.dig.reserve((size_t)n);
+        const float *d_env = ctx->seg.env.as<float>() + ctx->seg.base;
+        launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, 1, d_res, 0, n, st, "quantise");
+        if (digitalized && hi > lo)
+            CUDA_CHECK(cudaMemcpyAsync(digitalized, d_dig + lo, (size_t)(hi - lo), cudaMemcpyDefault, st));
+        if (demodulated && hi > lo) {
+            float *d_med = (float *)ctx->work_a.reserve((size_t)(hi - lo) * sizeof(float));
+            launch_segment_median(ctx, d_env, n, lo, hi, d_med);
+            CUDA_CHECK(cudaMemcpyAsync(demodulated, d_med, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault, st));
+        }
+        ctx->seg.have_dig = true;   // (stream-ordered: the search / raster calls that follow run on the same stream)
+    });
+}
+
 int wefax_segment_sync(wefax_ctx *ctx, double lpm, const wefax_batch_out *out) {
     if (!ctx) return WEFAX_ERR_INVALID;
     return guarded(ctx, [&] {

@@ -19,11 +19,16 @@ constexpr int kSegHistThreads = 256;
 // Envelope values are >= 0, so the bit pattern orders like the value.
 template <int LEVEL>
 __global__ void __launch_bounds__(kSegHistThreads)
-seg_hist_kernel(const float *env, long long n, long long core_lo, long long core_hi, uint4 prefix4, uint32_t *hist) {
+seg_hist_kernel(const float *env, long long n, long long core_lo, long long core_hi, uint4 prefix4,
+                const uint32_t *prefix_dev, uint32_t *hist) {
     constexpr int NH = LEVEL == 0 ? 1 : 4;
     __shared__ uint32_t s_hist[NH][2048];
     for (int i = threadIdx.x; i < NH * 2048; i += blockDim.x) (&s_hist[0][0])[i] = 0;
-    const uint32_t prefix[4] = {prefix4.x, prefix4.y, prefix4.z, prefix4.w};
+    uint32_t prefix[4] = {prefix4.x, prefix4.y, prefix4.z, prefix4.w};
+    if (prefix_dev) {   // device-resident exchange: the prefixes never visit the host
+#pragma unroll
+        for (int t = 0; t < 4; ++t) prefix[t] = prefix_dev[t];
+    }
     __syncthreads();
 
     const long long first = core_lo & ~3ll;
@@ -60,20 +65,117 @@ seg_hist_kernel(const float *env, long long n, long long core_lo, long long core
 }
 
 void launch_segment_hist(wefax_ctx *ctx, const float *env, long long n, long long core_lo, long long core_hi, int level,
-                         const uint32_t prefix[4], uint32_t *hist) {
+                         const uint32_t prefix[4], uint32_t *hist, const uint32_t *prefix_dev) {
     StageTimer timer(ctx, "seg_hist");
     CUDA_CHECK(cudaMemsetAsync(hist, 0, 4 * 2048 * sizeof(uint32_t), ctx->stream));
     if (core_hi <= core_lo) return;
     const long long quads = (core_hi - (core_lo & ~3ll) + 3) / 4;
     const int blocks = (int)std::max<long long>(
         1, std::min<long long>((quads + kSegHistThreads - 1) / kSegHistThreads, 4ll * ctx->sm_count));
-    const uint4 p4 = make_uint4(prefix[0], prefix[1], prefix[2], prefix[3]);
+    const uint4 p4 = prefix ? make_uint4(prefix[0], prefix[1], prefix[2], prefix[3]) : make_uint4(0, 0, 0, 0);
     if (level == 0)
-        seg_hist_kernel<0><<<blocks, kSegHistThreads, 0, ctx->stream>>>(env, n, core_lo, core_hi, p4, hist);
+        seg_hist_kernel<0><<<blocks, kSegHistThreads, 0, ctx->stream>>>(env, n, core_lo, core_hi, p4, prefix_dev, hist);
     else if (level == 1)
-        seg_hist_kernel<1><<<blocks, kSegHistThreads, 0, ctx->stream>>>(env, n, core_lo, core_hi, p4, hist);
+        seg_hist_kernel<1><<<blocks, kSegHistThreads, 0, ctx->stream>>>(env, n, core_lo, core_hi, p4, prefix_dev, hist);
     else
-        seg_hist_kernel<2><<<blocks, kSegHistThreads, 0, ctx->stream>>>(env, n, core_lo, core_hi, p4, hist);
+        seg_hist_kernel<2><<<blocks, kSegHistThreads, 0, ctx->stream>>>(env, n, core_lo, core_hi, p4, prefix_dev, hist);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// ---- device-resident exchange state (include/wefax_b200.h: WEFAX_SEG_STATE_*) ------------------------------------
+__global__ void seg_state_init_kernel(uint32_t *state, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, double t_lo,
+                                      double t_hi) {
+    if (threadIdx.x == 0) {
+        state[0] = r0; state[1] = r1; state[2] = r2; state[3] = r3;
+        state[4] = state[5] = state[6] = state[7] = 0u;
+        double *d = reinterpret_cast<double *>(state + 8);
+        d[0] = t_lo; d[1] = t_hi; d[2] = 0.0; d[3] = 0.0;
+        state[16] = 0u;
+    }
+}
+
+// One CTA of 256 threads: locates, for each of the 4 target ranks, the bin of the SUMMED histogram that holds it
+// (thread t owns bins 8t .. 8t+7), narrows rank and prefix; after the last level numpy's lerp gives low / high.
+__global__ void __launch_bounds__(256) seg_select_dev_kernel(uint32_t *state, int level) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_bin[4], s_before[4];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int bits = level == 2 ? 10 : 11;
+    const uint32_t *hist_all = state + WEFAX_SEG_STATE_HIST;
+    for (int t = 0; t < 4; ++t) {
+        const uint32_t *hist = hist_all + (level == 0 ? 0 : t) * 2048;
+        const uint32_t rank = state[t];
+        uint32_t c[8], local = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = hist[8 * tid + j];
+            local += c[j];
+        }
+        uint32_t incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < wid; ++w) woff += s_warp[w];
+        uint32_t before = woff + incl - local;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (rank >= before && rank < before + c[j]) {
+                s_bin[t] = 8 * tid + j;
+                s_before[t] = before;
+            }
+            before += c[j];
+        }
+        __syncthreads();
+    }
+    if (tid < 4) {
+        state[4 + tid] = (state[4 + tid] << bits) | s_bin[tid];
+        state[tid] -= s_before[tid];
+    }
+    __syncthreads();
+    if (level == 2 && tid == 0) {
+        double *d = reinterpret_cast<double *>(state + 8);
+        const double t_lo = d[0], t_hi = d[1];
+        double v[4];
+        for (int t = 0; t < 4; ++t) v[t] = (double)__uint_as_float(state[4 + t]);
+        const double d0 = __dsub_rn(v[1], v[0]), d1 = __dsub_rn(v[3], v[2]);
+        const double low = t_lo >= 0.5 ? __dsub_rn(v[1], __dmul_rn(d0, __dsub_rn(1.0, t_lo))) : __dadd_rn(v[0], __dmul_rn(d0, t_lo));
+        const double high = t_hi >= 0.5 ? __dsub_rn(v[3], __dmul_rn(d1, __dsub_rn(1.0, t_hi))) : __dadd_rn(v[2], __dmul_rn(d1, t_hi));
+        d[2] = low;
+        d[3] = high;
+        const double delta = __dsub_rn(high, low);
+        if (!(delta > 0.0) || isinf(delta)) state[16] |= WEFAX_REC_NAN;
+    }
+}
+
+__global__ void seg_state_to_result_kernel(const uint32_t *state, RecResult *res) {
+    if (threadIdx.x == 0) {
+        const double *d = reinterpret_cast<const double *>(state + 8);
+        res->low = d[2];
+        res->high = d[3];
+        res->status = (int32_t)state[16];
+    }
+}
+
+void launch_segment_state_init(wefax_ctx *ctx, uint32_t *state, const uint32_t ranks[4], double t_lo, double t_hi) {
+    seg_state_init_kernel<<<1, 32, 0, ctx->stream>>>(state, ranks[0], ranks[1], ranks[2], ranks[3], t_lo, t_hi);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+void launch_segment_select_dev(wefax_ctx *ctx, uint32_t *state, int level) {
+    seg_select_dev_kernel<<<1, 256, 0, ctx->stream>>>(state, level);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+void launch_segment_state_to_result(wefax_ctx *ctx, const uint32_t *state, RecResult *res) {
+    seg_state_to_result_kernel<<<1, 32, 0, ctx->stream>>>(state, res);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

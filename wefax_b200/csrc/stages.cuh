@@ -115,8 +115,12 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
 
 // ---- segment mode (segment.cu): radix-digit histograms of the median-filtered envelope of the core
 // samples [core_lo, core_hi) of an extended segment of n samples; hist: 4 x 2048 counters (device)
+// prefix_dev (may be null): the four prefixes in DEVICE memory (device-resident exchange) instead of `prefix`
 void launch_segment_hist(wefax_ctx *ctx, const float *env, long long n, long long core_lo, long long core_hi, int level,
-                         const uint32_t prefix[4], uint32_t *hist);
+                         const uint32_t prefix[4], uint32_t *hist, const uint32_t *prefix_dev = nullptr);
+void launch_segment_state_init(wefax_ctx *ctx, uint32_t *state, const uint32_t ranks[4], double t_lo, double t_hi);
+void launch_segment_select_dev(wefax_ctx *ctx, uint32_t *state, int level);
+void launch_segment_state_to_result(wefax_ctx *ctx, const uint32_t *state, RecResult *res);
 void launch_segment_median(wefax_ctx *ctx, const float *env, long long n, long long core_lo, long long core_hi,
                            float *out);
 

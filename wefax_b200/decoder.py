@@ -402,6 +402,36 @@ class Decoder:
             out["demodulated"] = dem
         return out
 
+    # device-resident form of the percentile exchange (state: CUDA int32 tensor of N.SEG_STATE_WORDS; nothing syncs)
+    def segment_select_init(self, state, ranks, t_lo: float, t_hi: float) -> None:
+        r = (C.c_uint32 * 4)(*[int(v) for v in ranks])
+        self._check(self._lib.wefax_segment_select_init(self._h, C.c_void_p(state.data_ptr()), r, float(t_lo), float(t_hi)))
+
+    def segment_histogram_dev(self, level: int, state) -> None:
+        self._check(self._lib.wefax_segment_histogram_dev(self._h, int(level), C.c_void_p(state.data_ptr())))
+
+    def segment_select_dev(self, level: int, state) -> None:
+        self._check(self._lib.wefax_segment_select_dev(self._h, int(level), C.c_void_p(state.data_ptr())))
+
+    def segment_quantise_dev(self, state, want=("digitalized",)) -> dict:
+        """Grey map with the low / high held in the device state; the core's share of ``want`` comes back in pinned
+        host arrays that are valid after the next synchronisation of this context."""
+        lo, hi = self._seg_core
+        out = {}
+        dig = np.empty(hi - lo, dtype=np.uint8) if "digitalized" in want else None
+        dem = np.empty(hi - lo, dtype=np.float32) if "demodulated" in want else None
+        self._check(self._lib.wefax_segment_quantise_dev(
+            self._h, C.c_void_p(state.data_ptr()),
+            C.c_void_p(dig.ctypes.data if dig is not None and dig.size else None),
+            C.c_void_p(dem.ctypes.data if dem is not None and dem.size else None)))
+        if dig is not None or dem is not None:
+            self.synchronize()   # pageable destinations: the copies above were staged, make them visible
+        if dig is not None:
+            out["digitalized"] = dig
+        if dem is not None:
+            out["demodulated"] = dem
+        return out
+
     def segment_sync(self, lpm) -> dict:
         """Phasing search on the resident grey levels (the segment that starts the recording)."""
         peaks = np.zeros(N.MAX_PEAKS, dtype=np.int32)

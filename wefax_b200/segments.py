@@ -26,6 +26,7 @@ drives one worker per local GPU context.
 from __future__ import annotations
 
 import math
+import os
 import sys
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
@@ -216,6 +217,20 @@ class HostExchange:
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.rank = self.dist.get_rank(group) if self.dist else 0
 
+    def device_exchange_possible(self, local_workers: int) -> bool:
+        """The device-resident percentile exchange needs one worker per rank and a NCCL group (WEFAX_SEG_HOST=1
+        forces the host exchange, for A/B measurements)."""
+        return (self.world > 1 and local_workers == 1 and self.dist.get_backend(self.group) == "nccl"
+                and os.environ.get("WEFAX_SEG_HOST", "0") != "1")
+
+    def device_state(self, device: int):
+        import torch
+        key = ("state", device)
+        if getattr(self, "_state_key", None) != key:
+            self._state = torch.zeros(N.SEG_STATE_WORDS, dtype=torch.int32, device=f"cuda:{device}")
+            self._state_key = key
+        return self._state
+
     def sum(self, arr: np.ndarray) -> np.ndarray:
         if self.world == 1:
             return arr
@@ -388,27 +403,49 @@ def _run_protocol(ex, each, workers, segs, L, pcm, sample_rate, lpm, w, n_total,
             raise RuntimeError(f"segment {sg.index}: {n_ext} samples at 11025 Hz, planned {sg.n_out}")
     each(envelope)
 
-    # 2. exact global percentiles (three histogram exchanges)
+    # 2. exact global percentiles
     ranks, fracs = percentile_targets(n_total)
-
-    def summed_histogram(level, prefix):
-        local = np.zeros((4, 2048), dtype=np.int64)
-        for h in each(lambda wk, sg: wk.segment_histogram(level, prefix)):
-            local += h
-        return ex.sum(local)
-
-    v = select_order_statistics(summed_histogram, ranks)
-    low, high = _lerp(v[0], v[1], fracs[0]), _lerp(v[2], v[3], fracs[1])
-    status = N.REC_OK if high != low else N.REC_NAN      # wefax.py:216: 0/0 -> nan -> int() raises
-
-    # 3. grey map everywhere; phasing search on the segment that starts the recording
     digitalized, demodulated = {}, {}
     small = tuple(x for x in want if x in ("digitalized", "demodulated"))
-    for sg, got in each(lambda wk, sg: (sg, wk.segment_quantise(low, high, small))):
+    if ex.device_exchange_possible(L):
+        # Everything stays on the devices: per radix level a histogram kernel, a 32 KiB all-reduce of the counters
+        # (NCCL, queued on the context's stream: control data, not the compute path) and a select kernel that every
+        # rank runs redundantly; the grey map reads low / high from device memory.  No host round trip, no sync.
+        import torch
+        wk, sg = workers[0], mine[0]
+        with torch.cuda.device(wk.device), torch.cuda.stream(torch.cuda.ExternalStream(wk.stream, device=wk.device)):
+            state = ex.device_state(wk.device)
+            wk.segment_select_init(state, ranks, fracs[0], fracs[1])
+            for level in (0, 1, 2):
+                wk.segment_histogram_dev(level, state)
+                ex.dist.all_reduce(state[N.SEG_STATE_HIST:], group=ex.group)
+                wk.segment_select_dev(level, state)
+            got = wk.segment_quantise_dev(state, small)
+            head = state[:N.SEG_STATE_HIST].cpu()          # low / high / status for the result (a local copy, no exchange)
+        low, high = (float(x) for x in head[12:16].numpy().view(np.float64))
+        status = int(head[16]) & N.REC_NAN
         if "digitalized" in got:
             digitalized[sg.core_begin] = got["digitalized"]
         if "demodulated" in got:
             demodulated[sg.core_begin] = got["demodulated"]
+    else:
+        # through the host: three histogram exchanges (any backend, several local workers, or no process group)
+        def summed_histogram(level, prefix):
+            local = np.zeros((4, 2048), dtype=np.int64)
+            for h in each(lambda wk, sg: wk.segment_histogram(level, prefix)):
+                local += h
+            return ex.sum(local)
+
+        v = select_order_statistics(summed_histogram, ranks)
+        low, high = _lerp(v[0], v[1], fracs[0]), _lerp(v[2], v[3], fracs[1])
+        status = N.REC_OK if high != low else N.REC_NAN      # wefax.py:216: 0/0 -> nan -> int() raises
+
+        # 3. grey map everywhere; phasing search on the segment that starts the recording
+        for sg, got in each(lambda wk, sg: (sg, wk.segment_quantise(low, high, small))):
+            if "digitalized" in got:
+                digitalized[sg.core_begin] = got["digitalized"]
+            if "demodulated" in got:
+                demodulated[sg.core_begin] = got["demodulated"]
     sync = None
     if ex.rank == 0:
         sync = workers[0].segment_sync(lpm)
