@@ -694,11 +694,12 @@ __device__ __forceinline__ void coop_barrier(CoopSync *cs, unsigned ncta, unsign
 template <int NT, class KeyAt>
 __device__ void coop_select(KeyAt key_at, long long count, int cta, unsigned ncta, CoopSync *cs, unsigned &phase,
                             uint32_t *ghist, uint32_t *s_hist /* NT*2048 */, uint32_t *s_rank, uint32_t *s_prefix,
-                            uint32_t *s_scan /* 32 */, unsigned nbar = 0) {
+                            uint32_t *s_scan /* 32 */, unsigned nbar = 0, int nlevels = 3) {
     if (nbar == 0) nbar = ncta;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid < NT) s_prefix[tid] = 0;
-    for (int level = 0; level < 3; ++level) {
+    // nlevels < 3: the prefixes stop after 11 or 22 bits (the caller completes them conservatively)
+    for (int level = 0; level < nlevels; ++level) {
         const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
         const uint32_t mask = level == 2 ? 0x3FFu : 0x7FFu;
         const int nh = level == 0 ? 1 : NT;           // level 0: all targets share one histogram
@@ -849,14 +850,17 @@ pct_bracket2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, Pc
     if (threadIdx.x < 4) s_rank[threadIdx.x] = g.s_rank[threadIdx.x];
     __syncthreads();
     unsigned phase = 0;
+    // Two radix levels (22 of the 32 key bits) are enough for a BRACKET: its lower ends round down, its upper ends
+    // round up to the 1024-pattern bin that holds the sample's order statistic (a few hundred more candidates out
+    // of tens of thousands), and one grid-wide barrier round less.
     coop_select<4>([&](long long i) { return s_keys[i]; }, (long long)cnt, 0, 1u, &coop->sync[0], phase, coop->hist[0], s_hist,
-                   s_rank, s_prefix, s_scan, (unsigned)ncta);
+                   s_rank, s_prefix, s_scan, (unsigned)ncta, 2);
     if (cta == 0 && threadIdx.x == 0) {
         PctState *st = st_all + rec;
-        st->key[0] = g.open_lo ? 0u : s_prefix[0];
-        st->key[1] = s_prefix[1];
-        st->key[2] = s_prefix[2];
-        st->key[3] = g.open_hi ? 0xFFFFFFFFu : s_prefix[3];
+        st->key[0] = g.open_lo ? 0u : (s_prefix[0] << 10);
+        st->key[1] = (s_prefix[1] << 10) | 0x3FFu;
+        st->key[2] = s_prefix[2] << 10;
+        st->key[3] = g.open_hi ? 0xFFFFFFFFu : ((s_prefix[3] << 10) | 0x3FFu);
         st->below[0] = st->below[1] = 0;
         st->len[0] = st->len[1] = 0;
         st->fallback = 0;

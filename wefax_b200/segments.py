@@ -412,7 +412,7 @@ def _run_protocol(ex, each, workers, segs, L, pcm, sample_rate, lpm, w, n_total,
         # (NCCL, queued on the context's stream: control data, not the compute path) and a select kernel that every
         # rank runs redundantly; the grey map reads low / high from device memory.  No host round trip, no sync.
         import torch
-        wk, sg = workers[0], mine[0]
+        wk, sg = workers[0], segs[ex.rank * L]
         with torch.cuda.device(wk.device), torch.cuda.stream(torch.cuda.ExternalStream(wk.stream, device=wk.device)):
             state = ex.device_state(wk.device)
             wk.segment_select_init(state, ranks, fracs[0], fracs[1])
