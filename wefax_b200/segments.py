@@ -267,11 +267,16 @@ class HostExchange:
         then a single copy into pinned host memory.  spans: ``(first_row, end_row)`` of every segment, known to
         every rank from the plan, so no metadata travels.  Returns the host image on rank 0, None elsewhere."""
         import torch
+        if self.world > 1 and self.dist.get_backend(self.group) != "nccl":
+            raise RuntimeError("rows_on_device needs a NCCL process group (gloo has no GPU send / recv); "
+                               "gather host rows instead (rows_on_device=False)")
+        if self.device is None:
+            raise ValueError("rows_on_device needs HostExchange(device=<this rank's GPU>)")
         img = None
         if self.rank == 0:
             key = (n_rows, width)
             if getattr(self, "_img_key", None) != key:
-                self._img = torch.empty(key, dtype=torch.uint8, device=f"cuda:{self.device or 0}")
+                self._img = torch.empty(key, dtype=torch.uint8, device=f"cuda:{self.device}")
                 self._img_host = torch.empty(key, dtype=torch.uint8, pin_memory=True)
                 self._img_key = key
             img = self._img
@@ -431,10 +436,21 @@ def _run_protocol(ex, each, workers, segs, L, pcm, sample_rate, lpm, w, n_total,
     else:
         # through the host: three histogram exchanges (any backend, several local workers, or no process group)
         def summed_histogram(level, prefix):
-            local = np.zeros((4, 2048), dtype=np.int64)
-            for h in each(lambda wk, sg: wk.segment_histogram(level, prefix)):
-                local += h
-            return ex.sum(local)
+            # one extra counter travels with the histogram: ranks whose kernels failed.  Every rank then raises
+            # together instead of leaving the others blocked in the collective.
+            local = np.zeros(4 * 2048 + 1, dtype=np.int64)
+            failure = None
+            try:
+                for h in each(lambda wk, sg: wk.segment_histogram(level, prefix)):
+                    local[:-1] += h.reshape(-1)
+            except Exception as exc:   # noqa: BLE001 - reported below, on every rank
+                failure = exc
+                local[:] = 0
+                local[-1] = 1
+            total = ex.sum(local)
+            if total[-1]:
+                raise RuntimeError(f"segment histogram failed on {int(total[-1])} rank(s)") from failure
+            return total[:-1].reshape(4, 2048)
 
         v = select_order_statistics(summed_histogram, ranks)
         low, high = _lerp(v[0], v[1], fracs[0]), _lerp(v[2], v[3], fracs[1])
@@ -447,18 +463,28 @@ def _run_protocol(ex, each, workers, segs, L, pcm, sample_rate, lpm, w, n_total,
             if "demodulated" in got:
                 demodulated[sg.core_begin] = got["demodulated"]
     sync = None
-    if ex.rank == 0:
-        sync = workers[0].segment_sync(lpm)
-        if len(sync["peaks"]) < N.MAX_PEAKS and segs[0].out_end < n_total:
-            # the search ran off the end of segment 0 before its 100th peak: more data would change it
-            raise ValueError("first segment too short for the phasing search (it found fewer than 100 peaks "
-                             "before its end); pass a larger head")
-    # one int64 tensor: [status, start_frame, n_peaks, n_phasing, peaks..., phasing...]
+    too_short = "first segment too short for the phasing search (it found fewer than 100 peaks before its end); " \
+                "pass a larger head"
+    # one int64 tensor: [status, start_frame, n_peaks, n_phasing, peaks..., phasing...]; status -1 / -2 = rank 0
+    # could not produce it (every rank raises, nobody is left waiting in the broadcast)
     flat = []
     if ex.rank == 0:
-        flat = [sync["status"], sync["start_frame"], len(sync["peaks"]), len(sync["phasing_signals"]),
-                *sync["peaks"], *sync["phasing_signals"]]
+        try:
+            sync = workers[0].segment_sync(lpm)
+            if len(sync["peaks"]) < N.MAX_PEAKS and segs[0].out_end < n_total:
+                flat = [-1, 0, 0, 0]   # the search ran off the end of segment 0 before its 100th peak
+            else:
+                flat = [sync["status"], sync["start_frame"], len(sync["peaks"]), len(sync["phasing_signals"]),
+                        *sync["peaks"], *sync["phasing_signals"]]
+        except Exception:   # noqa: BLE001
+            flat = [-2, 0, 0, 0]
+            if ex.world == 1:
+                raise
     flat = ex.broadcast_ints(flat, 4 + 2 * N.MAX_PEAKS, 0)
+    if flat[0] == -1:
+        raise ValueError(too_short)
+    if flat[0] == -2:
+        raise RuntimeError("the phasing search failed on rank 0")
     sync = {"status": flat[0], "start_frame": flat[1], "peaks": flat[4:4 + flat[2]],
             "phasing_signals": flat[4 + flat[2]:4 + flat[2] + flat[3]]}
     status |= sync["status"]
