@@ -150,3 +150,42 @@ def test_fused_matches_the_oracle_end_to_end(monkeypatch):
     if res.error(0) is None:
         ref_img = O.convert_to_image(res.digitalized[0].astype(np.int64)[int(res.start_frame[0]):], consts["width"])
         assert np.array_equal(res.image(0), ref_img)
+
+
+def test_graph_replay_of_a_repeated_device_resident_decode(monkeypatch):
+    """The third identical device-resident call replays a captured CUDA graph (api.cu, wefax_ctx::graph_exec).
+    It must see NEW data in the same buffers, survive other calls on the context in between, and equal the eager path."""
+    import torch
+    a = np.stack([synth.synth_recording(35.0, lpm=120, seed=40 + k, noise_sigma=0.03) for k in range(3)])
+    b = np.stack([synth.synth_recording(35.0, lpm=120, seed=50 + k, noise_sigma=0.05) for k in range(3)])
+    eager = _decoder(monkeypatch, WEFAX_GRAPH=0)
+    ref_a = eager.decode(a, 11025, 120, want=WANT)
+    ref_b = eager.decode(b, 11025, 120, want=WANT)
+    eager.close()
+    dec = _decoder(monkeypatch)
+    buf = torch.from_numpy(a).cuda()
+    res = dec.decode(buf, 11025, 120, want=WANT, device_outputs=True)
+    launches = []
+    for step in range(6):
+        src = a if step % 2 == 0 else b
+        buf.copy_(torch.from_numpy(src))
+        torch.cuda.synchronize()
+        before = dec.launch_count
+        dec.decode(buf, 11025, 120, want=WANT, device_outputs=True, out=res)
+        launches.append(dec.launch_count - before)
+        torch.cuda.synchronize()
+        ref = ref_a if step % 2 == 0 else ref_b
+        assert np.array_equal(res.status, ref.status)
+        assert np.array_equal(res.start_frame, ref.start_frame)
+        assert np.array_equal(res.height, ref.height)
+        assert res.peaks == ref.peaks
+        assert np.array_equal(res.digitalized.cpu().numpy(), ref.digitalized)
+        for i in range(3):
+            h, w = int(ref.height[i]), ref.width[i]
+            assert np.array_equal(res.raster_flat[i, : h * w].cpu().numpy(), ref.raster_flat[i][: h * w])
+        if step == 3:
+            # another call on the context (it may move scratch buffers): the graph must not be replayed blindly
+            other = dec.decode(b[:1, :200000], 11025, 120, want=WANT)
+            assert other.digitalized.shape == (1, 200000)
+    assert len(set(launches)) == 1, launches          # a replay reports the launches it stands for
+    dec.close()

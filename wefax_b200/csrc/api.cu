@@ -13,7 +13,8 @@ using namespace wefax;
 namespace {
 
 template <class F>
-int guarded(wefax_ctx *ctx, F &&f) {
+int guarded(wefax_ctx *ctx, F &&f, bool touches_scratch = true) {
+    if (ctx && touches_scratch) ctx->api_calls++;
     try {
         f();
         return WEFAX_OK;
@@ -342,6 +343,7 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
         ctx->use_fast = !(fastk && fastk[0] == '0');
         const char *tmaf = getenv("WEFAX_FFT_TMAFAST");
         ctx->use_tma_fast = !(tmaf && tmaf[0] == '0');
+        if (const char *gr = getenv("WEFAX_GRAPH")) ctx->use_graph = gr[0] != '0';
         if (const char *df = getenv("WEFAX_DEPTH_FIRST")) ctx->depth_first = atoi(df) != 0 ? 1 : 0;
         if (const char *ln = getenv("WEFAX_LANES")) ctx->lanes = std::max(1, std::min(8, atoi(ln)));
         if (const char *lw = getenv("WEFAX_LANE_WAVE")) ctx->lane_wave = std::max(1, atoi(lw));
@@ -379,6 +381,7 @@ void wefax_ctx_destroy(wefax_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     for (wefax_ctx *lane : ctx->lane_ctx) wefax_ctx_destroy(lane);
     ctx->lane_ctx.clear();
     if (ctx->ev_lane_fork) cudaEventDestroy(ctx->ev_lane_fork);
@@ -408,7 +411,7 @@ int wefax_ctx_sync(wefax_ctx *ctx) {
     return guarded(ctx, [&] {
         use_device(ctx);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    });
+    }, false);
 }
 
 void *wefax_ctx_stream(wefax_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -452,7 +455,7 @@ int wefax_ctx_timings(wefax_ctx *ctx, char *buf, long long buf_len, int reset) {
         if ((long long)out.size() + 1 > buf_len) WEFAX_THROW(WEFAX_ERR_INVALID, "timing buffer too small");
         memcpy(buf, out.c_str(), out.size() + 1);
         if (reset) ctx->stage_ms.clear();
-    });
+    }, false);
 }
 
 int wefax_line_constants_for(double lpm, int sample_rate, wefax_line_constants *out) {
@@ -549,8 +552,10 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
         RecResult *h_res = (RecResult *)pinned(ctx, sizeof(RecResult) * (size_t)wave + sizeof(LineDev) * (size_t)wave);
         LineDev *h_lines = (LineDev *)(h_res + wave);
 
-        for (int w0 = 0; w0 < nrec; w0 += wave) {
-            const int g = std::min(wave, nrec - w0);
+        uint8_t *d_raster = nullptr;
+        size_t rs = 0;
+        // everything of one wave up to (not including) the final synchronisation: asynchronous work on `st` only
+        auto issue_wave = [&](int w0, int g) {
             // ---- inputs ------------------------------------------------------------
             const int16_t *d_pcm = (const int16_t *)((const char *)pcm + (size_t)w0 * n_in * ch * esz);
             if (!pcm_dev) {
@@ -567,8 +572,8 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             float *d_env = (float *)ctx->work_e.reserve((size_t)g * n * sizeof(float));
             uint8_t *d_dig = (out_dev && out->digitalized) ? out->digitalized + (size_t)w0 * n
                                                            : (uint8_t *)ctx->out_dig.reserve((size_t)g * n);
-            const size_t rs = out_dev ? (size_t)rstride_user : (size_t)raster_cap;
-            uint8_t *d_raster = nullptr;
+            rs = out_dev ? (size_t)rstride_user : (size_t)raster_cap;
+            d_raster = nullptr;
             if (out->raster)
                 d_raster = out_dev ? out->raster + (size_t)w0 * rs : (uint8_t *)ctx->out_raster.reserve((size_t)g * rs);
 
@@ -657,6 +662,73 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                     CUDA_CHECK(cudaMemcpyAsync(out->digitalized + (size_t)w0 * n, d_dig, (size_t)g * n,
                                                cudaMemcpyDeviceToHost, st));
             }
+        };
+
+        // ---- CUDA graph of a device-resident single-wave decode (see wefax_ctx::graph_exec) --------------------
+        const bool graphable = ctx->use_graph && !ctx->graph_failed && pcm_dev && out_dev && wave >= nrec && !ctx->timing &&
+                               out->raster && ctx->use_fused && !ctx->is_lane && st != nullptr;
+        if (graphable) {
+            std::vector<unsigned long long> key = {
+                (unsigned long long)nrec, (unsigned long long)n_in, (unsigned long long)ch, (unsigned long long)desc->sample_rate,
+                (unsigned long long)desc->flags, (unsigned long long)(uintptr_t)pcm, (unsigned long long)(uintptr_t)out->audio,
+                (unsigned long long)(uintptr_t)out->demodulated, (unsigned long long)(uintptr_t)out->digitalized,
+                (unsigned long long)(uintptr_t)out->raster, (unsigned long long)out->raster_stride,
+                (unsigned long long)ctx->workspace_limit};
+            auto bits = [](double v) { unsigned long long u; memcpy(&u, &v, sizeof(u)); return u; };
+            key.push_back(bits(desc->notch_freq));
+            key.push_back(bits(desc->notch_q));
+            for (int r = 0; r < nrec; ++r) key.push_back(bits(lpm[r]));
+            const bool fresh = ctx->api_calls == ctx->graph_epoch + 1;         // nothing else ran on this context since
+            if (ctx->graph_exec && fresh && key == ctx->graph_key) {
+                CUDA_CHECK(cudaGraphLaunch(ctx->graph_exec, st));
+                ctx->launches += ctx->graph_launches;
+                ctx->graph_epoch = ctx->api_calls;
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                deliver_results(ctx, h_res, nrec, 0, ls, out, nullptr, 0, true);
+                return;
+            }
+            if (ctx->graph_exec) {
+                cudaGraphExecDestroy(ctx->graph_exec);
+                ctx->graph_exec = nullptr;
+            }
+            if (ctx->api_calls == ctx->graph_cand_epoch + 1 && key == ctx->graph_candidate) {
+                // second identical call in a row: every scratch buffer has its size, capture this one
+                const long long launches0 = ctx->launches;
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+                if (ok) {
+                    try {
+                        issue_wave(0, nrec);
+                    } catch (...) {
+                        ok = false;
+                    }
+                    if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+                }
+                if (ok && cudaGraphInstantiate(&ctx->graph_exec, graph, 0) != cudaSuccess) ok = false;
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) {
+                    ctx->graph_launches = ctx->launches - launches0;
+                    ctx->graph_key = key;
+                    CUDA_CHECK(cudaGraphLaunch(ctx->graph_exec, st));
+                    ctx->graph_epoch = ctx->api_calls;
+                    CUDA_CHECK(cudaStreamSynchronize(st));
+                    deliver_results(ctx, h_res, nrec, 0, ls, out, nullptr, 0, true);
+                    return;
+                }
+                // capture is not possible here (e.g. a launch the driver cannot record): stay eager on this context
+                (void)cudaGetLastError();
+                ctx->graph_exec = nullptr;
+                ctx->graph_failed = true;
+                ctx->launches = launches0;
+            } else {
+                ctx->graph_candidate = key;
+                ctx->graph_cand_epoch = ctx->api_calls;
+            }
+        }
+
+        for (int w0 = 0; w0 < nrec; w0 += wave) {
+            const int g = std::min(wave, nrec - w0);
+            issue_wave(w0, g);
             CUDA_CHECK(cudaStreamSynchronize(st));
             deliver_results(ctx, h_res, g, w0, ls, out, d_raster, rs, out_dev);
         }

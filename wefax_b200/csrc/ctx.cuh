@@ -59,6 +59,15 @@ struct wefax_ctx {
     int depth_first = -1;                     // WEFAX_DEPTH_FIRST: -1 auto, 0 off, 1 on
     int lanes = 3;                            // WEFAX_LANES
     int lane_wave = 1;                        // WEFAX_LANE_WAVE: recordings per wave on a lane
+    // CUDA graph of the last device-resident single-wave decode: when the very next decode has identical arguments the
+    // ~25 launches, memsets and small copies are replayed as ONE graph launch (the step then does not depend on how fast
+    // the host can launch).  Any other call on the context in between invalidates it (scratch may move).
+    bool use_graph = true;                    // WEFAX_GRAPH=0 turns it off
+    bool graph_failed = false;                // a capture failed on this context: stay eager
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned long long> graph_key, graph_candidate;
+    long long api_calls = 0, graph_epoch = -1, graph_cand_epoch = -1;
+    long long graph_launches = 0;
     bool is_lane = false;
     std::vector<wefax_ctx *> lane_ctx;        // owned
     cudaEvent_t ev_lane_fork = nullptr;
