@@ -189,3 +189,32 @@ def test_graph_replay_of_a_repeated_device_resident_decode(monkeypatch):
             assert other.digitalized.shape == (1, 200000)
     assert len(set(launches)) == 1, launches          # a replay reports the launches it stands for
     dec.close()
+
+
+def test_the_three_forms_of_the_greedy_picker_agree(monkeypatch):
+    """Run list (default), table walk over the settled bits (WEFAX_SYNC_FORCE_SCAN=2) and the sequential scan (=1):
+    same peaks on clean recordings (long plateaus of saturated grey), noisy ones, noise only and a constant signal,
+    and the same as the reference's picker (wefax.py:234-259) on the CUDA path's own grey levels."""
+    rng = np.random.default_rng(8)
+    n = 700000
+    recs = [synth.synth_recording(70.0, lpm=120, seed=1)[:n],
+            synth.synth_recording(70.0, lpm=120, seed=2, noise_sigma=0.05)[:n],
+            synth.synth_recording(70.0, lpm=120, seed=3, noise_sigma=0.4)[:n],
+            rng.normal(0, 2500, size=n).astype(np.int16),
+            np.where((np.arange(n) // 3) % 2 == 0, 12000, -12000).astype(np.int16),      # many tiny runs
+            np.full(n, 900, dtype=np.int16)]
+    pcm = np.stack(recs)
+    results = []
+    for mode in (None, 2, 1):
+        env = {} if mode is None else {"WEFAX_SYNC_FORCE_SCAN": mode}
+        dec = _decoder(monkeypatch, **env)
+        results.append(dec.decode(pcm, 11025, 120, want=WANT))
+        dec.close()
+    for other in results[1:]:
+        _same(results[0], other, len(recs))
+    consts = O.line_constants(120)
+    res = results[0]
+    for i in range(len(recs)):
+        if res.status[i] & 4:          # WEFAX_REC_NAN: no finite grey map (constant recording), the picker never ran
+            continue
+        assert res.peaks[i] == O.pattern_search(res.digitalized[i].astype(np.int64), consts), i

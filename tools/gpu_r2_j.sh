@@ -1,0 +1,24 @@
+#!/bin/bash
+# round-2 call J: graph replay, packed notch, lean untangle, run-list chain, TMA issuer warp: tests, A/B benches, ncu
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu > gpurun_out/j_test_all.log 2>&1
+echo "all tests exit $?" >> gpurun_out/j_test_all.log
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline"
+$B > gpurun_out/j_bench.json 2> gpurun_out/j_bench.err
+WEFAX_GRAPH=0 $B > gpurun_out/j_bench_nograph.json 2>> gpurun_out/j_bench.err
+WEFAX_TMA_ISSUER_WARP=0 $B > gpurun_out/j_bench_noissuer.json 2>> gpurun_out/j_bench.err
+WEFAX_NOTCH_MINB=5 $B > gpurun_out/j_bench_notch5.json 2>> gpurun_out/j_bench.err
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --duration 600 --batch 64 > gpurun_out/j_bench_b64.json 2>> gpurun_out/j_bench.err
+WEFAX_GRAPH=0 ncu --set full --clock-control none --import-source on -s 40 -c 20 -o gpurun_out/j_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --e2e-depth 1 > gpurun_out/j_ncu.log 2>&1
+tail -n 3 gpurun_out/j_test_all.log
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/j_bench*.json")):
+    try:
+        d=json.load(open(f))
+        print(f.split('/')[-1], round(d["value"],1), round(d["ms_per_step"],4), "e2e", round((d.get("e2e") or {}).get("value") or 0,1), "launches", d.get("gpu_launches"), d.get("parity"), {k:round(v["ms"]*1000,1) for k,v in (d.get("stages") or {}).items()}, {k:round(v["ms"]*1000,1) for k,v in (d.get("stage_parts") or {}).items()})
+    except Exception as e:
+        print(f, "ERR", e)
+PY
+tail -5 gpurun_out/j_bench.err

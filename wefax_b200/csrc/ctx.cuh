@@ -202,7 +202,11 @@ bool launch_fast_tma(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t
     }
     const long long total = (long long)p.fast_ntiles * batch;
     const int grid = (int)std::min<long long>(total, (long long)ctx->sm_count);
-    kern<<<grid, K::T, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total);
+    static const bool own_warp = [] {
+        const char *e = getenv("WEFAX_TMA_ISSUER_WARP");
+        return !(e && e[0] == '0');
+    }();
+    kern<<<grid, own_warp ? K::T + 32 : K::T, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total, own_warp ? K::T : 0);
     return true;
 }
 

@@ -420,14 +420,18 @@ template <int R1, int R2> struct TmaCfg {
 };
 
 template <int R1, int R2>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(512 + 32, 1)
 fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    int rbox, int total_tiles) {
+                    int rbox, int total_tiles, int issuer) {
+    // `issuer` = the thread that drives the copy engine: 512 (lane 0 of a 17th warp that does nothing else, so that no
+    // worker waits for a store to drain before the next load can be issued) or 0 (a worker; launched with 512 threads)
     using K = TmaCfg<R1, R2>;
     constexpr int R = K::R, C = K::C;
     extern __shared__ unsigned char tma_smem_raw[];
     // tile buffers are TMA destinations / sources: 128-byte aligned
-    float2 *A0 = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(tma_smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the shared array itself: a round trip through uintptr_t would make every tile access a
+    //  generic LD / ST instead of LDS / STS)
+    float2 *A0 = reinterpret_cast<float2 *>(tma_smem_raw + ((1024u - (smem_u32(tma_smem_raw) & 1023u)) & 1023u));
     float2 *A1 = A0 + K::TILE;
     float2 *tb = A1 + K::TILE;                 // exchange tile
     float2 *P = tb + K::TILE;                  // [R2][C]
@@ -458,7 +462,7 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
         for (int b = 0; b < nbox; ++b) tma_load_4d(dst + (size_t)b * rbox * C, &in_map, bar, 2 * m0, b * rbox, o, batch);
     };
 
-    if (tid == 0 && (int)blockIdx.x < total_tiles) issue_load(blockIdx.x, A0, mbar);
+    if (tid == issuer && (int)blockIdx.x < total_tiles) issue_load(blockIdx.x, A0, mbar);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         float2 *A = (it & 1) ? A1 : A0;
@@ -470,7 +474,7 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
         const uint32_t m = (uint32_t)(m0 + cc);
         const bool colok = m < (uint32_t)p.S;
 
-        if (tid == 0) {
+        if (tid == issuer) {
             // the other buffer was the source of the previous tile's store: reuse it for the next tile's load
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (tile + (int)gridDim.x < total_tiles) issue_load(tile + gridDim.x, Aoth, mbar + ((it + 1) & 1));
@@ -489,8 +493,9 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
             if (act1) Pval = pass_twiddle(p, (uint32_t)(row * R1) * de);
             if (act2) Aval = pass_twiddle(p, e0 + (uint32_t)row * de);
         }
-        while (!mbar_try_wait(mbar + (it & 1), (uint32_t)((it >> 1) & 1))) {
-        }
+        if (tid < K::T)
+            while (!mbar_try_wait(mbar + (it & 1), (uint32_t)((it >> 1) & 1))) {
+            }
         if (act1) {
             float2 v[R1];
 #pragma unroll
@@ -521,12 +526,12 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (tid == issuer) {
             for (int b = 0; b < nbox; ++b) tma_store_4d(&out_map, A + (size_t)b * rbox * C, 2 * m0, b * rbox, o, batch);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // (R1, R2) pairs with a compiled kernel; 0 when R has none

@@ -169,7 +169,8 @@ hilbert_mid_kernel(const MidArgs a) {
                 o2 = r.o2 == r.o ? -1 : r.o2;
                 kb = r.kb;
                 const uint32_t e = (uint32_t)kb;
-                s_wkb[tid] = cmul(__ldg(a.tw2_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw2_hi + (e >> kTwLoBits)));
+                const float2 wk = cmul(__ldg(a.tw2_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw2_hi + (e >> kTwLoBits)));
+                s_wkb[tid] = make_float2(wk.x * (0.5f * a.inv_m), wk.y * (0.5f * a.inv_m));   // scale folded into the twiddle
             }
             s_o[2 * tid] = o;
             s_o[2 * tid + 1] = o2;
@@ -206,14 +207,20 @@ hilbert_mid_kernel(const MidArgs a) {
         __syncthreads();
 
         // ---- untangle the real-input spectrum, apply -i*sgn, re-tangle, conjugate, scale
-        for (int pr = 0; pr < K::ROWS / 2; ++pr) {
-            if (s_o[2 * pr] < 0) continue;
-            const bool self = s_o[2 * pr + 1] < 0;
-            const int kb = s_kb[pr];
-            float2 *row = nat + (2 * pr) * R;
-            float2 *row2 = self ? row : row + R;
-            const float2 wkb = s_wkb[pr];
-            for (int j = tid; j < R; j += K::T) {
+        // With s = zk + conj(zm), d = zk - conj(zm), w = (inv_m / 2) * w_n^k:  a = conj(w) s,  b = w d,
+        //   row[j]   = conj(a - b)            row2[j2] = -(a + b)
+        // (the mirror's products are the conjugates of a and b, so one pair of complex multiplies serves both rows);
+        // the (pair, j) space is walked flat so that the 128 threads stay busy across the four row pairs.
+        {
+            constexpr int NPR = K::ROWS / 2;
+#pragma unroll 2
+            for (int idx = tid; idx < NPR * R; idx += K::T) {
+                const int pr = idx / R, j = idx - pr * R;
+                if (s_o[2 * pr] < 0) continue;
+                const bool self = s_o[2 * pr + 1] < 0;
+                const int kb = s_kb[pr];
+                float2 *row = nat + (2 * pr) * R;
+                float2 *row2 = self ? row : row + R;
                 const int j2 = kb ? R - 1 - j : (j ? R - j : 0);
                 if (self && j2 < j) continue;
                 if (kb == 0 && j == 0) {
@@ -221,16 +228,14 @@ hilbert_mid_kernel(const MidArgs a) {
                     continue;
                 }
                 const float2 zk = row[j], zm = row2[j2];
-                const float2 w = cmul(wkb, __ldg(a.twB + j));                                  // w_n^k, k = kb + ncols*j
-                const float2 s = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));   // (zk + conj zm)/2
-                const float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));   // (zk - conj zm)/2
-                const float2 aa = cmul(make_float2(w.x, -w.y), s), bb = cmul(w, d);
-                row[j] = make_float2((aa.x - bb.x) * a.inv_m, -(aa.y - bb.y) * a.inv_m);
-                if (!(self && j2 == j)) {
-                    const float2 a2 = cmul(w, make_float2(s.x, -s.y)),
-                                 b2 = cmul(make_float2(w.x, -w.y), make_float2(d.x, -d.y));
-                    row2[j2] = make_float2(-(a2.x + b2.x) * a.inv_m, (a2.y + b2.y) * a.inv_m);
-                }
+                const float2 w = pcmul3(__ldg(a.twB + j), s_wkb[pr]);                 // (inv_m / 2) * w_n^k, k = kb + ncols*j
+                const float2 sp = pfma(zm, make_float2(1.f, -1.f), zk);                 // zk + conj zm
+                const float2 dm = pfma(zm, make_float2(-1.f, 1.f), zk);                 // zk - conj zm
+                const float2 wa = bc(w.x);
+                const float2 aa = pfma(sp, wa, pmul(swp(sp), make_float2(w.y, -w.y)));  // conj(w) * sp
+                const float2 bb = pfma(dm, wa, pmul(swp(dm), make_float2(-w.y, w.y)));  // w * dm
+                row[j] = pmul(psub(aa, bb), make_float2(1.f, -1.f));
+                if (!(self && j2 == j)) row2[j2] = pmul(padd(aa, bb), make_float2(-1.f, -1.f));
             }
         }
         __syncthreads();

@@ -46,7 +46,39 @@ __global__ void __launch_bounds__(256) grey_table_kernel(const RecResult *res_al
         if (grey_level_exact(__uint_as_float(kInf), low, delta) < k) {
             t = 0xFFFFFFFFu;   // no float reaches this level
         } else {
-            uint32_t lo = 0u, hi = kInf;
+            // the step lies within a few ulps of low + (k - 1/2) * delta / 255: gallop away from that guess until the
+            // step is bracketed, then bisect (about 6 evaluations of the exact level instead of 31)
+            auto level = [&](uint32_t bits) { return grey_level_exact(__uint_as_float(bits), low, delta); };
+            const float guess = (float)(low + ((double)k - 0.5) * delta / 255.0);
+            uint32_t b = guess >= 0.f ? __float_as_uint(guess) : 0u;     // (NaN compares false)
+            if (b > kInf) b = kInf;
+            uint32_t lo, hi, step = 1u;
+            if (level(b) >= k) {
+                hi = b;
+                lo = 0u;
+                while (hi > 0u) {
+                    const uint32_t c = hi > step ? hi - step : 0u;
+                    if (level(c) >= k) {
+                        hi = c;
+                        step <<= 1;
+                    } else {
+                        lo = c + 1u;
+                        break;
+                    }
+                }
+            } else {
+                lo = b + 1u;
+                hi = kInf;
+                while (true) {
+                    const uint32_t c = (kInf - b > step) ? b + step : kInf;
+                    if (c == kInf || level(c) >= k) {
+                        hi = c;
+                        break;
+                    }
+                    lo = c + 1u;
+                    step <<= 1;
+                }
+            }
             while (lo < hi) {
                 const uint32_t mid = lo + ((hi - lo) >> 1);
                 if (grey_level_exact(__uint_as_float(mid), low, delta) >= k) hi = mid;

@@ -207,11 +207,35 @@ filtfilt_kernel(const void *in, size_t in_stride, float *out, size_t out_stride,
     }
 }
 
+// packed fp32 pairs (SASS FADD2 / FMUL2 / FFMA2): two samples per instruction, same IEEE roundings as the scalar forms
+__device__ __forceinline__ float2 fir_add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ta, tb, tr; mov.b64 ta, {%2,%3}; mov.b64 tb, {%4,%5}; add.rn.f32x2 tr, ta, tb; mov.b64 {%0,%1}, tr;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fir_mul2(float c, float2 a) {
+    float2 r;
+    asm("{.reg .b64 ta, tb, tr; mov.b64 ta, {%2,%3}; mov.b64 tb, {%4,%4}; mul.rn.f32x2 tr, ta, tb; mov.b64 {%0,%1}, tr;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float2 fir_fma2(float c, float2 a, float2 acc) {
+    float2 r;
+    asm("{.reg .b64 ta, tb, tc, tr; mov.b64 ta, {%2,%3}; mov.b64 tb, {%4,%4}; mov.b64 tc, {%5,%6}; "
+        "fma.rn.f32x2 tr, ta, tb, tc; mov.b64 {%0,%1}, tr;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(c), "f"(acc.x), "f"(acc.y));
+    return r;
+}
+
 // Interior tiles (further than the filter's memory from both ends of the signal): the two sections are one
 // symmetric FIR, out[i] = g0 x[i] + sum_k g_k (x[i-k] + x[i+k]).  One shared-memory stage instead of two, half the
 // multiplies; mono int16 comes in as one 16-byte load per thread.
-template <int MODE, int KC>
-__global__ void __launch_bounds__(kFirThreads)
+template <int MODE, int KC, int MINB>
+__global__ void __launch_bounds__(kFirThreads, MINB)
 notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout, size_t z_stride,
                  long long n, const FirParams fp, int tile0, int ntiles) {
     constexpr int TS = kFirTile;
@@ -279,20 +303,40 @@ notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride
         if (vec && tn < ntiles) prefetch(tn);
 
         const int i0 = 8 * tid;
-        float w[W];
+        // The window as aligned pairs wp[m] = (w[2m], w[2m+1]) (they are register pairs as the 16-byte loads deliver them),
+        // so that one packed instruction (FADD2 / FFMA2) works on two outputs.  Even taps pair up outputs (2m, 2m+1),
+        // odd taps outputs (2m+1, 2m+2): both then read only aligned pairs, and the two partial sums meet in 8 scalar adds.
+        float2 wp[W / 2];
 #pragma unroll
         for (int q = 0; q < W / 4; ++q) {
             const float4 x4 = *reinterpret_cast<const float4 *>(&sx[sidx(i0 + 4 * q)]);
-            w[4 * q] = x4.x; w[4 * q + 1] = x4.y; w[4 * q + 2] = x4.z; w[4 * q + 3] = x4.w;
+            wp[2 * q] = make_float2(x4.x, x4.y);
+            wp[2 * q + 1] = make_float2(x4.z, x4.w);
         }
-        float acc[8];
+        constexpr int H = KC / 2;               // wp[H + m] holds outputs (2m, 2m+1)
+        float2 ae[4], ao[5];                    // ae[m]: outputs (2m, 2m+1);  ao[m]: outputs (2m-1, 2m)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fp.g[0] * w[KC + i];
+        for (int m = 0; m < 4; ++m) ae[m] = fir_mul2(fp.g[0], wp[H + m]);
+#pragma unroll
+        for (int m = 0; m < 5; ++m) ao[m] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 1; k <= KC; ++k) {
             const float c = fp.g[k];
+            if (k % 2 == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(c, w[KC + i - k] + w[KC + i + k], acc[i]);
+                for (int m = 0; m < 4; ++m) ae[m] = fir_fma2(c, fir_add2(wp[H + m - k / 2], wp[H + m + k / 2]), ae[m]);
+            } else {
+                // outputs (2m-1, 2m): samples (KC + 2m - 1 -+ k, +1) = pairs H + m - (k+1)/2 and H + m + (k-1)/2
+#pragma unroll
+                for (int m = 0; m < 5; ++m)
+                    ao[m] = fir_fma2(c, fir_add2(wp[H + m - (k + 1) / 2], wp[H + m + (k - 1) / 2]), ao[m]);
+            }
+        }
+        float acc[8];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            acc[2 * m] = ae[m].x + ao[m].y;
+            acc[2 * m + 1] = ae[m].y + ao[m + 1].x;
         }
         const long long g = t0 + i0;
         if (out) {
@@ -319,11 +363,20 @@ notch_sym_kernel(const void *in, size_t in_stride, float *out, size_t out_stride
 template <int MODE, int KC>
 static void launch_notch_sym(wefax_ctx *ctx, const void *in, size_t in_stride, float *out, size_t out_stride, float2 *zout,
                              size_t z_stride, long long n, const FirParams &fp, int batch, int tile0, int ntiles) {
-    // persistent CTAs: 5 of 256 threads fit an SM (47 registers, 16.6 KiB of shared memory each)
-    const int per_rec = std::max(1, (ctx->sm_count * 5 + batch - 1) / batch);
+    // persistent CTAs of 256 threads: 4 per SM with the window and both partial sums in registers (62), or 5 with the
+    // register count capped at 48 (a 16-byte spill); WEFAX_NOTCH_MINB picks (measured: see DESIGN.md 4.1)
+    static const int minb = [] {
+        const char *e = getenv("WEFAX_NOTCH_MINB");
+        return e && atoi(e) == 5 ? 5 : 4;
+    }();
+    const int per_rec = std::max(1, (ctx->sm_count * minb + batch - 1) / batch);
     dim3 grid((unsigned)std::min(ntiles, per_rec), batch);
-    notch_sym_kernel<MODE, KC><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp,
-                                                                       tile0, ntiles);
+    if (minb == 5)
+        notch_sym_kernel<MODE, KC, 5><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n,
+                                                                              fp, tile0, ntiles);
+    else
+        notch_sym_kernel<MODE, KC, 4><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n,
+                                                                              fp, tile0, ntiles);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -1744,7 +1797,7 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
     __shared__ int s_np, s_ok;
     const LineDev ln = lines[blockIdx.x];
     const SyncDev sd = sd_all[blockIdx.x];
-    if (!sd.fast || force_scan) {   // force_scan: test hook (WEFAX_SYNC_FORCE_SCAN=1), the sequential scan decides
+    if (!sd.fast || force_scan == 1) {   // test hooks: WEFAX_SYNC_FORCE_SCAN=1 the sequential scan decides, =2 the table walk below
         if (threadIdx.x == 0) need_scan[blockIdx.x] = 1;
         return;
     }
@@ -1759,75 +1812,98 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    // ---- usual case: few settled positions.  Compact them into a sorted list S, let every entry look up its
-    // successor succ[i] = first entry >= S[i] + w + 1 in parallel; the sequential chain is then 100 dependent
-    // shared-memory loads of one thread.  (Degenerate data - e.g. a constant signal settles EVERY position - does
-    // not fit the list and takes the table walk below.)
+    // ---- usual case: the settled positions form few RUNS (isolated maxima of a noisy correlation; whole plateaus where
+    // the grey levels are saturated or constant).  Compact the runs [S_r, E_r] into two sorted lists in parallel; the
+    // sequential chain is then one thread stepping forward through them: first settled position >= a is max(a, S_r)
+    // of the first run with E_r >= a.  (Data with more than kListCap runs takes the table walk below.)
     uint32_t *s_aux = s_bits + (((size_t)nwords + 3) & ~(size_t)3);   // list / table area behind the bits
-    __shared__ int s_warp_tot[32];
+    __shared__ int s_warp_tot[2][32];
     __shared__ int s_total;
     constexpr int kListCap = 4096;
-    int *s_list = reinterpret_cast<int *>(s_aux), *s_succ = s_list + kListCap;
+    int *s_start = reinterpret_cast<int *>(s_aux), *s_end = s_start + kListCap;
     {
         const int per = (nwords + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int w0 = (int)threadIdx.x * per, w1 = min(w0 + per, nwords);
-        int cnt = 0;
-        for (int wi = w0; wi < w1; ++wi) cnt += __popc(s_bits[wi]);
+        const int w0 = min((int)threadIdx.x * per, nwords), w1 = min(w0 + per, nwords);
+        auto starts_of = [&](int wi) {
+            const uint32_t v = s_bits[wi];
+            const uint32_t prev_top = wi > 0 ? s_bits[wi - 1] >> 31 : 0u;
+            return v & ~((v << 1) | prev_top);
+        };
+        auto ends_of = [&](int wi) {
+            const uint32_t v = s_bits[wi];
+            const uint32_t next_low = wi + 1 < nwords ? s_bits[wi + 1] & 1u : 0u;
+            return v & ~((v >> 1) | (next_low << 31));
+        };
+        int cs = 0, ce = 0;
+        for (int wi = w0; wi < w1; ++wi) {
+            cs += __popc(starts_of(wi));
+            ce += __popc(ends_of(wi));
+        }
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        int incl = cnt;
+        int is = cs, ie = ce;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += o;
+            const int os = __shfl_up_sync(0xFFFFFFFFu, is, d), oe = __shfl_up_sync(0xFFFFFFFFu, ie, d);
+            if (lane >= d) {
+                is += os;
+                ie += oe;
+            }
         }
-        if (lane == 31) s_warp_tot[wid] = incl;
+        if (lane == 31) {
+            s_warp_tot[0][wid] = is;
+            s_warp_tot[1][wid] = ie;
+        }
         __syncthreads();
-        int woff = 0;
-        for (int k = 0; k < wid; ++k) woff += s_warp_tot[k];
-        if (threadIdx.x == blockDim.x - 1) s_total = woff + incl;
+        int offs = 0, offe = 0;
+        for (int k = 0; k < wid; ++k) {
+            offs += s_warp_tot[0][k];
+            offe += s_warp_tot[1][k];
+        }
+        if (threadIdx.x == blockDim.x - 1) s_total = offs + is;
         __syncthreads();
-        const int M = s_total;
-        if (M <= kListCap) {
-            int off = woff + incl - cnt;
+        const int M = s_total;                 // number of runs (as many starts as ends)
+        if (M <= kListCap && force_scan != 2) {
+            int ps = offs + is - cs, pe = offe + ie - ce;
             for (int wi = w0; wi < w1; ++wi) {
-                uint32_t v = s_bits[wi];
+                uint32_t v = starts_of(wi);
                 while (v) {
-                    s_list[off++] = (wi << 5) + (__ffs(v) - 1);
+                    s_start[ps++] = (wi << 5) + (__ffs(v) - 1);
                     v &= v - 1;
                 }
-            }
-            __syncthreads();
-            const int wdist = ln.mindistance;
-            for (int i = threadIdx.x; i < M; i += blockDim.x) {
-                const int target = s_list[i] + wdist + 1;
-                int lo = i + 1, hi = M;             // first index with S[idx] >= target
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_list[mid] >= target) hi = mid;
-                    else lo = mid + 1;
+                v = ends_of(wi);
+                while (v) {
+                    s_end[pe++] = (wi << 5) + (__ffs(v) - 1);
+                    v &= v - 1;
                 }
-                s_succ[i] = lo;
             }
             __syncthreads();
             if (threadIdx.x == 0) {
                 const int w = ln.mindistance;
                 const int lim = (int)sd.lim;
                 const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
-                int np = 1, ok = 1, P = 0, idx = -1;
-                const int j0 = first_pos[blockIdx.x];
-                if (sd.m > 0 && j0 != 0x7F7F7F7F) {
-                    int lo = 0, hi = M;
+                // first run at or after `from` that ends at or after x: a few steps forward as a rule, a binary
+                // search when the runs are dense
+                auto run_with = [&](int from, int x) -> int {
+                    int idx = from;
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {
+                        if (idx >= M || s_end[idx] >= x) return idx;
+                        ++idx;
+                    }
+                    int lo = idx, hi = M;
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
-                        if (s_list[mid] >= j0) hi = mid;
+                        if (s_end[mid] >= x) hi = mid;
                         else lo = mid + 1;
                     }
-                    if (lo < M) {
-                        idx = lo;
-                        P = s_list[lo];
-                    } else {
-                        ok = 0;
-                    }
+                    return lo;
+                };
+                int np = 1, ok = 1, P = 0, idx = 0;
+                const int j0 = first_pos[blockIdx.x];
+                if (sd.m > 0 && j0 != 0x7F7F7F7F) {
+                    idx = run_with(0, j0);
+                    if (idx < M) P = max(j0, s_start[idx]);
+                    else ok = 0;
                 }
                 s_peaks[0] = P;
                 while (ok && sd.m > 0) {
@@ -1842,32 +1918,17 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
                         ok = 0;
                         break;
                     }
-                    if (idx >= 0) {
-                        idx = s_succ[idx];
-                    } else {                     // the chain started at the unrefined (0, 0): first entry >= a
-                        int lo = 0, hi = M;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (s_list[mid] >= a) hi = mid;
-                            else lo = mid + 1;
-                        }
-                        idx = lo;
-                    }
+                    idx = run_with(idx, a);
                     if (idx >= M) {
                         ok = 0;
                         break;
                     }
-                    P = s_list[idx];
+                    P = max(a, s_start[idx]);
                     s_peaks[np - 1] = P;
                 }
-                s_np = np;
-                s_ok = ok;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                if (s_ok) {
+                if (ok) {
                     need_scan[blockIdx.x] = 0;
-                    finish_sync(s_peaks, s_np, ln, n, res_all + blockIdx.x);
+                    finish_sync(s_peaks, np, ln, n, res_all + blockIdx.x);
                 } else {
                     need_scan[blockIdx.x] = 1;   // ran out of precomputed region: let the sequential scan do it
                 }
@@ -1996,7 +2057,7 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
     StageTimer timer(ctx, "sync_search");
     cudaStream_t st = ctx->stream;
     const char *fs = getenv("WEFAX_SYNC_FORCE_SCAN");
-    const int force_scan = fs && fs[0] == '1';
+    const int force_scan = fs ? atoi(fs) : 0;
     if (sp.any_fast) {
         CUDA_CHECK(cudaMemsetAsync(sp.first_pos, 0x7F, sizeof(int) * batch, st));   // 0x7F7F7F7F = no positive correlation yet
         dim3 g1((unsigned)std::max<long long>(1, (sp.max_limc + kCorrTile - 1) / kCorrTile), batch);
