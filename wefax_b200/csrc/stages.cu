@@ -1794,10 +1794,9 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
                   const int *first_pos, RecResult *res_all, int *need_scan, int force_scan) {
     extern __shared__ uint32_t s_bits[];
     __shared__ int s_peaks[WEFAX_MAX_PEAKS];
-    __shared__ int s_np, s_ok;
     const LineDev ln = lines[blockIdx.x];
     const SyncDev sd = sd_all[blockIdx.x];
-    if (!sd.fast || force_scan == 1) {   // test hooks: WEFAX_SYNC_FORCE_SCAN=1 the sequential scan decides, =2 the table walk below
+    if (!sd.fast || force_scan == 1) {   // test hook: WEFAX_SYNC_FORCE_SCAN=1, the sequential scan decides
         if (threadIdx.x == 0) need_scan[blockIdx.x] = 1;
         return;
     }
@@ -1812,172 +1811,31 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    // ---- usual case: the settled positions form few RUNS (isolated maxima of a noisy correlation; whole plateaus where
-    // the grey levels are saturated or constant).  Compact the runs [S_r, E_r] into two sorted lists in parallel; the
-    // sequential chain is then one thread stepping forward through them: first settled position >= a is max(a, S_r)
-    // of the first run with E_r >= a.  (Data with more than kListCap runs takes the table walk below.)
-    uint32_t *s_aux = s_bits + (((size_t)nwords + 3) & ~(size_t)3);   // list / table area behind the bits
-    __shared__ int s_warp_tot[2][32];
-    __shared__ int s_total;
-    constexpr int kListCap = 4096;
-    int *s_start = reinterpret_cast<int *>(s_aux), *s_end = s_start + kListCap;
+    // Two summary levels over the mask (bit k of s_l1[j]: word 32 j + k is non-empty; s_l2 likewise over s_l1), built by
+    // warp votes: "first settled position >= x" is then three dependent shared-memory loads of ONE thread (the word
+    // of x, the summary word, the word it points at) however the settled positions are spread - isolated maxima of a
+    // noisy correlation, plateaus of saturated grey or everything at once (a constant signal settles every position).
+    uint32_t *s_l1 = s_bits + (((size_t)nwords + 3) & ~(size_t)3);
+    const int nl1 = (nwords + 31) >> 5, nl2 = (nl1 + 31) >> 5;
+    uint32_t *s_l2 = s_l1 + ((nl1 + 3) & ~3);
     {
-        const int per = (nwords + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int w0 = min((int)threadIdx.x * per, nwords), w1 = min(w0 + per, nwords);
-        auto starts_of = [&](int wi) {
-            const uint32_t v = s_bits[wi];
-            const uint32_t prev_top = wi > 0 ? s_bits[wi - 1] >> 31 : 0u;
-            return v & ~((v << 1) | prev_top);
-        };
-        auto ends_of = [&](int wi) {
-            const uint32_t v = s_bits[wi];
-            const uint32_t next_low = wi + 1 < nwords ? s_bits[wi + 1] & 1u : 0u;
-            return v & ~((v >> 1) | (next_low << 31));
-        };
-        int cs = 0, ce = 0;
-        for (int wi = w0; wi < w1; ++wi) {
-            cs += __popc(starts_of(wi));
-            ce += __popc(ends_of(wi));
-        }
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        int is = cs, ie = ce;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int os = __shfl_up_sync(0xFFFFFFFFu, is, d), oe = __shfl_up_sync(0xFFFFFFFFu, ie, d);
-            if (lane >= d) {
-                is += os;
-                ie += oe;
-            }
-        }
-        if (lane == 31) {
-            s_warp_tot[0][wid] = is;
-            s_warp_tot[1][wid] = ie;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int j = wid; j < nl1; j += nwarps) {
+            const int wi = 32 * j + lane;
+            const unsigned word = __ballot_sync(0xFFFFFFFFu, wi < nwords && s_bits[wi] != 0u);
+            if (lane == 0) s_l1[j] = word;
         }
         __syncthreads();
-        int offs = 0, offe = 0;
-        for (int k = 0; k < wid; ++k) {
-            offs += s_warp_tot[0][k];
-            offe += s_warp_tot[1][k];
-        }
-        if (threadIdx.x == blockDim.x - 1) s_total = offs + is;
-        __syncthreads();
-        const int M = s_total;                 // number of runs (as many starts as ends)
-        if (M <= kListCap && force_scan != 2) {
-            int ps = offs + is - cs, pe = offe + ie - ce;
-            for (int wi = w0; wi < w1; ++wi) {
-                uint32_t v = starts_of(wi);
-                while (v) {
-                    s_start[ps++] = (wi << 5) + (__ffs(v) - 1);
-                    v &= v - 1;
-                }
-                v = ends_of(wi);
-                while (v) {
-                    s_end[pe++] = (wi << 5) + (__ffs(v) - 1);
-                    v &= v - 1;
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const int w = ln.mindistance;
-                const int lim = (int)sd.lim;
-                const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
-                // first run at or after `from` that ends at or after x: a few steps forward as a rule, a binary
-                // search when the runs are dense
-                auto run_with = [&](int from, int x) -> int {
-                    int idx = from;
-#pragma unroll 1
-                    for (int k = 0; k < 4; ++k) {
-                        if (idx >= M || s_end[idx] >= x) return idx;
-                        ++idx;
-                    }
-                    int lo = idx, hi = M;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_end[mid] >= x) hi = mid;
-                        else lo = mid + 1;
-                    }
-                    return lo;
-                };
-                int np = 1, ok = 1, P = 0, idx = 0;
-                const int j0 = first_pos[blockIdx.x];
-                if (sd.m > 0 && j0 != 0x7F7F7F7F) {
-                    idx = run_with(0, j0);
-                    if (idx < M) P = max(j0, s_start[idx]);
-                    else ok = 0;
-                }
-                s_peaks[0] = P;
-                while (ok && sd.m > 0) {
-                    const int a = P + w + 1;
-                    if (a > last) break;
-                    np++;
-                    if (np == WEFAX_MAX_PEAKS) {
-                        s_peaks[np - 1] = a;   // the 100th peak is never refined (wefax.py:251)
-                        break;
-                    }
-                    if (a >= lim) {
-                        ok = 0;
-                        break;
-                    }
-                    idx = run_with(idx, a);
-                    if (idx >= M) {
-                        ok = 0;
-                        break;
-                    }
-                    P = max(a, s_start[idx]);
-                    s_peaks[np - 1] = P;
-                }
-                if (ok) {
-                    need_scan[blockIdx.x] = 0;
-                    finish_sync(s_peaks, np, ln, n, res_all + blockIdx.x);
-                } else {
-                    need_scan[blockIdx.x] = 1;   // ran out of precomputed region: let the sequential scan do it
-                }
-            }
-            return;
+        for (int j = wid; j < nl2; j += nwarps) {
+            const int k = 32 * j + lane;
+            const unsigned word = __ballot_sync(0xFFFFFFFFu, k < nl1 && s_l1[k] != 0u);
+            if (lane == 0) s_l2[j] = word;
         }
         __syncthreads();
     }
-    // "next non-empty word" table, one entry per group of 4 words (uint16: <= 46 875 words for the 1.5 M positions
-    // the region is capped at; 0xFFFF = none): with it one step of the chain is a handful of dependent
-    // instructions of ONE thread instead of warp-wide ballots over many words.  Built in parallel: every thread
-    // walks its run of groups backwards, a suffix minimum over the threads supplies what lies beyond the run.
-    uint16_t *s_nw = reinterpret_cast<uint16_t *>(s_aux);
-    __shared__ int s_first[1024 / 32];
-    const int ngroups = (nwords + 3) >> 2;
-    {
-        const int per = (ngroups + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int g0 = (int)threadIdx.x * per, g1 = min(g0 + per, ngroups);
-        int cur = 0x7FFFFFFF;   // first non-empty word at or after the group being visited, inside this run
-        for (int g = g1 - 1; g >= g0; --g) {
-#pragma unroll
-            for (int k = 3; k >= 0; --k) {
-                const int wi = 4 * g + k;
-                if (wi < nwords && s_bits[wi] != 0u) cur = wi;
-            }
-            s_nw[g] = cur == 0x7FFFFFFF ? (uint16_t)0xFFFF : (uint16_t)cur;
-        }
-        // exclusive suffix minimum of `cur` over the threads (word indices grow with the thread index)
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        int incl = cur;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_down_sync(0xFFFFFFFFu, incl, d);
-            if (lane + d < 32) incl = min(incl, o);
-        }
-        if (lane == 0) s_first[wid] = incl;
-        __syncthreads();
-        int beyond = 0x7FFFFFFF;
-        for (int k = wid + 1; k < (int)(blockDim.x >> 5); ++k) beyond = min(beyond, s_first[k]);
-        const int next_lane = __shfl_down_sync(0xFFFFFFFFu, incl, 1);
-        if (lane < 31) beyond = min(beyond, next_lane);
-        if (beyond != 0x7FFFFFFF)
-            for (int g = g1 - 1; g >= g0 && s_nw[g] == (uint16_t)0xFFFF; --g) s_nw[g] = (uint16_t)beyond;
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
         // every position of the precomputed region fits 31 bits (lim <= 1.5 M): 32-bit arithmetic keeps the
         // dependent instruction chain of this single thread short (it is pure latency)
-        const int lane = 0;
         const int w = ln.mindistance;
         const int lim = (int)sd.lim;
         const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
@@ -1987,36 +1845,41 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
             if (wi >= nwords) return -1;
             uint32_t v = s_bits[wi] & (~0u << (x & 31));
             if (v == 0u) {
-                const int g = (wi >> 2) + 1;              // the rest of this group, then the table
-                for (++wi; wi < 4 * g && wi < nwords; ++wi) {
-                    v = s_bits[wi];
-                    if (v != 0u) break;
+                const int nx = wi + 1;                     // first non-empty word at or after nx
+                if (nx >= nwords) return -1;
+                int j = nx >> 5;
+                uint32_t u = s_l1[j] & (~0u << (nx & 31));
+                if (u == 0u) {
+                    const int nj = j + 1;
+                    if (nj >= nl1) return -1;
+                    int jj = nj >> 5;
+                    uint32_t t = s_l2[jj] & (~0u << (nj & 31));
+                    while (t == 0u) {
+                        if (++jj >= nl2) return -1;
+                        t = s_l2[jj];
+                    }
+                    j = (jj << 5) + (__ffs(t) - 1);
+                    u = s_l1[j];
                 }
-                if (v == 0u) {
-                    if (g >= ngroups) return -1;
-                    const uint32_t nxt = s_nw[g];
-                    if (nxt == 0xFFFFu) return -1;
-                    wi = (int)nxt;
-                    v = s_bits[wi];
-                }
+                wi = (j << 5) + (__ffs(u) - 1);
+                v = s_bits[wi];
             }
             return (wi << 5) + (__ffs(v) - 1);
         };
-        int np = 0, ok = 1;
+        int np = 1, ok = 1;
         int P = 0;
         const int j0 = first_pos[blockIdx.x];
         if (sd.m > 0 && j0 != 0x7F7F7F7F) {
             P = next_settled(j0);
             if (P < 0) ok = 0;
         }
-        if (lane == 0) s_peaks[0] = P;
-        np = 1;
+        s_peaks[0] = P;
         while (ok && sd.m > 0) {
             const int a = P + w + 1;
             if (a > last) break;
             np++;
             if (np == WEFAX_MAX_PEAKS) {
-                if (lane == 0) s_peaks[np - 1] = a;   // the 100th peak is never refined (wefax.py:251)
+                s_peaks[np - 1] = a;   // the 100th peak is never refined (wefax.py:251)
                 break;
             }
             if (a >= lim) {
@@ -2028,18 +1891,11 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
                 ok = 0;
                 break;
             }
-            if (lane == 0) s_peaks[np - 1] = P;
+            s_peaks[np - 1] = P;
         }
-        if (lane == 0) {
-            s_np = np;
-            s_ok = ok;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_ok) {
+        if (ok) {
             need_scan[blockIdx.x] = 0;
-            finish_sync(s_peaks, s_np, ln, n, res_all + blockIdx.x);
+            finish_sync(s_peaks, np, ln, n, res_all + blockIdx.x);
         } else {
             need_scan[blockIdx.x] = 1;   // ran out of precomputed region: let the sequential scan do it
         }
@@ -2080,10 +1936,9 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         }
         {
             StageTimer t1(ctx, "sync_chain");
-            // the settled bits + one uint16 per 4 words (the "next non-empty word" table)
+            // the settled bits and their two summary levels (1/32 and 1/1024 of the mask)
             const size_t chain_words = (size_t)(((sp.max_lim + 31) / 32 + 4 + 3) & ~3ll);
-            // ... or, in the same area, the compacted list of settled positions and its successor table (2 x 4096 ints)
-            const size_t chain_aux = std::max<size_t>((chain_words / 4 + 4) * sizeof(uint16_t), 2 * 4096 * sizeof(int));
+            const size_t chain_aux = (chain_words / 32 + 8 + chain_words / 1024 + 8) * sizeof(uint32_t);
             sync_chain_kernel<<<batch, 1024, chain_words * sizeof(uint32_t) + chain_aux, st>>>(
                 n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan, force_scan);
         }
