@@ -179,11 +179,12 @@ void launch_fast_variant(wefax_ctx *ctx, const PassDev &p, const float2 *src, si
     kern<<<grid, K::T, K::SMEM, ctx->stream>>>(p, src, bstride, st, (int)total);
 }
 
-template <int R1, int R2>
+template <int R1, int R2, class Epi = fast::TileOut>
 bool launch_fast_tma(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t src_bs, float2 *dst, size_t dst_bs,
-                     int batch) {
+                     int batch, const Epi &epi = Epi()) {
     using K = fast::TmaCfg<R1, R2>;
     static_assert(fast::kFastCW == K::C, "tile geometry of the plan");
+    constexpr bool kTileOut = std::is_same<Epi, fast::TileOut>::value;
     int rbox = 0;
     for (int rb = std::min(K::R, 256); rb >= 1; --rb)
         if (K::R % rb == 0) {
@@ -193,8 +194,12 @@ bool launch_fast_tma(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t
     if (K::R / rbox > 8) return false;
     alignas(64) CUtensorMap in_map, out_map;
     if (!encode_strided_map(p, src, src_bs, batch, K::C, rbox, &in_map)) return false;
-    if (!encode_strided_map(p, dst, dst_bs, batch, K::C, rbox, &out_map)) return false;
-    auto kern = fast::fft_fast_tma_kernel<R1, R2>;
+    if (kTileOut) {
+        if (!encode_strided_map(p, dst, dst_bs, batch, K::C, rbox, &out_map)) return false;
+    } else {
+        out_map = in_map;   // (unused: the functor stores)
+    }
+    auto kern = fast::fft_fast_tma_kernel<R1, R2, Epi>;
     const void *fn = (const void *)kern;
     if (!ctx->smem_configured.count(fn)) {
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
@@ -206,7 +211,8 @@ bool launch_fast_tma(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t
         const char *e = getenv("WEFAX_TMA_ISSUER_WARP");
         return !(e && e[0] == '0');
     }();
-    kern<<<grid, own_warp ? K::T + 32 : K::T, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total, own_warp ? K::T : 0);
+    kern<<<grid, own_warp ? K::T + 32 : K::T, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total, own_warp ? K::T : 0,
+                                                                        epi);
     return true;
 }
 
@@ -230,6 +236,27 @@ bool try_launch_fast(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const S
                     case 1514: done = launch_fast_tma<15, 14>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
                     case 1414: done = launch_fast_tma<14, 14>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
                     case 1507: done = launch_fast_tma<15, 7>(ctx, p, ld.src, ld.bstride, st.dst, st.bstride, batch); break;
+                    default: break;
+                }
+                if (done) {
+                    CUDA_CHECK(cudaGetLastError());
+                    ctx->launches++;
+                    return true;
+                }
+            }
+        }
+        if constexpr (std::is_same<StoreOp, StoreEnvPairs>::value) {
+            // the envelope store of the last inverse pass: input tile by TMA a whole tile ahead, side input and
+            // results by direct loads / stores (WEFAX_TMA_ENV=0: the register-direct kernel below)
+            static const bool tma_env = [] {
+                const char *e = getenv("WEFAX_TMA_ENV");
+                return !(e && e[0] == '0');
+            }();
+            if (ctx->use_tma_fast && tma_env) {
+                bool done = false;
+                switch (p.fast_R1 * 100 + p.fast_R2) {
+                    case 1515: done = launch_fast_tma<15, 15, StoreEnvPairs>(ctx, p, ld.src, ld.bstride, nullptr, 0, batch, st); break;
+                    case 1616: done = launch_fast_tma<16, 16, StoreEnvPairs>(ctx, p, ld.src, ld.bstride, nullptr, 0, batch, st); break;
                     default: break;
                 }
                 if (done) {

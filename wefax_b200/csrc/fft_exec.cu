@@ -340,14 +340,21 @@ static void ensure_mid_tables(wefax_ctx *ctx, FftPlan *half) {
 
 template <int R1, int R2>
 static void launch_mid(wefax_ctx *ctx, FftPlan *half, float2 *z, size_t zs, int batch) {
+    // warp-autonomous form (one row pair per warp) unless WEFAX_MID_WARP=0 asks for the 8-row CTA tile
+    static const bool by_warp = [] {
+        const char *e = getenv("WEFAX_MID_WARP");
+        return !(e && e[0] == '0');
+    }();
     using K = fast::MidCfg<R1, R2>;
-    auto kern = fast::hilbert_mid_kernel<R1, R2>;
+    using KW = fast::MidWarpCfg<R1, R2>;
+    auto kern = by_warp ? fast::hilbert_mid_warp_kernel<R1, R2> : fast::hilbert_mid_kernel<R1, R2>;
+    const int smem = by_warp ? KW::SMEM : K::SMEM;
     const void *fn = (const void *)kern;
     auto it = ctx->smem_configured.find(fn);
     int per_sm;
     if (it == ctx->smem_configured.end()) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K::T, K::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K::T, smem));
         if (per_sm < 1) per_sm = 1;
         ctx->smem_configured[fn] = per_sm;
     } else {
@@ -362,8 +369,13 @@ static void launch_mid(wefax_ctx *ctx, FftPlan *half, float2 *z, size_t zs, int 
     a.rows = half->mid_tab.as<fast::MidRow>();
     a.twB = (const float2 *)(half->mid_tab.as<char>() + rows_bytes);
     a.npairs = half->mid_npairs;
-    a.tiles_per_batch = (a.npairs + K::ROWS / 2 - 1) / (K::ROWS / 2);
-    a.total_tiles = a.tiles_per_batch * batch;
+    if (by_warp) {
+        a.tiles_per_batch = a.npairs;               // one pair per warp and round
+        a.total_tiles = a.npairs * batch;
+    } else {
+        a.tiles_per_batch = (a.npairs + K::ROWS / 2 - 1) / (K::ROWS / 2);
+        a.total_tiles = a.tiles_per_batch * batch;
+    }
     a.ncols = (int)(half->n / K::R);
     a.twR = pi.twR;
     a.tw2_lo = half->tw2_lo;
@@ -373,9 +385,10 @@ static void launch_mid(wefax_ctx *ctx, FftPlan *half, float2 *z, size_t zs, int 
     a.tw_mode = pi.tw_mode;
     a.ko_R = pi.ko_R;
     a.inv_m = (float)(1.0 / (double)half->n);
-    const int grid = std::min(a.total_tiles, ctx->sm_count * per_sm);
+    const int ctas = by_warp ? (a.total_tiles + KW::WARPS - 1) / KW::WARPS : a.total_tiles;
+    const int grid = std::min(ctas, ctx->sm_count * per_sm);
     StageTimer timer(ctx, "hilbert_mid");
-    kern<<<grid, K::T, K::SMEM, ctx->stream>>>(a);
+    kern<<<grid, K::T, smem, ctx->stream>>>(a);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

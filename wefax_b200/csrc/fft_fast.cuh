@@ -419,10 +419,16 @@ template <int R1, int R2> struct TmaCfg {
     static_assert(R1 <= 16 && R2 <= 16, "512 threads = 16 rows x 32 columns");
 };
 
-template <int R1, int R2>
+// Epi = TileOut: the finished tile goes back by TMA (plain complex out).  Any other Epi is a store functor of fft.cuh
+// (the envelope store of the last inverse pass): its side input is fetched into registers before the second
+// stage reads the exchange tile, its results leave by direct global stores; only the input tile uses the copy engine.
+struct TileOut {};
+
+template <int R1, int R2, class Epi = TileOut>
 __global__ void __launch_bounds__(512 + 32, 1)
 fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    int rbox, int total_tiles, int issuer) {
+                    int rbox, int total_tiles, int issuer, const Epi epi = Epi()) {
+    constexpr bool kTileOut = std::is_same<Epi, TileOut>::value;
     // `issuer` = the thread that drives the copy engine: 512 (lane 0 of a 17th warp that does nothing else, so that no
     // worker waits for a store to drain before the next load can be issued) or 0 (a worker; launched with 512 threads)
     using K = TmaCfg<R1, R2>;
@@ -476,7 +482,7 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
 
         if (tid == issuer) {
             // the other buffer was the source of the previous tile's store: reuse it for the next tile's load
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (kTileOut) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (tile + (int)gridDim.x < total_tiles) issue_load(tile + gridDim.x, Aoth, mbar + ((it + 1) & 1));
         }
         uint32_t e0 = 0, de = 0;
@@ -507,31 +513,64 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
 #pragma unroll
             for (int u = 1; u < R1; ++u) tb[(row + R2 * u) * C + cc] = pcmul3(v[u], tq[u]);
         }
-        __syncthreads();
-        if (act2) {
-            float2 y[R2];
+        if constexpr (kTileOut) {
+            __syncthreads();
+            if (act2) {
+                float2 y[R2];
 #pragma unroll
-            for (int t = 0; t < R2; ++t) y[t] = tb[(row * R2 + t) * C + cc];
-            Dft<R2>::run(y);
-            const float2 Aa = bc(Aval.x), Ab = make_float2(-Aval.y, Aval.y);
+                for (int t = 0; t < R2; ++t) y[t] = tb[(row * R2 + t) * C + cc];
+                Dft<R2>::run(y);
+                const float2 Aa = bc(Aval.x), Ab = make_float2(-Aval.y, Aval.y);
 #pragma unroll
-            for (int k2 = 0; k2 < R2; ++k2) {
-                float2 val = y[k2];
-                if (p.tw_mode != 0) {
-                    val = pcmul2(val, Aa, Ab);
-                    if (k2 > 0) val = pcmul3(val, P[k2 * C + cc]);
+                for (int k2 = 0; k2 < R2; ++k2) {
+                    float2 val = y[k2];
+                    if (p.tw_mode != 0) {
+                        val = pcmul2(val, Aa, Ab);
+                        if (k2 > 0) val = pcmul3(val, P[k2 * C + cc]);
+                    }
+                    A[(row + R1 * k2) * C + cc] = val;      // natural row order: the tile is stored as it lies
                 }
-                A[(row + R1 * k2) * C + cc] = val;      // natural row order: the tile is stored as it lies
             }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == issuer) {
-            for (int b = 0; b < nbox; ++b) tma_store_4d(&out_map, A + (size_t)b * rbox * C, 2 * m0, b * rbox, o, batch);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == issuer) {
+                for (int b = 0; b < nbox; ++b) tma_store_4d(&out_map, A + (size_t)b * rbox * C, 2 * m0, b * rbox, o, batch);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            // element index of this thread's output row k = row + R1 * k2: base + k2 * step
+            const size_t gbase = (size_t)o * (size_t)R * (size_t)p.S + m + (size_t)row * (size_t)p.S;
+            const size_t gstep = (size_t)R1 * (size_t)p.S;
+            typename Epi::Side side[R2];
+            if (act2 && colok) {
+#pragma unroll
+                for (int k2 = 0; k2 < R2; ++k2) side[k2] = epi.side_load(gbase + k2 * gstep, batch);
+            }
+            __syncthreads();
+            if (act2) {
+                float2 y[R2];
+#pragma unroll
+                for (int t = 0; t < R2; ++t) y[t] = tb[(row * R2 + t) * C + cc];
+                Dft<R2>::run(y);
+                const float2 Aa = bc(Aval.x), Ab = make_float2(-Aval.y, Aval.y);
+                if (colok) {
+#pragma unroll
+                    for (int k2 = 0; k2 < R2; ++k2) {
+                        float2 val = y[k2];
+                        if (p.tw_mode != 0) {
+                            val = pcmul2(val, Aa, Ab);
+                            if (k2 > 0) val = pcmul3(val, P[k2 * C + cc]);
+                        }
+                        epi(gbase + k2 * gstep, batch, val, row + R1 * k2, 0, side[k2]);
+                    }
+                }
+            }
+            // (the exchange tile is read by this iteration's second stage and written by the next one's first: the
+            //  barrier after the next first stage's loads is not enough, so the iterations are separated here)
+            __syncthreads();
         }
     }
-    if (tid == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (kTileOut && tid == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // (R1, R2) pairs with a compiled kernel; 0 when R has none

@@ -74,15 +74,15 @@ template <int R1, int R2> struct MidCfg {
     static constexpr int SMEM = (ROWS * R + ROWS * MIDP + R + ROWS * R2) * (int)sizeof(float2) + 16;
 };
 
-template <int R1, int R2>
+template <int R1, int R2, int ROWS = 8, int T = 128>
 __device__ __forceinline__ void mid_stage1(const float2 *nat, float2 *mid, const float2 *twQ, int tid) {
-    using K = MidCfg<R1, R2>;
+    using K = MidCfg<R1, R2>;   // (row length and exchange pitches only; ROWS / T are this call's own)
     // G1 lanes per row (power of two >= R2): a half-warp never straddles two rows, so the 64-bit
     // shared-memory accesses stay conflict-free
     constexpr int G1 = R2 <= 16 ? 16 : 32;
     static_assert(R2 <= 32, "stage-1 lane group");
 #pragma unroll 1
-    for (int item = tid; item < G1 * K::ROWS; item += K::T) {
+    for (int item = tid; item < G1 * ROWS; item += T) {
         const int row = item / G1, q = item % G1;
         if (q >= R2) continue;
         float2 v[R1];
@@ -98,14 +98,14 @@ __device__ __forceinline__ void mid_stage1(const float2 *nat, float2 *mid, const
     }
 }
 
-template <int R1, int R2, bool TW>
+template <int R1, int R2, bool TW, int ROWS = 8, int T = 128>
 __device__ __forceinline__ void mid_stage2(const float2 *mid, float2 *nat, const float2 *P, const MidArgs &a,
                                            const int *s_ko, int tid) {
-    using K = MidCfg<R1, R2>;
+    using K = MidCfg<R1, R2>;   // (row length and exchange pitches only; ROWS / T are this call's own)
     constexpr int G2 = R1 <= 16 ? 16 : 32;
     static_assert(R1 <= 32, "stage-2 lane group");
 #pragma unroll 1
-    for (int item = tid; item < G2 * K::ROWS; item += K::T) {
+    for (int item = tid; item < G2 * ROWS; item += T) {
         const int row = item / G2, u = item % G2;
         if (u >= R1) continue;
         float2 Aval = make_float2(1.f, 0.f);
@@ -258,6 +258,126 @@ hilbert_mid_kernel(const MidArgs a) {
         __syncthreads();
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same sandwich with every WARP on its own: a warp owns one (row, mirrored row) pair - its two bulk loads, both
+// transforms, the untangling and its two bulk stores - and meets nobody: __syncwarp between the phases instead of seven
+// CTA-wide barriers per tile, and the sixteen warps of an SM drift apart so that one warp's copies hide behind the
+// arithmetic of the others.  Same shared-memory footprint as the 8-row tile (4 warps x 2 rows + 2 exchange rows).
+template <int R1, int R2> struct MidWarpCfg {
+    static constexpr int R = R1 * R2;
+    static constexpr int WARPS = 4, T = 32 * WARPS;
+    static constexpr int BP = R2 | 1, MIDP = R1 * BP;
+    static constexpr int PER_WARP = 2 * R + 2 * MIDP + 2 * R2;   // float2: rows, exchange rows, inter-pass twiddles
+    static constexpr int SMEM = (R + WARPS * PER_WARP) * (int)sizeof(float2) + WARPS * 8 + 16;
+    static_assert(R % 2 == 0 && PER_WARP % 2 == 0, "bulk copies need 16-byte aligned rows");
+};
+
+template <int R1, int R2>
+__global__ void __launch_bounds__(128, 4)
+hilbert_mid_warp_kernel(const MidArgs a) {
+    using K = MidWarpCfg<R1, R2>;
+    constexpr int R = K::R;
+    extern __shared__ __align__(128) unsigned char mid_smem[];
+    float2 *twQ = reinterpret_cast<float2 *>(mid_smem);               // [q][u] stage twiddles (shared by the warps)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float2 *nat = twQ + R + warp * K::PER_WARP;                        // [2][R] natural-order rows
+    float2 *mid = nat + 2 * R;                                         // [2][R1][BP] exchange rows
+    float2 *P = mid + 2 * K::MIDP;                                     // [2][R2] w^(ko*R1*k2)
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(twQ + R + K::WARPS * K::PER_WARP) + warp;
+    __shared__ int s_ko[K::WARPS][2];
+
+    for (int i = tid; i < R; i += K::T) {
+        const int q = i / R1, u = i - q * R1;
+        twQ[i] = __ldg(a.twR + q * u);
+    }
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncthreads();
+
+    constexpr uint32_t kRowBytes = R * sizeof(float2);
+    int it = 0;
+    for (int tile = blockIdx.x * K::WARPS + warp; tile < a.total_tiles; tile += gridDim.x * K::WARPS, ++it) {
+        const int batch = tile / a.npairs;
+        const MidRow r = a.rows[tile - batch * a.npairs];
+        float2 *zb = a.z + (size_t)batch * a.zs;
+        const int o = r.o, o2 = r.o2 == r.o ? -1 : r.o2, kb = r.kb;
+        const bool self = o2 < 0;
+        if (lane == 0) {
+            mbar_expect_tx(mbar, self ? kRowBytes : 2 * kRowBytes);
+            tma_load_bulk(nat, zb + (size_t)o * R, kRowBytes, mbar);
+            if (!self) tma_load_bulk(nat + R, zb + (size_t)o2 * R, kRowBytes, mbar);
+            s_ko[warp][0] = o % a.ko_R;
+            s_ko[warp][1] = self ? 0 : o2 % a.ko_R;
+        }
+        if (self)   // the second slot transforms zeros
+            for (int i = lane; i < R; i += 32) nat[R + i] = make_float2(0.f, 0.f);
+        float2 wkb;   // (inv_m / 2) * w_n^kb
+        {
+            const uint32_t e = (uint32_t)kb;
+            const float2 wk = cmul(__ldg(a.tw2_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw2_hi + (e >> kTwLoBits)));
+            wkb = make_float2(wk.x * (0.5f * a.inv_m), wk.y * (0.5f * a.inv_m));
+        }
+        __syncwarp();
+        if (a.tw_mode != 0) {
+            for (int i = lane; i < 2 * R2; i += 32) {
+                const int row = i / R2, k2 = i - row * R2;
+                const uint32_t e = (uint32_t)s_ko[warp][row] * (uint32_t)(R1 * k2);
+                P[i] = cmul(__ldg(a.tw_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw_hi + (e >> kTwLoBits)));
+            }
+        }
+        __syncwarp();
+        mbar_wait(mbar, it & 1);
+
+        // ---- last forward pass
+        mid_stage1<R1, R2, 2, 32>(nat, mid, twQ, lane);
+        __syncwarp();
+        mid_stage2<R1, R2, false, 2, 32>(mid, nat, P, a, s_ko[warp], lane);
+        __syncwarp();
+
+        // ---- untangle, -i*sgn, re-tangle, conjugate, scale (see hilbert_mid_kernel)
+        {
+            float2 *row = nat;
+            float2 *row2 = self ? row : row + R;
+#pragma unroll 2
+            for (int j = lane; j < R; j += 32) {
+                const int j2 = kb ? R - 1 - j : (j ? R - j : 0);
+                if (self && j2 < j) continue;
+                if (kb == 0 && j == 0) {
+                    row[0] = make_float2(0.f, 0.f);
+                    continue;
+                }
+                const float2 zk = row[j], zm = row2[j2];
+                const float2 w = pcmul3(__ldg(a.twB + j), wkb);
+                const float2 sp = pfma(zm, make_float2(1.f, -1.f), zk);
+                const float2 dm = pfma(zm, make_float2(-1.f, 1.f), zk);
+                const float2 wa = bc(w.x);
+                const float2 aa = pfma(sp, wa, pmul(swp(sp), make_float2(w.y, -w.y)));
+                const float2 bb = pfma(dm, wa, pmul(swp(dm), make_float2(-w.y, w.y)));
+                row[j] = pmul(psub(aa, bb), make_float2(1.f, -1.f));
+                if (!(self && j2 == j)) row2[j2] = pmul(padd(aa, bb), make_float2(-1.f, -1.f));
+            }
+        }
+        __syncwarp();
+
+        // ---- first inverse pass (forward kernels on conjugated data)
+        mid_stage1<R1, R2, 2, 32>(nat, mid, twQ, lane);
+        __syncwarp();
+        if (a.tw_mode != 0)
+            mid_stage2<R1, R2, true, 2, 32>(mid, nat, P, a, s_ko[warp], lane);
+        else
+            mid_stage2<R1, R2, false, 2, 32>(mid, nat, P, a, s_ko[warp], lane);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_bulk(zb + (size_t)o * R, nat, kRowBytes);
+            if (!self) tma_store_bulk(zb + (size_t)o2 * R, nat + R, kRowBytes);
+            tma_store_commit();
+            tma_store_wait_read();   // the rows may be overwritten by the next pair's loads
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 inline bool mid_pair(int R, int *R1, int *R2) {

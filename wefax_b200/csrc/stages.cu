@@ -890,6 +890,7 @@ pct_bracket2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, Pc
     PctCoop *coop = coop_all + rec;
     const long long s0 = (long long)cta * per;
     const int cnt = (int)max(0ll, min((long long)per, g.ns - s0));
+#pragma unroll 4
     for (int j = threadIdx.x; j < cnt; j += kSelThreads) {
         const long long i = (s0 + j) * kPctStride;
         float w[5];
@@ -987,6 +988,10 @@ pct_collect_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, flo
 // between the brackets) cost one subtract, one compare and one warp vote each; only warps that hold a sample
 // in a tail or a bracket enter the classification.  Counts: below[0] = samples under the low bracket,
 // below[1] = samples ABOVE the high bracket (the final selection derives its rank offset from it).
+// PRE = true: the flags-first form described above.  PRE = false: always the 8 medians (their shared min / max tree
+// costs 8.5 instructions a sample), two instructions a sample to test them against the middle, ONE vote per thread
+// and round; data-independent, and fewer instructions even when every warp can skip (12 against 4.5 + votes).
+template <bool PRE>
 __global__ void __launch_bounds__(256)
 pct_collect2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, float *lists, size_t ls) {
     __shared__ unsigned long long s_cnt_out[2];
@@ -1036,15 +1041,19 @@ pct_collect2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, fl
                 // A median of 5 lies outside the middle only if at least 3 of its 5 values do: fewer than 3 such
                 // values among the 12 this thread's 8 windows cover settles all 8 at once (the usual case: 99 % of
                 // the samples are in the middle), without a single median.
-                int outside = 0;
+                if (PRE) {
+                    int outside = 0;
 #pragma unroll
-                for (int j = 2; j < 14; ++j) outside += (__float_as_uint(f[j]) - mid_lo >= mid_span) ? 1 : 0;
-                need = outside >= 3;
+                    for (int j = 2; j < 14; ++j) outside += (__float_as_uint(f[j]) - mid_lo >= mid_span) ? 1 : 0;
+                    need = outside >= 3;
+                } else {
+                    need = true;
+                }
             } else {
                 need = true;
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, need)) continue;
+        if (PRE && !__any_sync(0xFFFFFFFFu, need)) continue;
         if (i0 < n) {
             if (fast) med8_from16<2>(f, m);
             else load_med8(e, i0, n, m);
@@ -1052,12 +1061,33 @@ pct_collect2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, fl
 #pragma unroll
             for (int j = 0; j < 8; ++j) m[j] = 0.f;
         }
+        if (PRE) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t key = __float_as_uint(m[j]);
-            const bool out_mid = (key - mid_lo >= mid_span) && j < nvalid;
-            if (__any_sync(0xFFFFFFFFu, out_mid)) {
-                if (out_mid) {
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t key = __float_as_uint(m[j]);
+                const bool out_mid = (key - mid_lo >= mid_span) && j < nvalid;
+                if (__any_sync(0xFFFFFFFFu, out_mid)) {
+                    if (out_mid) {
+                        if (key <= k1) {
+                            if (key < k0) n_under++;
+                            else append(0, m[j]);
+                        }
+                        if (key >= k2) {
+                            if (key > k3) n_over++;
+                            else append(1, m[j]);
+                        }
+                    }
+                }
+            }
+        } else {
+            bool any_out = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) any_out |= (__float_as_uint(m[j]) - mid_lo >= mid_span) && j < nvalid;
+            if (__any_sync(0xFFFFFFFFu, any_out) && any_out) {
+#pragma unroll 1
+                for (int j = 0; j < nvalid; ++j) {
+                    const uint32_t key = __float_as_uint(m[j]);
+                    if (key - mid_lo < mid_span) continue;
                     if (key <= k1) {
                         if (key < k0) n_under++;
                         else append(0, m[j]);
@@ -1273,7 +1303,13 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     CUDA_CHECK(cudaMemsetAsync(coop, 0, sizeof(PctCoop) * batch, st));
     // CTAs of one recording spin at a barrier, so all of them must be resident at once:
     // 1024-thread CTAs, two per SM
-    const int ncta = std::max(1, std::min(32, ctx->sm_count / batch));
+    // (WEFAX_PCT_NCTA: CTAs per recording, default up to 32; more CTAs shorten the latency-bound sample read)
+    static const int ncta_cap = [] {
+        const char *e = getenv("WEFAX_PCT_NCTA");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 148 ? v : 32;
+    }();
+    const int ncta = std::max(1, std::min(ncta_cap, ctx->sm_count / batch));
 
     const int per = (int)((g.ns + ncta - 1) / ncta);
     const size_t fused_smem = ((size_t)4 * 2048 + (size_t)per) * sizeof(uint32_t);
@@ -1318,7 +1354,10 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     {
         StageTimer t1(ctx, "pct_collect");
         if (g.over_mode)
-            pct_collect2_kernel<<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
+            if (pc && pc[0] == '2')   // "2": the flags-first form (A/B measurements)
+                pct_collect2_kernel<true><<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
+            else
+                pct_collect2_kernel<false><<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
         else
             pct_collect_kernel<<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
     }
