@@ -19,7 +19,15 @@ int guarded(wefax_ctx *ctx, F &&f, bool touches_scratch = true) {
         f();
         return WEFAX_OK;
     } catch (const Error &e) {
-        if (ctx) ctx->last_error = e.msg;
+        if (ctx) {
+            ctx->last_error = e.msg;
+            // (a call that failed half way: nothing of it may still be running when the caller reuses its buffers)
+            if (ctx->stream && cudaStreamQuery(ctx->stream) != cudaErrorStreamCaptureUnsupported) {
+                cudaStreamSynchronize(ctx->stream);
+                if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+                (void)cudaGetLastError();
+            }
+        }
         return e.code;
     } catch (const std::bad_alloc &) {
         if (ctx) ctx->last_error = "host allocation failed";
@@ -360,6 +368,16 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
             CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
             ctx->own_stream = true;
         }
+        {
+            const char *sd = getenv("WEFAX_SIDE");
+            if (!(sd && sd[0] == '0')) {
+                CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_greatest));
+                for (int i = 0; i < wefax_ctx::kSideForks; ++i) {
+                    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_side_fork[i], cudaEventDisableTiming));
+                    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_side_join[i], cudaEventDisableTiming));
+                }
+            }
+        }
         // WEFAX_OVERLAP=1: grey-map tail on a side stream under the phasing search.  Measured on B200: the
         // search's 1024-thread CTAs starve behind the bulk kernel (search 85 -> 131 us, step -0.5 %), so off by default.
         const char *ovl = getenv("WEFAX_OVERLAP");
@@ -386,6 +404,14 @@ void wefax_ctx_destroy(wefax_ctx *ctx) {
     ctx->lane_ctx.clear();
     if (ctx->ev_lane_fork) cudaEventDestroy(ctx->ev_lane_fork);
     for (cudaEvent_t e : ctx->ev_lane_join) cudaEventDestroy(e);
+    if (ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+        for (int i = 0; i < wefax_ctx::kSideForks; ++i) {
+            cudaEventDestroy(ctx->ev_side_fork[i]);
+            cudaEventDestroy(ctx->ev_side_join[i]);
+        }
+    }
     if (ctx->aux_stream) {
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamDestroy(ctx->aux_stream);
@@ -568,6 +594,9 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             CUDA_CHECK(cudaMemcpyAsync(d_lines, h_lines, sizeof(LineDev) * g, cudaMemcpyHostToDevice, st));
             CUDA_CHECK(cudaMemsetAsync(d_res, 0, sizeof(RecResult) * g, st));
             const SyncPlan splan = prepare_sync(ctx, lines.data() + w0, g, n);   // (asynchronous upload from pinned staging)
+            // the phasing search's scratch is cleared beside the first kernels instead of between two latency-bound ones
+            SideFork clears(ctx, 1);
+            clear_sync_scratch(ctx, splan, g, clears.stream());
 
             float *d_env = (float *)ctx->work_e.reserve((size_t)g * n * sizeof(float));
             uint8_t *d_dig = (out_dev && out->digitalized) ? out->digitalized + (size_t)w0 * n
@@ -623,7 +652,9 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                 // fused demod-to-pixel path: grey levels of the head for the phasing search (wefax.py:218-294),
                 // then ONE sweep over the envelope writes digitalized_data and the raster (wefax.py:296-327)
                 GreyTable *d_tab = (GreyTable *)ctx->grey_tab.reserve(sizeof(GreyTable) * (size_t)g);
-                launch_grey_table(ctx, d_res, d_tab, g);
+                // (the threshold table is first read by the search's sequential fallback: built beside the search)
+                SideFork table(ctx, 2);
+                launch_grey_table(ctx, d_res, d_tab, g, table.stream());
                 const long long head = sync_head(splan, n);
                 launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res, 0, head, st, "quantise_head");
                 LazyGrey lazy;
@@ -631,13 +662,13 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
                 lazy.es = (size_t)n;
                 lazy.tables = d_tab;
                 lazy.valid = head;
-                launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, nullptr, lazy);
+                launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, nullptr, lazy, &clears, &table);
                 launch_grey_raster(ctx, d_env, (size_t)n, out->digitalized ? d_dig : nullptr, (size_t)n, d_raster, rs, n, g,
                                    d_lines, lines.data() + w0, d_res, d_tab);
             } else {
                 cudaEvent_t tail_done = launch_quantise_split(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res, splan);
                 // ---- phasing search (wefax.py:218-294) and raster (wefax.py:296-327) -----
-                launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, tail_done);
+                launch_sync_search(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, min_mind, splan, tail_done, LazyGrey(), &clears);
                 if (d_raster)
                     launch_raster(ctx, d_dig, (size_t)n, n, g, d_lines, d_res, d_raster, rs, max_width, (int)(n / min_width));
             }

@@ -49,6 +49,14 @@ struct wefax_ctx {
     // low-priority side stream for bulk work that may overlap latency-bound kernels of the main stream
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Side stream for the small independent pieces of a step (edge tiles of the notch, scratch clears, the grey
+    // threshold table): forked from / joined to the main stream by events, so that they run beside the kernel the main
+    // stream is busy with instead of between two of its latency-bound ones.  Off while stage timing is on (the
+    // per-stage event pairs live on the main stream) and with WEFAX_SIDE=0.
+    cudaStream_t side_stream = nullptr;
+    static constexpr int kSideForks = 4;
+    cudaEvent_t ev_side_fork[kSideForks] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_side_join[kSideForks] = {nullptr, nullptr, nullptr, nullptr};
     std::string last_error;
     long long launches = 0;
     long long workspace_limit = 24ll << 30;
@@ -144,6 +152,35 @@ struct StageTimer {
         if (e1) cudaEventRecord(e1, stream);
     }
 };
+
+// One fork / join of the side stream (see wefax_ctx::side_stream).  `slot` picks the event pair: forks that are open at
+// the same time use different slots.  When the side stream is not in use everything simply stays on the main stream.
+struct SideFork {
+    wefax_ctx *ctx;
+    int slot;
+    bool on;
+    SideFork(wefax_ctx *c, int slot_) : ctx(c), slot(slot_), on(c->side_stream != nullptr && !c->timing) {
+        if (!on) return;
+        CUDA_CHECK(cudaEventRecord(ctx->ev_side_fork[slot], ctx->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side_fork[slot], 0));
+    }
+    ~SideFork() {   // (an exception between fork and join: never leave the side stream dangling)
+        if (!on) return;
+        cudaEventRecord(ctx->ev_side_join[slot], ctx->side_stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_side_join[slot], 0);
+    }
+    SideFork(const SideFork &) = delete;
+    SideFork &operator=(const SideFork &) = delete;
+    cudaStream_t stream() const { return on ? ctx->side_stream : ctx->stream; }
+    // the side work is complete as far as it has been issued: the main stream waits for it here
+    void join() {
+        if (!on) return;
+        CUDA_CHECK(cudaEventRecord(ctx->ev_side_join[slot], ctx->side_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side_join[slot], 0));
+        on = false;
+    }
+};
+
 
 template <class LoadOp, class StoreOp, int MINB>
 void launch_pass_variant(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const StoreOp &st, int batch,
@@ -246,11 +283,13 @@ bool try_launch_fast(wefax_ctx *ctx, const PassDev &p, const LoadOp &ld, const S
             }
         }
         if constexpr (std::is_same<StoreOp, StoreEnvPairs>::value) {
-            // the envelope store of the last inverse pass: input tile by TMA a whole tile ahead, side input and
-            // results by direct loads / stores (WEFAX_TMA_ENV=0: the register-direct kernel below)
+            // the envelope store of the last inverse pass with its input tile by TMA a whole tile ahead (side input and
+            // results by direct loads / stores): measured SLOWER than the register-direct kernel below (122 us against
+            // 103 us for the 60-min recording: one 544-thread CTA per SM hides the side loads worse than two CTAs of
+            // 480), so it only runs on request (WEFAX_TMA_ENV=1)
             static const bool tma_env = [] {
                 const char *e = getenv("WEFAX_TMA_ENV");
-                return !(e && e[0] == '0');
+                return e && e[0] == '1';
             }();
             if (ctx->use_tma_fast && tma_env) {
                 bool done = false;

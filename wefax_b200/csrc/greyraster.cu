@@ -545,9 +545,9 @@ __global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid
     }
 }
 
-void launch_grey_table(wefax_ctx *ctx, const RecResult *res, GreyTable *tables, int batch) {
+void launch_grey_table(wefax_ctx *ctx, const RecResult *res, GreyTable *tables, int batch, cudaStream_t stream) {
     StageTimer timer(ctx, "grey_table");
-    grey_table_kernel<<<batch, 256, 0, ctx->stream>>>(res, tables);
+    grey_table_kernel<<<batch, 256, 0, stream ? stream : ctx->stream>>>(res, tables);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

@@ -394,6 +394,10 @@ static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_strid
         ti_hi = (int)std::max<long long>(0, (n - margin) / kFirTile);
         if (ti_hi <= ti_lo) ti_lo = ti_hi = 0;
     }
+    // the few edge tiles (two-section kernel) write other samples than the interior ones: side by side
+    SideFork edge(ctx, 0);
+    if (ti_hi <= ti_lo) edge.join();   // (nothing to overlap with)
+    cudaStream_t edge_stream = edge.stream();
     if (ti_hi > ti_lo) {
         switch (fp.KC) {
 #define WEFAX_SYM_CASE(KC_) \
@@ -411,10 +415,11 @@ static void launch_filtfilt_mode(wefax_ctx *ctx, const void *in, size_t in_strid
     dim3 grid((unsigned)(ntiles - tiles_skip), batch);
 #define WEFAX_FIR_CASE(KP_)                                                                                   \
     if (fp.KP == KP_) {                                                                                       \
-        filtfilt_kernel<MODE, KP_><<<grid, kFirThreads, 0, ctx->stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp, \
+        filtfilt_kernel<MODE, KP_><<<grid, kFirThreads, 0, edge_stream>>>(in, in_stride, out, out_stride, zout, z_stride, n, fp, \
                                                                          tiles_first, tiles_skip);          \
         CUDA_CHECK(cudaGetLastError());                                                                       \
         ctx->launches++;                                                                                      \
+        edge.join();                                                                                          \
         return;                                                                                               \
     }
     WEFAX_FIR_CASE(16)
@@ -990,7 +995,7 @@ pct_collect_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, flo
 // below[1] = samples ABOVE the high bracket (the final selection derives its rank offset from it).
 // PRE = true: the flags-first form described above.  PRE = false: always the 8 medians (their shared min / max tree
 // costs 8.5 instructions a sample), two instructions a sample to test them against the middle, ONE vote per thread
-// and round; data-independent, and fewer instructions even when every warp can skip (12 against 4.5 + votes).
+// and round: data-independent, but measured slower on the 60-min recording (75 us against 61 us), kept for A/B runs.
 template <bool PRE>
 __global__ void __launch_bounds__(256)
 pct_collect2_kernel(const float *env, size_t es, PctGeom g, PctState *st_all, float *lists, size_t ls) {
@@ -1303,11 +1308,12 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     CUDA_CHECK(cudaMemsetAsync(coop, 0, sizeof(PctCoop) * batch, st));
     // CTAs of one recording spin at a barrier, so all of them must be resident at once:
     // 1024-thread CTAs, two per SM
-    // (WEFAX_PCT_NCTA: CTAs per recording, default up to 32; more CTAs shorten the latency-bound sample read)
+    // (WEFAX_PCT_NCTA: CTAs per recording, default up to 128: 41 -> 31 us for the bracket kernel against 32 CTAs,
+    //  whose latency-bound sample read gets four times shorter)
     static const int ncta_cap = [] {
         const char *e = getenv("WEFAX_PCT_NCTA");
         const int v = e ? atoi(e) : 0;
-        return v >= 1 && v <= 148 ? v : 32;
+        return v >= 1 && v <= 148 ? v : 128;
     }();
     const int ncta = std::max(1, std::min(ncta_cap, ctx->sm_count / batch));
 
@@ -1354,10 +1360,10 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
     {
         StageTimer t1(ctx, "pct_collect");
         if (g.over_mode)
-            if (pc && pc[0] == '2')   // "2": the flags-first form (A/B measurements)
-                pct_collect2_kernel<true><<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
-            else
+            if (pc && pc[0] == 'm')   // "median": always the 8 medians (measured slower: 75 us against 61 us)
                 pct_collect2_kernel<false><<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
+            else
+                pct_collect2_kernel<true><<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
         else
             pct_collect_kernel<<<dim3(blocks, batch), 256, 0, st>>>(env, es, g, pst, lists, ls);
     }
@@ -1490,7 +1496,9 @@ __device__ __forceinline__ int key_idx(unsigned long long k) { return 0x7FFFFFFF
 // wefax.py:263-294 (find_sync_pulses / find_peak_groups, quirks included), then
 // start_frame (wefax.py:80) and the image height (wefax.py:299).  One thread.
 __device__ void finish_sync(const int *peaks, int np, const LineDev &ln, long long n, RecResult *res) {
-    auto regular = [&](int x) { return ln.dev_max > (double)x && (double)x > ln.dev_min; };
+    // dev_max > x > dev_min (wefax.py:268) on integers: x <= ceil(dev_max) - 1 and x >= floor(dev_min) + 1
+    const int reg_hi = (int)ceil(ln.dev_max) - 1, reg_lo = (int)floor(ln.dev_min) + 1;
+    auto regular = [&](int x) { return x <= reg_hi && x >= reg_lo; };
     int nclear = 0;
     for (int i = 1; i < np - 1; ++i)
         if (regular(peaks[i] - peaks[i - 1])) nclear++;
@@ -1856,10 +1864,10 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
     // noisy correlation, plateaus of saturated grey or everything at once (a constant signal settles every position).
     uint32_t *s_l1 = s_bits + (((size_t)nwords + 3) & ~(size_t)3);
     const int nl1 = (nwords + 31) >> 5, nl2 = (nl1 + 31) >> 5;
-    uint32_t *s_l2 = s_l1 + ((nl1 + 3) & ~3);
+    uint32_t *s_l2 = s_l1 + ((nl1 + 1 + 3) & ~3);
     {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        for (int j = wid; j < nl1; j += nwarps) {
+        for (int j = wid; j <= nl1; j += nwarps) {          // (one zero word past the end: the chain reads s_l1[nl1])
             const int wi = 32 * j + lane;
             const unsigned word = __ballot_sync(0xFFFFFFFFu, wi < nwords && s_bits[wi] != 0u);
             if (lane == 0) s_l1[j] = word;
@@ -1873,64 +1881,68 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        // every position of the precomputed region fits 31 bits (lim <= 1.5 M): 32-bit arithmetic keeps the
-        // dependent instruction chain of this single thread short (it is pure latency)
+        // One thread, pure latency: every step is the dependent chain  a -> (word of a | summary word) -> word the
+        // summary points at -> position.  The loop below keeps that chain short: one bound check per step (the
+        // 100-peak stop and both range ends are sorted out after the loop), the word of `a` and the summary word
+        // are loaded side by side, the rare walk through the second summary level is out of line.
         const int w = ln.mindistance;
         const int lim = (int)sd.lim;
-        const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > m - 1 ends the picker
-        // first settled position >= x inside [0, lim); -1 when the mask ends first
-        auto next_settled = [&](int x) -> int {
-            int wi = x >> 5;
-            if (wi >= nwords) return -1;
-            uint32_t v = s_bits[wi] & (~0u << (x & 31));
-            if (v == 0u) {
-                const int nx = wi + 1;                     // first non-empty word at or after nx
-                if (nx >= nwords) return -1;
-                int j = nx >> 5;
-                uint32_t u = s_l1[j] & (~0u << (nx & 31));
-                if (u == 0u) {
-                    const int nj = j + 1;
-                    if (nj >= nl1) return -1;
-                    int jj = nj >> 5;
-                    uint32_t t = s_l2[jj] & (~0u << (nj & 31));
-                    while (t == 0u) {
-                        if (++jj >= nl2) return -1;
-                        t = s_l2[jj];
-                    }
-                    j = (jj << 5) + (__ffs(t) - 1);
-                    u = s_l1[j];
-                }
-                wi = (j << 5) + (__ffs(u) - 1);
-                v = s_bits[wi];
+        const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > last ends the picker
+        const int amax = min(last, lim - 1);                          // a > amax: the picker ends or the mask does
+        // first non-empty word at or after nx when its own summary word holds none; -1: the mask ends first
+        auto far_word = [&](int nx) -> int {
+            const int nj = (nx >> 5) + 1;
+            if (nj >= nl1) return -1;
+            int jj = nj >> 5;
+            uint32_t t = s_l2[jj] & (~0u << (nj & 31));
+            while (t == 0u) {
+                if (++jj >= nl2) return -1;
+                t = s_l2[jj];
             }
-            return (wi << 5) + (__ffs(v) - 1);
+            const int j = (jj << 5) + (__ffs(t) - 1);
+            return (j << 5) + (__ffs(s_l1[j]) - 1);
+        };
+        // first settled position >= x (x < lim); -1 when the mask ends first
+        auto next_settled = [&](int x) -> int {
+            const int wi = x >> 5, nx = wi + 1;
+            const uint32_t v0 = s_bits[wi] & (~0u << (x & 31));
+            const uint32_t u0 = s_l1[nx >> 5] & (~0u << (nx & 31));   // (s_l1 is zero-padded past the mask)
+            if (v0 != 0u) return (wi << 5) + (__ffs(v0) - 1);
+            int w2;
+            if (u0 != 0u) {
+                w2 = (nx & ~31) + (__ffs(u0) - 1);
+            } else {
+                w2 = far_word(nx);
+                if (w2 < 0) return -1;
+            }
+            return (w2 << 5) + (__ffs(s_bits[w2]) - 1);
         };
         int np = 1, ok = 1;
         int P = 0;
         const int j0 = first_pos[blockIdx.x];
         if (sd.m > 0 && j0 != 0x7F7F7F7F) {
-            P = next_settled(j0);
+            P = j0 < lim ? next_settled(j0) : -1;
             if (P < 0) ok = 0;
         }
         s_peaks[0] = P;
-        while (ok && sd.m > 0) {
-            const int a = P + w + 1;
-            if (a > last) break;
-            np++;
-            if (np == WEFAX_MAX_PEAKS) {
-                s_peaks[np - 1] = a;   // the 100th peak is never refined (wefax.py:251)
-                break;
+        if (ok && sd.m > 0) {
+            int a = P + w + 1;
+#pragma unroll 1
+            while (np < WEFAX_MAX_PEAKS - 1 && a <= amax) {
+                P = next_settled(a);
+                if (P < 0) {
+                    ok = 0;
+                    break;
+                }
+                s_peaks[np++] = P;
+                a = P + w + 1;
             }
-            if (a >= lim) {
-                ok = 0;
-                break;
+            if (ok && a <= last) {
+                // the loop stopped at the 100-peak limit (the 100th peak is never refined, wefax.py:251) or at the
+                // end of the precomputed region
+                if (np == WEFAX_MAX_PEAKS - 1) s_peaks[np++] = a;
+                else ok = 0;
             }
-            P = next_settled(a);
-            if (P < 0) {
-                ok = 0;
-                break;
-            }
-            s_peaks[np - 1] = P;
         }
         if (ok) {
             need_scan[blockIdx.x] = 0;
@@ -1946,15 +1958,23 @@ long long sync_head(const SyncPlan &sp, long long n) {
     return sp.any_fast ? std::min(n, ((sp.max_limc + kSyncMaxL + 2047) / 2048) * 2048) : n;
 }
 
+void clear_sync_scratch(wefax_ctx *ctx, const SyncPlan &sp, int batch, cudaStream_t stream) {
+    (void)ctx;
+    if (!sp.any_fast) return;
+    CUDA_CHECK(cudaMemsetAsync(sp.first_pos, 0x7F, sizeof(int) * batch, stream));   // 0x7F7F7F7F = no positive correlation yet
+    CUDA_CHECK(cudaMemsetAsync(sp.bits, 0, sp.bs * batch * sizeof(uint32_t), stream));
+}
+
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                         RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready,
-                        const LazyGrey &lazy) {
+                        const LazyGrey &lazy, SideFork *clears, SideFork *table) {
     StageTimer timer(ctx, "sync_search");
     cudaStream_t st = ctx->stream;
     const char *fs = getenv("WEFAX_SYNC_FORCE_SCAN");
     const int force_scan = fs ? atoi(fs) : 0;
+    if (clears) clears->join();
+    else clear_sync_scratch(ctx, sp, batch, st);
     if (sp.any_fast) {
-        CUDA_CHECK(cudaMemsetAsync(sp.first_pos, 0x7F, sizeof(int) * batch, st));   // 0x7F7F7F7F = no positive correlation yet
         dim3 g1((unsigned)std::max<long long>(1, (sp.max_limc + kCorrTile - 1) / kCorrTile), batch);
         {
             StageTimer t1(ctx, "sync_corr");
@@ -1969,7 +1989,6 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         }
         {
             StageTimer t1(ctx, "sync_settled");
-            CUDA_CHECK(cudaMemsetAsync(sp.bits, 0, sp.bs * batch * sizeof(uint32_t), st));
             sync_settled_kernel<<<g2, kSyncThreads, (size_t)3 * sp.max_w * sizeof(int), st>>>(lines, sp.sd, sp.corr, sp.cs,
                                                                                            sp.bits, sp.bs);
         }
@@ -1987,6 +2006,7 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
     }
     // the parallel search above only reads the head of the recording; the sequential fallback may read all of it
     if (all_data_ready) CUDA_CHECK(cudaStreamWaitEvent(st, all_data_ready, 0));
+    if (table) table->join();
     if (min_mindistance >= 4096)
         sync_search_kernel<4, false><<<batch, kSyncThreads, 0, st>>>(dig, ds, n, lines, res, sp.need_scan, lazy);
     else if (min_mindistance >= 2048)

@@ -93,9 +93,14 @@ cudaEvent_t launch_quantise_split(wefax_ctx *ctx, const float *env, size_t es, u
                                   int batch, const RecResult *res, const SyncPlan &sp);
 // min_mindistance: smallest LineDev.mindistance of the batch (sizes the scan chunk; must be >= 1024)
 // all_data_ready (may be null): event to wait for before the sequential fallback scan, which reads all of dig
+struct SideFork;
+// clears: fork whose side work is clear_sync_scratch() (joined before the first kernel; nullptr: cleared here);
+// table: fork whose side work produces what `lazy` reads (joined before the sequential fallback, the only reader)
 void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int batch, const LineDev *lines,
                         RecResult *res, int min_mindistance, const SyncPlan &sp, cudaEvent_t all_data_ready = nullptr,
-                        const LazyGrey &lazy = LazyGrey());
+                        const LazyGrey &lazy = LazyGrey(), SideFork *clears = nullptr, SideFork *table = nullptr);
+// the scratch the parallel search expects cleared (first positive correlation, settled bits), on `stream`
+void clear_sync_scratch(wefax_ctx *ctx, const SyncPlan &sp, int batch, cudaStream_t stream);
 void launch_packet_pulse_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, int n_packets,
                                 const LineDev *line, RecResult *res, int mindistance);
 // samples the parallel phasing search reads: [0, sync_head(sp, n))
@@ -106,7 +111,7 @@ void launch_raster(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long n, i
                    const RecResult *res, uint8_t *raster, size_t rs, int max_width, int max_lines);
 // ---- fused median-5 + grey map + raster (greyraster.cu) ----
 // threshold tables of the grey map from RecResult.low/high (one per recording)
-void launch_grey_table(wefax_ctx *ctx, const RecResult *res, GreyTable *tables, int batch);
+void launch_grey_table(wefax_ctx *ctx, const RecResult *res, GreyTable *tables, int batch, cudaStream_t stream = nullptr);
 // envelope -> digitalized (all n samples; dig may be null) + raster (rows of recordings with status OK; raster may
 // be null).  Needs RecResult.start_frame / height / status, i.e. runs after the phasing search.
 void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, uint8_t *raster, size_t rs,
