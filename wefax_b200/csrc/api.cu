@@ -369,8 +369,11 @@ int wefax_ctx_create(int device, void *stream, wefax_ctx **out) {
             ctx->own_stream = true;
         }
         {
+            // Measured on B200 (60-min recording): without the graph the side stream gains 0.5 % (828 -> 832 us the other
+            // way round), inside the graph it LOSES 2 % (781 -> 797 us: a graph that is one straight chain of kernel nodes
+            // is scheduled tighter than one with forks), and the graph is the default: WEFAX_SIDE=1 to turn it on.
             const char *sd = getenv("WEFAX_SIDE");
-            if (!(sd && sd[0] == '0')) {
+            if (sd && sd[0] == '1') {
                 CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_greatest));
                 for (int i = 0; i < wefax_ctx::kSideForks; ++i) {
                     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_side_fork[i], cudaEventDisableTiming));

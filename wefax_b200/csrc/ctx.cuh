@@ -51,8 +51,8 @@ struct wefax_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // Side stream for the small independent pieces of a step (edge tiles of the notch, scratch clears, the grey
     // threshold table): forked from / joined to the main stream by events, so that they run beside the kernel the main
-    // stream is busy with instead of between two of its latency-bound ones.  Off while stage timing is on (the
-    // per-stage event pairs live on the main stream) and with WEFAX_SIDE=0.
+    // stream is busy with instead of between two of its latency-bound ones.  Only with WEFAX_SIDE=1 (api.cu has the
+    // measurements), and never while stage timing is on (the per-stage event pairs live on the main stream).
     cudaStream_t side_stream = nullptr;
     static constexpr int kSideForks = 4;
     cudaEvent_t ev_side_fork[kSideForks] = {nullptr, nullptr, nullptr, nullptr};
@@ -248,8 +248,12 @@ bool launch_fast_tma(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t
         const char *e = getenv("WEFAX_TMA_ISSUER_WARP");
         return !(e && e[0] == '0');
     }();
+    static const int l2_hint = [] {
+        const char *e = getenv("WEFAX_L2_HINT");
+        return e ? atoi(e) : 0;
+    }();
     kern<<<grid, own_warp ? K::T + 32 : K::T, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total, own_warp ? K::T : 0,
-                                                                        epi);
+                                                                        l2_hint, epi);
     return true;
 }
 

@@ -385,6 +385,11 @@ static void launch_mid(wefax_ctx *ctx, FftPlan *half, float2 *z, size_t zs, int 
     a.tw_mode = pi.tw_mode;
     a.ko_R = pi.ko_R;
     a.inv_m = (float)(1.0 / (double)half->n);
+    static const int l2_hint = [] {
+        const char *e = getenv("WEFAX_L2_HINT");
+        return e ? atoi(e) : 0;
+    }();
+    a.l2_hint = l2_hint;
     const int ctas = by_warp ? (a.total_tiles + KW::WARPS - 1) / KW::WARPS : a.total_tiles;
     const int grid = std::min(ctas, ctx->sm_count * per_sm);
     StageTimer timer(ctx, "hilbert_mid");

@@ -404,6 +404,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -427,8 +433,11 @@ struct TileOut {};
 template <int R1, int R2, class Epi = TileOut>
 __global__ void __launch_bounds__(512 + 32, 1)
 fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                    int rbox, int total_tiles, int issuer, const Epi epi = Epi()) {
+                    int rbox, int total_tiles, int issuer, int l2_hint, const Epi epi = Epi()) {
     constexpr bool kTileOut = std::is_same<Epi, TileOut>::value;
+    // l2_hint: 0 none, 1 loads evict-first, 2 loads evict-first and stores evict-last (see fft.cuh)
+    const uint64_t pol_ld = l2_hint >= 1 ? l2_policy_evict_first() : 0ull;
+    const uint64_t pol_st = l2_hint >= 2 ? l2_policy_evict_last() : 0ull;
     // `issuer` = the thread that drives the copy engine: 512 (lane 0 of a 17th warp that does nothing else, so that no
     // worker waits for a store to drain before the next load can be issued) or 0 (a worker; launched with 512 threads)
     using K = TmaCfg<R1, R2>;
@@ -465,7 +474,10 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
         const int o = p.fast_divTpo.div(t_in);
         const int m0 = (t_in - o * p.fast_tiles_per_o) * C;
         mbar_expect_tx(bar, kTileBytes);
-        for (int b = 0; b < nbox; ++b) tma_load_4d(dst + (size_t)b * rbox * C, &in_map, bar, 2 * m0, b * rbox, o, batch);
+        for (int b = 0; b < nbox; ++b) {
+            if (l2_hint >= 1) tma_load_4d_hint(dst + (size_t)b * rbox * C, &in_map, bar, 2 * m0, b * rbox, o, batch, pol_ld);
+            else tma_load_4d(dst + (size_t)b * rbox * C, &in_map, bar, 2 * m0, b * rbox, o, batch);
+        }
     };
 
     if (tid == issuer && (int)blockIdx.x < total_tiles) issue_load(blockIdx.x, A0, mbar);
@@ -534,7 +546,10 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             if (tid == issuer) {
-                for (int b = 0; b < nbox; ++b) tma_store_4d(&out_map, A + (size_t)b * rbox * C, 2 * m0, b * rbox, o, batch);
+                for (int b = 0; b < nbox; ++b) {
+                    if (l2_hint >= 2) tma_store_4d_hint(&out_map, A + (size_t)b * rbox * C, 2 * m0, b * rbox, o, batch, pol_st);
+                    else tma_store_4d(&out_map, A + (size_t)b * rbox * C, 2 * m0, b * rbox, o, batch);
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {

@@ -54,6 +54,7 @@ struct MidArgs {
     int tw_mode;                   // 2 when a pass follows (e = ko*k), 0 when R is the whole transform
     int ko_R;
     float inv_m;
+    int l2_hint;                   // 0 none, >= 1 row loads evict-first (fft.cuh)
 };
 
 __device__ __forceinline__ void tma_store_bulk(void *gdst, const void *ssrc, uint32_t bytes) {
@@ -305,8 +306,14 @@ hilbert_mid_warp_kernel(const MidArgs a) {
         const bool self = o2 < 0;
         if (lane == 0) {
             mbar_expect_tx(mbar, self ? kRowBytes : 2 * kRowBytes);
-            tma_load_bulk(nat, zb + (size_t)o * R, kRowBytes, mbar);
-            if (!self) tma_load_bulk(nat + R, zb + (size_t)o2 * R, kRowBytes, mbar);
+            if (a.l2_hint >= 1) {
+                const uint64_t pol = l2_policy_evict_first();
+                tma_load_bulk_hint(nat, zb + (size_t)o * R, kRowBytes, mbar, pol);
+                if (!self) tma_load_bulk_hint(nat + R, zb + (size_t)o2 * R, kRowBytes, mbar, pol);
+            } else {
+                tma_load_bulk(nat, zb + (size_t)o * R, kRowBytes, mbar);
+                if (!self) tma_load_bulk(nat + R, zb + (size_t)o2 * R, kRowBytes, mbar);
+            }
             s_ko[warp][0] = o % a.ko_R;
             s_ko[warp][1] = self ? 0 : o2 % a.ko_R;
         }

@@ -1835,6 +1835,13 @@ sync_settled_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr
     }
 }
 
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // the sequential part: <= 100 jumps over the settled-bit mask held in shared memory
 __global__ void __launch_bounds__(1024)
 sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, const uint32_t *bits_all, size_t bs,
@@ -1858,13 +1865,18 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    // Two summary levels over the mask (bit k of s_l1[j]: word 32 j + k is non-empty; s_l2 likewise over s_l1), built by
-    // warp votes: "first settled position >= x" is then three dependent shared-memory loads of ONE thread (the word
-    // of x, the summary word, the word it points at) however the settled positions are spread - isolated maxima of a
-    // noisy correlation, plateaus of saturated grey or everything at once (a constant signal settles every position).
+    // Summary of the mask, built by warp votes and a short parallel walk:
+    //   s_l1[j]   bit k: word 32 j + k is non-empty                         (one word per 1024 positions)
+    //   s_l2[j]   bit k: s_l1[32 j + k] != 0                                 (only used to build s_nxt)
+    //   s_nxt[b]  first settled position >= 1024 b, or -1                    (one int per 1024 positions)
+    // "First settled position >= a" is then ONE round of three independent shared-memory loads for the usual case
+    // (the word of a, the summary word of its 1024-block, s_nxt of the next block) and a second load only when the
+    // answer lies in the same block but another word - however the settled positions are spread: isolated maxima of
+    // a noisy correlation, plateaus of saturated grey, or everything at once (a constant signal).
     uint32_t *s_l1 = s_bits + (((size_t)nwords + 3) & ~(size_t)3);
     const int nl1 = (nwords + 31) >> 5, nl2 = (nl1 + 31) >> 5;
     uint32_t *s_l2 = s_l1 + ((nl1 + 1 + 3) & ~3);
+    int *s_nxt = reinterpret_cast<int *>(s_l2 + ((nl2 + 3) & ~3));   // nl1 + 1 entries
     {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         for (int j = wid; j <= nl1; j += nwarps) {          // (one zero word past the end: the chain reads s_l1[nl1])
@@ -1879,43 +1891,49 @@ sync_chain_kernel(long long n, const LineDev *lines, const SyncDev *sd_all, cons
             if (lane == 0) s_l2[j] = word;
         }
         __syncthreads();
+        for (int b = threadIdx.x; b <= nl1; b += blockDim.x) {
+            int pos = -1;
+            if (b < nl1) {
+                int j = -1;                                   // first non-empty summary word at or after b
+                if (s_l1[b] != 0u) {
+                    j = b;
+                } else if (b + 1 < nl1) {
+                    int jj = (b + 1) >> 5;
+                    uint32_t t = s_l2[jj] & (~0u << ((b + 1) & 31));
+                    while (t == 0u && ++jj < nl2) t = s_l2[jj];
+                    if (t != 0u) j = (jj << 5) + (__ffs(t) - 1);
+                }
+                if (j >= 0) {
+                    const int wi = (j << 5) + (__ffs(s_l1[j]) - 1);
+                    pos = (wi << 5) + (__ffs(s_bits[wi]) - 1);
+                }
+            }
+            s_nxt[b] = pos;
+        }
+        __syncthreads();
     }
     if (threadIdx.x == 0) {
-        // One thread, pure latency: every step is the dependent chain  a -> (word of a | summary word) -> word the
-        // summary points at -> position.  The loop below keeps that chain short: one bound check per step (the
-        // 100-peak stop and both range ends are sorted out after the loop), the word of `a` and the summary word
-        // are loaded side by side, the rare walk through the second summary level is out of line.
+        // One thread, pure latency (a dependent instruction of a lone warp issues every ~5 cycles): the loop is kept
+        // to a few dozen instructions - 32-bit shared addresses, one bound check per step (the 100-peak stop and both
+        // range ends are sorted out after the loop), the three look-ups issued side by side.
         const int w = ln.mindistance;
         const int lim = (int)sd.lim;
         const int last = (int)min(sd.m - 1, (long long)0x7ffffff0);   // a > last ends the picker
         const int amax = min(last, lim - 1);                          // a > amax: the picker ends or the mask does
-        // first non-empty word at or after nx when its own summary word holds none; -1: the mask ends first
-        auto far_word = [&](int nx) -> int {
-            const int nj = (nx >> 5) + 1;
-            if (nj >= nl1) return -1;
-            int jj = nj >> 5;
-            uint32_t t = s_l2[jj] & (~0u << (nj & 31));
-            while (t == 0u) {
-                if (++jj >= nl2) return -1;
-                t = s_l2[jj];
-            }
-            const int j = (jj << 5) + (__ffs(t) - 1);
-            return (j << 5) + (__ffs(s_l1[j]) - 1);
-        };
-        // first settled position >= x (x < lim); -1 when the mask ends first
+        const uint32_t a_bits = smem_addr_u32(s_bits), a_l1 = smem_addr_u32(s_l1), a_nxt = smem_addr_u32(s_nxt);
+        // first settled position >= x (0 <= x < lim); -1 when the mask ends first
         auto next_settled = [&](int x) -> int {
-            const int wi = x >> 5, nx = wi + 1;
-            const uint32_t v0 = s_bits[wi] & (~0u << (x & 31));
-            const uint32_t u0 = s_l1[nx >> 5] & (~0u << (nx & 31));   // (s_l1 is zero-padded past the mask)
+            const int wi = x >> 5, blk = x >> 10;
+            const uint32_t v0 = lds_u32(a_bits + 4u * (uint32_t)wi) & (~0u << (x & 31));
+            // words wi + 1 .. 31 of this block (bit 31 shifted out when wi is the block's last word)
+            const uint32_t u0 = lds_u32(a_l1 + 4u * (uint32_t)blk) & ((0xFFFFFFFEu << (wi & 31)));
+            const int far = (int)lds_u32(a_nxt + 4u * (uint32_t)(blk + 1));
             if (v0 != 0u) return (wi << 5) + (__ffs(v0) - 1);
-            int w2;
             if (u0 != 0u) {
-                w2 = (nx & ~31) + (__ffs(u0) - 1);
-            } else {
-                w2 = far_word(nx);
-                if (w2 < 0) return -1;
+                const int w2 = (blk << 5) + (__ffs(u0) - 1);
+                return (w2 << 5) + (__ffs(lds_u32(a_bits + 4u * (uint32_t)w2)) - 1);
             }
-            return (w2 << 5) + (__ffs(s_bits[w2]) - 1);
+            return far;
         };
         int np = 1, ok = 1;
         int P = 0;
@@ -1994,9 +2012,9 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         }
         {
             StageTimer t1(ctx, "sync_chain");
-            // the settled bits and their two summary levels (1/32 and 1/1024 of the mask)
+            // the settled bits, their two summary levels (1/32 and 1/1024 of the mask) and one int per 1024 positions
             const size_t chain_words = (size_t)(((sp.max_lim + 31) / 32 + 4 + 3) & ~3ll);
-            const size_t chain_aux = (chain_words / 32 + 8 + chain_words / 1024 + 8) * sizeof(uint32_t);
+            const size_t chain_aux = (2 * (chain_words / 32 + 8) + chain_words / 1024 + 8) * sizeof(uint32_t);
             sync_chain_kernel<<<batch, 1024, chain_words * sizeof(uint32_t) + chain_aux, st>>>(
                 n, lines, sp.sd, sp.bits, sp.bs, sp.first_pos, res, sp.need_scan, force_scan);
         }
