@@ -278,54 +278,16 @@ __device__ __forceinline__ float2 bic_phase2(float2 a, float2 b, float2 c, float
     return acc;
 }
 
-// The newest line goes to ring slot S; the window's lines, oldest first, are then slots S+1, S+2, S+3, S+4, S (mod 5).
-// emit: the line two below the newest is complete - write its four raster rows (phases 0 / 1 read window lines 0..3,
-// phases 2 / 3 lines 1..4) and advance `orow` by four rows.
-template <int S, int ALIGN>
-__device__ __forceinline__ void ring_emit(float2 (&ring)[5][kGrCols / 2], const float2 (&cur)[kGrCols / 2], uint8_t *&orow,
-                                          int w, bool emit) {
-    constexpr int NP = kGrCols / 2;
-#pragma unroll
-    for (int c = 0; c < NP; ++c) ring[S][c] = cur[c];
-    if (!emit) return;
-    constexpr int L0 = (S + 1) % 5, L1 = (S + 2) % 5, L2 = (S + 3) % 5, L3 = (S + 4) % 5, L4 = S;
-    uint8_t *o = orow;
-    auto put = [&](const float2 (&v)[NP]) {
-        const uint32_t lo = pack4_sat(gr_floor(v[0].x), gr_floor(v[0].y), gr_floor(v[1].x), gr_floor(v[1].y));
-        const uint32_t hi = pack4_sat(gr_floor(v[2].x), gr_floor(v[2].y), gr_floor(v[3].x), gr_floor(v[3].y));
-        if (ALIGN == 8) {
-            *reinterpret_cast<uint2 *>(o) = make_uint2(lo, hi);
-        } else if (ALIGN == 4) {
-            reinterpret_cast<uint32_t *>(o)[0] = lo;
-            reinterpret_cast<uint32_t *>(o)[1] = hi;
-        } else {
-            store_any(o, lo, hi, kGrCols);
-        }
-        o += w;
-    };
-    float2 v[NP];
-#pragma unroll
-    for (int c = 0; c < NP; ++c) v[c] = bic_phase2<0>(ring[L0][c], ring[L1][c], ring[L2][c], ring[L3][c]);
-    put(v);
-#pragma unroll
-    for (int c = 0; c < NP; ++c) v[c] = bic_phase2<1>(ring[L0][c], ring[L1][c], ring[L2][c], ring[L3][c]);
-    put(v);
-#pragma unroll
-    for (int c = 0; c < NP; ++c) v[c] = bic_phase2<2>(ring[L1][c], ring[L2][c], ring[L3][c], ring[L4][c]);
-    put(v);
-#pragma unroll
-    for (int c = 0; c < NP; ++c) v[c] = bic_phase2<3>(ring[L1][c], ring[L2][c], ring[L3][c], ring[L4][c]);
-    put(v);
-    orow = o;
-}
-
 // One interior item: all its lines are image lines at least 2 lines from the image's first / last line, every
 // load stays inside the recording, the fp32 estimate is valid, the column group is complete.  OFF: offset (in
 // floats, mod 4) of the envelope element two to the left of the item's first column from a 16-byte boundary, the
 // same for every line when the width is a multiple of 4; OFF < 0: evaluated per line.  ALIGN: alignment every
 // raster row of the item is known to have (8, 4, or 0 = anything).  HAS_DIG: digitalized is written.
-// The line loop is deliberately NOT unrolled (its body must stay resident in the instruction cache); only the short
-// bicubic part exists five times, once per position of the 5-line ring (ring_emit).
+// The line loop is deliberately NOT unrolled: its body stays resident in the instruction cache; the price is the
+// moves that shift the 5-line window (grey levels as floats, two columns per register pair: 17 % of the kernel's
+// instructions).  Measured alternatives on B200, 60-min recording, 94.8 us as it stands: the loop unrolled five times
+// (window positions become register names) 120 us, instruction-cache misses; only the bicubic part five times, one copy
+// per position of a 5-line ring chosen by a switch, 100.8 us (10 880 instructions of code per kernel, 32 bytes spilled).
 template <int OFF, int ALIGN, bool HAS_DIG>
 __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e, uint8_t *dg, uint8_t *out,
                                               long long i_first, long long r_a, int nrows, int w, int c0) {
@@ -347,7 +309,6 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
 #pragma unroll
         for (int c = 0; c < NP; ++c) win[t][c] = make_float2(0.f, 0.f);
 
-    int slot = 0;
 #pragma unroll 1
     for (int j = 0; j < nrows; ++j) {
         // ---- grey levels of line r_a - 2 + j ----------------------------------------------------------------
@@ -369,6 +330,10 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
         }
         prow += w;
         if (j + 1 < nrows) fetch();   // the medians have consumed nx: the next line streams in under the rest of this one
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int c = 0; c < NP; ++c) win[t][c] = win[t + 1][c];
         uint32_t g[kGrCols];
         uint32_t bad = 0u;
 #pragma unroll
@@ -381,9 +346,8 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
 #pragma unroll
             for (int c = 0; c < kGrCols; ++c) g[c] = (uint32_t)Q.level_fast(m[c]);
         }
-        float2 cur[NP];
 #pragma unroll
-        for (int c = 0; c < NP; ++c) cur[c] = make_float2((float)g[2 * c], (float)g[2 * c + 1]);
+        for (int c = 0; c < NP; ++c) win[4][c] = make_float2((float)g[2 * c], (float)g[2 * c + 1]);
         if (HAS_DIG) {
             if (j >= 2 && j < nrows - 2) {
                 const uint32_t lo = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24);
@@ -416,18 +380,37 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
             }
             drow += w;
         }
-        // ---- the new line enters the 5-line ring; line r_a + j - 4 is then complete: its 4 raster rows -----------
-        // The ring slot of the newest line is j % 5.  Five copies of the (short) bicubic part, one per slot, name the
-        // window's registers at compile time: no moves to shift the window, and the long median / grey part above
-        // exists once, so the loop body still sits in the instruction cache.
-        switch (slot) {
-            case 0: ring_emit<0, ALIGN>(win, cur, orow, w, j >= 4); break;
-            case 1: ring_emit<1, ALIGN>(win, cur, orow, w, j >= 4); break;
-            case 2: ring_emit<2, ALIGN>(win, cur, orow, w, j >= 4); break;
-            case 3: ring_emit<3, ALIGN>(win, cur, orow, w, j >= 4); break;
-            default: ring_emit<4, ALIGN>(win, cur, orow, w, j >= 4); break;
+        // ---- line r_a + j - 4 is complete: its 4 raster rows ---------------------------------------------------
+        if (j >= 4) {
+            uint8_t *o = orow;
+            auto put = [&](const float2 (&v)[NP]) {
+                const uint32_t lo = pack4_sat(gr_floor(v[0].x), gr_floor(v[0].y), gr_floor(v[1].x), gr_floor(v[1].y));
+                const uint32_t hi = pack4_sat(gr_floor(v[2].x), gr_floor(v[2].y), gr_floor(v[3].x), gr_floor(v[3].y));
+                if (ALIGN == 8) {
+                    *reinterpret_cast<uint2 *>(o) = make_uint2(lo, hi);
+                } else if (ALIGN == 4) {
+                    reinterpret_cast<uint32_t *>(o)[0] = lo;
+                    reinterpret_cast<uint32_t *>(o)[1] = hi;
+                } else {
+                    store_any(o, lo, hi, kGrCols);
+                }
+                o += w;
+            };
+            float2 v[NP];
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<0>(win[0][c], win[1][c], win[2][c], win[3][c]);
+            put(v);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<1>(win[0][c], win[1][c], win[2][c], win[3][c]);
+            put(v);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<2>(win[1][c], win[2][c], win[3][c], win[4][c]);
+            put(v);
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = bic_phase2<3>(win[1][c], win[2][c], win[3][c], win[4][c]);
+            put(v);
+            orow = o;
         }
-        slot = slot == 4 ? 0 : slot + 1;
     }
 }
 
