@@ -223,12 +223,13 @@ def test_both_forms_of_the_greedy_picker_agree(monkeypatch):
 
 @pytest.mark.parametrize("env", [{"WEFAX_SIDE": 1}, {"WEFAX_L2_HINT": 2}, {"WEFAX_MID_WARP": 0}, {"WEFAX_TMA_ENV": 1},
                                  {"WEFAX_PCT_COLLECT": "median"}, {"WEFAX_PCT_NCTA": 32}, {"WEFAX_NOTCH_MINB": 5},
-                                 {"WEFAX_TMA_ISSUER_WARP": 0}])
+                                 {"WEFAX_TMA_ISSUER_WARP": 0}, {"WEFAX_TMA_PIPE": 0},
+                                 {"WEFAX_TMA_PIPE": 0, "WEFAX_TMA_ISSUER_WARP": 0}])
 def test_measurement_switches_do_not_change_results(monkeypatch, env):
     """The A/B switches kept in the library (side stream, L2 hints, CTA-tile middle kernel, TMA-fed envelope pass,
     always-median collection, selection width, notch occupancy, copy-issuing thread) only move work around."""
     for k in ("WEFAX_SIDE", "WEFAX_L2_HINT", "WEFAX_MID_WARP", "WEFAX_TMA_ENV", "WEFAX_PCT_COLLECT", "WEFAX_PCT_NCTA",
-              "WEFAX_NOTCH_MINB", "WEFAX_TMA_ISSUER_WARP"):
+              "WEFAX_NOTCH_MINB", "WEFAX_TMA_ISSUER_WARP", "WEFAX_TMA_PIPE"):
         monkeypatch.delenv(k, raising=False)
     want = ("audio", "demodulated", "digitalized", "raster")
     # 176 400 samples: half-length transform 225 x 392 (TMA-staged pass, fused middle, TMA / direct envelope pass);

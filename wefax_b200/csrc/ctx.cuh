@@ -252,6 +252,21 @@ bool launch_fast_tma(wefax_ctx *ctx, const PassDev &p, const float2 *src, size_t
         const char *e = getenv("WEFAX_L2_HINT");
         return e ? atoi(e) : 0;
     }();
+    // three tiles in flight (fft_fast_tma3_kernel) for the plain complex pass unless WEFAX_TMA_PIPE=0
+    static const bool pipe3 = [] {
+        const char *e = getenv("WEFAX_TMA_PIPE");
+        return !(e && e[0] == '0');
+    }();
+    if (kTileOut && pipe3) {
+        auto kern3 = fast::fft_fast_tma3_kernel<R1, R2>;
+        const void *fn3 = (const void *)kern3;
+        if (!ctx->smem_configured.count(fn3)) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+            ctx->smem_configured[fn3] = 1;
+        }
+        kern3<<<grid, K::T + 32, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total);
+        return true;
+    }
     kern<<<grid, own_warp ? K::T + 32 : K::T, K::SMEM, ctx->stream>>>(p, in_map, out_map, rbox, (int)total, own_warp ? K::T : 0,
                                                                         l2_hint, epi);
     return true;

@@ -421,7 +421,7 @@ template <int R1, int R2> struct TmaCfg {
     static constexpr int C = 32;
     static constexpr int T = 512;
     static constexpr int TILE = R * C;                               // float2 per tile buffer
-    static constexpr int SMEM = (R + 3 * TILE + R2 * C) * (int)sizeof(float2) + 64 + 1024;   // + alignment slack
+    static constexpr int SMEM = (R + 3 * TILE + 2 * R2 * C) * (int)sizeof(float2) + 64 + 1024;   // + alignment slack
     static_assert(R1 <= 16 && R2 <= 16, "512 threads = 16 rows x 32 columns");
 };
 
@@ -586,6 +586,143 @@ fft_fast_tma_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map,
         }
     }
     if (kTileOut && tid == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ----------------------------- the pass, TMA-staged, three tiles in flight -------------------------------------------
+// Same arithmetic and tile as fft_fast_tma_kernel, but the copy engine runs two tiles ahead of the arithmetic instead
+// of one.  Both register stages work IN PLACE on the tile buffer (stage 1 reads and writes the same rows of a column;
+// stage 2 reads its 15 rows, meets the other workers at a barrier, and writes the permuted rows), so there is no
+// exchange tile and the shared memory holds three tile buffers: one being computed, one landing, one leaving.  A
+// 17th warp does nothing but drive the copy engine: it learns through an mbarrier that a tile is finished, stores it,
+// waits (alone) until the store has read the buffer, and at once loads the tile three ahead into it.  The 16 worker
+// warps never wait for a store and meet only each other (named barrier), twice a tile.
+template <int R1, int R2>
+__global__ void __launch_bounds__(512 + 32, 1)
+fft_fast_tma3_kernel(const PassDev p, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                     int rbox, int total_tiles) {
+    using K = TmaCfg<R1, R2>;
+    constexpr int R = K::R, C = K::C;
+    extern __shared__ unsigned char tma_smem_raw[];
+    float2 *B0 = reinterpret_cast<float2 *>(tma_smem_raw + ((1024u - (smem_u32(tma_smem_raw) & 1023u)) & 1023u));
+    float2 *P0 = B0 + 3 * K::TILE;             // [2][R2][C] inter-pass twiddle columns, double-buffered
+    float2 *twQ = P0 + 2 * R2 * C;             // [q][u]
+    uint64_t *full = reinterpret_cast<uint64_t *>(twQ + R);   // [3] tile landed
+    uint64_t *done = full + 3;                                 // [3] tile computed
+
+    const int tid = threadIdx.x;
+    const int cc = tid % C, row = tid / C;
+    for (int i = tid; i < R; i += K::T) {
+        const int q = i / R1, u = i - q * R1;
+        twQ[i] = __ldg(p.twR + q * u);
+    }
+    if (tid == 0) {
+        for (int b = 0; b < 3; ++b) {
+            mbar_init(full + b, 1);
+            mbar_init(done + b, K::T / 32);
+        }
+    }
+    __syncthreads();
+    const int nt = (int)blockIdx.x < total_tiles ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    constexpr uint32_t kTileBytes = (uint32_t)(K::TILE * sizeof(float2));
+    const int nbox = R / rbox;
+    auto tile_coords = [&](int k, int &batch, int &o, int &m0) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        batch = tile / p.fast_ntiles;
+        const int t_in = tile - batch * p.fast_ntiles;
+        o = p.fast_divTpo.div(t_in);
+        m0 = (t_in - o * p.fast_tiles_per_o) * C;
+    };
+
+    if (tid >= K::T) {
+        // ---- the copy warp ------------------------------------------------------------------------------------------
+        if (tid == K::T) {
+            auto issue_load = [&](int k) {
+                int batch, o, m0;
+                tile_coords(k, batch, o, m0);
+                float2 *dst = B0 + (size_t)(k % 3) * K::TILE;
+                uint64_t *bar = full + (k % 3);
+                mbar_expect_tx(bar, kTileBytes);
+                for (int b = 0; b < nbox; ++b) tma_load_4d(dst + (size_t)b * rbox * C, &in_map, bar, 2 * m0, b * rbox, o, batch);
+            };
+            for (int k = 0; k < 3 && k < nt; ++k) issue_load(k);
+            for (int k = 0; k < nt; ++k) {
+                while (!mbar_try_wait(done + (k % 3), (uint32_t)((k / 3) & 1))) {
+                }
+                int batch, o, m0;
+                tile_coords(k, batch, o, m0);
+                const float2 *src = B0 + (size_t)(k % 3) * K::TILE;
+                for (int b = 0; b < nbox; ++b) tma_store_4d(&out_map, src + (size_t)b * rbox * C, 2 * m0, b * rbox, o, batch);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (k + 3 < nt) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the buffer has been read out
+                    issue_load(k + 3);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
+
+    // ---- the sixteen worker warps ---------------------------------------------------------------------------------------
+    const bool act1 = row < R2, act2 = row < R1;
+    for (int k = 0; k < nt; ++k) {
+        float2 *A = B0 + (size_t)(k % 3) * K::TILE;
+        float2 *P = P0 + (size_t)(k & 1) * R2 * C;
+        int batch, o, m0;
+        tile_coords(k, batch, o, m0);
+        const uint32_t m = (uint32_t)(m0 + cc);
+        const bool colok = m < (uint32_t)p.S;
+        uint32_t e0 = 0, de = 0;
+        if (p.tw_mode == 1) {
+            de = m;
+        } else if (p.tw_mode == 2) {
+            const uint32_t ko = (uint32_t)o % (uint32_t)p.ko_R;
+            e0 = ko * m;
+            de = ko * (uint32_t)p.S;
+        }
+        if (!colok) e0 = de = 0;
+        float2 Pval = make_float2(1.f, 0.f), Aval = make_float2(1.f, 0.f);
+        if (p.tw_mode != 0) {
+            if (act1) Pval = pass_twiddle(p, (uint32_t)(row * R1) * de);
+            if (act2) Aval = pass_twiddle(p, e0 + (uint32_t)row * de);
+        }
+        while (!mbar_try_wait(full + (k % 3), (uint32_t)((k / 3) & 1))) {
+        }
+        if (act1) {
+            float2 v[R1];
+#pragma unroll
+            for (int t = 0; t < R1; ++t) v[t] = A[(row + R2 * t) * C + cc];
+            Dft<R1>::run(v);
+            if (p.tw_mode != 0) P[row * C + cc] = Pval;
+            const float2 *tq = twQ + row * R1;
+            A[row * C + cc] = v[0];
+#pragma unroll
+            for (int u = 1; u < R1; ++u) A[(row + R2 * u) * C + cc] = pcmul3(v[u], tq[u]);   // the rows it read
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        float2 y[R2];
+        if (act2) {
+#pragma unroll
+            for (int t = 0; t < R2; ++t) y[t] = A[(row * R2 + t) * C + cc];
+            Dft<R2>::run(y);
+            const float2 Aa = bc(Aval.x), Ab = make_float2(-Aval.y, Aval.y);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                if (p.tw_mode != 0) {
+                    y[k2] = pcmul2(y[k2], Aa, Ab);
+                    if (k2 > 0) y[k2] = pcmul3(y[k2], P[k2 * C + cc]);
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // every block of rows has been read: they may be overwritten
+        if (act2) {
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) A[(row + R1 * k2) * C + cc] = y[k2];   // natural row order
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(done + (k % 3))) : "memory");
+    }
 }
 
 // (R1, R2) pairs with a compiled kernel; 0 when R has none
