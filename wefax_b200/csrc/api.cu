@@ -650,14 +650,16 @@ int wefax_decode_batch(wefax_ctx *ctx, const wefax_batch_desc *desc, const int16
             else
                 hilbert_envelope_bluestein(ctx, n, d_audio, (size_t)n, d_env, (size_t)n, g);
             // ---- median-5, percentiles, grey map (wefax.py:175,196-200) ---------------
-            launch_percentiles(ctx, d_env, (size_t)n, n, g, d_sel, d_res);
-            if (d_raster && ctx->use_fused) {
+            const bool fused = d_raster && ctx->use_fused;
+            GreyTable *d_tab = fused ? (GreyTable *)ctx->grey_tab.reserve(sizeof(GreyTable) * (size_t)g) : nullptr;
+            const bool have_table = launch_percentiles(ctx, d_env, (size_t)n, n, g, d_sel, d_res, 5, d_tab);
+            if (fused) {
                 // fused demod-to-pixel path: grey levels of the head for the phasing search (wefax.py:218-294),
                 // then ONE sweep over the envelope writes digitalized_data and the raster (wefax.py:296-327)
-                GreyTable *d_tab = (GreyTable *)ctx->grey_tab.reserve(sizeof(GreyTable) * (size_t)g);
-                // (the threshold table is first read by the search's sequential fallback: built beside the search)
+                // (the threshold table is first read by the search's sequential fallback: built beside the search,
+                //  unless the percentile stage has left it behind already)
                 SideFork table(ctx, 2);
-                launch_grey_table(ctx, d_res, d_tab, g, table.stream());
+                if (!have_table) launch_grey_table(ctx, d_res, d_tab, g, table.stream());
                 const long long head = sync_head(splan, n);
                 launch_quantise(ctx, d_env, (size_t)n, d_dig, (size_t)n, n, g, d_res, 0, head, st, "quantise_head");
                 LazyGrey lazy;

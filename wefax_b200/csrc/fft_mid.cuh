@@ -99,9 +99,10 @@ __device__ __forceinline__ void mid_stage1(const float2 *nat, float2 *mid, const
     }
 }
 
+// pre_aval (optional, only when every thread has at most one item): the item's inter-pass twiddle, fetched earlier
 template <int R1, int R2, bool TW, int ROWS = 8, int T = 128>
 __device__ __forceinline__ void mid_stage2(const float2 *mid, float2 *nat, const float2 *P, const MidArgs &a,
-                                           const int *s_ko, int tid) {
+                                           const int *s_ko, int tid, const float2 *pre_aval = nullptr) {
     using K = MidCfg<R1, R2>;   // (row length and exchange pitches only; ROWS / T are this call's own)
     constexpr int G2 = R1 <= 16 ? 16 : 32;
     static_assert(R1 <= 32, "stage-2 lane group");
@@ -111,8 +112,12 @@ __device__ __forceinline__ void mid_stage2(const float2 *mid, float2 *nat, const
         if (u >= R1) continue;
         float2 Aval = make_float2(1.f, 0.f);
         if (TW) {
-            const uint32_t e = (uint32_t)s_ko[row] * (uint32_t)u;
-            Aval = cmul(__ldg(a.tw_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw_hi + (e >> kTwLoBits)));
+            if (G2 * ROWS <= T && pre_aval) {
+                Aval = *pre_aval;
+            } else {
+                const uint32_t e = (uint32_t)s_ko[row] * (uint32_t)u;
+                Aval = cmul(__ldg(a.tw_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw_hi + (e >> kTwLoBits)));
+            }
         }
         float2 y[R2];
         const float2 *src = mid + row * K::MIDP + u * K::BP;
@@ -333,6 +338,17 @@ hilbert_mid_warp_kernel(const MidArgs a) {
                 P[i] = cmul(__ldg(a.tw_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw_hi + (e >> kTwLoBits)));
             }
         }
+        // this lane's inter-pass twiddle of the inverse pass (its one stage-2 item: row lane / G2, u = lane % G2):
+        // the two table reads travel while the rows are still landing
+        float2 aval = make_float2(1.f, 0.f);
+        {
+            constexpr int G2 = R1 <= 16 ? 16 : 32;
+            const int row = lane / G2, u = lane % G2;
+            if (a.tw_mode != 0 && 2 * G2 <= 32 && u < R1) {
+                const uint32_t e = (uint32_t)s_ko[warp][row] * (uint32_t)u;
+                aval = cmul(__ldg(a.tw_lo + (e & ((1u << kTwLoBits) - 1))), __ldg(a.tw_hi + (e >> kTwLoBits)));
+            }
+        }
         __syncwarp();
         mbar_wait(mbar, it & 1);
 
@@ -371,7 +387,7 @@ hilbert_mid_warp_kernel(const MidArgs a) {
         mid_stage1<R1, R2, 2, 32>(nat, mid, twQ, lane);
         __syncwarp();
         if (a.tw_mode != 0)
-            mid_stage2<R1, R2, true, 2, 32>(mid, nat, P, a, s_ko[warp], lane);
+            mid_stage2<R1, R2, true, 2, 32>(mid, nat, P, a, s_ko[warp], lane, &aval);
         else
             mid_stage2<R1, R2, false, 2, 32>(mid, nat, P, a, s_ko[warp], lane);
         fence_async_smem();

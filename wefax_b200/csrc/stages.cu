@@ -752,12 +752,14 @@ __device__ __forceinline__ void coop_barrier(CoopSync *cs, unsigned ncta, unsign
 template <int NT, class KeyAt>
 __device__ void coop_select(KeyAt key_at, long long count, int cta, unsigned ncta, CoopSync *cs, unsigned &phase,
                             uint32_t *ghist, uint32_t *s_hist /* NT*2048 */, uint32_t *s_rank, uint32_t *s_prefix,
-                            uint32_t *s_scan /* 32 */, unsigned nbar = 0, int nlevels = 3) {
+                            uint32_t *s_scan /* 32 */, unsigned nbar = 0, int nlevels = 3, int first_level = 0,
+                            uint32_t known_prefix = 0) {
     if (nbar == 0) nbar = ncta;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < NT) s_prefix[tid] = 0;
+    // first_level > 0: every key is known to start with known_prefix (11 or 22 bits), those levels are skipped
+    if (tid < NT) s_prefix[tid] = known_prefix;
     // nlevels < 3: the prefixes stop after 11 or 22 bits (the caller completes them conservatively)
-    for (int level = 0; level < nlevels; ++level) {
+    for (int level = first_level; level < nlevels; ++level) {
         const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
         const uint32_t mask = level == 2 ? 0x3FFu : 0x7FFu;
         const int nh = level == 0 ? 1 : NT;           // level 0: all targets share one histogram
@@ -1169,6 +1171,11 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
         const unsigned gn = (unsigned)((ncta + 1 - h) >> 1);
         const float *lst = h ? list_hi : list_lo;
         if (threadIdx.x < 2) s_rank[threadIdx.x] = g.r[2 * h + threadIdx.x] - (uint32_t)below_of[h];
+        // every key of the list lies inside its bracket: the leading bits the bracket's two ends share are known, and a
+        // radix level that only confirms them (one grid-wide barrier round each) is skipped
+        const uint32_t klo = st->key[2 * h], khi = st->key[2 * h + 1];
+        const int first = ((klo ^ khi) >> 21) != 0u ? 0 : (((klo ^ khi) >> 10) != 0u ? 1 : 2);
+        const uint32_t known = first == 0 ? 0u : (first == 1 ? klo >> 21 : klo >> 10);
         if (local_per > 0) {
             // this CTA's slice of the list goes to shared memory once; the three radix levels read it from there
             extern __shared__ uint32_t s_fin[];
@@ -1178,11 +1185,11 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
             for (int j = threadIdx.x; j < cnt; j += kSelThreads) s_fin[j] = __float_as_uint(__ldg(lst + s0 + j));
             __syncthreads();
             coop_select<2>([&](long long i) { return s_fin[i]; }, (long long)cnt, 0, 1u, &coop->sync[1 + h], phase,
-                           coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan, gn);
+                           coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan, gn, 3, first, known);
         } else {
             __syncthreads();
             coop_select<2>([&](long long i) { return __float_as_uint(__ldg(lst + i)); }, (long long)st->len[h], gcta, gn,
-                           &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan);
+                           &coop->sync[1 + h], phase, coop->hist[1 + h], s_hist, s_rank, s_prefix, s_scan, 0, 3, first, known);
         }
         if (gcta == 0 && threadIdx.x == 0) {
             st->out_key[2 * h] = s_prefix[0];
@@ -1211,12 +1218,17 @@ pct_final_kernel(PctGeom g, PctState *st_all, const float *lists, size_t ls, Rec
 }
 
 // exact selection over the whole recording by one CTA (only when a bracket failed)
+// ... and, bracket or not, the last kernel of the percentile stage: it leaves the recording's grey threshold table
+// behind (tables != nullptr) so that the fused grey map needs no kernel of its own for it.
 __global__ void __launch_bounds__(kSelThreads)
 pct_fallback_kernel(const float *env, size_t es, PctGeom g, const PctState *st_all, RecResult *res_all,
-                    PctCoop *coop_all) {
+                    PctCoop *coop_all, GreyTable *tables) {
     __shared__ uint32_t s_hist[4 * 2048];
     __shared__ uint32_t s_rank[4], s_prefix[4], s_scan[32];
-    if (!st_all[blockIdx.x].fallback) return;
+    if (!st_all[blockIdx.x].fallback) {
+        if (tables) build_grey_table(res_all + blockIdx.x, tables + blockIdx.x);
+        return;
+    }
     const float *e = env + (size_t)blockIdx.x * es;
     PctCoop *coop = coop_all + blockIdx.x;
     // reuse the sample histogram space (its selection is long finished): clear it first
@@ -1238,10 +1250,15 @@ pct_fallback_kernel(const float *env, size_t es, PctGeom g, const PctState *st_a
         },
         n, 0, 1u, &coop->sync[0], phase, coop->hist[0], s_hist, s_rank, s_prefix, s_scan);
     if (threadIdx.x == 0) write_percentiles(res_all + blockIdx.x, s_prefix, g.t_lo, g.t_hi);
+    if (tables) {
+        __threadfence_block();
+        __syncthreads();
+        build_grey_table(res_all + blockIdx.x, tables + blockIdx.x);
+    }
 }
 
-void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
-                        RecResult *res, int med) {
+bool launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
+                        RecResult *res, int med, GreyTable *tables) {
     StageTimer timer(ctx, "percentiles");
     cudaStream_t st = ctx->stream;
     // numpy 'linear' method: virtual index (n-1)*q, q = 0.5/100 and 99.5/100
@@ -1277,7 +1294,7 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
         }
         CUDA_CHECK(cudaGetLastError());
         ctx->launches += 7;
-        return;
+        return false;   // (short recordings: the caller builds the threshold table itself)
     }
     PctGeom g;
     memset(&g, 0, sizeof(g));
@@ -1393,10 +1410,11 @@ void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n
                                                    args, fin_smem, st));
         else
             pct_final_kernel<<<batch, kSelThreads, 0, st>>>(g, pst, lists, ls, res, coop, 1, 0);
-        pct_fallback_kernel<<<batch, kSelThreads, 0, st>>>(env, es, g, pst, res, coop);
+        pct_fallback_kernel<<<batch, kSelThreads, 0, st>>>(env, es, g, pst, res, coop, tables);
     }
     CUDA_CHECK(cudaGetLastError());
     ctx->launches += 5;
+    return tables != nullptr;
 }
 
 // ===========================================================================

@@ -80,8 +80,11 @@ void launch_filtfilt(wefax_ctx *ctx, IngestMode mode, const void *in, size_t in_
 void launch_median5(wefax_ctx *ctx, const float *env, size_t es, float *out, size_t os, long long n, int batch);
 // 0.5 / 99.5 percentiles of median5(env) -> RecResult.low/high (+ WEFAX_REC_NAN)
 // med: median window in front of the percentiles (5: file path, wefax.py:175; 3: packets, data_packet.py:440)
-void launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
-                        RecResult *res, int med = 5);
+// tables != nullptr: the stage also leaves the grey threshold table of every recording there when it can (returns
+// true; false: the caller launches launch_grey_table itself)
+struct GreyTable;
+bool launch_percentiles(wefax_ctx *ctx, const float *env, size_t es, long long n, int batch, SelState *sel,
+                        RecResult *res, int med = 5, GreyTable *tables = nullptr);
 // eps: added to high - low (0 on the file path, 0.000001 for packets: data_packet.py:461)
 void launch_quantise(wefax_ctx *ctx, const float *env, size_t es, uint8_t *dig, size_t ds, long long n, int batch,
                      const RecResult *res, long long i_begin, long long i_end, cudaStream_t stream, const char *tag,
