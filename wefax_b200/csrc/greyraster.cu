@@ -85,6 +85,33 @@ __device__ __forceinline__ uint32_t pack4_sat(int v0, int v1, int v2, int v3) {
     return d;
 }
 
+// 8 bytes (lo = bytes 0..3) to an address of any alignment, inline: the alignment is the same for every thread of a warp
+// (adjacent threads own adjacent groups of 8 columns), so the branches are uniform.  (The out-of-line store_any below
+// costs ~50 instructions a call under the ABI - measured 2.4x on the whole sweep for widths that are not multiples of 8.)
+__device__ __forceinline__ void store8_inline(uint8_t *p, uint32_t lo, uint32_t hi) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7u);
+    if (a == 0u) {
+        *reinterpret_cast<uint2 *>(p) = make_uint2(lo, hi);
+    } else if (a == 4u) {
+        reinterpret_cast<uint32_t *>(p)[0] = lo;
+        reinterpret_cast<uint32_t *>(p)[1] = hi;
+    } else if ((a & 1u) == 0u) {   // 2 or 6
+        *reinterpret_cast<uint16_t *>(p) = (uint16_t)lo;
+        *reinterpret_cast<uint32_t *>(p + 2) = __funnelshift_r(lo, hi, 16);
+        *reinterpret_cast<uint16_t *>(p + 6) = (uint16_t)(hi >> 16);
+    } else if ((a & 3u) == 3u) {   // 3 or 7: p + 1 is 4-byte aligned
+        p[0] = (uint8_t)lo;
+        *reinterpret_cast<uint32_t *>(p + 1) = __funnelshift_r(lo, hi, 8);
+        *reinterpret_cast<uint16_t *>(p + 5) = (uint16_t)(hi >> 8);
+        p[7] = (uint8_t)(hi >> 24);
+    } else {                       // 1 or 5: p + 3 is 4-byte aligned
+        p[0] = (uint8_t)lo;
+        *reinterpret_cast<uint16_t *>(p + 1) = (uint16_t)(lo >> 8);
+        *reinterpret_cast<uint32_t *>(p + 3) = __funnelshift_r(lo, hi, 24);
+        p[7] = (uint8_t)(hi >> 24);
+    }
+}
+
 // kGrCols bytes (lo = bytes 0..3) to an address of any alignment, first `count` bytes only when count < kGrCols
 // (out of line: the hot loop only comes here for rows of unaligned widths; the generic items use it throughout)
 __device__ __noinline__ void store_any(uint8_t *p, uint32_t lo, uint32_t hi, int count) {
@@ -198,7 +225,10 @@ __device__ __forceinline__ float2 bic_phase2(float2 a, float2 b, float2 c, float
 // per position of a 5-line ring chosen by a switch, 100.8 us (10 880 instructions of code per kernel, 32 bytes spilled).
 template <int OFF, int ALIGN, bool HAS_DIG>
 __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e, uint8_t *dg, uint8_t *out,
-                                              long long i_first, long long r_a, int nrows, int w, int c0) {
+                                              long long i_first, long long r_a, int nrows, int w, int c0, int ncols) {
+    // ncols < kGrCols: the last, partial column group of a line (widths that are not multiples of 8).  All 8 columns
+    // are computed (the loads run on into the next line, which is inside the recording); only the stores are cut.
+    const bool whole = ALIGN == 8 || ncols == kGrCols;
     constexpr int NP = kGrCols / 2;
     float2 win[5][NP];
     const float *prow = e + i_first - 2;   // x[0] of the line being fetched
@@ -211,7 +241,6 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
     fetch();
     uint8_t *drow = dg + i_first;                       // digitalized of the line being computed
     uint8_t *orow = out + (size_t)(4 * r_a) * w + c0;   // raster rows of the line being emitted
-    const uint32_t dal = (uint32_t)(reinterpret_cast<uintptr_t>(drow) & 7u);   // fixed per item when ALIGN == 8
 #pragma unroll
     for (int t = 0; t < 5; ++t)
 #pragma unroll
@@ -260,31 +289,10 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
             if (j >= 2 && j < nrows - 2) {
                 const uint32_t lo = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24);
                 const uint32_t hi = g[4] | (g[5] << 8) | (g[6] << 16) | (g[7] << 24);
-                if (ALIGN == 8) {
-                    // start_frame fixes the alignment of every digitalized row of the item
-                    if (dal == 0u) {
-                        *reinterpret_cast<uint2 *>(drow) = make_uint2(lo, hi);
-                    } else if (dal == 4u) {
-                        reinterpret_cast<uint32_t *>(drow)[0] = lo;
-                        reinterpret_cast<uint32_t *>(drow)[1] = hi;
-                    } else if ((dal & 1u) == 0u) {
-                        *reinterpret_cast<uint16_t *>(drow) = (uint16_t)lo;
-                        *reinterpret_cast<uint32_t *>(drow + 2) = __funnelshift_r(lo, hi, 16);
-                        *reinterpret_cast<uint16_t *>(drow + 6) = (uint16_t)(hi >> 16);
-                    } else if ((dal & 3u) == 3u) {
-                        drow[0] = (uint8_t)lo;
-                        *reinterpret_cast<uint32_t *>(drow + 1) = __funnelshift_r(lo, hi, 8);
-                        *reinterpret_cast<uint16_t *>(drow + 5) = (uint16_t)(hi >> 8);
-                        drow[7] = (uint8_t)(hi >> 24);
-                    } else {
-                        drow[0] = (uint8_t)lo;
-                        *reinterpret_cast<uint16_t *>(drow + 1) = (uint16_t)(lo >> 8);
-                        *reinterpret_cast<uint32_t *>(drow + 3) = __funnelshift_r(lo, hi, 24);
-                        drow[7] = (uint8_t)(hi >> 24);
-                    }
-                } else {
-                    store_any(drow, lo, hi, kGrCols);
-                }
+                // (start_frame fixes the alignment of the digitalized rows: the same for every line when the width is
+                //  a multiple of 8, changing from line to line otherwise; always the same across a warp)
+                if (whole) store8_inline(drow, lo, hi);
+                else store_any(drow, lo, hi, ncols);
             }
             drow += w;
         }
@@ -296,11 +304,13 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
                 const uint32_t hi = pack4_sat(gr_floor(v[2].x), gr_floor(v[2].y), gr_floor(v[3].x), gr_floor(v[3].y));
                 if (ALIGN == 8) {
                     *reinterpret_cast<uint2 *>(o) = make_uint2(lo, hi);
+                } else if (!whole) {
+                    store_any(o, lo, hi, ncols);
                 } else if (ALIGN == 4) {
                     reinterpret_cast<uint32_t *>(o)[0] = lo;
                     reinterpret_cast<uint32_t *>(o)[1] = hi;
                 } else {
-                    store_any(o, lo, hi, kGrCols);
+                    store8_inline(o, lo, hi);
                 }
                 o += w;
             };
@@ -324,8 +334,11 @@ __device__ __forceinline__ void interior_item(const GreyQuant &Q, const float *e
 
 // ALIGN: alignment every raster row of the launch's recordings is known to have: 8 (width % 8 == 0), 4 (width % 4 == 0)
 // or 0 (anything); for 8 and 4 the envelope rows of a recording also share one 16-byte phase.
+// (5 CTAs per SM at 96 registers when the rows keep their alignment; odd widths carry per-line alignments, and at 96
+//  registers the allocator reused a destination of the in-flight envelope load as a temporary, a full DRAM latency per
+//  line: they get 128 registers and 4 CTAs)
 template <int ALIGN>
-__global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
+__global__ void __launch_bounds__(kGrThreads, ALIGN == 0 ? 4 : 5) grey_raster_kernel(const __grid_constant__ GreyRasterParams P) {
     __shared__ uint32_t s_T[260];
     __shared__ uint2 s_pairs[256];
     const int rec = blockIdx.y;
@@ -362,7 +375,10 @@ __global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid
     long long tile = item / ng;
     const int grp = (int)(item - tile * ng);
     tile = tile == 0 ? ntiles - 1 : tile - 1;
-    const int c0 = grp * kGrCols;
+    // the last column group of a width that is not a multiple of 8 is moved left so that it is whole: it recomputes a
+    // few columns of its neighbour (both write the same bytes) instead of being the one partial group whose stores
+    // have to be cut - that one thread used to hold its whole warp back in every tile
+    const int c0 = w >= kGrCols ? min(grp * kGrCols, w - kGrCols) : 0;
     const int ncols = min(kGrCols, w - c0);
     const long long r_a = r_lo + tile * U, r_b = min(r_a + U, r_hi);
 
@@ -371,13 +387,12 @@ __global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid
     uint8_t *out = P.raster ? P.raster + (size_t)rec * P.rs : nullptr;
 
     const long long i_first = s + (r_a - 2) * w + c0;   // sample (line r_a - 2, column c0)
-    const bool interior = Q.est_ok && ncols == kGrCols && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 &&
-                          s + (r_b + 1) * w + c0 + 14 <= n;
+    const bool interior = Q.est_ok && r_a >= 2 && r_b + 2 <= h && i_first - 2 >= 4 && s + (r_b + 1) * w + c0 + 14 <= n;
     if (interior) {
         const int nrows = (int)(r_b - r_a) + 4;
 #define WEFAX_GR_RUN(OFF_)                                                                        \
-    if (dg) interior_item<OFF_, ALIGN, true>(Q, e, dg, out, i_first, r_a, nrows, w, c0);          \
-    else interior_item<OFF_, ALIGN, false>(Q, e, dg, out, i_first, r_a, nrows, w, c0);
+    if (dg) interior_item<OFF_, ALIGN, true>(Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols);   \
+    else interior_item<OFF_, ALIGN, false>(Q, e, dg, out, i_first, r_a, nrows, w, c0, ncols);
         if (ALIGN >= 4) {
             switch ((int)((reinterpret_cast<uintptr_t>(e + i_first - 2) >> 2) & 3u)) {
                 case 0: WEFAX_GR_RUN(0) break;
@@ -392,7 +407,7 @@ __global__ void __launch_bounds__(kGrThreads, 5) grey_raster_kernel(const __grid
         return;
     }
 
-    // ---- generic items: recording / image edges, partial column groups, recordings without an image ------
+    // ---- generic items: recording / image edges, recordings without an image ------------------------------
     int win[5][kGrCols];
 #pragma unroll
     for (int t = 0; t < 5; ++t)
@@ -510,21 +525,24 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
     const bool base4 = (reinterpret_cast<uintptr_t>(raster) & 3) == 0 && rs % 4 == 0;
     int count[3] = {0, 0, 0};   // 0: generic widths, 1: width % 4 == 0, 2: width % 8 == 0
     for (int r = 0; r < batch; ++r) count[h_lines[r].gr_class]++;
-    int per_sm = 5;
-    {
-        const void *fn = (const void *)grey_raster_kernel<8>;
+    auto resident_ctas = [&](const void *fn, int fallback) {
         auto it = ctx->smem_configured.find(fn);
-        if (it == ctx->smem_configured.end()) {
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grey_raster_kernel<8>, kGrThreads, 0));
-            if (per_sm < 1) per_sm = 1;
-            ctx->smem_configured[fn] = per_sm;
-        } else {
-            per_sm = it->second;
+        if (it != ctx->smem_configured.end()) return it->second;
+        int per_sm = fallback;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGrThreads, 0) != cudaSuccess || per_sm < 1) {
+            (void)cudaGetLastError();
+            per_sm = fallback;
         }
-    }
-    const double resident = (double)ctx->sm_count * per_sm * kGrThreads;
+        ctx->smem_configured[fn] = per_sm;
+        return per_sm;
+    };
     for (int cls = 2; cls >= 0; --cls) {
         if (!count[cls]) continue;
+        const int align = (cls == 2 && base8) ? 8 : ((cls >= 1 && base4) ? 4 : 0);
+        const int per_sm = align == 8   ? resident_ctas((const void *)grey_raster_kernel<8>, 5)
+                           : align == 4 ? resident_ctas((const void *)grey_raster_kernel<4>, 5)
+                                        : resident_ctas((const void *)grey_raster_kernel<0>, 4);
+        const double resident = (double)ctx->sm_count * per_sm * kGrThreads;
         auto items_for = [&](int U, long long *max_items) {
             double total = 0;
             long long mx = 0;
@@ -558,9 +576,9 @@ void launch_grey_raster(wefax_ctx *ctx, const float *env, size_t es, uint8_t *di
         long long max_items = 0;
         items_for(best_u, &max_items);
         dim3 grid((unsigned)((max_items + kGrThreads - 1) / kGrThreads), batch);
-        if (cls == 2 && base8)
+        if (align == 8)
             grey_raster_kernel<8><<<grid, kGrThreads, 0, ctx->stream>>>(P);
-        else if (cls >= 1 && base4)
+        else if (align == 4)
             grey_raster_kernel<4><<<grid, kGrThreads, 0, ctx->stream>>>(P);
         else
             grey_raster_kernel<0><<<grid, kGrThreads, 0, ctx->stream>>>(P);
