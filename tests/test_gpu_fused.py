@@ -245,3 +245,34 @@ def test_measurement_switches_do_not_change_results(monkeypatch, env):
         _same(res, ref, 2)
         assert np.array_equal(res.audio, ref.audio)
         assert np.array_equal(res.demodulated, ref.demodulated)
+
+
+def test_repeated_decode_into_the_same_result_takes_the_short_way_and_stays_right(monkeypatch):
+    """``decode(..., out=res)`` with the arguments of the call that made ``res`` skips argument checking and allocation
+    (Decoder.decode fast path): same object back, updated in place, equal to a fresh decode; anything different (other
+    input buffer, other settings, a replaced output buffer) goes the long way and is right too."""
+    import torch
+    a = synth.synth_recording(30.0, lpm=120, seed=81, noise_sigma=0.03)
+    b = synth.synth_recording(30.0, lpm=120, seed=82, noise_sigma=0.05)
+    dec = _decoder(monkeypatch)
+    fresh_a = dec.decode(a, 11025, 120, want=WANT)
+    fresh_b = dec.decode(b, 11025, 120, want=WANT)
+    host = a.copy()
+    res = dec.decode(host, 11025, 120, want=WANT)
+    for src, ref in ((b, fresh_b), (a, fresh_a), (b, fresh_b)):
+        host[...] = src
+        again = dec.decode(host, 11025, 120, want=WANT, out=res)
+        assert again is res
+        _same(res, ref, 1)
+    other = dec.decode(b.copy(), 11025, 120, want=WANT, out=res)           # another input buffer: the long way
+    _same(other, fresh_b, 1)
+    res90 = dec.decode(host, 11025, 90, want=WANT)                         # other settings never reuse the 120-LPM shortcut
+    assert res90.width[0] != res.width[0]
+    dev = torch.from_numpy(a).cuda()
+    dres = dec.decode(dev, 11025, 120, want=WANT, device_outputs=True)
+    dres.digitalized = torch.empty_like(dres.digitalized)                   # a replaced buffer must be written, not the old one
+    dev.copy_(torch.from_numpy(b))
+    dres2 = dec.decode(dev, 11025, 120, want=WANT, device_outputs=True, out=dres)
+    torch.cuda.synchronize()
+    assert np.array_equal(dres2.digitalized.cpu().numpy(), fresh_b.digitalized)
+    dec.close()

@@ -44,6 +44,9 @@ class BatchResult:
     raster_flat: object = None      # (B, raster_stride) uint8
     on_device: bool = False
     _keepalive: list = field(default_factory=list, repr=False)
+    # what a repeated ``decode(..., out=this)`` with identical arguments needs to skip the argument checking and the
+    # allocation of the small result arrays (set by Decoder.decode; the arrays above are then updated in place)
+    _fast: object = field(default=None, repr=False, compare=False)
 
     def image(self, i: int):
         """Raster of recording ``i`` as a ``(height, width)`` uint8 array (a view)."""
@@ -151,6 +154,22 @@ class Decoder:
         """
         on_dev_in = _is_torch(pcm) and pcm.is_cuda
         shape = tuple(pcm.shape)
+        # ---- the steady state of a service: the same buffers and settings again, results into the same object --------
+        if out is not None and out._fast is not None:
+            f = out._fast
+            ptr = pcm.data_ptr() if on_dev_in else (pcm.ctypes.data if isinstance(pcm, np.ndarray) else None)
+            key = (self._h.value if hasattr(self._h, "value") else id(self._h), ptr, shape, str(pcm.dtype), int(sample_rate),
+                   lpm if np.isscalar(lpm) else tuple(lpm), notch_freq, notch_q, tuple(want), device_outputs, pinned)
+            same_bufs = (out.audio is f["bufs"].get("audio") and out.demodulated is f["bufs"].get("demodulated")
+                         and out.digitalized is f["bufs"].get("digitalized") and out.raster_flat is f["bufs"].get("raster"))
+            if (ptr is not None and same_bufs and key == f["key"]
+                    and (pcm.is_contiguous() if on_dev_in else pcm.flags["C_CONTIGUOUS"])):
+                self._check(self._lib.wefax_decode_batch(self._h, f["desc"], C.c_void_p(ptr), f["lpm"], f["out"]))
+                peaks, n_peaks, phasing, n_phasing = f["peaks"], f["n_peaks"], f["phasing"], f["n_phasing"]
+                B = len(out.lpm)
+                out.peaks = [peaks[i, : n_peaks[i]].tolist() for i in range(B)]
+                out.phasing_signals = [phasing[i, : n_phasing[i]].tolist() for i in range(B)]
+                return out
         if len(shape) == 1:
             B, n, ch = 1, shape[0], 1
         elif len(shape) == 2 and shape[1] == 2 and shape[0] != 2:
@@ -254,9 +273,9 @@ class Decoder:
                            (N.F_PCM_ON_DEVICE if on_dev_in else 0) | (N.F_OUT_ON_DEVICE if device_outputs else 0) |
                            (N.F_PCM_FLOAT32 if as_float else 0))
         lpm_arr = (C.c_double * B)(*lpms)
-        self._check(self._lib.wefax_decode_batch(self._h, C.byref(desc), C.c_void_p(pcm_ptr),
-                                                 C.cast(lpm_arr, C.c_void_p), C.byref(o)))
-        return BatchResult(
+        lpm_ptr = C.cast(lpm_arr, C.c_void_p)
+        self._check(self._lib.wefax_decode_batch(self._h, C.byref(desc), C.c_void_p(pcm_ptr), lpm_ptr, C.byref(o)))
+        result = BatchResult(
             n_out=n_out, sample_rate=N.TARGET_RATE, lpm=lpms, width=widths, status=status,
             peaks=[peaks[i, : n_peaks[i]].tolist() for i in range(B)],
             phasing_signals=[phasing[i, : n_phasing[i]].tolist() for i in range(B)],
@@ -264,6 +283,16 @@ class Decoder:
             audio=bufs.get("audio"), demodulated=bufs.get("demodulated"),
             digitalized=bufs.get("digitalized"), raster_flat=bufs.get("raster"),
             on_device=device_outputs, _keepalive=keep)
+        if on_dev_in or isinstance(pcm, np.ndarray):
+            result._fast = {
+                "key": (self._h.value if hasattr(self._h, "value") else id(self._h), pcm_ptr, shape, str(pcm.dtype),
+                        sample_rate, lpm if np.isscalar(lpm) else tuple(lpm), notch_freq, notch_q, tuple(want),
+                        device_outputs, pinned),
+                "desc": C.byref(desc), "lpm": lpm_ptr, "out": C.byref(o),
+                "hold": (desc, lpm_arr, o),           # the ctypes objects behind the references above
+                "bufs": bufs,                         # the large buffers the native side writes through raw pointers
+                "peaks": peaks, "n_peaks": n_peaks, "phasing": phasing, "n_phasing": n_phasing}
+        return result
 
     # -- stage-level entry points (parity tests) --------------------------------
     def fft(self, x: np.ndarray, inverse: bool = False) -> np.ndarray:
