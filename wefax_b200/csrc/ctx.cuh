@@ -76,6 +76,7 @@ struct wefax_ctx {
     std::vector<unsigned long long> graph_key, graph_candidate;
     long long api_calls = 0, graph_epoch = -1, graph_cand_epoch = -1;
     long long graph_launches = 0;
+    void *graph_h_res = nullptr;              // pinned result records (RecResult[]) the graph's last copy fills
     bool is_lane = false;
     std::vector<wefax_ctx *> lane_ctx;        // owned
     cudaEvent_t ev_lane_fork = nullptr;
