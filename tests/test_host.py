@@ -223,3 +223,54 @@ def test_fft_plan_prefers_the_specialised_kernels():
         assert all(r in fast for r in lens[:-1]), lens
         assert lens[-1] in mid, lens
     assert N.fft_plan_describe(39_690_000 // 2)[0] == [225, 225, 392]
+
+
+def test_decode_short_way_is_keyed_on_everything_the_native_call_reads():
+    """Decoder.decode(out=res): the call that made ``res`` left its ctypes arguments behind; they are reused only when
+    the input pointer, shape, dtype, settings AND the large output buffers are the ones of that call.  (Host logic only:
+    the native entry point is replaced by a recorder that fills the scalar outputs.)"""
+    from wefax_b200.decoder import Decoder
+
+    calls = []
+
+    class FakeLib:
+        def wefax_decode_batch(self, h, desc_ref, pcm, lpm, out_ref):
+            o = out_ref._obj
+            n_rec = desc_ref._obj.n_recordings
+            start = np.ctypeslib.as_array(ctypes.cast(o.start_frame, ctypes.POINTER(ctypes.c_int64)), shape=(n_rec,))
+            start[:] = len(calls) + 1                      # something that changes from call to call
+            calls.append((desc_ref._obj, out_ref._obj, pcm.value, o.digitalized))
+            return 0
+
+        def wefax_last_error(self, h):
+            return b""
+
+    dec = Decoder.__new__(Decoder)
+    dec._lib, dec._h, dec.device = FakeLib(), ctypes.c_void_p(0x1234), 0
+    pcm = np.zeros(110250, dtype=np.int16)
+    res = dec.decode(pcm, 11025, 120, want=("digitalized",))
+    assert res._fast is not None and int(res.start_frame[0]) == 1
+    again = dec.decode(pcm, 11025, 120, want=("digitalized",), out=res)
+    assert again is res and int(res.start_frame[0]) == 2           # same object, scalars updated in place
+    assert calls[1][0] is calls[0][0] and calls[1][1] is calls[0][1] and calls[1][2] == pcm.ctypes.data
+    # a view of the same memory is the same input
+    assert dec.decode(pcm[:], 11025, 120, want=("digitalized",), out=res) is res
+    # anything the native call reads differently goes the long way (a new result object)
+    for kwargs, arr in (({"lpm": 90}, pcm), ({"lpm": 120, "notch_q": 2}, pcm), ({"lpm": 120}, pcm.copy()),
+                        ({"lpm": 120, "want": ("digitalized", "raster")}, pcm), ({"lpm": 120}, pcm[:-2])):
+        kw = dict(want=("digitalized",))
+        kw.update(kwargs)
+        lpm = kw.pop("lpm")
+        other = dec.decode(arr, 11025, lpm, out=res if kw["want"] == ("digitalized",) and len(arr) == len(pcm) else None, **kw)
+        assert other is not res
+    # a replaced output buffer is written, not the one the shortcut remembers
+    n_before = len(calls)
+    res.digitalized = np.empty_like(res.digitalized)
+    newer = dec.decode(pcm, 11025, 120, want=("digitalized",), out=res)
+    assert newer is not res and calls[n_before][3] == res.digitalized.ctypes.data
+    # a non-contiguous input is copied by the long way, never handed over by pointer
+    strided = np.zeros(2 * len(pcm), dtype=np.int16)[::2]
+    r2 = dec.decode(strided, 11025, 120, want=("digitalized",))
+    r3 = dec.decode(strided, 11025, 120, want=("digitalized",), out=r2)
+    assert r3 is not r2
+    dec._h = None                                                   # nothing native to destroy
