@@ -1782,7 +1782,7 @@ sync_corr_kernel(const uint8_t *dig_all, size_t ds, long long n, const LineDev *
 // inclusive running maximum of s[0..len) (dir 0: left to right, dir 1: right to left) by one CTA
 __device__ __forceinline__ void block_running_max(const int *src, int *dst, int len, int dir, int *s_w) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int per = (len + (int)blockDim.x - 1) / (int)blockDim.x;   // (launched with 1024 or 256 threads)
+    const int per = (len + kSyncThreads - 1) / kSyncThreads;
     const int NEG = (int)0x80000000;
     const int lo = tid * per, hi = min(lo + per, len);
     int run = NEG;
@@ -1828,15 +1828,15 @@ sync_settled_kernel(const LineDev *lines, const SyncDev *sd_all, const int *corr
     const int len0 = (int)min((long long)w, sd.limc - b0);
     const int len1 = (int)max(0ll, min((long long)w, sd.limc - (b0 + w)));
     const int *corr = corr_all + (size_t)blockIdx.y * cs;
-    for (int i = threadIdx.x; i < len0; i += blockDim.x) s_c[i] = corr[b0 + i];
-    for (int i = threadIdx.x; i < len1; i += blockDim.x) s_pre[i] = corr[b0 + w + i];
+    for (int i = threadIdx.x; i < len0; i += kSyncThreads) s_c[i] = corr[b0 + i];
+    for (int i = threadIdx.x; i < len1; i += kSyncThreads) s_pre[i] = corr[b0 + w + i];
     __syncthreads();
     block_running_max(s_c, s_suf, len0, 1, s_w);
     if (len1 > 0) block_running_max(s_pre, s_pre, len1, 0, s_w);
     uint32_t *bits = bits_all + (size_t)blockIdx.y * bs;
     const long long p_first = b0 & ~31ll;
     const long long p_end = min(b0 + len0, sd.lim);
-    for (long long p = p_first + threadIdx.x; p < ((p_end + 31) & ~31ll); p += blockDim.x) {
+    for (long long p = p_first + threadIdx.x; p < ((p_end + 31) & ~31ll); p += kSyncThreads) {
         bool settled = false;
         if (p >= b0 && p < p_end) {
             const int i = (int)(p - b0);
@@ -2025,10 +2025,10 @@ void launch_sync_search(wefax_ctx *ctx, const uint8_t *dig, size_t ds, long long
         }
         {
             StageTimer t1(ctx, "sync_settled");
-            // (1024 threads per block of `mindistance` positions also in batches: with 256 the kernel took twice as long on
-            //  64 recordings, 434 -> 877 us - its 53 KB of shared memory per CTA, not its thread count, limits residency)
-            const int settled_threads = kSyncThreads;
-            sync_settled_kernel<<<g2, settled_threads, (size_t)3 * sp.max_w * sizeof(int), st>>>(lines, sp.sd, sp.corr, sp.cs,
+            // (1024 threads per block of `mindistance` positions also in batches: with 256 / 512 threads per CTA - and the
+            //  thread count a run-time value - the kernel took 877 / 609 us instead of 434 us on 64 recordings: its 53 KB of
+            //  shared memory per CTA, not its thread count, limits residency, and the compile-time stride matters)
+            sync_settled_kernel<<<g2, kSyncThreads, (size_t)3 * sp.max_w * sizeof(int), st>>>(lines, sp.sd, sp.corr, sp.cs,
                                                                                            sp.bits, sp.bs);
         }
         {
